@@ -1,0 +1,157 @@
+/*
+ * tm_gpu.h -- C ABI of libtm_gpu.so: the B200 (sm_100a) replacement for the native layer the TileMotion encoder
+ * (gligli/tiler) calls on its data-parallel hot path.
+ *
+ * Two groups of entry points:
+ *
+ *  1. DROP-IN symbols: the exact exports the FreePascal host binds today in extern.pas:178-223 (ANN.dll,
+ *     ANN_short.dll, yakmo.dll, BICO.dll).  Same argument meaning, same ownership rules, same "no error code"
+ *     behaviour (a failed search returns an out-of-range index, which the host already maps to "no result",
+ *     tilingencoder.pas:1549,1566).  ANN.dll and ANN_short.dll both export `ann_kdtree_*`; in one library the int16
+ *     flavour takes the names the Pascal side already uses for it (`ann_kdtree_short_*`, extern.pas:182-185).
+ *
+ *  2. BATCHED symbols (tm_*): one call per stage / frame instead of one call per 8x8 tile -- what the host calls
+ *     after hoisting the DLL call out of its per-tile loop (INTEGRATION.md shows the Pascal bindings).  Every array
+ *     argument may be a HOST pointer or a DEVICE pointer (detected with cudaPointerGetAttributes): host arrays are
+ *     staged through device scratch and the call returns with results on the host; with device arrays the work is
+ *     only enqueued on the stream set by tm_set_stream and nothing is copied.
+ *
+ * All tm_* functions return 0 (TM_OK) or a TM_ERR_* code; tm_last_error() gives the text.  There is no CPU
+ * fallback: without an sm_100 device every compute entry point fails with TM_ERR_NOGPU.
+ *
+ * Data conventions (those of the reference):
+ *   pixel      int32 0x00BBGGRR                     (ToRGB, utils.pas:243-246)
+ *   tile       64 pixels row-major [y][x]           (TRGBPixels / TPalPixels, tilingencoder.pas:101-104)
+ *   feature    int16[192] = [Y|U|V][zig-zag(v,u)]   (TDCT, utils.pas:129-132)
+ *   palette    int32[pal_size], unused = 0xFFFF00FF (cDitheringNullColor, utils.pas:45)
+ *   mirror     bit0 = H, bit1 = V                   (tfHMirror_Initial / tfVMirror_Initial, tilingencoder.pas:120)
+ */
+#ifndef TM_GPU_H
+#define TM_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TM_OK 0
+#define TM_ERR_ARG 1
+#define TM_ERR_CUDA 2
+#define TM_ERR_DRIVER 3
+#define TM_ERR_NOGPU 4
+#define TM_ERR_NOMEM 5
+
+/* ---------------------------------------------------------------- runtime */
+int tm_version(void);                      /* 100 * major + minor */
+int tm_device_count(void);                 /* number of sm_100 devices visible */
+int tm_set_device(int device);             /* device used by the calling thread's subsequent calls */
+int tm_set_stream(void *cuda_stream);      /* cudaStream_t used by subsequent calls of this thread (NULL = default) */
+const char *tm_last_error(void);
+int64_t tm_kernel_launches(void);          /* kernels launched by this library since load (bench.py's gpu_launches) */
+int tm_synchronize(void);
+
+/* ---------------------------------------------------------------- drop-in: ANN_short.dll (extern.pas:182-185) */
+typedef struct tm_knn_short tm_knn_short;
+/* rows: n pointers to int16[dim]; dim must be 192 (cTileDCTSize).  bucket/split are kd-tree knobs: ignored. The rows
+   are copied (the host keeps them alive anyway, tilingencoder.pas:4600-4620). */
+tm_knn_short *ann_kdtree_short_create(int16_t **rows, int n, int dim, int bucket, int split);
+void ann_kdtree_short_destroy(tm_knn_short *h);
+/* exact NN (eps ignored: always exact); returns index, *err = sum (a-b)^2 as uint32; -1 on failure */
+int ann_kdtree_short_search(tm_knn_short *h, const int16_t *q, uint32_t eps, uint32_t *err);
+/* k nearest, ascending (distance, index); slots beyond the dataset size get idx -1 / err 0xFFFFFFFF */
+void ann_kdtree_short_search_multi(tm_knn_short *h, int *idxs, uint32_t *errs, int k, const int16_t *q, uint32_t eps);
+
+/* ---------------------------------------------------------------- drop-in: ANN.dll (extern.pas:178-180) */
+typedef struct tm_knn_double tm_knn_double;
+tm_knn_double *ann_kdtree_create(double **rows, int n, int dim, int bucket, int split);
+void ann_kdtree_destroy(tm_knn_double *h);
+int ann_kdtree_search(tm_knn_double *h, const double *q, double eps, double *err);
+
+/* ---------------------------------------------------------------- drop-in: yakmo.dll (extern.pas:198-203) */
+typedef struct tm_yakmo tm_yakmo;
+tm_yakmo *yakmo_create(uint32_t k, uint32_t restarts, int max_iter, int init_type, int init_seed, int normalize, int verbose);
+void yakmo_destroy(tm_yakmo *y);
+void yakmo_set_num_threads(int n);                                         /* no-op: the GPU is the pool */
+void yakmo_load_train_data(tm_yakmo *y, uint32_t rows, uint32_t cols, double **data);   /* copies */
+void yakmo_train_on_data(tm_yakmo *y, int *point_to_cluster);
+void yakmo_get_centroids(tm_yakmo *y, double **centroids);
+
+/* ---------------------------------------------------------------- drop-in: BICO.dll (extern.pas:218-223) */
+/* The CPU-era streaming coreset is replaced, not ported: points are buffered and get_results runs weighted Lloyd
+   (seeded k-means++) on the full set on the GPU, returning <= coresetsize weighted centres -- the same contract
+   (a weighted summary of at most `coresetsize` points). */
+typedef struct tm_bico tm_bico;
+tm_bico *bico_create(int64_t dim, int64_t n, int64_t k, int64_t nrandproj, int64_t coresetsize, int seed);
+void bico_destroy(tm_bico *b);
+void bico_set_num_threads(int n);
+void bico_set_rebuild_properties(tm_bico *b, uint32_t interval, double initial, double grow);
+void bico_insert_line(tm_bico *b, const double *row, double weight);
+int64_t bico_get_results(tm_bico *b, double *centroids, double *weights);
+
+/* ---------------------------------------------------------------- batched: features (tilingencoder.pas:3049-3182) */
+/* RGB tiles [n][64] -> int16 features [n][192] (ConvertToCpnPixels + ComputeCpnPixelsPsyVisFeatures, pvsWeightedDCT, YUV) */
+int tm_features_from_rgb(const int32_t *rgb, int64_t n, int16_t *out);
+/* palette-index tiles [n][64] + tile_pal[n] + palettes[n_pal][pal_size] -> features (PrepareReconstruct.DoPsyV, :4570-4583) */
+int tm_features_from_pal(const uint8_t *pal_idx, const int32_t *tile_pal, const int32_t *palettes, int pal_size, int n_pal,
+                         int64_t n, int16_t *out);
+/* ComputeTilePsyVisFeatures: f64, mode = TPsyVisMode ordinal (0 DCT, 1 weighted, 3 special, 4 weighted special) */
+int tm_features_f64(const int32_t *rgb, int64_t n, int mode, int use_lab, double *out);
+/* load-time canonicalisation (TFrame.AsyncLoadFromImage, :1393-1411): flips tiles in place, writes mirror flags */
+int tm_mirror_canonicalise(int32_t *rgb, int64_t n, uint8_t *flags);
+/* sum (a-b)^2 mod 2^32 for n vector pairs (CompareEuclideanDCTPtr, utils.pas:541-557) */
+int tm_distance_pairs(const int16_t *a, const int16_t *b, int64_t n, uint32_t *out);
+
+/* ---------------------------------------------------------------- batched: k-NN */
+/* dictionary from contiguous features [n][192] (host or device) */
+int tm_knn_short_create(const int16_t *feat, int64_t n, tm_knn_short **out);
+int tm_knn_short_destroy(tm_knn_short *h);
+/* n_q queries [n_q][192] -> idx/dist [n_q][k], 1 <= k <= 64; sorted != 0 orders each row by (distance, index) */
+int tm_knn_short_batch(tm_knn_short *h, const int16_t *q, int64_t n_q, int k, int32_t *idx, uint32_t *dist, int sorted);
+/* exact NN of f64 vectors: dict [n_dict][dim], q [n_q][dim] -> idx[n_q], dist[n_q] (may be NULL) */
+int tm_knn_double_batch(const double *dict, int64_t n_dict, int dim, const double *q, int64_t n_q, int32_t *idx, double *dist);
+
+/* ---------------------------------------------------------------- batched: dithering (tilingencoder.pas:1873-1907, 2268-2724) */
+/* pair p dithers tile pair_tile[p] (p itself when pair_tile == NULL) against palette pair_pal[p].
+   rgb [n_tiles][64] in stored (canonical) orientation, mirror_flags[n_tiles] or NULL.  out [n_pairs][64]. */
+int tm_dither(const int32_t *rgb, const uint8_t *mirror_flags, int64_t n_tiles, const int32_t *pair_tile, const int32_t *pair_pal,
+              int64_t n_pairs, const int32_t *palettes, int pal_size, int n_pal, int use_thomas_knoll, int y2_mixed_colors,
+              uint8_t *out_idx);
+
+/* ---------------------------------------------------------------- batched: k-means (yakmo semantics) */
+/* Lloyd on f64 rows x[n][dim] from explicit initial centroids init[k][dim] (NULL: seeded k-means++).
+   Stops when no label changes or after max_iter updates.  labels[n], centroids[k][dim] out; inertia/iters optional. */
+int tm_kmeans_fit(const double *x, int64_t n, int dim, int k, int max_iter, const double *init, uint64_t seed, int nan_empty,
+                  int32_t *labels, double *centroids, double *inertia, int *iters);
+/* one Lloyd step for a SHARD of the points (multi-GPU): assignment against replicated centroids, then per-cluster
+   partial sums [k][dim] and counts [k] that the caller all-reduces (NCCL) before tm_kmeans_finish_step. */
+int tm_kmeans_partial_step(const double *x, int64_t n, int dim, int k, const double *centroids, int32_t *labels,
+                           double *partial_sums, int64_t *partial_counts, int64_t *changed, double *inertia);
+int tm_kmeans_finish_step(const double *sums, const int64_t *counts, int k, int dim, int nan_empty, double *centroids);
+
+/* ---------------------------------------------------------------- batched: palette colour quantisation (:4434-4564) */
+/* all palettes at once: rgb tiles [n_tiles][64], tile_pal[n_tiles] in [0, n_pal) -> palettes[n_pal][pal_size]
+   (k-means on the palette's pixels sorted by (G,R,B), centroids rounded, sorted by (V,S,H), padded with the null colour).
+   init [n_pal][pal_size][3] explicit start or NULL (k-means++ from `seed`, same generator as the oracle). */
+int tm_palquant_kmeans(const int32_t *rgb, const int32_t *tile_pal, int64_t n_tiles, int n_pal, int pal_size, const double *init,
+                       uint64_t seed, int32_t *palettes, int *iters);
+
+/* ---------------------------------------------------------------- batched: matcher (tilingencoder.pas:4566-4613, 1464-1659) */
+typedef struct tm_matcher tm_matcher;
+/* PrepareReconstruct: dictionary tiles as palette indices [n_dict][64] + their palette dict_pal[n_dict] + palettes.
+   extended != 0 also builds the (tile x palette) feature table used by the extended-palette re-rank. */
+int tm_matcher_create(const uint8_t *dict_idx, const int32_t *dict_pal, int64_t n_dict, const int32_t *palettes, int pal_size,
+                      int n_pal, int extended, tm_matcher **out);
+int tm_matcher_destroy(tm_matcher *m);
+/* DoXY for tiles with no usable motion prediction (first frame of a keyframe sequence, or mpErr above the dead band):
+   source tiles as RGB [n_q][64] (already canonicalised) -> TTileMapItem fields TileIdx / PalIdx and the error. */
+int tm_match_tiles_rgb(tm_matcher *m, const int32_t *rgb, int64_t n_q, int k, int32_t *tile_idx, int32_t *pal_idx, uint32_t *err);
+/* same from precomputed features [n_q][192] */
+int tm_match_tiles_feat(tm_matcher *m, const int16_t *feat, int64_t n_q, int k, int32_t *tile_idx, int32_t *pal_idx, uint32_t *err);
+/* the dictionary's own features (device pointer, [n_dict][192]) for inspection/tests */
+int tm_matcher_dict_features(tm_matcher *m, int16_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -14,7 +14,7 @@ _LIB = None
 _REF = None
 
 DCT = 192
-NULL_COLOR = np.int32(-16776961)  # 0xffff00ff as int32 (cDitheringNullColor, utils.pas:45)
+NULL_COLOR = np.int32(-65281)  # 0xffff00ff as int32 (cDitheringNullColor, utils.pas:45)
 
 PVS_DCT, PVS_WEIGHTED_DCT, PVS_WAVELETS, PVS_SPE_DCT, PVS_WEIGHTED_SPE_DCT = range(5)
 

@@ -1,0 +1,416 @@
+"""Host-side mirror of the reference's operator interface for the hot path, over the C ABI of libtm_gpu.so.
+
+Names follow the reference (tilingencoder.pas / extern.pas): tiles, palettes, features (TDCT), tilemap items.  Every
+function accepts either numpy arrays (host buffers: copied to the GPU and back inside the call) or torch CUDA tensors
+(device buffers: nothing is copied, work is enqueued on torch's current stream and results are CUDA tensors).
+torch is used for device memory and streams only.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import TmError, check  # noqa: F401
+
+DCT = 192           # cTileDCTSize (utils.pas:40)
+TILE_PX = 64
+NULL_COLOR = np.int32(-65281)  # cDitheringNullColor 0xFFFF00FF (utils.pas:45)
+PVS_DCT, PVS_WEIGHTED_DCT, PVS_WAVELETS, PVS_SPE_DCT, PVS_WEIGHTED_SPE_DCT = range(5)  # TPsyVisMode (tilingencoder.pas:21)
+
+try:  # torch is optional for pure host use
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+_NP2T = {}
+if torch is not None:
+    _NP2T = {np.dtype(np.int16): torch.int16, np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8,
+             np.dtype(np.float64): torch.float64, np.dtype(np.int64): torch.int64, np.dtype(np.uint32): torch.int32}
+
+
+def _is_dev(x):
+    return torch is not None and isinstance(x, torch.Tensor) and x.is_cuda
+
+
+class _Call:
+    """Collects the arguments of one ABI call; decides host vs device from the first array argument."""
+
+    def __init__(self, *arrays):
+        self.dev = any(_is_dev(a) for a in arrays)
+        self.keep = []
+        if self.dev:
+            self.device = next(a.device for a in arrays if _is_dev(a))
+            torch.cuda.set_device(self.device)
+            check(_lib.lib().tm_set_stream(C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+        else:
+            check(_lib.lib().tm_set_stream(None))
+
+    def inp(self, x, dtype, shape=None):
+        if x is None:
+            return None
+        if self.dev:
+            if not _is_dev(x):
+                x = torch.as_tensor(np.ascontiguousarray(x, dtype=dtype)).to(self.device)
+            t = x.contiguous()
+            want = _NP2T[np.dtype(dtype)]
+            if t.dtype != want:
+                raise TypeError(f"expected {want}, got {t.dtype}")
+            self.keep.append(t)
+            return C.c_void_p(t.data_ptr())
+        a = np.ascontiguousarray(x, dtype=dtype)
+        self.keep.append(a)
+        return C.c_void_p(a.ctypes.data)
+
+    def out(self, shape, dtype):
+        if self.dev:
+            t = torch.empty(shape, dtype=_NP2T[np.dtype(dtype)], device=self.device)
+            self.keep.append(t)
+            return t, C.c_void_p(t.data_ptr())
+        a = np.empty(shape, dtype=dtype)
+        return a, C.c_void_p(a.ctypes.data)
+
+
+def _n_rows(x, width):
+    n = int(np.prod(x.shape)) // width
+    return n
+
+
+def device_count():
+    return int(_lib.lib().tm_device_count())
+
+
+def kernel_launches():
+    return int(_lib.lib().tm_kernel_launches())
+
+
+def synchronize():
+    check(_lib.lib().tm_synchronize())
+
+
+# ------------------------------------------------------------------ features (tilingencoder.pas:3049-3182)
+def features_from_rgb(rgb):
+    """ConvertToCpnPixels + ComputeCpnPixelsPsyVisFeatures(pvsWeightedDCT): RGB tiles [n,64] int32 -> int16 [n,192]."""
+    c = _Call(rgb)
+    n = _n_rows(rgb, 64)
+    out, po = c.out((n, DCT), np.int16)
+    check(_lib.lib().tm_features_from_rgb(c.inp(rgb, np.int32), n, po))
+    return out
+
+
+def features_from_pal(pal_idx, tile_pal, palettes):
+    """PrepareReconstruct.DoPsyV (tilingencoder.pas:4570-4583): indexed tiles + their palettes -> int16 [n,192]."""
+    c = _Call(pal_idx, tile_pal, palettes)
+    n = _n_rows(pal_idx, 64)
+    n_pal, pal_size = palettes.shape
+    out, po = c.out((n, DCT), np.int16)
+    check(_lib.lib().tm_features_from_pal(c.inp(pal_idx, np.uint8), c.inp(tile_pal, np.int32), c.inp(palettes, np.int32),
+                                          int(pal_size), int(n_pal), n, po))
+    return out
+
+
+def features_f64(rgb, mode=PVS_WEIGHTED_SPE_DCT, use_lab=True):
+    """ComputeTilePsyVisFeatures (tilingencoder.pas:3133-3182): f64 [n,192]."""
+    c = _Call(rgb)
+    n = _n_rows(rgb, 64)
+    out, po = c.out((n, DCT), np.float64)
+    check(_lib.lib().tm_features_f64(c.inp(rgb, np.int32), n, int(mode), int(use_lab), po))
+    return out
+
+
+def mirror_canonicalise(rgb):
+    """TFrame.AsyncLoadFromImage mirror step (tilingencoder.pas:1393-1411). Returns (flipped tiles, flags bit0=H bit1=V)."""
+    c = _Call(rgb)
+    n = _n_rows(rgb, 64)
+    if c.dev:
+        tiles = rgb.clone().contiguous().view(n, 64)
+        c.keep.append(tiles)
+        pt = C.c_void_p(tiles.data_ptr())
+    else:
+        tiles = np.array(rgb, dtype=np.int32, copy=True).reshape(n, 64)
+        pt = C.c_void_p(tiles.ctypes.data)
+    flags, pf = c.out((n,), np.uint8)
+    check(_lib.lib().tm_mirror_canonicalise(pt, n, pf))
+    return tiles, flags
+
+
+def distance_pairs(a, b):
+    """CompareEuclideanDCTPtr (utils.pas:541-557) for n vector pairs -> uint32 (int32 bit pattern on device)."""
+    c = _Call(a, b)
+    n = _n_rows(a, DCT)
+    out, po = c.out((n,), np.uint32)
+    check(_lib.lib().tm_distance_pairs(c.inp(a, np.int16), c.inp(b, np.int16), n, po))
+    return out
+
+
+# ------------------------------------------------------------------ k-NN
+class KnnShort:
+    """Exact k-NN over int16[192] rows: the ANN_short.dll kd-tree (extern.pas:182-185), batched."""
+
+    def __init__(self, feat):
+        c = _Call(feat)
+        self.n = _n_rows(feat, DCT)
+        h = C.c_void_p()
+        check(_lib.lib().tm_knn_short_create(c.inp(feat, np.int16), self.n, C.byref(h)))
+        self._h = h
+
+    def search(self, q, k=1, sorted=True):
+        """-> (idx [n_q,k] int32, dist [n_q,k] uint32), rows ordered by (distance, index) when sorted."""
+        c = _Call(q)
+        n_q = _n_rows(q, DCT)
+        idx, pi = c.out((n_q, k), np.int32)
+        dist, pd = c.out((n_q, k), np.uint32)
+        check(_lib.lib().tm_knn_short_batch(self._h, c.inp(q, np.int16), n_q, int(k), pi, pd, int(sorted)))
+        return idx, dist
+
+    def close(self):
+        if self._h:
+            _lib.lib().tm_knn_short_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def knn_double(dict_pts, q):
+    """Exact NN of f64 vectors: ann_kdtree_search with eps 0 (extern.pas:180), batched. -> (idx, dist)."""
+    c = _Call(dict_pts, q)
+    n_dict, dim = dict_pts.shape
+    n_q = q.shape[0]
+    idx, pi = c.out((n_q,), np.int32)
+    dist, pd = c.out((n_q,), np.float64)
+    check(_lib.lib().tm_knn_double_batch(c.inp(dict_pts, np.float64), n_dict, int(dim), c.inp(q, np.float64), n_q, pi, pd))
+    return idx, dist
+
+
+# ------------------------------------------------------------------ dithering (tilingencoder.pas:1873-1907)
+def dither(rgb, mirror_flags, pair_pal, palettes, use_thomas_knoll=True, y2_mixed_colors=4, pair_tile=None):
+    """TTilingEncoder.Dither generalised to (tile, palette) pair lists. -> uint8 [n_pairs,64] palette indices."""
+    c = _Call(rgb, pair_pal, palettes)
+    n_tiles = _n_rows(rgb, 64)
+    n_pairs = int(np.prod(pair_pal.shape))
+    n_pal, pal_size = palettes.shape
+    out, po = c.out((n_pairs, 64), np.uint8)
+    check(_lib.lib().tm_dither(c.inp(rgb, np.int32), c.inp(mirror_flags, np.uint8), n_tiles, c.inp(pair_tile, np.int32),
+                               c.inp(pair_pal, np.int32), n_pairs, c.inp(palettes, np.int32), int(pal_size), int(n_pal),
+                               int(use_thomas_knoll), int(y2_mixed_colors), po))
+    return out
+
+
+# ------------------------------------------------------------------ k-means (yakmo contract, extern.pas:198-203)
+def kmeans_fit(x, k, init=None, seed=1, max_iter=300, nan_empty=False):
+    """Lloyd from explicit initial centroids (or seeded k-means++). -> labels, centroids, inertia, iterations."""
+    c = _Call(x, init)
+    n, dim = x.shape
+    labels, pl = c.out((n,), np.int32)
+    cent, pc = c.out((k, dim), np.float64)
+    inertia, iters = C.c_double(), C.c_int()
+    check(_lib.lib().tm_kmeans_fit(c.inp(x, np.float64), n, int(dim), int(k), int(max_iter), c.inp(init, np.float64),
+                                   C.c_uint64(seed), int(nan_empty), pl, pc, C.byref(inertia), C.byref(iters)))
+    return labels, cent, inertia.value, iters.value
+
+
+def kmeans_partial_step(x, centroids, labels):
+    """One Lloyd step on a shard: assignment + per-cluster partial sums/counts (to be all-reduced across GPUs)."""
+    c = _Call(x, centroids, labels)
+    n, dim = x.shape
+    k = centroids.shape[0]
+    sums, ps = c.out((k, dim), np.float64)
+    counts, pc = c.out((k,), np.int64)
+    changed, inertia = C.c_int64(), C.c_double()
+    if c.dev:
+        lab = labels.contiguous()
+        c.keep.append(lab)
+        plab = C.c_void_p(lab.data_ptr())
+    else:
+        lab = np.ascontiguousarray(labels, dtype=np.int32)
+        plab = C.c_void_p(lab.ctypes.data)
+    check(_lib.lib().tm_kmeans_partial_step(c.inp(x, np.float64), n, int(dim), int(k), c.inp(centroids, np.float64), plab,
+                                            ps, pc, C.byref(changed), C.byref(inertia)))
+    return lab, sums, counts, changed.value, inertia.value
+
+
+def kmeans_finish_step(sums, counts, centroids, nan_empty=False):
+    c = _Call(sums, counts, centroids)
+    k, dim = sums.shape
+    if c.dev:
+        cent = centroids.clone().contiguous()
+        c.keep.append(cent)
+        pc = C.c_void_p(cent.data_ptr())
+    else:
+        cent = np.array(centroids, dtype=np.float64, copy=True)
+        pc = C.c_void_p(cent.ctypes.data)
+    check(_lib.lib().tm_kmeans_finish_step(c.inp(sums, np.float64), c.inp(counts, np.int64), int(k), int(dim), int(nan_empty), pc))
+    return cent
+
+
+# ------------------------------------------------------------------ palette colour quantisation (:4434-4564)
+def palquant_kmeans(rgb, tile_pal, n_pal, pal_size, init=None, seed=1):
+    """QuantizeUsingYakmo + DoQuantization for every palette. -> palettes int32 [n_pal,pal_size], iterations."""
+    c = _Call(rgb, tile_pal)
+    n_tiles = _n_rows(rgb, 64)
+    out, po = c.out((n_pal, pal_size), np.int32)
+    iters = C.c_int()
+    check(_lib.lib().tm_palquant_kmeans(c.inp(rgb, np.int32), c.inp(tile_pal, np.int32), n_tiles, int(n_pal), int(pal_size),
+                                        c.inp(init, np.float64), C.c_uint64(seed), po, C.byref(iters)))
+    return out, iters.value
+
+
+# ------------------------------------------------------------------ matcher (tilingencoder.pas:4566-4613, 1464-1659)
+class Matcher:
+    """PrepareReconstruct + the k-NN / extended-palette part of TFrame.Reconstruct.DoXY."""
+
+    K_EPU = 64  # cEpuKnnK (tilingencoder.pas:1433)
+
+    def __init__(self, dict_idx, dict_pal, palettes, extended=True):
+        c = _Call(dict_idx, dict_pal, palettes)
+        self.n_dict = _n_rows(dict_idx, 64)
+        self.n_pal, self.pal_size = palettes.shape
+        self.extended = bool(extended)
+        h = C.c_void_p()
+        check(_lib.lib().tm_matcher_create(c.inp(dict_idx, np.uint8), c.inp(dict_pal, np.int32), self.n_dict,
+                                           c.inp(palettes, np.int32), int(self.pal_size), int(self.n_pal), int(extended),
+                                           C.byref(h)))
+        self._h = h
+
+    def _run(self, fn, x, width, dtype, k):
+        c = _Call(x)
+        n_q = _n_rows(x, width)
+        tile, pt = c.out((n_q,), np.int32)
+        pal, pp = c.out((n_q,), np.int32)
+        err, pe = c.out((n_q,), np.uint32)
+        check(fn(self._h, c.inp(x, dtype), n_q, int(k), pt, pp, pe))
+        return tile, pal, err
+
+    def match_rgb(self, rgb, k=None):
+        """Source tiles as RGB [n,64] -> (TileIdx, PalIdx, err) per tile."""
+        return self._run(_lib.lib().tm_match_tiles_rgb, rgb, 64, np.int32, k or (self.K_EPU if self.extended else 1))
+
+    def match_feat(self, feat, k=None):
+        return self._run(_lib.lib().tm_match_tiles_feat, feat, DCT, np.int16, k or (self.K_EPU if self.extended else 1))
+
+    def dict_features(self):
+        out = np.empty((self.n_dict, DCT), dtype=np.int16)
+        check(_lib.lib().tm_matcher_dict_features(self._h, C.c_void_p(out.ctypes.data)))
+        return out
+
+    def close(self):
+        if self._h:
+            _lib.lib().tm_matcher_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------ drop-in symbols, exercised the way extern.pas binds them
+class AnnKdTreeShort:
+    """ann_kdtree_short_create / _search / _search_multi / _destroy with the Pascal calling pattern (row pointers)."""
+
+    def __init__(self, rows, bucket=32, split=0):
+        self._rows = np.ascontiguousarray(rows, dtype=np.int16)
+        n, dim = self._rows.shape
+        ptrs = (C.c_void_p * n)(*[self._rows[i].ctypes.data for i in range(n)])
+        self._h = _lib.lib().ann_kdtree_short_create(ptrs, n, dim, bucket, split)
+        if not self._h:
+            raise TmError(-1, _lib.lib().tm_last_error().decode())
+
+    def search(self, q):
+        q = np.ascontiguousarray(q, dtype=np.int16)
+        err = C.c_uint32()
+        idx = _lib.lib().ann_kdtree_short_search(self._h, C.c_void_p(q.ctypes.data), 0, C.byref(err))
+        return int(idx), int(err.value)
+
+    def search_multi(self, q, k):
+        q = np.ascontiguousarray(q, dtype=np.int16)
+        idxs = np.empty(k, dtype=np.int32)
+        errs = np.empty(k, dtype=np.uint32)
+        _lib.lib().ann_kdtree_short_search_multi(self._h, C.c_void_p(idxs.ctypes.data), C.c_void_p(errs.ctypes.data), k,
+                                                 C.c_void_p(q.ctypes.data), 0)
+        return idxs, errs
+
+    def destroy(self):
+        if self._h:
+            _lib.lib().ann_kdtree_short_destroy(self._h)
+            self._h = None
+
+
+class AnnKdTree:
+    """ann_kdtree_create / _search / _destroy (ANN.dll, doubles)."""
+
+    def __init__(self, rows, bucket=32, split=0):
+        self._rows = np.ascontiguousarray(rows, dtype=np.float64)
+        n, dim = self._rows.shape
+        ptrs = (C.c_void_p * n)(*[self._rows[i].ctypes.data for i in range(n)])
+        self._h = _lib.lib().ann_kdtree_create(ptrs, n, dim, bucket, split)
+        if not self._h:
+            raise TmError(-1, _lib.lib().tm_last_error().decode())
+
+    def search(self, q):
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        err = C.c_double()
+        idx = _lib.lib().ann_kdtree_search(self._h, C.c_void_p(q.ctypes.data), 0.0, C.byref(err))
+        return int(idx), float(err.value)
+
+    def destroy(self):
+        if self._h:
+            _lib.lib().ann_kdtree_destroy(self._h)
+            self._h = None
+
+
+class Yakmo:
+    """yakmo_create / load_train_data / train_on_data / get_centroids / destroy (extern.pas:198-203)."""
+
+    def __init__(self, k, restarts=1, max_iter=300, init_type=1, init_seed=0, normalize=0, verbose=0):
+        self.k = k
+        self._h = _lib.lib().yakmo_create(k, restarts, max_iter, init_type, init_seed, normalize, verbose)
+
+    def load_train_data(self, data):
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        self.rows, self.cols = data.shape
+        ptrs = (C.c_void_p * self.rows)(*[data[i].ctypes.data for i in range(self.rows)])
+        _lib.lib().yakmo_load_train_data(self._h, self.rows, self.cols, ptrs)
+
+    def train_on_data(self):
+        labels = np.full(self.rows, -1, dtype=np.int32)
+        _lib.lib().yakmo_train_on_data(self._h, C.c_void_p(labels.ctypes.data))
+        return labels
+
+    def get_centroids(self):
+        cent = np.zeros((self.k, self.cols), dtype=np.float64)
+        ptrs = (C.c_void_p * self.k)(*[cent[i].ctypes.data for i in range(self.k)])
+        _lib.lib().yakmo_get_centroids(self._h, ptrs)
+        return cent
+
+    def destroy(self):
+        if self._h:
+            _lib.lib().yakmo_destroy(self._h)
+            self._h = None
+
+
+class Bico:
+    """bico_create / insert_line / get_results / destroy (extern.pas:218-223)."""
+
+    def __init__(self, dim, n, k, nrandproj, coresetsize, seed):
+        self.dim, self.coreset = dim, coresetsize
+        self._h = _lib.lib().bico_create(dim, n, k, nrandproj, coresetsize, seed)
+
+    def insert_line(self, row, weight):
+        row = np.ascontiguousarray(row, dtype=np.float64)
+        _lib.lib().bico_insert_line(self._h, C.c_void_p(row.ctypes.data), float(weight))
+
+    def get_results(self):
+        cent = np.zeros((self.coreset, self.dim), dtype=np.float64)
+        w = np.zeros(self.coreset, dtype=np.float64)
+        m = _lib.lib().bico_get_results(self._h, C.c_void_p(cent.ctypes.data), C.c_void_p(w.ctypes.data))
+        return cent[:m], w[:m]
+
+    def destroy(self):
+        if self._h:
+            _lib.lib().bico_destroy(self._h)
+            self._h = None

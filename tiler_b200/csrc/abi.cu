@@ -1,0 +1,677 @@
+// abi.cu -- the C ABI of libtm_gpu.so (include/tm_gpu.h): drop-in exports for the DLLs the FreePascal host binds
+// (extern.pas:178-223) and the batched tm_* entry points.  Host-side plumbing only: argument checks, host<->device
+// staging, handle lifetime; every computation is a kernel from knn_i8.cu / features.cu / dither.cu / match.cu /
+// kmeans.cu.  No CPU implementation of any stage lives here.
+#include "../../include/tm_gpu.h"
+#include "tm_kernels.h"
+
+#include <cuda_runtime.h>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <cstring>
+#include <cstdio>
+#include <cmath>
+
+namespace tmg {
+std::atomic<long long> g_launches{0};
+}
+using namespace tmg;
+
+// ------------------------------------------------------------------ thread state / errors
+static thread_local cudaStream_t t_stream = nullptr;
+static thread_local std::string t_err;
+static std::recursive_mutex g_mu;   // one batched call at a time per process (the GPU serialises them anyway)
+
+static int fail(int code, const char *what) {
+  char buf[512];
+  cudaError_t ce = cudaGetLastError();
+  snprintf(buf, sizeof buf, "%s%s%s", what, ce != cudaSuccess ? ": " : "", ce != cudaSuccess ? cudaGetErrorString(ce) : "");
+  t_err = buf;
+  return code;
+}
+#define CU(x) do { if ((x) != cudaSuccess) return fail(TM_ERR_CUDA, #x); } while (0)
+#define RC(x) do { int _rc = (x); if (_rc != TM_OK) return fail(_rc, #x); } while (0)
+
+static int g_gpu_ok = -1;
+static int require_gpu() {
+  if (g_gpu_ok < 0) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); g_gpu_ok = 0; }
+    else {
+      int dev = 0; cudaGetDevice(&dev);
+      cudaDeviceProp p;
+      g_gpu_ok = (cudaGetDeviceProperties(&p, dev) == cudaSuccess && p.major == 10) ? 1 : 0;
+      if (g_gpu_ok) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+          unsigned long long thr = ~0ull;
+          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+      }
+    }
+  }
+  if (!g_gpu_ok) return fail(TM_ERR_NOGPU, "no sm_100 (B200) device: libtm_gpu has no CPU fallback");
+  return TM_OK;
+}
+
+static bool is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Staging of one call's arguments: host arrays get a stream-ordered device twin; outputs are copied back at finish().
+struct Stage {
+  cudaStream_t st;
+  std::vector<void *> temps;
+  struct Out { void *host; void *dev; size_t bytes; };
+  std::vector<Out> outs;
+  bool any_host = false;
+  int err = TM_OK;
+  explicit Stage(cudaStream_t s) : st(s) {}
+  void *temp(size_t bytes) {
+    void *d = nullptr;
+    if (bytes == 0) bytes = 16;
+    if (cudaMallocAsync(&d, bytes, st) != cudaSuccess) { err = TM_ERR_NOMEM; return nullptr; }
+    temps.push_back(d);
+    return d;
+  }
+  template <class T> const T *in(const T *p, size_t count) {
+    if (!p || is_device_ptr(p)) return p;
+    any_host = true;
+    void *d = temp(count * sizeof(T));
+    if (d && cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, st) != cudaSuccess) err = TM_ERR_CUDA;
+    return (const T *)d;
+  }
+  template <class T> T *out(T *p, size_t count) {
+    if (!p || is_device_ptr(p)) return p;
+    any_host = true;
+    void *d = temp(count * sizeof(T));
+    outs.push_back({p, d, count * sizeof(T)});
+    return (T *)d;
+  }
+  template <class T> T *inout(T *p, size_t count) {
+    if (!p || is_device_ptr(p)) return p;
+    T *d = out(p, count);
+    if (d && cudaMemcpyAsync(d, p, count * sizeof(T), cudaMemcpyHostToDevice, st) != cudaSuccess) err = TM_ERR_CUDA;
+    return d;
+  }
+  int finish(bool force_sync = false) {
+    int rc = err;
+    for (auto &o : outs)
+      if (rc == TM_OK && cudaMemcpyAsync(o.host, o.dev, o.bytes, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = TM_ERR_CUDA;
+    for (void *t : temps) cudaFreeAsync(t, st);
+    temps.clear();
+    if ((any_host || force_sync) && cudaStreamSynchronize(st) != cudaSuccess) rc = rc == TM_OK ? TM_ERR_CUDA : rc;
+    return rc;
+  }
+  ~Stage() { for (void *t : temps) cudaFreeAsync(t, st); }
+};
+
+static int num_sms() {
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+  return sms;
+}
+
+// ------------------------------------------------------------------ handles
+struct tm_knn_short {
+  int64_t n = 0;
+  uint8_t *limbs = nullptr;    // [n][384]
+  uint32_t *norms = nullptr;   // [ceil64(n)]
+};
+struct tm_knn_double {
+  int64_t n = 0; int dim = 0;
+  double *pts = nullptr;
+};
+struct tm_yakmo {
+  uint32_t k = 0; int max_iter = 300; uint64_t seed = 0;
+  uint32_t rows = 0, cols = 0;
+  std::vector<double> data, cent;
+};
+struct tm_bico {
+  int64_t dim = 0, k = 0, coreset = 0; uint64_t seed = 0;
+  std::vector<double> rows, weights;
+};
+struct tm_matcher {
+  int64_t n_dict = 0; int n_pal = 0, pal_size = 0, extended = 0;
+  uint8_t *dict_idx = nullptr; int32_t *dict_pal = nullptr; int32_t *palettes = nullptr;
+  int16_t *dict_feat = nullptr; int16_t *pair_feat = nullptr;
+  tm_knn_short *knn = nullptr;
+};
+
+static void *g_knn_ws = nullptr;
+static size_t g_knn_ws_bytes = 0;
+
+// ------------------------------------------------------------------ runtime
+extern "C" int tm_version(void) { return 100; }
+extern "C" int tm_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok; }
+  return ok;
+}
+extern "C" int tm_set_device(int device) { CU(cudaSetDevice(device)); g_gpu_ok = -1; return TM_OK; }
+extern "C" int tm_set_stream(void *s) { t_stream = (cudaStream_t)s; return TM_OK; }
+extern "C" const char *tm_last_error(void) { return t_err.c_str(); }
+extern "C" int64_t tm_kernel_launches(void) { return (int64_t)g_launches.load(); }
+extern "C" int tm_synchronize(void) { CU(cudaStreamSynchronize(t_stream)); return TM_OK; }
+
+// ------------------------------------------------------------------ features
+extern "C" int tm_features_from_rgb(const int32_t *rgb, int64_t n, int16_t *out) {
+  RC(require_gpu());
+  if (n < 0 || (n > 0 && (!rgb || !out))) return fail(TM_ERR_ARG, "tm_features_from_rgb: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int32_t *d_rgb = s.in(rgb, (size_t)n * 64);
+  int16_t *d_out = s.out(out, (size_t)n * 192);
+  if (s.err == TM_OK) s.err = launch_features_rgb(d_rgb, n, d_out, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+extern "C" int tm_features_from_pal(const uint8_t *pal_idx, const int32_t *tile_pal, const int32_t *palettes, int pal_size, int n_pal,
+                                    int64_t n, int16_t *out) {
+  RC(require_gpu());
+  if (n < 0 || pal_size < 1 || n_pal < 1 || (n > 0 && (!pal_idx || !tile_pal || !palettes || !out)))
+    return fail(TM_ERR_ARG, "tm_features_from_pal: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const uint8_t *d_idx = s.in(pal_idx, (size_t)n * 64);
+  const int32_t *d_tp = s.in(tile_pal, (size_t)n);
+  const int32_t *d_pal = s.in(palettes, (size_t)n_pal * pal_size);
+  int16_t *d_out = s.out(out, (size_t)n * 192);
+  if (s.err == TM_OK) s.err = launch_features_pal(d_idx, d_tp, d_pal, pal_size, n, d_out, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+extern "C" int tm_features_f64(const int32_t *rgb, int64_t n, int mode, int use_lab, double *out) {
+  RC(require_gpu());
+  if (n < 0 || mode < 0 || mode > 4 || mode == 2 || (n > 0 && (!rgb || !out))) return fail(TM_ERR_ARG, "tm_features_f64: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int32_t *d_rgb = s.in(rgb, (size_t)n * 64);
+  double *d_out = s.out(out, (size_t)n * 192);
+  if (s.err == TM_OK) s.err = launch_features_f64(d_rgb, n, mode, use_lab, d_out, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+extern "C" int tm_mirror_canonicalise(int32_t *rgb, int64_t n, uint8_t *flags) {
+  RC(require_gpu());
+  if (n < 0 || (n > 0 && (!rgb || !flags))) return fail(TM_ERR_ARG, "tm_mirror_canonicalise: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  int32_t *d_rgb = s.inout(rgb, (size_t)n * 64);
+  uint8_t *d_fl = s.out(flags, (size_t)n);
+  if (s.err == TM_OK) s.err = launch_mirror_canonicalise(d_rgb, n, d_fl, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+extern "C" int tm_distance_pairs(const int16_t *a, const int16_t *b, int64_t n, uint32_t *out) {
+  RC(require_gpu());
+  if (n < 0 || (n > 0 && (!a || !b || !out))) return fail(TM_ERR_ARG, "tm_distance_pairs: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int16_t *da = s.in(a, (size_t)n * 192), *db = s.in(b, (size_t)n * 192);
+  uint32_t *d_out = s.out(out, (size_t)n);
+  if (s.err == TM_OK) s.err = launch_distance_pairs(da, db, n, d_out, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+// ------------------------------------------------------------------ k-NN (int16)
+static int knn_short_create_dev(const int16_t *d_feat, int64_t n, cudaStream_t st, tm_knn_short **out) {
+  tm_knn_short *h = new tm_knn_short();
+  h->n = n;
+  const int64_t npad = (n + 63) / 64 * 64;
+  if (cudaMalloc(&h->limbs, (size_t)(n > 0 ? n : 1) * 384) != cudaSuccess || cudaMalloc(&h->norms, (size_t)(npad > 0 ? npad : 64) * 4) != cudaSuccess) {
+    cudaFree(h->limbs); delete h;
+    return TM_ERR_NOMEM;
+  }
+  cudaMemsetAsync(h->norms, 0, (size_t)(npad > 0 ? npad : 64) * 4, st);
+  int rc = launch_limb_split(d_feat, n, h->limbs, h->norms, st);
+  if (rc != TM_OK) { cudaFree(h->limbs); cudaFree(h->norms); delete h; return rc; }
+  *out = h;
+  return TM_OK;
+}
+
+extern "C" int tm_knn_short_create(const int16_t *feat, int64_t n, tm_knn_short **out) {
+  RC(require_gpu());
+  if (n < 1 || n > 0x7fffffff || !feat || !out) return fail(TM_ERR_ARG, "tm_knn_short_create: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int16_t *d_feat = s.in(feat, (size_t)n * 192);
+  if (s.err == TM_OK) s.err = knn_short_create_dev(d_feat, n, s.st, out);
+  RC(s.finish(true));
+  return TM_OK;
+}
+
+extern "C" int tm_knn_short_destroy(tm_knn_short *h) {
+  if (!h) return TM_OK;
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  cudaFree(h->limbs); cudaFree(h->norms);
+  delete h;
+  return TM_OK;
+}
+
+// queries already on the device
+static int knn_short_batch_dev(tm_knn_short *h, const int16_t *d_q, int64_t n_q, int k, int32_t *d_idx, uint32_t *d_dist, int sorted,
+                               Stage &s) {
+  if (n_q == 0) return TM_OK;
+  uint8_t *q_limbs = (uint8_t *)s.temp((size_t)n_q * 384);
+  uint32_t *q_norm = (uint32_t *)s.temp((size_t)n_q * 4);
+  if (s.err) return s.err;
+  const int ctas = num_sms();
+  void *ws = nullptr;
+  if (k > 1) {
+    const size_t need = knn_workspace_bytes(ctas);
+    if (need > g_knn_ws_bytes) {
+      if (g_knn_ws) { cudaStreamSynchronize(s.st); cudaFree(g_knn_ws); }
+      g_knn_ws = nullptr; g_knn_ws_bytes = 0;
+      if (cudaMalloc(&g_knn_ws, need) != cudaSuccess) return TM_ERR_NOMEM;
+      g_knn_ws_bytes = need;
+    }
+    ws = g_knn_ws;
+  }
+  int rc = launch_limb_split(d_q, n_q, q_limbs, q_norm, s.st);
+  if (rc) return rc;
+  return launch_knn_i8(q_limbs, q_norm, (int)n_q, h->limbs, h->norms, (int)h->n, k, d_idx, d_dist, ws, ctas, sorted, s.st);
+}
+
+extern "C" int tm_knn_short_batch(tm_knn_short *h, const int16_t *q, int64_t n_q, int k, int32_t *idx, uint32_t *dist, int sorted) {
+  RC(require_gpu());
+  if (!h || n_q < 0 || n_q > 0x7fffffff || k < 1 || k > 64 || (n_q > 0 && (!q || !idx || !dist)))
+    return fail(TM_ERR_ARG, "tm_knn_short_batch: bad argument (1 <= k <= 64)");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int16_t *d_q = s.in(q, (size_t)n_q * 192);
+  int32_t *d_idx = s.out(idx, (size_t)n_q * k);
+  uint32_t *d_dist = s.out(dist, (size_t)n_q * k);
+  if (s.err == TM_OK) s.err = knn_short_batch_dev(h, d_q, n_q, k, d_idx, d_dist, sorted, s);
+  RC(s.finish());
+  return TM_OK;
+}
+
+extern "C" int tm_knn_double_batch(const double *dict, int64_t n_dict, int dim, const double *q, int64_t n_q, int32_t *idx, double *dist) {
+  RC(require_gpu());
+  if (n_dict < 1 || dim < 1 || n_q < 0 || !dict || (n_q > 0 && (!q || !idx))) return fail(TM_ERR_ARG, "tm_knn_double_batch: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const double *d_dict = s.in(dict, (size_t)n_dict * dim), *d_q = s.in(q, (size_t)n_q * dim);
+  int32_t *d_idx = s.out(idx, (size_t)n_q);
+  double *d_dist = s.out(dist, (size_t)n_q);
+  if (s.err == TM_OK) s.err = launch_knn_f64(d_dict, n_dict, dim, d_q, n_q, d_idx, d_dist, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+// ------------------------------------------------------------------ dithering
+extern "C" int tm_dither(const int32_t *rgb, const uint8_t *mirror_flags, int64_t n_tiles, const int32_t *pair_tile, const int32_t *pair_pal,
+                         int64_t n_pairs, const int32_t *palettes, int pal_size, int n_pal, int use_tk, int y2_mixed, uint8_t *out_idx) {
+  RC(require_gpu());
+  if (n_tiles < 0 || n_pairs < 0 || pal_size < 1 || pal_size > 256 || n_pal < 1 || y2_mixed < 1 || y2_mixed > 16 ||
+      (n_pairs > 0 && (!rgb || !pair_pal || !palettes || !out_idx)) || (!pair_tile && n_pairs > n_tiles))
+    return fail(TM_ERR_ARG, "tm_dither: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int32_t *d_rgb = s.in(rgb, (size_t)n_tiles * 64);
+  const uint8_t *d_fl = s.in(mirror_flags, (size_t)n_tiles);
+  const int32_t *d_pt = s.in(pair_tile, (size_t)n_pairs), *d_pp = s.in(pair_pal, (size_t)n_pairs);
+  const int32_t *d_pal = s.in(palettes, (size_t)n_pal * pal_size);
+  uint8_t *d_out = s.out(out_idx, (size_t)n_pairs * 64);
+  if (s.err == TM_OK) s.err = launch_dither(d_rgb, d_fl, d_pt, d_pp, n_pairs, d_pal, pal_size, n_pal, use_tk, y2_mixed, d_out, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+// ------------------------------------------------------------------ k-means
+static int kmeans_fit_dev(const double *d_x, const double *d_w, int64_t n, int dim, int k, int max_iter, const double *d_init, uint64_t seed,
+                          int nan_empty, int32_t *d_labels, double *d_cent, double *d_wsum, double *inertia, int *iters, Stage &s) {
+  int32_t *d_changed = (int32_t *)s.temp(4);
+  double *d_dist = (double *)s.temp((size_t)n * 8);
+  const size_t ws_bytes = kmeans_update_ws_bytes(n, k);
+  void *ws = s.temp(ws_bytes);
+  if (s.err) return s.err;
+  if (d_init) { if (cudaMemcpyAsync(d_cent, d_init, (size_t)k * dim * 8, cudaMemcpyDeviceToDevice, s.st) != cudaSuccess) return TM_ERR_CUDA; }
+  else { int rc = launch_kmeanspp_f64(d_x, n, dim, k, seed, d_dist, d_cent, s.st); if (rc) return rc; }
+  if (cudaMemsetAsync(d_labels, 0xFF, (size_t)n * 4, s.st) != cudaSuccess) return TM_ERR_CUDA;
+  int it = 0;
+  for (;;) {
+    int32_t h_changed = 0;
+    if (cudaMemsetAsync(d_changed, 0, 4, s.st) != cudaSuccess) return TM_ERR_CUDA;
+    int rc = launch_kmeans_assign_f64(d_x, n, dim, d_cent, k, d_labels, d_dist, d_changed, s.st);
+    if (rc) return rc;
+    if (cudaMemcpyAsync(&h_changed, d_changed, 4, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaStreamSynchronize(s.st) != cudaSuccess) return TM_ERR_CUDA;
+    if (h_changed == 0 || it >= max_iter) break;
+    ++it;
+    rc = launch_kmeans_update_f64(d_x, d_w, n, dim, d_labels, k, d_cent, nullptr, d_wsum, ws, ws_bytes, nan_empty, 1, s.st);
+    if (rc) return rc;
+  }
+  if (iters) *iters = it;
+  if (inertia) {
+    std::vector<double> h((size_t)n);
+    if (cudaMemcpyAsync(h.data(), d_dist, (size_t)n * 8, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaStreamSynchronize(s.st) != cudaSuccess) return TM_ERR_CUDA;
+    double t = 0.0;
+    for (double v : h) t += v;   // reporting scalar only
+    *inertia = t;
+  }
+  return TM_OK;
+}
+
+extern "C" int tm_kmeans_fit(const double *x, int64_t n, int dim, int k, int max_iter, const double *init, uint64_t seed, int nan_empty,
+                             int32_t *labels, double *centroids, double *inertia, int *iters) {
+  RC(require_gpu());
+  if (n < 1 || n > 0x7fffffff || dim < 1 || dim > 1024 || k < 1 || max_iter < 0 || !x || !labels || !centroids)
+    return fail(TM_ERR_ARG, "tm_kmeans_fit: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const double *d_x = s.in(x, (size_t)n * dim), *d_init = s.in(init, (size_t)k * dim);
+  int32_t *d_labels = s.out(labels, (size_t)n);
+  double *d_cent = s.out(centroids, (size_t)k * dim);
+  if (s.err == TM_OK) s.err = kmeans_fit_dev(d_x, nullptr, n, dim, k, max_iter, d_init, seed, nan_empty, d_labels, d_cent, nullptr, inertia, iters, s);
+  RC(s.finish(true));
+  return TM_OK;
+}
+
+extern "C" int tm_kmeans_partial_step(const double *x, int64_t n, int dim, int k, const double *centroids, int32_t *labels,
+                                      double *partial_sums, int64_t *partial_counts, int64_t *changed, double *inertia) {
+  RC(require_gpu());
+  if (n < 0 || n > 0x7fffffff || dim < 1 || dim > 1024 || k < 1 || !centroids || !partial_sums || !partial_counts || (n > 0 && (!x || !labels)))
+    return fail(TM_ERR_ARG, "tm_kmeans_partial_step: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const double *d_x = s.in(x, (size_t)n * dim), *d_cent = s.in(centroids, (size_t)k * dim);
+  int32_t *d_labels = s.inout(labels, (size_t)n);
+  double *d_sums = s.out(partial_sums, (size_t)k * dim);
+  int64_t *d_counts = s.out(partial_counts, (size_t)k);
+  int32_t *d_changed = (int32_t *)s.temp(4);
+  double *d_dist = (double *)s.temp((size_t)(n > 0 ? n : 1) * 8);
+  const size_t ws_bytes = kmeans_update_ws_bytes(n > 0 ? n : 1, k);
+  void *ws = s.temp(ws_bytes);
+  int32_t h_changed = 0;
+  if (s.err == TM_OK) {
+    cudaMemsetAsync(d_changed, 0, 4, s.st);
+    if (n > 0) {
+      s.err = launch_kmeans_assign_f64(d_x, n, dim, d_cent, k, d_labels, d_dist, d_changed, s.st);
+      if (s.err == TM_OK) s.err = launch_kmeans_update_f64(d_x, nullptr, n, dim, d_labels, k, d_sums, d_counts, nullptr, ws, ws_bytes, 0, 0, s.st);
+    } else {
+      cudaMemsetAsync(d_sums, 0, (size_t)k * dim * 8, s.st);
+      cudaMemsetAsync(d_counts, 0, (size_t)k * 8, s.st);
+    }
+    if (s.err == TM_OK && (changed || inertia)) {
+      std::vector<double> h((size_t)n);
+      cudaMemcpyAsync(&h_changed, d_changed, 4, cudaMemcpyDeviceToHost, s.st);
+      if (inertia && n > 0) cudaMemcpyAsync(h.data(), d_dist, (size_t)n * 8, cudaMemcpyDeviceToHost, s.st);
+      if (cudaStreamSynchronize(s.st) != cudaSuccess) s.err = TM_ERR_CUDA;
+      if (changed) *changed = h_changed;
+      if (inertia) { double t = 0.0; for (double v : h) t += v; *inertia = t; }
+    }
+  }
+  RC(s.finish());
+  return TM_OK;
+}
+
+extern "C" int tm_kmeans_finish_step(const double *sums, const int64_t *counts, int k, int dim, int nan_empty, double *centroids) {
+  RC(require_gpu());
+  if (k < 1 || dim < 1 || !sums || !counts || !centroids) return fail(TM_ERR_ARG, "tm_kmeans_finish_step: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const double *d_sums = s.in(sums, (size_t)k * dim);
+  const int64_t *d_counts = s.in(counts, (size_t)k);
+  double *d_cent = s.inout(centroids, (size_t)k * dim);
+  if (s.err == TM_OK) s.err = launch_kmeans_finish(d_sums, d_counts, k, dim, nan_empty, d_cent, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+// ------------------------------------------------------------------ palette colour quantisation
+extern "C" int tm_palquant_kmeans(const int32_t *rgb, const int32_t *tile_pal, int64_t n_tiles, int n_pal, int pal_size, const double *init,
+                                  uint64_t seed, int32_t *palettes, int *iters) {
+  RC(require_gpu());
+  if (n_tiles < 1 || n_tiles * 64 > 0x7fffffff || n_pal < 1 || pal_size < 1 || pal_size > 256 || !rgb || !tile_pal || !palettes)
+    return fail(TM_ERR_ARG, "tm_palquant_kmeans: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int32_t *d_rgb = s.in(rgb, (size_t)n_tiles * 64), *d_tp = s.in(tile_pal, (size_t)n_tiles);
+  const double *d_init = s.in(init, (size_t)n_pal * pal_size * 3);
+  int32_t *d_out = s.out(palettes, (size_t)n_pal * pal_size);
+  int32_t it = 0;
+  if (s.err == TM_OK) s.err = run_palette_quantise(d_rgb, d_tp, n_tiles, n_pal, pal_size, d_init, seed, 300, d_out, &it, s.st);
+  if (iters) *iters = it;
+  RC(s.finish(true));
+  return TM_OK;
+}
+
+// ------------------------------------------------------------------ matcher
+extern "C" int tm_matcher_destroy(tm_matcher *m) {
+  if (!m) return TM_OK;
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  cudaFree(m->dict_idx); cudaFree(m->dict_pal); cudaFree(m->palettes); cudaFree(m->dict_feat); cudaFree(m->pair_feat);
+  tm_knn_short_destroy(m->knn);
+  delete m;
+  return TM_OK;
+}
+
+extern "C" int tm_matcher_create(const uint8_t *dict_idx, const int32_t *dict_pal, int64_t n_dict, const int32_t *palettes, int pal_size,
+                                 int n_pal, int extended, tm_matcher **out) {
+  RC(require_gpu());
+  if (n_dict < 1 || n_dict > 0x7fffffff || pal_size < 1 || pal_size > 256 || n_pal < 1 || !dict_idx || !dict_pal || !palettes || !out)
+    return fail(TM_ERR_ARG, "tm_matcher_create: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  cudaStream_t st = t_stream;
+  tm_matcher *m = new tm_matcher();
+  m->n_dict = n_dict; m->n_pal = n_pal; m->pal_size = pal_size; m->extended = extended;
+  const size_t pair_bytes = extended ? (size_t)n_dict * n_pal * 384 : 0;
+  size_t free_b = 0, total_b = 0;
+  cudaMemGetInfo(&free_b, &total_b);
+  int rc = TM_OK;
+  if (pair_bytes + (size_t)n_dict * 1024 > free_b * 9 / 10) rc = TM_ERR_NOMEM;
+  if (rc == TM_OK && (cudaMalloc(&m->dict_idx, (size_t)n_dict * 64) != cudaSuccess || cudaMalloc(&m->dict_pal, (size_t)n_dict * 4) != cudaSuccess ||
+                      cudaMalloc(&m->palettes, (size_t)n_pal * pal_size * 4) != cudaSuccess ||
+                      cudaMalloc(&m->dict_feat, (size_t)n_dict * 384) != cudaSuccess ||
+                      (extended && cudaMalloc(&m->pair_feat, pair_bytes) != cudaSuccess)))
+    rc = TM_ERR_NOMEM;
+  if (rc == TM_OK) {
+    if (cudaMemcpyAsync(m->dict_idx, dict_idx, (size_t)n_dict * 64, cudaMemcpyDefault, st) != cudaSuccess ||
+        cudaMemcpyAsync(m->dict_pal, dict_pal, (size_t)n_dict * 4, cudaMemcpyDefault, st) != cudaSuccess ||
+        cudaMemcpyAsync(m->palettes, palettes, (size_t)n_pal * pal_size * 4, cudaMemcpyDefault, st) != cudaSuccess)
+      rc = TM_ERR_CUDA;
+  }
+  if (rc == TM_OK) rc = launch_features_pal(m->dict_idx, m->dict_pal, m->palettes, pal_size, n_dict, m->dict_feat, st);
+  if (rc == TM_OK) rc = knn_short_create_dev(m->dict_feat, n_dict, st, &m->knn);
+  if (rc == TM_OK && extended) rc = launch_features_allpairs(m->dict_idx, n_dict, m->palettes, pal_size, n_pal, m->pair_feat, st);
+  if (rc == TM_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = TM_ERR_CUDA;
+  if (rc != TM_OK) { tm_matcher_destroy(m); return fail(rc, "tm_matcher_create"); }
+  *out = m;
+  return TM_OK;
+}
+
+static int match_feat_dev(tm_matcher *m, const int16_t *d_feat, int64_t n_q, int k, int32_t *d_tile, int32_t *d_pal, uint32_t *d_err, Stage &s) {
+  if (n_q == 0) return TM_OK;
+  const int kk = m->extended ? k : 1;
+  int32_t *d_idx = (int32_t *)s.temp((size_t)n_q * kk * 4);
+  uint32_t *d_dist = (uint32_t *)s.temp((size_t)n_q * kk * 4);
+  if (s.err) return s.err;
+  int rc = knn_short_batch_dev(m->knn, d_feat, n_q, kk, d_idx, d_dist, 0, s);
+  if (rc) return rc;
+  if (m->extended)
+    return launch_match_rerank(d_feat, n_q, d_idx, kk, m->dict_pal, m->dict_idx, m->n_dict, m->palettes, m->pal_size, m->n_pal, m->pair_feat,
+                               d_tile, d_pal, d_err, s.st);
+  return launch_match_plain(d_idx, d_dist, n_q, m->dict_pal, m->n_dict, d_tile, d_pal, d_err, s.st);
+}
+
+extern "C" int tm_match_tiles_feat(tm_matcher *m, const int16_t *feat, int64_t n_q, int k, int32_t *tile_idx, int32_t *pal_idx, uint32_t *err) {
+  RC(require_gpu());
+  if (!m || n_q < 0 || n_q > 0x7fffffff || k < 1 || k > 64 || (n_q > 0 && (!feat || !tile_idx || !pal_idx || !err)))
+    return fail(TM_ERR_ARG, "tm_match_tiles_feat: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int16_t *d_feat = s.in(feat, (size_t)n_q * 192);
+  int32_t *d_tile = s.out(tile_idx, (size_t)n_q), *d_pal = s.out(pal_idx, (size_t)n_q);
+  uint32_t *d_err = s.out(err, (size_t)n_q);
+  if (s.err == TM_OK) s.err = match_feat_dev(m, d_feat, n_q, k, d_tile, d_pal, d_err, s);
+  RC(s.finish());
+  return TM_OK;
+}
+
+extern "C" int tm_match_tiles_rgb(tm_matcher *m, const int32_t *rgb, int64_t n_q, int k, int32_t *tile_idx, int32_t *pal_idx, uint32_t *err) {
+  RC(require_gpu());
+  if (!m || n_q < 0 || n_q > 0x7fffffff || k < 1 || k > 64 || (n_q > 0 && (!rgb || !tile_idx || !pal_idx || !err)))
+    return fail(TM_ERR_ARG, "tm_match_tiles_rgb: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int32_t *d_rgb = s.in(rgb, (size_t)n_q * 64);
+  int32_t *d_tile = s.out(tile_idx, (size_t)n_q), *d_pal = s.out(pal_idx, (size_t)n_q);
+  uint32_t *d_err = s.out(err, (size_t)n_q);
+  int16_t *d_feat = (int16_t *)s.temp((size_t)n_q * 384);
+  if (s.err == TM_OK) s.err = launch_features_rgb(d_rgb, n_q, d_feat, s.st);
+  if (s.err == TM_OK) s.err = match_feat_dev(m, d_feat, n_q, k, d_tile, d_pal, d_err, s);
+  RC(s.finish());
+  return TM_OK;
+}
+
+extern "C" int tm_matcher_dict_features(tm_matcher *m, int16_t *out) {
+  RC(require_gpu());
+  if (!m || !out) return fail(TM_ERR_ARG, "tm_matcher_dict_features: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  CU(cudaMemcpyAsync(out, m->dict_feat, (size_t)m->n_dict * 384, cudaMemcpyDefault, t_stream));
+  CU(cudaStreamSynchronize(t_stream));
+  return TM_OK;
+}
+
+// ================================================================== drop-in exports (extern.pas:178-223)
+extern "C" tm_knn_short *ann_kdtree_short_create(int16_t **rows, int n, int dim, int bucket, int split) {
+  (void)bucket; (void)split;
+  if (!rows || n < 1 || dim != 192) { fail(TM_ERR_ARG, "ann_kdtree_short_create: dim must be 192"); return nullptr; }
+  std::vector<int16_t> flat((size_t)n * 192);
+  for (int i = 0; i < n; ++i) memcpy(&flat[(size_t)i * 192], rows[i], 192 * sizeof(int16_t));   // marshal the row-pointer array
+  tm_knn_short *h = nullptr;
+  if (tm_knn_short_create(flat.data(), n, &h) != TM_OK) return nullptr;
+  return h;
+}
+extern "C" void ann_kdtree_short_destroy(tm_knn_short *h) { tm_knn_short_destroy(h); }
+extern "C" int ann_kdtree_short_search(tm_knn_short *h, const int16_t *q, uint32_t eps, uint32_t *err) {
+  (void)eps;
+  int32_t idx = -1; uint32_t d = 0xFFFFFFFFu;
+  if (tm_knn_short_batch(h, q, 1, 1, &idx, &d, 1) != TM_OK) idx = -1;
+  if (err) *err = d;
+  return idx;
+}
+extern "C" void ann_kdtree_short_search_multi(tm_knn_short *h, int *idxs, uint32_t *errs, int k, const int16_t *q, uint32_t eps) {
+  (void)eps;
+  if (k < 1 || !idxs || !errs) return;
+  if (k > 64 || tm_knn_short_batch(h, q, 1, k, idxs, errs, 1) != TM_OK)
+    for (int i = 0; i < k; ++i) { idxs[i] = -1; errs[i] = 0xFFFFFFFFu; }   // out-of-range = "no result" for the host (:1566)
+}
+
+extern "C" tm_knn_double *ann_kdtree_create(double **rows, int n, int dim, int bucket, int split) {
+  (void)bucket; (void)split;
+  if (require_gpu() != TM_OK) return nullptr;
+  if (!rows || n < 1 || dim < 1) { fail(TM_ERR_ARG, "ann_kdtree_create: bad argument"); return nullptr; }
+  std::vector<double> flat((size_t)n * dim);
+  for (int i = 0; i < n; ++i) memcpy(&flat[(size_t)i * dim], rows[i], (size_t)dim * sizeof(double));
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  tm_knn_double *h = new tm_knn_double();
+  h->n = n; h->dim = dim;
+  if (cudaMalloc(&h->pts, flat.size() * 8) != cudaSuccess || cudaMemcpy(h->pts, flat.data(), flat.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(h->pts); delete h; fail(TM_ERR_NOMEM, "ann_kdtree_create"); return nullptr;
+  }
+  return h;
+}
+extern "C" void ann_kdtree_destroy(tm_knn_double *h) {
+  if (!h) return;
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  cudaFree(h->pts); delete h;
+}
+extern "C" int ann_kdtree_search(tm_knn_double *h, const double *q, double eps, double *err) {
+  (void)eps;
+  int32_t idx = -1; double d = INFINITY;
+  if (!h || tm_knn_double_batch(h->pts, h->n, h->dim, q, 1, &idx, &d) != TM_OK) idx = -1;
+  if (err) *err = d;
+  return idx;
+}
+
+extern "C" tm_yakmo *yakmo_create(uint32_t k, uint32_t restarts, int max_iter, int init_type, int init_seed, int normalize, int verbose) {
+  (void)restarts; (void)init_type; (void)normalize; (void)verbose;
+  tm_yakmo *y = new tm_yakmo();
+  y->k = k; y->max_iter = max_iter; y->seed = (uint64_t)(uint32_t)init_seed;
+  return y;
+}
+extern "C" void yakmo_destroy(tm_yakmo *y) { delete y; }
+extern "C" void yakmo_set_num_threads(int n) { (void)n; }
+extern "C" void yakmo_load_train_data(tm_yakmo *y, uint32_t rows, uint32_t cols, double **data) {
+  if (!y || !data) return;
+  y->rows = rows; y->cols = cols;
+  y->data.resize((size_t)rows * cols);
+  for (uint32_t i = 0; i < rows; ++i) memcpy(&y->data[(size_t)i * cols], data[i], (size_t)cols * sizeof(double));   // the host frees its rows right after (:4495)
+}
+extern "C" void yakmo_train_on_data(tm_yakmo *y, int *point_to_cluster) {
+  if (!y || !point_to_cluster || y->rows == 0) return;
+  y->cent.assign((size_t)y->k * y->cols, NAN);
+  const int k = (int)(y->k < y->rows ? y->k : y->rows);
+  std::vector<double> cent((size_t)k * y->cols);
+  if (tm_kmeans_fit(y->data.data(), y->rows, (int)y->cols, k, y->max_iter, nullptr, y->seed, 1, point_to_cluster, cent.data(), nullptr, nullptr) != TM_OK) {
+    for (uint32_t i = 0; i < y->rows; ++i) point_to_cluster[i] = 0;
+    return;
+  }
+  memcpy(y->cent.data(), cent.data(), cent.size() * sizeof(double));
+}
+extern "C" void yakmo_get_centroids(tm_yakmo *y, double **centroids) {
+  if (!y || !centroids) return;
+  for (uint32_t c = 0; c < y->k; ++c)
+    if (centroids[c]) memcpy(centroids[c], &y->cent[(size_t)c * y->cols], (size_t)y->cols * sizeof(double));
+}
+
+extern "C" tm_bico *bico_create(int64_t dim, int64_t n, int64_t k, int64_t nrandproj, int64_t coresetsize, int seed) {
+  (void)nrandproj;
+  tm_bico *b = new tm_bico();
+  b->dim = dim; b->k = k; b->coreset = coresetsize; b->seed = (uint64_t)(uint32_t)seed;
+  if (n > 0 && dim > 0) { b->rows.reserve((size_t)n * dim); b->weights.reserve((size_t)n); }
+  return b;
+}
+extern "C" void bico_destroy(tm_bico *b) { delete b; }
+extern "C" void bico_set_num_threads(int n) { (void)n; }
+extern "C" void bico_set_rebuild_properties(tm_bico *b, uint32_t interval, double initial, double grow) { (void)b; (void)interval; (void)initial; (void)grow; }
+extern "C" void bico_insert_line(tm_bico *b, const double *row, double weight) {
+  if (!b || !row) return;
+  b->rows.insert(b->rows.end(), row, row + b->dim);
+  b->weights.push_back(weight);
+}
+extern "C" int64_t bico_get_results(tm_bico *b, double *centroids, double *weights) {
+  if (!b || !centroids) return 0;
+  const int64_t n = (int64_t)b->weights.size();
+  const int dim = (int)b->dim;
+  if (n == 0) return 0;
+  if (n <= b->coreset) {   // every point is its own summary
+    memcpy(centroids, b->rows.data(), (size_t)n * dim * sizeof(double));
+    if (weights) memcpy(weights, b->weights.data(), (size_t)n * sizeof(double));
+    return n;
+  }
+  if (require_gpu() != TM_OK) return 0;
+  const int k = (int)b->coreset;
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const double *d_x = s.in(b->rows.data(), (size_t)n * dim), *d_w = s.in(b->weights.data(), (size_t)n);
+  int32_t *d_labels = (int32_t *)s.temp((size_t)n * 4);
+  std::vector<double> h_cent((size_t)k * dim), h_ws((size_t)k);
+  double *d_cent = s.out(h_cent.data(), (size_t)k * dim), *d_ws = s.out(h_ws.data(), (size_t)k);
+  // weighted Lloyd (bounded effort: a coreset is a summary, not a converged clustering)
+  if (s.err == TM_OK) s.err = kmeans_fit_dev(d_x, d_w, n, dim, k, 8, nullptr, b->seed, 0, d_labels, d_cent, d_ws, nullptr, nullptr, s);
+  if (s.finish(true) != TM_OK) { fail(TM_ERR_CUDA, "bico_get_results"); return 0; }
+  int64_t m = 0;
+  for (int c = 0; c < k; ++c) {
+    if (!(h_ws[c] > 0.0)) continue;   // drop empty clusters: the host accepts any count <= coresetsize (:4168)
+    memcpy(centroids + (size_t)m * dim, &h_cent[(size_t)c * dim], (size_t)dim * sizeof(double));
+    if (weights) weights[m] = h_ws[c];
+    ++m;
+  }
+  return m;
+}

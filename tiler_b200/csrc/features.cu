@@ -1,0 +1,286 @@
+// features.cu -- tile -> 192-d psycho-visual feature vectors, and the load-time mirror canonicalisation.
+//
+//   int16 path  : ConvertToCpnPixels (YUV) + ComputeCpnPixelsPsyVisFeatures(pvsWeightedDCT)
+//                 (tilingencoder.pas:3049-3131) with DCTInner_asm's exact summation order (utils.pas:874-1035):
+//                 f32 products, f32 adds of lanes i/i+4 and i+8/i+12, then f64 accumulation in two lanes.
+//                 Rounding of the weighted coefficient is half-to-even (Pascal Round) -> bit-exact vs the oracle.
+//   f64 path    : ComputeTilePsyVisFeatures (tilingencoder.pas:3133-3182), LAB or YUV, any DCT mode.
+//   mirrors     : GetTileHVMirrorHeuristics + H/VMirrorTile (tilingencoder.pas:4865-4878, 3257-3311, 1393-1411).
+//
+// Mapping: one thread per output coefficient (192 threads = one tile per pass), the 3x64 colour-plane samples of the
+// tile broadcast from shared memory, the DCT basis held TRANSPOSED in shared memory ([pixel][coefficient]) so the 32
+// threads of a warp read 32 consecutive words.  Blocks are persistent over tiles (grid = k * SM count).
+#include "tm_kernels.h"
+#include <math.h>
+
+namespace tmg {
+
+__constant__ uint8_t c_snake[64] = {0,  1,  5,  6,  14, 15, 27, 28, 2,  4,  7,  13, 16, 26, 29, 42, 3,  8,  12, 17, 25, 30,
+                                    41, 43, 9,  11, 18, 24, 31, 40, 44, 53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38,
+                                    46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63};
+
+// cDCTWeights, utils.pas:72-97
+__constant__ double c_weights[192] = {
+    1.6193873005, 2.2901594831, 2.08509755623, 1.48366094411, 1.00227514334, 0.678296995242, 0.466224900598, 0.3265091542,
+    2.2901594831, 1.94321815382, 2.04793073064, 1.68731108984, 1.2305666963, 0.868920337363, 0.61280991668, 0.436405793551,
+    2.08509755623, 2.04793073064, 1.34329019223, 1.09205635862, 0.875748795257, 0.670882927016, 0.501731932449, 0.372504254596,
+    1.48366094411, 1.68731108984, 1.09205635862, 0.772819797575, 0.605636379554, 0.48309405692, 0.380429446972, 0.295774038565,
+    1.00227514334, 1.2305666963, 0.875748795257, 0.605636379554, 0.448996256676, 0.352889268808, 0.283006984131, 0.226951348204,
+    0.678296995242, 0.868920337363, 0.670882927016, 0.48309405692, 0.352889268808, 0.27032073436, 0.215017739696, 0.17408067321,
+    0.466224900598, 0.61280991668, 0.501731932449, 0.380429446972, 0.283006984131, 0.215017739696, 0.168869545842, 0.136153931001,
+    0.3265091542, 0.436405793551, 0.372504254596, 0.295774038565, 0.226951348204, 0.17408067321, 0.136153931001, 0.109083846276,
+    1.91113096927, 2.46074210438, 1.18284184739, 1.14982565193, 1.05017074788, 0.898018824055, 0.74725392039, 0.615105596242,
+    2.46074210438, 1.58529308355, 1.21363250036, 1.38190029285, 1.33100189972, 1.17428548929, 0.996404342439, 0.830890433625,
+    1.18284184739, 1.21363250036, 0.978712413627, 1.02624506078, 1.03145147362, 0.960060382087, 0.849823426169, 0.731221236837,
+    1.14982565193, 1.38190029285, 1.02624506078, 0.861317501629, 0.801821139099, 0.751437590932, 0.685398513368, 0.608694761374,
+    1.05017074788, 1.33100189972, 1.03145147362, 0.801821139099, 0.676555426187, 0.605503172737, 0.55002013668, 0.495804539034,
+    0.898018824055, 1.17428548929, 0.960060382087, 0.751437590932, 0.605503172737, 0.514674450957, 0.454353482512, 0.407050308965,
+    0.74725392039, 0.996404342439, 0.849823426169, 0.685398513368, 0.55002013668, 0.454353482512, 0.389234902883, 0.342353999733,
+    0.615105596242, 0.830890433625, 0.731221236837, 0.608694761374, 0.495804539034, 0.407050308965, 0.342353999733, 0.295530605237,
+    2.03871978502, 2.62502345193, 1.26180942886, 1.11019789803, 1.01397751469, 0.867069376285, 0.721500455585, 0.593906509971,
+    2.62502345193, 1.69112867013, 1.17180569821, 1.3342742857, 1.28513006198, 1.13381474809, 0.962064122248, 0.802254508198,
+    1.26180942886, 1.17180569821, 0.944981930573, 0.990876405848, 0.995903384143, 0.926972725286, 0.820534991409, 0.706020324706,
+    1.11019789803, 1.3342742857, 0.990876405848, 0.831632933426, 0.77418706195, 0.725539939514, 0.661776842059, 0.587716619023,
+    1.01397751469, 1.28513006198, 0.995903384143, 0.77418706195, 0.653238524286, 0.584635025748, 0.531064164893, 0.478717061273,
+    0.867069376285, 1.13381474809, 0.926972725286, 0.725539939514, 0.584635025748, 0.496936637883, 0.438694579826, 0.393021669543,
+    0.721500455585, 0.962064122248, 0.820534991409, 0.661776842059, 0.531064164893, 0.438694579826, 0.375820256136, 0.330555063063,
+    0.593906509971, 0.802254508198, 0.706020324706, 0.587716619023, 0.478717061273, 0.393021669543, 0.330555063063, 0.285345396658};
+
+// DCT bases built on the host exactly as InitLuts does (tilingencoder.pas:1703-1714): [special][v][u][y][x].
+// Device copies are transposed to [special][pixel][coefficient].
+static float *g_lutT_f32 = nullptr;   // [2][64][64]
+static double *g_lutT_f64 = nullptr;  // [2][64][64]
+
+int features_init(cudaStream_t st) {
+  if (g_lutT_f32) return TM_OK;
+  static float hf[2][64][64];
+  static double hd[2][64][64];
+  const double PI = 3.14159265358979323846;
+  for (int v = 0; v < 8; ++v)
+    for (int u = 0; u < 8; ++u)
+      for (int y = 0; y < 8; ++y)
+        for (int x = 0; x < 8; ++x) {
+          // cDCTUVRatio is a single-precision table (utils.pas:100)
+          const float rf = (v == 0 && u == 0) ? 0.5f : ((v == 0 || u == 0) ? (float)sqrt(0.5) : 1.0f);
+          const double r = (double)rf;
+          const double d0 = cos((x + 0.5) * u * PI / 8.0) * cos((y + 0.5) * v * PI / 8.0) * r;
+          const double d1 = cos((x + 0.5) * u * PI / 16.0) * cos((y + 0.5) * v * PI / 16.0) * r;
+          hd[0][y * 8 + x][v * 8 + u] = d0;
+          hd[1][y * 8 + x][v * 8 + u] = d1;
+          hf[0][y * 8 + x][v * 8 + u] = (float)d0;
+          hf[1][y * 8 + x][v * 8 + u] = (float)d1;
+        }
+  float *pf = nullptr;
+  double *pd = nullptr;
+  if (cudaMalloc(&pf, sizeof(hf)) != cudaSuccess) return TM_ERR_NOMEM;
+  if (cudaMalloc(&pd, sizeof(hd)) != cudaSuccess) return TM_ERR_NOMEM;
+  if (cudaMemcpyAsync(pf, hf, sizeof(hf), cudaMemcpyHostToDevice, st) != cudaSuccess) return TM_ERR_CUDA;
+  if (cudaMemcpyAsync(pd, hd, sizeof(hd), cudaMemcpyHostToDevice, st) != cudaSuccess) return TM_ERR_CUDA;
+  if (cudaStreamSynchronize(st) != cudaSuccess) return TM_ERR_CUDA;
+  g_lutT_f32 = pf;
+  g_lutT_f64 = pd;
+  return TM_OK;
+}
+
+// RGBToYUV, utils.pas:478-490: double evaluation, single storage
+__device__ __forceinline__ void rgb_to_yuv(int r, int g, int b, float &y, float &u, float &v) {
+  const double yd = __dadd_rn(__dadd_rn(__dmul_rn((double)r, 299.0 / 1000.0), __dmul_rn((double)g, 587.0 / 1000.0)),
+                              __dmul_rn((double)b, 114.0 / 1000.0));
+  y = (float)yd;
+  u = (float)__dmul_rn(__dsub_rn((double)b, (double)y), 0.492);
+  v = (float)__dmul_rn(__dsub_rn((double)r, (double)y), 0.877);
+}
+
+// RGBToLAB, utils.pas:374-410 (D50).  pow() is the CUDA libm one: agrees with the oracle's to ~1 ulp -> LAB features
+// are compared with a tolerance (they only feed the palette clustering).
+__device__ void rgb_to_lab(int ir, int ig, int ib, float &ol, float &oa, float &ob) {
+  float r = (float)(ir / 255.0), g = (float)(ig / 255.0), b = (float)(ib / 255.0);
+  r = (r > 0.04045) ? (float)pow(((double)r + 0.055) / 1.055, 2.4) : (float)((double)r / 12.92);
+  g = (g > 0.04045) ? (float)pow(((double)g + 0.055) / 1.055, 2.4) : (float)((double)g / 12.92);
+  b = (b > 0.04045) ? (float)pow(((double)b + 0.055) / 1.055, 2.4) : (float)((double)b / 12.92);
+  float x = (float)(((double)r * 0.49000 + (double)g * 0.31000 + (double)b * 0.20000) / 0.17697);
+  float y = (float)(((double)r * 0.17697 + (double)g * 0.81240 + (double)b * 0.01063) / 0.17697);
+  float z = (float)(((double)r * 0.00000 + (double)g * 0.01000 + (double)b * 0.99000) / 0.17697);
+  x = (float)((double)x * (1 / (96.6797 / 100)));
+  y = (float)((double)y * (1 / (100.000 / 100)));
+  z = (float)((double)z * (1 / (82.5188 / 100)));
+  x = (x > 0.008856) ? (float)pow((double)x, 1.0 / 3) : (float)((7.787 * (double)x) + 16.0 / 116);
+  y = (y > 0.008856) ? (float)pow((double)y, 1.0 / 3) : (float)((7.787 * (double)y) + 16.0 / 116);
+  z = (z > 0.008856) ? (float)pow((double)z, 1.0 / 3) : (float)((7.787 * (double)z) + 16.0 / 116);
+  ol = (float)((116 * (double)y) - 16);
+  oa = (float)(500 * ((double)x - (double)y));
+  ob = (float)(200 * ((double)y - (double)z));
+}
+
+// DCTInner_asm order for coefficient `co` of the plane s_c[64], basis transposed in s_lut[pixel*64 + co]
+__device__ __forceinline__ double dct_inner(const float *__restrict__ s_c, const float *__restrict__ s_lut, int co) {
+  double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    float p[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) p[i] = __fmul_rn(s_c[s * 16 + i], s_lut[(s * 16 + i) * 64 + co]);
+    const float a0 = __fadd_rn(p[0], p[4]), a1 = __fadd_rn(p[1], p[5]), a2 = __fadd_rn(p[2], p[6]), a3 = __fadd_rn(p[3], p[7]);
+    const float b0 = __fadd_rn(p[8], p[12]), b1 = __fadd_rn(p[9], p[13]), b2 = __fadd_rn(p[10], p[14]), b3 = __fadd_rn(p[11], p[15]);
+    const double l0 = __dadd_rn(__dadd_rn((double)a0, (double)b0), __dadd_rn((double)a2, (double)b2));
+    const double l1 = __dadd_rn(__dadd_rn((double)a1, (double)b1), __dadd_rn((double)a3, (double)b3));
+    acc0 = __dadd_rn(acc0, l0);
+    acc1 = __dadd_rn(acc1, l1);
+  }
+  return __dadd_rn(acc0, acc1);
+}
+
+// MODE 0: RGB tiles; 1: palette indices with per-tile palette; 2: every (tile, palette) pair, item = tile*n_pal + pal
+template <int MODE>
+__global__ void __launch_bounds__(192, 4)
+features_i16_kernel(const int32_t *__restrict__ rgb, const uint8_t *__restrict__ pal_idx, int n_pal_all,
+                    const int32_t *__restrict__ sel_pal, const int32_t *__restrict__ palettes, int pal_size, int64_t n,
+                    const float *__restrict__ lutT, int16_t *__restrict__ out) {
+  extern __shared__ float s_lut[];       // 4096 floats
+  __shared__ float s_cpn[3][64];
+  __shared__ int16_t s_out[192];
+  for (int i = threadIdx.x; i < 4096; i += 192) s_lut[i] = lutT[i];
+  const int t = threadIdx.x;
+  const int c = t >> 6, vu = t & 63;
+  const double wgt = c_weights[t];
+  const int dst = c * 64 + c_snake[vu];
+  for (int64_t tile = blockIdx.x; tile < n; tile += gridDim.x) {
+    __syncthreads();  // previous s_cpn / s_out consumed (and s_lut ready on the first pass)
+    if (t < 64) {
+      int32_t col;
+      if (MODE == 0) {
+        col = __ldg(rgb + tile * 64 + t);
+      } else {
+        const int64_t src = (MODE == 2) ? tile / n_pal_all : tile;
+        const int32_t p = (MODE == 2) ? (int32_t)(tile % n_pal_all) : __ldg(sel_pal + tile);
+        col = __ldg(palettes + (int64_t)p * pal_size + __ldg(pal_idx + src * 64 + t));
+      }
+      float y, u, v;
+      rgb_to_yuv(col & 255, (col >> 8) & 255, (col >> 16) & 255, y, u, v);
+      s_cpn[0][t] = y; s_cpn[1][t] = u; s_cpn[2][t] = v;
+    }
+    __syncthreads();
+    double z = dct_inner(s_cpn[c], s_lut, vu);
+    z = __dmul_rn(z, wgt);
+    s_out[dst] = (int16_t)__double2int_rn(z);
+    __syncthreads();
+    if (t < 96) reinterpret_cast<uint32_t *>(out + tile * 192)[t] = reinterpret_cast<const uint32_t *>(s_out)[t];
+  }
+}
+
+// ComputeTilePsyVisFeatures: f64, sequential 64-term sums (DCTInner<PDouble>, utils.pas:782-872)
+__global__ void __launch_bounds__(192, 2)
+features_f64_kernel(const int32_t *__restrict__ rgb, int64_t n, int weighted, int use_lab, const double *__restrict__ lutT,
+                    double *__restrict__ out) {
+  extern __shared__ double s_lutd[];  // 4096 doubles
+  __shared__ double s_cpn[3][64];
+  for (int i = threadIdx.x; i < 4096; i += 192) s_lutd[i] = lutT[i];
+  const int t = threadIdx.x;
+  const int c = t >> 6, vu = t & 63;
+  const double wgt = weighted ? c_weights[t] : 1.0;
+  const int dst = c * 64 + c_snake[vu];
+  for (int64_t tile = blockIdx.x; tile < n; tile += gridDim.x) {
+    __syncthreads();
+    if (t < 64) {
+      const int32_t col = __ldg(rgb + tile * 64 + t);
+      float y, u, v;
+      if (use_lab) rgb_to_lab(col & 255, (col >> 8) & 255, (col >> 16) & 255, y, u, v);
+      else rgb_to_yuv(col & 255, (col >> 8) & 255, (col >> 16) & 255, y, u, v);
+      s_cpn[0][t] = (double)y; s_cpn[1][t] = (double)u; s_cpn[2][t] = (double)v;
+    }
+    __syncthreads();
+    double z = 0.0;
+#pragma unroll 8
+    for (int i = 0; i < 64; ++i) z = __dadd_rn(z, __dmul_rn(s_cpn[c][i], s_lutd[i * 64 + vu]));
+    if (weighted) z = __dmul_rn(z, wgt);
+    out[tile * 192 + dst] = z;
+  }
+}
+
+// One thread per tile: quadrant luma sums, flags, in-place flip (tile stays 256 bytes in registers/L1)
+__global__ void __launch_bounds__(128) mirror_kernel(int32_t *__restrict__ rgb, int64_t n, uint8_t *__restrict__ flags) {
+  const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tile >= n) return;
+  int32_t *p = rgb + tile * 64;
+  int q[4] = {0, 0, 0, 0};
+  for (int j = 0; j < 8; ++j)
+    for (int i = 0; i < 8; ++i) {
+      const int32_t col = p[j * 8 + i];
+      q[(j >> 2) * 2 + (i >> 2)] += (col & 255) * 299 + ((col >> 8) & 255) * 587 + ((col >> 16) & 255) * 114;
+    }
+  const bool hm = (q[0] + q[2]) < (q[1] + q[3]);
+  const bool vm = (q[0] + q[1]) < (q[2] + q[3]);
+  flags[tile] = (uint8_t)((hm ? 1 : 0) | (vm ? 2 : 0));
+  if (hm)
+    for (int j = 0; j < 8; ++j)
+      for (int i = 0; i < 4; ++i) { const int32_t a = p[j * 8 + i]; p[j * 8 + i] = p[j * 8 + 7 - i]; p[j * 8 + 7 - i] = a; }
+  if (vm)
+    for (int j = 0; j < 4; ++j)
+      for (int i = 0; i < 8; ++i) { const int32_t a = p[j * 8 + i]; p[j * 8 + i] = p[(7 - j) * 8 + i]; p[(7 - j) * 8 + i] = a; }
+}
+
+static int grid_for(int64_t n, int per_sm) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int64_t g = (int64_t)sms * per_sm;
+  return (int)(n < g ? n : g);
+}
+
+int launch_features_rgb(const int32_t *rgb, int64_t n, int16_t *out, cudaStream_t st) {
+  if (n <= 0) return TM_OK;
+  int rc = features_init(st);
+  if (rc) return rc;
+  features_i16_kernel<0><<<grid_for(n, 4), 192, 4096 * sizeof(float), st>>>(rgb, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+int launch_features_pal(const uint8_t *pal_idx, const int32_t *tile_pal, const int32_t *palettes, int pal_size, int64_t n,
+                        int16_t *out, cudaStream_t st) {
+  if (n <= 0) return TM_OK;
+  int rc = features_init(st);
+  if (rc) return rc;
+  features_i16_kernel<1><<<grid_for(n, 4), 192, 4096 * sizeof(float), st>>>(nullptr, pal_idx, 0, tile_pal, palettes, pal_size, n,
+                                                                             g_lutT_f32, out);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+int launch_features_allpairs(const uint8_t *pal_idx, int64_t n_tiles, const int32_t *palettes, int pal_size, int n_pal,
+                             int16_t *out, cudaStream_t st) {
+  const int64_t n_pairs = n_tiles * n_pal;
+  if (n_pairs <= 0) return TM_OK;
+  int rc = features_init(st);
+  if (rc) return rc;
+  features_i16_kernel<2><<<grid_for(n_pairs, 4), 192, 4096 * sizeof(float), st>>>(nullptr, pal_idx, n_pal, nullptr, palettes, pal_size,
+                                                                                   n_pairs, g_lutT_f32, out);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+int launch_features_f64(const int32_t *rgb, int64_t n, int mode, int use_lab, double *out, cudaStream_t st) {
+  if (n <= 0) return TM_OK;
+  if (mode == 2) return TM_ERR_ARG;  // wavelets: not on the hot path
+  int rc = features_init(st);
+  if (rc) return rc;
+  const int special = (mode == 3 || mode == 4), weighted = (mode == 1 || mode == 4);
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(features_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int)sizeof(double)) != cudaSuccess)
+      return TM_ERR_CUDA;
+    attr = true;
+  }
+  features_f64_kernel<<<grid_for(n, 2), 192, 4096 * sizeof(double), st>>>(rgb, n, weighted, use_lab, g_lutT_f64 + special * 4096, out);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+int launch_mirror_canonicalise(int32_t *rgb, int64_t n, uint8_t *flags, cudaStream_t st) {
+  if (n <= 0) return TM_OK;
+  mirror_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rgb, n, flags);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+}  // namespace tmg

@@ -1,0 +1,534 @@
+// kmeans.cu -- Lloyd's algorithm with yakmo's contract (extern.pas:198-203; call sites tilingencoder.pas:4198-4207 for
+// the 192-d palette clustering and :4492-4500 for 3-d colour quantisation), plus the colour-quantisation tail of
+// QuantizeUsingYakmo / DoQuantization (:4511-4564).
+//
+//   f64 path (any dim): assignment with the oracle's summation order (bit-identical distances, first minimum), update
+//     as an ORDERED segmented sum -- points are stably sorted by label (cub radix sort) and one thread per
+//     (cluster, dimension) adds its members in index order, so centroids are bit-identical to a sequential CPU loop
+//     and independent of scheduling.
+//   RGB path (dim 3, integer points): sums are integers < 2^53, so any summation order is exact; per-block shared
+//     memory accumulators + a few global integer atomics per block.  All palettes are clustered in one launch per
+//     Lloyd iteration (pixels grouped by palette).
+#include "tm_kernels.h"
+#include <cub/cub.cuh>
+#include <math.h>
+#include <vector>
+
+namespace tmg {
+
+__device__ __forceinline__ unsigned long long xorshift64s(unsigned long long &s) {
+  unsigned long long x = s;
+  x ^= x >> 12; x ^= x << 25; x ^= x >> 27;
+  s = x;
+  return x * 0x2545F4914F6CDD1DULL;
+}
+
+// ------------------------------------------------------------------ f64 assignment
+constexpr int KA_P = 32;  // points per block (lane = point), 4 warps split the centroids
+__global__ void __launch_bounds__(128)
+kmeans_assign_f64_kernel(const double *__restrict__ x, int64_t n, int dim, const double *__restrict__ cent, int k,
+                         int32_t *__restrict__ labels, double *__restrict__ dist, int32_t *__restrict__ changed) {
+  extern __shared__ double s_x[];  // [KA_P][dim+1]
+  __shared__ double s_best[4][KA_P];
+  __shared__ int32_t s_bi[4][KA_P];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t p0 = (int64_t)blockIdx.x * KA_P;
+  const int ld = dim + 1;
+  for (int i = threadIdx.x; i < KA_P * dim; i += 128) {
+    const int r = i / dim, c = i % dim;
+    s_x[r * ld + c] = (p0 + r < n) ? x[(p0 + r) * dim + c] : 0.0;
+  }
+  __syncthreads();
+  const double *xv = s_x + lane * ld;
+  const int per = (k + 3) / 4, lo = w * per, hi = min(lo + per, k);
+  double best = INFINITY;
+  int32_t bi = -1;
+  for (int c = lo; c < hi; ++c) {
+    const double *cv = cent + (int64_t)c * dim;
+    double s = 0.0;
+    for (int j = 0; j < dim; ++j) {
+      const double df = __dsub_rn(xv[j], __ldg(cv + j));
+      s = __dadd_rn(s, __dmul_rn(df, df));
+    }
+    if (s < best) { best = s; bi = c; }  // NaN centroids (empty clusters) never win
+  }
+  s_best[w][lane] = best;
+  s_bi[w][lane] = bi;
+  __syncthreads();
+  if (w == 0 && p0 + lane < n) {
+    for (int o = 1; o < 4; ++o)
+      if (s_best[o][lane] < best) { best = s_best[o][lane]; bi = s_bi[o][lane]; }
+    const int32_t old = labels[p0 + lane];
+    if (bi < 0) bi = old >= 0 ? old : 0;
+    if (bi != old) { labels[p0 + lane] = bi; atomicAdd(changed, 1); }
+    if (dist) dist[p0 + lane] = best;
+  }
+}
+
+// ------------------------------------------------------------------ f64 ordered update
+__global__ void iota_kernel(int32_t *p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int32_t)i;
+}
+__global__ void hist_kernel(const int32_t *__restrict__ labels, int64_t n, int32_t *__restrict__ counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicAdd(counts + labels[i], 1);
+}
+// thread = (cluster, dim); members of a cluster are contiguous in `order` and in ascending point index
+__global__ void __launch_bounds__(256)
+kmeans_update_f64_kernel(const double *__restrict__ x, const double *__restrict__ wts, int dim, const int32_t *__restrict__ order,
+                         const int32_t *__restrict__ offs, const int32_t *__restrict__ counts, int k, int nan_empty, int divide,
+                         double *__restrict__ cent, int64_t *__restrict__ counts_out, double *__restrict__ wsum_out) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)k * dim) return;
+  const int c = (int)(t / dim), j = (int)(t % dim);
+  const int cnt = counts[c], o0 = offs[c];
+  if (j == 0 && counts_out) counts_out[c] = cnt;
+  if (cnt == 0) {
+    if (!divide) cent[t] = 0.0;
+    else if (nan_empty) cent[t] = NAN;
+    if (j == 0 && wsum_out) wsum_out[c] = 0.0;
+    return;
+  }
+  double s = 0.0, ws = 0.0;
+  if (wts) {
+    for (int m = 0; m < cnt; ++m) {
+      const int32_t i = order[o0 + m];
+      const double w = __ldg(wts + i);
+      s = __dadd_rn(s, __dmul_rn(w, __ldg(x + (int64_t)i * dim + j)));
+      ws = __dadd_rn(ws, w);
+    }
+  } else {
+    for (int m = 0; m < cnt; ++m) s = __dadd_rn(s, __ldg(x + (int64_t)order[o0 + m] * dim + j));
+    ws = (double)cnt;
+  }
+  cent[t] = divide ? __ddiv_rn(s, ws) : s;
+  if (j == 0 && wsum_out) wsum_out[c] = ws;
+}
+
+__global__ void kmeans_finish_kernel(const double *__restrict__ sums, const int64_t *__restrict__ counts, int k, int dim, int nan_empty,
+                                     double *__restrict__ cent) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)k * dim) return;
+  const int64_t cnt = counts[t / dim];
+  if (cnt > 0) cent[t] = __ddiv_rn(sums[t], (double)cnt);
+  else if (nan_empty) cent[t] = NAN;
+}
+
+// k-means++ seeding for f64 rows, same draw sequence as the oracle's tmo_kmeanspp_init (xorshift64*, D^2 sampling by the
+// first prefix sum exceeding u).  One block; thread t owns a contiguous slice of the points.
+__global__ void __launch_bounds__(256)
+kmeanspp_f64_kernel(const double *__restrict__ x, int64_t n, int dim, int k, unsigned long long seed, double *__restrict__ d2,
+                    double *__restrict__ cent) {
+  extern __shared__ double s_last[];  // [dim]
+  __shared__ double s_part[256];
+  __shared__ long long s_pick;
+  const int t = threadIdx.x;
+  const int64_t per = (n + 255) / 256, a = min((int64_t)t * per, n), b = min(a + per, n);
+  unsigned long long st = seed ? seed : 0x9E3779B97F4A7C15ULL;
+  if (t == 0) s_pick = (long long)(xorshift64s(st) % (unsigned long long)n);
+  for (int64_t i = a; i < b; ++i) d2[i] = INFINITY;
+  for (int c = 0; c < k; ++c) {
+    __syncthreads();
+    const int64_t pick = s_pick;
+    for (int j = t; j < dim; j += 256) { const double v = x[pick * dim + j]; s_last[j] = v; cent[(int64_t)c * dim + j] = v; }
+    __syncthreads();
+    if (c == k - 1) break;
+    double part = 0.0;
+    for (int64_t i = a; i < b; ++i) {
+      double s = 0.0;
+      for (int j = 0; j < dim; ++j) { const double df = __dsub_rn(x[i * dim + j], s_last[j]); s = __dadd_rn(s, __dmul_rn(df, df)); }
+      double cur = d2[i];
+      if (s < cur) { cur = s; d2[i] = s; }
+      part = __dadd_rn(part, cur);
+    }
+    s_part[t] = part;
+    __syncthreads();
+    if (t == 0) {
+      double total = 0.0;
+      for (int i = 0; i < 256; ++i) total = __dadd_rn(total, s_part[i]);
+      const double u = (double)(xorshift64s(st) >> 11) * (1.0 / 9007199254740992.0) * total;
+      double acc = 0.0;
+      int owner = 255;
+      for (int i = 0; i < 256; ++i) {
+        if (__dadd_rn(acc, s_part[i]) > u) { owner = i; break; }
+        acc = __dadd_rn(acc, s_part[i]);
+      }
+      const int64_t oa = min((int64_t)owner * per, n), ob = min(oa + per, n);
+      long long pk = n - 1;
+      for (int64_t i = oa; i < ob; ++i) {
+        acc = __dadd_rn(acc, d2[i]);
+        if (acc > u) { pk = i; break; }
+      }
+      s_pick = pk;
+    }
+  }
+}
+
+size_t kmeans_update_ws_bytes(int64_t n, int k) {
+  size_t sort_tmp = 0, scan_tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const int32_t *)nullptr, (int32_t *)nullptr, (const int32_t *)nullptr,
+                                  (int32_t *)nullptr, (int)n);
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const int32_t *)nullptr, (int32_t *)nullptr, k);
+  size_t tmp = sort_tmp > scan_tmp ? sort_tmp : scan_tmp;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  return al(tmp) + 3 * al((size_t)n * 4) + 2 * al((size_t)k * 4);
+}
+
+int launch_kmeans_assign_f64(const double *x, int64_t n, int dim, const double *cent, int k, int32_t *labels, double *dist,
+                             int32_t *changed, cudaStream_t st) {
+  if (n <= 0) return TM_OK;
+  if (dim < 1 || dim > 1024 || k < 1) return TM_ERR_ARG;
+  const size_t smem = (size_t)KA_P * (dim + 1) * sizeof(double);
+  if (smem > 48 * 1024)
+    if (cudaFuncSetAttribute(kmeans_assign_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return TM_ERR_CUDA;
+  kmeans_assign_f64_kernel<<<(unsigned)((n + KA_P - 1) / KA_P), 128, smem, st>>>(x, n, dim, cent, k, labels, dist, changed);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+int launch_kmeans_update_f64(const double *x, const double *weights, int64_t n, int dim, const int32_t *labels, int k, double *cent,
+                             int64_t *counts_out, double *wsum_out, void *ws, size_t ws_bytes, int nan_empty, int divide,
+                             cudaStream_t st) {
+  if (n <= 0) return TM_OK;
+  if (ws_bytes < kmeans_update_ws_bytes(n, k)) return TM_ERR_ARG;
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t sort_tmp = 0, scan_tmp = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const int32_t *)nullptr, (int32_t *)nullptr, (const int32_t *)nullptr,
+                                  (int32_t *)nullptr, (int)n);
+  cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const int32_t *)nullptr, (int32_t *)nullptr, k);
+  size_t tmp = sort_tmp > scan_tmp ? sort_tmp : scan_tmp;
+  uint8_t *p = (uint8_t *)ws;
+  void *d_tmp = p; p += al(tmp);
+  int32_t *keys_out = (int32_t *)p; p += al((size_t)n * 4);
+  int32_t *vals_in = (int32_t *)p; p += al((size_t)n * 4);
+  int32_t *vals_out = (int32_t *)p; p += al((size_t)n * 4);
+  int32_t *counts = (int32_t *)p; p += al((size_t)k * 4);
+  int32_t *offs = (int32_t *)p;
+  int bits = 1;
+  while ((1ll << bits) < k) ++bits;
+  iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(vals_in, n);
+  cudaMemsetAsync(counts, 0, (size_t)k * 4, st);
+  hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(labels, n, counts);
+  cub::DeviceRadixSort::SortPairs(d_tmp, sort_tmp, labels, keys_out, vals_in, vals_out, (int)n, 0, bits, st);  // stable
+  cub::DeviceScan::ExclusiveSum(d_tmp, scan_tmp, counts, offs, k, st);
+  const int64_t total = (int64_t)k * dim;
+  kmeans_update_f64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, weights, dim, vals_out, offs, counts, k, nan_empty, divide,
+                                                                            cent, counts_out, wsum_out);
+  note_launch(8);
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+int launch_kmeanspp_f64(const double *x, int64_t n, int dim, int k, unsigned long long seed, double *d2_ws, double *cent,
+                        cudaStream_t st) {
+  if (n <= 0 || k < 1 || dim < 1 || dim > 4096) return TM_ERR_ARG;
+  kmeanspp_f64_kernel<<<1, 256, (size_t)dim * sizeof(double), st>>>(x, n, dim, k, seed, d2_ws, cent);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+int launch_kmeans_finish(const double *sums, const int64_t *counts, int k, int dim, int nan_empty, double *cent, cudaStream_t st) {
+  const int64_t total = (int64_t)k * dim;
+  kmeans_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(sums, counts, k, dim, nan_empty, cent);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------ RGB (3-d) k-means, all palettes at once
+// pixels: packed 0x00BBGGRR grouped by palette (segment p = [off[p], off[p+1])), cent [n_pal][k][3] f64.
+// One Lloyd iteration = assign+accumulate kernel, then a centroid kernel.
+struct RgbAcc { unsigned long long r, g, b, n; };
+
+__global__ void __launch_bounds__(256)
+rgb_assign_kernel(const int32_t *__restrict__ px, const int64_t *__restrict__ off, int n_pal, int k, const double *__restrict__ cent,
+                  uint16_t *__restrict__ labels, RgbAcc *__restrict__ acc, int32_t *__restrict__ changed, int64_t chunk,
+                  const int32_t *__restrict__ kcount) {
+  extern __shared__ uint8_t s_mem[];
+  double *s_c = reinterpret_cast<double *>(s_mem);                     // [k][3]
+  unsigned int *s_a = reinterpret_cast<unsigned int *>(s_c + 3 * k);  // [k][4]
+  const int64_t n_total = off[n_pal];
+  const int64_t c0 = (int64_t)blockIdx.x * chunk, c1 = min(c0 + chunk, n_total);
+  if (c0 >= c1) return;
+  // first palette whose segment ends after c0
+  int p = 0;
+  {
+    int lo = 0, hi = n_pal - 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (off[mid + 1] > c0) hi = mid; else lo = mid + 1; }
+    p = lo;
+  }
+  int local_changed = 0;
+  for (; p < n_pal && off[p] < c1; ++p) {
+    const int64_t s0 = max(c0, off[p]), s1 = min(c1, off[p + 1]);
+    if (s0 >= s1) continue;
+    const int kk = kcount[p];  // slots beyond Min(AColorCount, DSLen) do not exist (:4464)
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * k; i += 256) s_c[i] = cent[(int64_t)p * k * 3 + i];
+    for (int i = threadIdx.x; i < 4 * k; i += 256) s_a[i] = 0;
+    __syncthreads();
+    for (int64_t i = s0 + threadIdx.x; i < s1; i += 256) {
+      const int32_t c = __ldg(px + i);
+      const double r = (double)(c & 255), g = (double)((c >> 8) & 255), b = (double)((c >> 16) & 255);
+      double best = INFINITY;
+      int bi = -1;
+      for (int j = 0; j < kk; ++j) {
+        const double dr = __dsub_rn(r, s_c[3 * j]), dg = __dsub_rn(g, s_c[3 * j + 1]), db = __dsub_rn(b, s_c[3 * j + 2]);
+        const double s = __dadd_rn(__dadd_rn(__dmul_rn(dr, dr), __dmul_rn(dg, dg)), __dmul_rn(db, db));
+        if (s < best) { best = s; bi = j; }
+      }
+      const int old = labels[i];
+      if (bi < 0) bi = old != 0xFFFF ? old : 0;
+      if (bi != old) { labels[i] = (uint16_t)bi; ++local_changed; }
+      atomicAdd(&s_a[4 * bi], (unsigned)(c & 255));
+      atomicAdd(&s_a[4 * bi + 1], (unsigned)((c >> 8) & 255));
+      atomicAdd(&s_a[4 * bi + 2], (unsigned)((c >> 16) & 255));
+      atomicAdd(&s_a[4 * bi + 3], 1u);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < k; j += 256) {
+      if (s_a[4 * j + 3]) {
+        RgbAcc *a = acc + (int64_t)p * k + j;
+        atomicAdd(&a->r, (unsigned long long)s_a[4 * j]);
+        atomicAdd(&a->g, (unsigned long long)s_a[4 * j + 1]);
+        atomicAdd(&a->b, (unsigned long long)s_a[4 * j + 2]);
+        atomicAdd(&a->n, (unsigned long long)s_a[4 * j + 3]);
+      }
+    }
+  }
+  if (local_changed) atomicAdd(changed, local_changed);
+}
+
+__global__ void rgb_centroid_kernel(const RgbAcc *__restrict__ acc, int64_t total, double *__restrict__ cent, const int32_t *__restrict__ kcount,
+                                    int k) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int p = (int)(i / k), j = (int)(i % k);
+  if (j >= kcount[p]) return;  // unused slots (k clipped to the pixel count)
+  const RgbAcc a = acc[i];
+  if (a.n) {
+    cent[3 * i] = __ddiv_rn((double)a.r, (double)a.n);
+    cent[3 * i + 1] = __ddiv_rn((double)a.g, (double)a.n);
+    cent[3 * i + 2] = __ddiv_rn((double)a.b, (double)a.n);
+  } else {
+    cent[3 * i] = NAN; cent[3 * i + 1] = NAN; cent[3 * i + 2] = NAN;  // empty cluster (host tolerates NaN, :4521)
+  }
+}
+
+// k-means++ seeding identical to the oracle's tmo_kmeanspp_init (explicit xorshift64* stream, D^2 sampling by first
+// prefix sum exceeding u).  Integer distances -> prefix sums are exact in any order.  One block per palette.
+
+__global__ void __launch_bounds__(256)
+rgb_kmeanspp_kernel(const int32_t *__restrict__ px, const int64_t *__restrict__ off, int k, const int32_t *__restrict__ kcount,
+                    unsigned long long seed, unsigned int *__restrict__ d2, double *__restrict__ cent) {
+  const int p = blockIdx.x;
+  const int64_t s0 = off[p], n = off[p + 1] - s0;
+  const int kk = kcount[p];
+  if (n <= 0 || kk <= 0) return;
+  __shared__ unsigned long long s_part[256];
+  __shared__ int s_last[3];
+  unsigned long long st = seed ? seed : 0x9E3779B97F4A7C15ULL;
+  const int t = threadIdx.x;
+  const int64_t per = (n + 255) / 256, a = min((int64_t)t * per, n), b = min(a + per, n);
+  if (t == 0) {
+    const int64_t first = (int64_t)(xorshift64s(st) % (unsigned long long)n);
+    const int32_t c = px[s0 + first];
+    s_last[0] = c & 255; s_last[1] = (c >> 8) & 255; s_last[2] = (c >> 16) & 255;
+    double *cv = cent + ((int64_t)p * k) * 3;
+    cv[0] = s_last[0]; cv[1] = s_last[1]; cv[2] = s_last[2];
+  }
+  for (int64_t i = a; i < b; ++i) d2[s0 + i] = 0xFFFFFFFFu;
+  for (int c = 1; c < kk; ++c) {
+    __syncthreads();
+    const int lr = s_last[0], lg = s_last[1], lb = s_last[2];
+    unsigned long long part = 0;
+    for (int64_t i = a; i < b; ++i) {
+      const int32_t v = px[s0 + i];
+      const int dr = (v & 255) - lr, dg = ((v >> 8) & 255) - lg, db = ((v >> 16) & 255) - lb;
+      const unsigned int s = (unsigned)(dr * dr + dg * dg + db * db);
+      unsigned int cur = d2[s0 + i];
+      if (s < cur) { cur = s; d2[s0 + i] = s; }
+      part += cur;
+    }
+    s_part[t] = part;
+    __syncthreads();
+    if (t == 0) {
+      unsigned long long total = 0;
+      for (int i = 0; i < 256; ++i) total += s_part[i];
+      const double u = (double)(xorshift64s(st) >> 11) * (1.0 / 9007199254740992.0) * (double)total;
+      // owner thread = first whose inclusive prefix exceeds u; stash u's remainder search bounds
+      unsigned long long acc = 0;
+      int owner = 255;
+      for (int i = 0; i < 256; ++i) {
+        if ((double)(acc + s_part[i]) > u) { owner = i; break; }
+        acc += s_part[i];
+      }
+      // sequential scan inside the owner's range (<= n/256 elements)
+      const int64_t oa = min((int64_t)owner * per, n), ob = min(oa + per, n);
+      int64_t pick = n - 1;
+      for (int64_t i = oa; i < ob; ++i) {
+        acc += d2[s0 + i];
+        if ((double)acc > u) { pick = i; break; }
+      }
+      if (owner == 255 && !((double)acc > u)) pick = n - 1;
+      const int32_t v = px[s0 + pick];
+      s_last[0] = v & 255; s_last[1] = (v >> 8) & 255; s_last[2] = (v >> 16) & 255;
+      double *cv = cent + ((int64_t)p * k + c) * 3;
+      cv[0] = s_last[0]; cv[1] = s_last[1]; cv[2] = s_last[2];
+    }
+  }
+}
+
+// centroids -> palette (round half-even, clamp, integer HSV, sort by (V,S,H), pad with the null colour)
+__device__ int muldiv_rn(int a, int b, int c) {  // Win32 MulDiv
+  if (c == 0) return -1;
+  const long long p = (long long)a * b;
+  const long long ac = c < 0 ? -(long long)c : c, ap = p < 0 ? -p : p;
+  const long long q = (ap + ac / 2) / ac;
+  return (int)(((p < 0) != (c < 0)) ? -q : q);
+}
+__device__ void rgb_to_hsv(int rr, int gg, int bb, int &h, int &s, int &v) {  // utils.pas:278-325
+  const int mx = max(rr, max(gg, bb)), mn = min(rr, min(gg, bb));
+  int hh = 0, ss = 0;
+  if (mx != mn) {
+    const int delta = mx - mn;
+    ss = muldiv_rn(delta, 255, mx);
+    if (rr == mx) hh = muldiv_rn(42, gg - bb, delta);
+    else if (gg == mx) hh = muldiv_rn(42, bb - rr, delta) + 84;
+    else hh = muldiv_rn(42, rr - gg, delta) + 168;
+    hh = hh % 252;
+  }
+  h = hh & 255; s = ss & 255; v = mx & 255;
+}
+
+__global__ void palette_finish_kernel(const double *__restrict__ cent, const int32_t *__restrict__ kcount, int n_pal, int k,
+                                      int pal_size, int32_t *__restrict__ palettes) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pal) return;
+  int32_t *out = palettes + (int64_t)p * pal_size;
+  const int kk = kcount[p];
+  // insertion sort on keys (V,S,H,order) kept in the output row itself plus a key array in local memory
+  unsigned int keys[256];
+  for (int i = 0; i < kk; ++i) {
+    const double *c = cent + ((int64_t)p * k + i) * 3;
+    int r = 0, g = 0, b = 0;
+    if (!isnan(c[0]) && !isnan(c[1]) && !isnan(c[2])) {
+      r = min(max(__double2int_rn(c[0]), 0), 255);
+      g = min(max(__double2int_rn(c[1]), 0), 255);
+      b = min(max(__double2int_rn(c[2]), 0), 255);
+    }
+    int h, s, v;
+    rgb_to_hsv(r, g, b, h, s, v);
+    const unsigned int key = ((unsigned)v << 24) | ((unsigned)s << 16) | ((unsigned)h << 8) | (unsigned)i;
+    const int32_t col = (b << 16) | (g << 8) | r;
+    int j = i;
+    while (j > 0 && keys[j - 1] > key) { keys[j] = keys[j - 1]; out[j] = out[j - 1]; --j; }
+    keys[j] = key;
+    out[j] = col;
+  }
+  for (int i = kk; i < pal_size; ++i) out[i] = (int32_t)0xffff00ff;
+}
+
+// keys for grouping pixels by palette and ordering them (G,R,B) like CompareDSPixel (tilingencoder.pas:1046-1056)
+__global__ void pixel_keys_kernel(const int32_t *__restrict__ rgb, const int32_t *__restrict__ tile_pal, int64_t n_tiles,
+                                  unsigned long long *__restrict__ keys) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_tiles * 64) return;
+  const int32_t c = rgb[i];
+  const unsigned int r = c & 255, g = (c >> 8) & 255, b = (c >> 16) & 255;
+  keys[i] = ((unsigned long long)(unsigned)tile_pal[i >> 6] << 24) | (g << 16) | (r << 8) | b;
+}
+__global__ void keys_to_pixels_kernel(const unsigned long long *__restrict__ keys, int64_t n, int32_t *__restrict__ px,
+                                      unsigned long long *__restrict__ counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long kx = keys[i];
+  const unsigned int g = (kx >> 16) & 255, r = (kx >> 8) & 255, b = kx & 255;
+  px[i] = (int32_t)((b << 16) | (g << 8) | r);
+  atomicAdd(counts + (kx >> 24), 1ull);
+}
+
+// Full colour-quantisation stage for all palettes (QuantizeUsingYakmo + DoQuantization over PreparePalettes' loop,
+// tilingencoder.pas:1864, 4434-4564).  init: [n_pal][pal_size][3] explicit centroids or nullptr (seeded k-means++).
+int run_palette_quantise(const int32_t *rgb, const int32_t *tile_pal, int64_t n_tiles, int n_pal, int pal_size, const double *init,
+                         unsigned long long seed, int max_iter, int32_t *palettes_out, int32_t *iters_out, cudaStream_t st) {
+  if (n_tiles <= 0 || n_pal < 1 || pal_size < 1 || pal_size > 256) return TM_ERR_ARG;
+  const int64_t n = n_tiles * 64;
+  const int k = pal_size;
+  int bits = 24;
+  while ((1ll << (bits - 24)) < n_pal) ++bits;
+  unsigned long long *keys = nullptr, *keys2 = nullptr, *counts = nullptr;
+  int32_t *px = nullptr, *kcount = nullptr, *changed = nullptr;
+  int64_t *off = nullptr;
+  double *cent = nullptr;
+  uint16_t *labels = nullptr;
+  RgbAcc *acc = nullptr;
+  unsigned int *d2 = nullptr;
+  void *tmp = nullptr;
+  size_t tmp_bytes = 0;
+  int rc = TM_OK;
+  std::vector<unsigned long long> h_counts(n_pal);
+  std::vector<int64_t> h_off(n_pal + 1);
+  std::vector<int32_t> h_kcount(n_pal);
+  int it = 0;
+#define CK(x) do { if ((x) != cudaSuccess) { rc = TM_ERR_CUDA; goto done; } } while (0)
+  CK(cudaMalloc(&keys, n * 8)); CK(cudaMalloc(&keys2, n * 8)); CK(cudaMalloc(&counts, (size_t)n_pal * 8));
+  CK(cudaMalloc(&px, n * 4)); CK(cudaMalloc(&kcount, (size_t)n_pal * 4)); CK(cudaMalloc(&changed, 4));
+  CK(cudaMalloc(&off, (size_t)(n_pal + 1) * 8)); CK(cudaMalloc(&cent, (size_t)n_pal * k * 3 * 8));
+  CK(cudaMalloc(&labels, n * 2)); CK(cudaMalloc(&acc, (size_t)n_pal * k * sizeof(RgbAcc))); CK(cudaMalloc(&d2, n * 4));
+  cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, keys2, (int)n, 0, bits, st);
+  CK(cudaMalloc(&tmp, tmp_bytes));
+  note_launch(6);
+  pixel_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rgb, tile_pal, n_tiles, keys);
+  cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys, keys2, (int)n, 0, bits, st);
+  CK(cudaMemsetAsync(counts, 0, (size_t)n_pal * 8, st));
+  keys_to_pixels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys2, n, px, counts);
+  CK(cudaMemcpyAsync(h_counts.data(), counts, (size_t)n_pal * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  h_off[0] = 0;
+  for (int p = 0; p < n_pal; ++p) {
+    h_off[p + 1] = h_off[p] + (int64_t)h_counts[p];
+    h_kcount[p] = (int32_t)((int64_t)h_counts[p] < k ? (int64_t)h_counts[p] : k);  // AColorCount := Min(AColorCount, DSLen), :4464
+  }
+  CK(cudaMemcpyAsync(off, h_off.data(), (size_t)(n_pal + 1) * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(kcount, h_kcount.data(), (size_t)n_pal * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(labels, 0xFF, n * 2, st));
+  if (init) CK(cudaMemcpyAsync(cent, init, (size_t)n_pal * k * 3 * 8, cudaMemcpyDefault, st));
+  else {
+    CK(cudaMemsetAsync(cent, 0xFF, (size_t)n_pal * k * 3 * 8, st));  // NaN fill: unused slots never win
+    rgb_kmeanspp_kernel<<<n_pal, 256, 0, st>>>(px, off, k, kcount, seed, d2, cent);
+  }
+  {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t chunk = (n + (int64_t)sms * 8 - 1) / ((int64_t)sms * 8);
+    if (chunk < 2048) chunk = 2048;
+    if (chunk > 16 * 1024 * 1024) chunk = 16 * 1024 * 1024;  // 255 * chunk must fit the 32-bit block accumulators
+    const unsigned grid = (unsigned)((n + chunk - 1) / chunk);
+    const size_t smem = (size_t)k * (3 * 8 + 4 * 4);
+    // Lloyd: a palette with k == 1 is a plain mean (:4502-4509) = one update from any start
+    for (;;) {
+      int32_t h_changed = 0;
+      CK(cudaMemsetAsync(changed, 0, 4, st));
+      CK(cudaMemsetAsync(acc, 0, (size_t)n_pal * k * sizeof(RgbAcc), st));
+      note_launch(2);
+      rgb_assign_kernel<<<grid, 256, smem, st>>>(px, off, n_pal, k, cent, labels, acc, changed, chunk, kcount);
+      CK(cudaMemcpyAsync(&h_changed, changed, 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (h_changed == 0 || it >= max_iter) break;
+      ++it;
+      rgb_centroid_kernel<<<(unsigned)(((int64_t)n_pal * k + 255) / 256), 256, 0, st>>>(acc, (int64_t)n_pal * k, cent, kcount, k);
+    }
+  }
+  palette_finish_kernel<<<(n_pal + 63) / 64, 64, 0, st>>>(cent, kcount, n_pal, k, pal_size, palettes_out);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  if (iters_out) *iters_out = it;
+done:
+#undef CK
+  cudaFree(keys); cudaFree(keys2); cudaFree(counts); cudaFree(px); cudaFree(kcount); cudaFree(changed); cudaFree(off);
+  cudaFree(cent); cudaFree(labels); cudaFree(acc); cudaFree(d2); cudaFree(tmp);
+  return rc;
+}
+
+}  // namespace tmg

@@ -1,0 +1,71 @@
+// tm_kernels.h -- internal launcher interface between the CUDA translation units and the C-ABI layer (abi.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#define TM_OK 0
+#define TM_ERR_ARG 1      // invalid argument
+#define TM_ERR_CUDA 2     // CUDA runtime error (see tm_last_error)
+#define TM_ERR_DRIVER 3   // driver entry point / tensor-map encoding failed
+#define TM_ERR_NOGPU 4    // no sm_100 device
+#define TM_ERR_NOMEM 5
+
+#include <atomic>
+
+namespace tmg {
+
+// kernels launched by this library since load (reported as gpu_launches by bench.py)
+extern std::atomic<long long> g_launches;
+inline void note_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ---- knn_i8.cu
+size_t knn_workspace_bytes(int num_ctas);
+int knn_rows_per_cta();
+int launch_limb_split(const int16_t *in, int64_t n, uint8_t *limbs, uint32_t *norms, cudaStream_t st);
+int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const uint8_t *d_limbs, const uint32_t *d_norm,
+                  int n_dict, int k, int32_t *out_idx, uint32_t *out_dist, void *ws, int num_ctas, int sort_rows,
+                  cudaStream_t st);
+
+// ---- features.cu
+int launch_features_rgb(const int32_t *rgb, int64_t n, int16_t *out, cudaStream_t st);
+int launch_features_pal(const uint8_t *pal_idx, const int32_t *tile_pal, const int32_t *palettes, int pal_size, int64_t n,
+                        int16_t *out, cudaStream_t st);
+// features of every (dictionary tile, palette) pair: out [n_tiles][n_pal][192]
+int launch_features_allpairs(const uint8_t *pal_idx, int64_t n_tiles, const int32_t *palettes, int pal_size, int n_pal,
+                             int16_t *out, cudaStream_t st);
+int launch_features_f64(const int32_t *rgb, int64_t n, int mode, int use_lab, double *out, cudaStream_t st);
+int launch_mirror_canonicalise(int32_t *rgb, int64_t n, uint8_t *flags, cudaStream_t st);
+int features_init(cudaStream_t st);
+
+// ---- dither.cu
+int launch_dither(const int32_t *rgb, const uint8_t *mirror_flags, const int32_t *pair_tile, const int32_t *pair_pal,
+                  int64_t n_pairs, const int32_t *palettes, int pal_size, int n_pal, int use_tk, int y2_mixed, uint8_t *out_idx,
+                  cudaStream_t st);
+
+// ---- match.cu
+int launch_distance_pairs(const int16_t *a, const int16_t *b, int64_t n, uint32_t *out, cudaStream_t st);
+int launch_match_rerank(const int16_t *q_feat, int64_t n_q, const int32_t *knn_idx, int k, const int32_t *dict_pal,
+                        const uint8_t *dict_idx, int64_t n_dict, const int32_t *palettes, int pal_size, int n_pal,
+                        const int16_t *pair_feat /* [n_dict][n_pal][192] or null */, int32_t *out_tile, int32_t *out_pal,
+                        uint32_t *out_err, cudaStream_t st);
+int launch_knn_f64(const double *dict, int64_t n_dict, int dim, const double *q, int64_t n_q, int32_t *idx, double *dist,
+                   cudaStream_t st);
+
+// ---- kmeans.cu
+int launch_kmeans_assign_f64(const double *x, int64_t n, int dim, const double *cent, int k, int32_t *labels, double *dist,
+                             int32_t *changed, cudaStream_t st);
+// weights may be null (all 1); divide == 0 writes raw per-cluster sums instead of means (multi-GPU partial step)
+int launch_kmeans_update_f64(const double *x, const double *weights, int64_t n, int dim, const int32_t *labels, int k, double *cent,
+                             int64_t *counts, double *wsum_out, void *ws, size_t ws_bytes, int nan_empty, int divide,
+                             cudaStream_t st);
+int launch_kmeanspp_f64(const double *x, int64_t n, int dim, int k, unsigned long long seed, double *d2_ws, double *cent,
+                        cudaStream_t st);
+int launch_kmeans_finish(const double *sums, const int64_t *counts, int k, int dim, int nan_empty, double *cent, cudaStream_t st);
+int launch_match_plain(const int32_t *knn_idx, const uint32_t *knn_dist, int64_t n_q, const int32_t *dict_pal, int64_t n_dict,
+                       int32_t *out_tile, int32_t *out_pal, uint32_t *out_err, cudaStream_t st);
+size_t kmeans_update_ws_bytes(int64_t n, int k);
+int run_palette_quantise(const int32_t *rgb, const int32_t *tile_pal, int64_t n_tiles, int n_pal, int pal_size, const double *init,
+                         unsigned long long seed, int max_iter, int32_t *palettes_out, int32_t *iters_out, cudaStream_t st);
+
+}  // namespace tmg
