@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the TileMotion data-parallel core on B200.
+
+Workload (BASELINE.json configs[1]): 720p 240-frame synthetic clip = 8 keyframe sequences of 30 frames,
+65,536-tile dictionary, 16 palettes x 16 colours.  A STEP is the match stage of one keyframe sequence
+(TFrame.Reconstruct's k-NN branch, tilingencoder.pas:1534-1610): 432,000 source tiles ->
+features (int16[192]) -> exact 64-NN against the dictionary on tensor cores -> extended-palette re-rank ->
+(TileIdx, PalIdx, err).  metric = tile->dictionary distance evaluations per second (n_tiles x n_dict per step);
+frames/s of the match stage is reported beside it.  Palettisation, colour quantisation and dithering of the
+dictionary run once in the (untimed) setup through the same library and are timed separately under "stages".
+
+  value : device-timed (CUDA events), inputs resident in HBM; 8 distinct 110 MB input batches are rotated, so no
+          step re-reads the previous step's input from L2.
+  e2e   : same step through the C ABI with HOST (pinned) buffers: H2D of the tiles and D2H of the tilemap inside
+          the timed region.
+  --impl reference : the CPU restatement of the reference's path (oracle/, OpenMP over tiles like MTProcs) on a bounded
+          sample of the same workload.  The reference itself is FreePascal + Windows DLLs and cannot be built here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, FRAMES_PER_SEQ, N_SEQ = 1280, 720, 30, 8
+N_DICT, N_PAL, PAL_SIZE, K_EPU = 65536, 16, 16, 64
+TILES_PER_FRAME = (W // 8) * (H // 8)
+TILES_PER_STEP = TILES_PER_FRAME * FRAMES_PER_SEQ
+METRIC = "tile->dictionary 192-d distance evals/sec (720p match stage; frames/sec in frames_per_sec)"
+UNIT = "evals/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return {"hbm_gbs": j["hbm_gbs"], "bf16_tflops": j["bf16_tflops"], "bf16_tflops_sustained": j["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def make_inputs(seed_base, n_seq):
+    """Canonicalised source tiles of n_seq keyframe sequences: int32 [n_seq, TILES_PER_STEP, 64] (host)."""
+    from tiler_b200 import synth
+    out = np.empty((n_seq, TILES_PER_STEP, 64), dtype=np.int32)
+    for s in range(n_seq):
+        clip = synth.make_clip(W, H, FRAMES_PER_SEQ, cut_every=0, seed=synth.SEED + seed_base + s)
+        out[s] = synth.clip_to_tiles(clip).reshape(-1, 64)
+    return out
+
+
+def build_dictionary(enc, canon_tiles, canon_flags, stages):
+    """Reduce stand-in + PreparePalettes + Dither + PrepareReconstruct, each timed (setup, not the metric)."""
+    import torch
+
+    def timed(name, fn):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        stages[name + "_ms"] = round((time.perf_counter() - t0) * 1e3, 2)
+        return r
+
+    enc.reduce(canon_tiles, canon_flags, N_DICT)
+    timed("prepare_palettes", enc.prepare_palettes)
+    timed("dither", enc.dither)
+    timed("prepare_reconstruct", enc.prepare_reconstruct)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tiler_b200 import api
+    from tiler_b200.encoder import TilingEncoder
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- setup (untimed): clip, dictionary, palettes ----
+    n_seq_local = N_SEQ if world == 1 else max(2, N_SEQ // world)   # weak scaling: every rank keeps full-size batches
+    host_raw = make_inputs(1000 * rank, n_seq_local)
+    enc = TilingEncoder(palette_size=PAL_SIZE, palette_count=N_PAL, device=dev, seed=0x42381337)
+    host_tiles = torch.empty((n_seq_local, TILES_PER_STEP, 64), dtype=torch.int32).pin_memory()
+    dev_tiles = []
+    flags_all = []
+    for s in range(n_seq_local):
+        ct, fl = enc.load_tiles(torch.from_numpy(host_raw[s]).to(dev).view(1, TILES_PER_STEP, 64))
+        dev_tiles.append(ct.view(TILES_PER_STEP, 64))
+        flags_all.append(fl.view(-1))
+        host_tiles[s].copy_(ct.view(TILES_PER_STEP, 64).cpu())
+    del host_raw
+    stages = {}
+    build_dictionary(enc, torch.stack(dev_tiles), torch.stack(flags_all), stages)
+    m = enc.matcher
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for i in range(args.warmup):
+        m.match_rgb(dev_tiles[i % n_seq_local], K_EPU)
+    barrier()
+    api.profile_enable(True)
+    api.profile_read("knn_topk"); api.profile_read("rerank"); api.profile_read("features_rgb")
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = api.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        res = m.match_rgb(dev_tiles[(args.warmup + i) % n_seq_local], K_EPU)
+    e1.record()
+    barrier()
+    sampler.stop_flag.set()
+    launches = api.kernel_launches() - launches0
+    ms_total = e0.elapsed_time(e1)
+    knn_ms, knn_n = api.profile_read("knn_topk")
+    rr_ms, _ = api.profile_read("rerank")
+    ft_ms, _ = api.profile_read("features_rgb")
+    api.profile_enable(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    evals_per_step = TILES_PER_STEP * N_DICT
+    value = world * evals_per_step / (ms_per_step * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ----
+    host_np = [host_tiles[s].numpy() for s in range(n_seq_local)]
+    m.match_rgb(host_np[0], K_EPU)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        ti, pi, er = m.match_rgb(host_np[(1 + i) % n_seq_local], K_EPU)
+        checksum = int(er[:16].astype(np.uint64).sum())          # the step's result is read on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * evals_per_step * args.steps / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    knn_launch_ms = knn_ms / max(knn_n, 1)
+    achieved_tflops = evals_per_step * 384 / (knn_launch_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16 features; int8-limb tensor-core MMA with int32 accumulation (exact)", "data": "synthetic",
+        "frames_per_sec": world * FRAMES_PER_SEQ / (ms_per_step * 1e-3),
+        "config": {"workload": "configs[1]: 720p 240-frame synthetic clip (8 sequences x 30 frames), 65536-tile dictionary, "
+                               "16 palettes x 16 colours; step = match stage of one 30-frame sequence (432000 tiles, k=64, "
+                               "extended palette re-rank)",
+                   "tiles_per_step": TILES_PER_STEP, "dictionary_tiles": N_DICT, "palettes": N_PAL, "palette_size": PAL_SIZE,
+                   "knn_k": K_EPU, "l2_policy": "8 distinct 110 MB input batches rotated; each step's inputs+intermediates "
+                                                 "(~0.6 GB) exceed the 126 MB L2",
+                   "sharding": "keyframe sequences per rank, dictionary replicated, no collective"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": TILES_PER_STEP * 256, "d2h_bytes_per_step": TILES_PER_STEP * 12},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "roofline": {"bound": "tensor", "kernel": "knn_i8_kernel<TOPK>", "achieved": achieved_tflops,
+                     "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tflops / pk["bf16_tflops_sustained"],
+                     "traffic": None, "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                     "algorithmic_flops_per_launch": evals_per_step * 384, "kernel_ms_per_launch": knn_launch_ms,
+                     "note": "384 flop per 192-d distance evaluation; the exact int8-limb scheme issues 4 int8 MMAs (= 2 "
+                             "bf16-equivalent passes) per evaluation, so the algorithmic fraction is capped at 0.5"},
+        "kernel_share_of_step": {"knn_topk": knn_ms / ms_total, "rerank": rr_ms / ms_total, "features_rgb": ft_ms / ms_total},
+        "stages": stages,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample(enc, host_np[0])
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline_sample(enc, canon_tiles_host, n_sample=1536):
+    """The oracle (CPU restatement of the reference's per-tile path: features, brute-force 64-NN with the SSE distance,
+    extended-palette re-rank), OpenMP over tiles like MTProcs, on a bounded sample of the step's tiles."""
+    from oracle import oracle as O
+    pal = enc.palettes.cpu().numpy()
+    didx = enc.tile_idx.cpu().numpy()
+    dpal = enc.tile_pal.cpu().numpy()
+    dict_feat = O.features_from_pal(didx, dpal, pal)
+    sel = np.linspace(0, canon_tiles_host.shape[0] - 1, n_sample).astype(np.int64)
+    q = np.ascontiguousarray(canon_tiles_host[sel])
+    t0 = time.perf_counter()
+    qf = O.features_from_rgb(q)
+    O.match_tiles(qf, dict_feat, didx, dpal, pal, k=K_EPU, extended=True)
+    dt = time.perf_counter() - t0
+    return {"value": n_sample * N_DICT / dt, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+            "sample": f"{n_sample} of the step's {TILES_PER_STEP} tiles (features + brute-force 64-NN + extended-palette re-rank), "
+                      f"{dt:.1f} s on {O.num_threads()} threads"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The FreePascal encoder and its DLLs cannot be
+    built or run here (no fpc/wine, binaries only), so this arm times the oracle port of that path (oracle/), with all the
+    host threads OpenMP gives it, on a bounded sample per step of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from tiler_b200 import synth
+    rng = np.random.default_rng(5)
+    # same shapes as our arm: 65536-tile dictionary of dithered tiles, 16x16 palettes (built with the oracle itself)
+    clip = synth.make_clip(W, H, 6, cut_every=0, seed=synth.SEED)
+    tiles = synth.clip_to_tiles(clip).reshape(-1, 64)
+    sel = np.linspace(0, tiles.shape[0] - 1, N_DICT).astype(np.int64)
+    dtiles = np.ascontiguousarray(tiles[sel])
+    dpal = (rng.integers(0, N_PAL, size=N_DICT)).astype(np.int32)
+    pal = np.stack([O.quantize_palette(dtiles[dpal == p][:64].reshape(-1), PAL_SIZE, seed=p + 1)[0] for p in range(N_PAL)])
+    # dithering 65536 tiles on the CPU takes minutes: indices from a nearest-colour pass are enough for the matcher's cost
+    didx = O.dither(dtiles[:2048], None, dpal[:2048], pal, use_tk=True)
+    didx = np.ascontiguousarray(np.tile(didx, (N_DICT // 2048, 1)))
+    dict_feat = O.features_from_pal(didx, dpal, pal)
+    n_sample = args.ref_sample
+    times = []
+    for i in range(args.warmup + args.steps):
+        q = np.ascontiguousarray(tiles[rng.choice(tiles.shape[0], size=n_sample, replace=False)])
+        t0 = time.perf_counter()
+        qf = O.features_from_rgb(q)
+        O.match_tiles(qf, dict_feat, didx, dpal, pal, k=K_EPU, extended=True)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+    dt = float(np.mean(times))
+    value = n_sample * N_DICT / dt
+    sample = (f"{n_sample} tiles per step of the {TILES_PER_STEP}-tile step (features + brute-force 64-NN + extended-palette "
+              f"re-rank per tile), {O.num_threads()} OpenMP threads")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16 features / uint32 distances (SSE2-class scalar C port)", "data": "synthetic",
+        "frames_per_sec": (n_sample / TILES_PER_FRAME) / dt,
+        "config": {"workload": "configs[1] (bounded sample per step): 65536-tile dictionary, 16 palettes x 16 colours, k=64, "
+                               "extended palette re-rank", "tiles_per_step": n_sample, "dictionary_tiles": N_DICT},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-sample", type=int, default=1024)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

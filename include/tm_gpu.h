@@ -50,6 +50,9 @@ int tm_set_stream(void *cuda_stream);      /* cudaStream_t used by subsequent ca
 const char *tm_last_error(void);
 int64_t tm_kernel_launches(void);          /* kernels launched by this library since load (bench.py's gpu_launches) */
 int tm_synchronize(void);
+/* per-kernel CUDA-event timing on the launching stream (names: "knn_k1", "knn_topk", "rerank", "features_rgb") */
+int tm_profile_enable(int on);
+int tm_profile_read(const char *name, double *total_ms, int64_t *count);
 
 /* ---------------------------------------------------------------- drop-in: ANN_short.dll (extern.pas:182-185) */
 typedef struct tm_knn_short tm_knn_short;

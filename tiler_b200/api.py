@@ -83,6 +83,17 @@ def kernel_launches():
     return int(_lib.lib().tm_kernel_launches())
 
 
+def profile_enable(on=True):
+    check(_lib.lib().tm_profile_enable(int(on)))
+
+
+def profile_read(name):
+    """-> (total_ms, launches) of the kernels recorded under `name` since the last read."""
+    ms, n = C.c_double(), C.c_int64()
+    check(_lib.lib().tm_profile_read(name.encode(), C.byref(ms), C.byref(n)))
+    return ms.value, n.value
+
+
 def synchronize():
     check(_lib.lib().tm_synchronize())
 

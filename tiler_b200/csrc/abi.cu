@@ -15,6 +15,26 @@
 
 namespace tmg {
 std::atomic<long long> g_launches{0};
+
+struct ProfRec { std::string name; cudaEvent_t e0, e1; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::mutex g_prof_mu;
+void prof_begin(const char *name, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  r.name = name;
+  cudaEventCreate(&r.e0);
+  cudaEventCreate(&r.e1);
+  cudaEventRecord(r.e0, st);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  if (!g_prof.empty()) cudaEventRecord(g_prof.back().e1, st);
+}
 }
 using namespace tmg;
 
@@ -158,6 +178,31 @@ extern "C" int tm_set_device(int device) { CU(cudaSetDevice(device)); g_gpu_ok =
 extern "C" int tm_set_stream(void *s) { t_stream = (cudaStream_t)s; return TM_OK; }
 extern "C" const char *tm_last_error(void) { return t_err.c_str(); }
 extern "C" int64_t tm_kernel_launches(void) { return (int64_t)g_launches.load(); }
+extern "C" int tm_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  return TM_OK;
+}
+// total milliseconds and launch count of the kernels recorded under `name` since the last read (synchronises)
+extern "C" int tm_profile_read(const char *name, double *total_ms, int64_t *count) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  double tot = 0.0;
+  int64_t n = 0;
+  std::vector<ProfRec> keep;
+  for (auto &r : g_prof) {
+    if (name && r.name != name) { keep.push_back(r); continue; }
+    float ms = 0.f;
+    cudaEventSynchronize(r.e1);
+    if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { tot += ms; ++n; }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  cudaGetLastError();
+  g_prof.swap(keep);
+  if (total_ms) *total_ms = tot;
+  if (count) *count = n;
+  return TM_OK;
+}
 extern "C" int tm_synchronize(void) { CU(cudaStreamSynchronize(t_stream)); return TM_OK; }
 
 // ------------------------------------------------------------------ features

@@ -231,6 +231,7 @@ int launch_features_rgb(const int32_t *rgb, int64_t n, int16_t *out, cudaStream_
   if (n <= 0) return TM_OK;
   int rc = features_init(st);
   if (rc) return rc;
+  ProfScope prof("features_rgb", st);
   features_i16_kernel<0><<<grid_for(n, 4), 192, 4096 * sizeof(float), st>>>(rgb, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;

@@ -20,7 +20,6 @@
 namespace tmg {
 
 constexpr int BM = 128;          // rows per M tile (UMMA M)
-constexpr int MT = 2;            // M tiles per CTA
 constexpr int BN = 64;           // rows per N tile (UMMA N)
 constexpr int STAGES = 4;        // dictionary ring depth
 constexpr int ROWB = 384;        // bytes per limb row
@@ -28,10 +27,7 @@ constexpr int CHUNK_A = BM * 128;  // one 128-byte-wide swizzle chunk of an A ti
 constexpr int CHUNK_B = BN * 128;
 constexpr int A_TILE = 3 * CHUNK_A;  // 49152
 constexpr int B_TILE = 3 * CHUNK_B;  // 24576
-constexpr int CAP = 256;         // candidate slots per query row (k <= 64)
 constexpr int ACC_COLS = 3 * BN; // TMEM columns per stage
-constexpr int KNN_THREADS = 320; // 8 epilogue warps + TMA warp + MMA warp
-constexpr int SMEM_BYTES = MT * A_TILE + STAGES * B_TILE + 256 + 1024;
 
 // ------------------------------------------------------------------ limb split + norms
 // in: [n][192] int16 -> limbs [n][384] (hi bytes then lo bytes), norms[n] = sum v^2 mod 2^32
@@ -70,88 +66,81 @@ __global__ void __launch_bounds__(192) limb_split_kernel(const int16_t *__restri
   }
 }
 
-// ------------------------------------------------------------------ candidate-list select (top-k path)
-// Cut the candidate list of the row owned by lane L of this warp back to its k smallest (ties at the threshold
-// keep the earliest = lowest dictionary index, the list being in ascending index order).  Returns the k-th
-// smallest distance (the row's new admission threshold).  Whole warp must call; n > k required.
-__device__ __forceinline__ uint32_t select_k(uint2 *b, int n, int k, int lane) {
-  __syncwarp();
-  uint2 e[CAP / 32];
-#pragma unroll
-  for (int i = 0; i < CAP / 32; ++i) {
-    const int p = i * 32 + lane;
-    e[i] = p < n ? b[p] : make_uint2(0xFFFFFFFFu, 0x7FFFFFFFu);
+// ------------------------------------------------------------------ top-k state in shared memory
+// Per query row (= per epilogue thread): a max-heap of the k best (distance << 32 | index) keys and a small queue of
+// admitted-but-not-yet-inserted candidates.  Arrays are [slot][row] so a warp touches 32 consecutive words whatever
+// slot each lane is at.  Insertions are deferred and done by all lanes together (the sift-down loop is divergent:
+// batching makes every trip through it serve many rows at once).
+constexpr int KMAX = 64;         // heap slots per row
+constexpr int QCAP = 16;         // queue slots per row
+constexpr int TK_ROWS = 128;     // rows per CTA on the top-k path
+
+__device__ __forceinline__ void heap_replace_root(unsigned long long *heap, int row, int k, unsigned long long key) {
+  // heap[slot * TK_ROWS + row]; root holds the largest key; key < root guaranteed by the caller
+  int i = 0;
+  for (;;) {
+    const int l = 2 * i + 1;
+    if (l >= k) break;
+    int c = l;
+    unsigned long long ck = heap[l * TK_ROWS + row];
+    if (l + 1 < k) {
+      const unsigned long long rk = heap[(l + 1) * TK_ROWS + row];
+      if (rk > ck) { ck = rk; c = l + 1; }
+    }
+    if (ck <= key) break;
+    heap[i * TK_ROWS + row] = ck;
+    i = c;
   }
-  uint32_t T = 0;
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t trial = T | (1u << bit);
-    int c = 0;
-#pragma unroll
-    for (int i = 0; i < CAP / 32; ++i) c += (e[i].x < trial);
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c < k) T = trial;
-  }
-  int cl = 0;
-#pragma unroll
-  for (int i = 0; i < CAP / 32; ++i) cl += (e[i].x < T);
-  cl = __reduce_add_sync(0xffffffffu, cl);
-  const int need = k - cl;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  int outp = 0, eqseen = 0;
-#pragma unroll
-  for (int i = 0; i < CAP / 32; ++i) {
-    const bool lt = e[i].x < T;
-    const bool eq = e[i].x == T;
-    const uint32_t em = __ballot_sync(0xffffffffu, eq);
-    const int rank = eqseen + __popc(em & lt_mask);
-    const bool keep = lt || (eq && rank < need);
-    eqseen += __popc(em);
-    const uint32_t km = __ballot_sync(0xffffffffu, keep);
-    if (keep) b[outp + __popc(km & lt_mask)] = e[i];
-    outp += __popc(km);
-  }
-  __syncwarp();
-  return T;
+  heap[i * TK_ROWS + row] = key;
 }
 
 // ------------------------------------------------------------------ main kernel
-template <bool TOPK>
-__global__ void __launch_bounds__(KNN_THREADS, 1)
+// MT = M tiles (128 query rows each) per CTA.  Work is a flat sequence of units u = (dictionary tile j, M tile g),
+// u = j*MT + g; unit u accumulates into TMEM stage u & 1.  MT = 2: epilogue warps 0-3 own M tile 0 / stage 0, warps
+// 4-7 own M tile 1 / stage 1 (k = 1 path).  MT = 1: the four epilogue warps alternate between the two stages (top-k
+// path, which needs the shared memory for the heaps).
+template <int MT, bool TOPK>
+__global__ void __launch_bounds__(64 + 128 * MT, 1)
 knn_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
               const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict, int k,
-              int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist, uint2 *__restrict__ ws) {
+              int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *sA = smem;
   uint8_t *sB = smem + MT * A_TILE;
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + MT * A_TILE + STAGES * B_TILE);
+  uint8_t *sX = sB + STAGES * B_TILE;                                   // top-k state (TOPK only)
+  unsigned long long *s_heap = reinterpret_cast<unsigned long long *>(sX);                  // [KMAX][TK_ROWS]
+  unsigned long long *s_queue = s_heap + KMAX * TK_ROWS;                                     // [QCAP][TK_ROWS]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sX + (TOPK ? (KMAX + QCAP) * TK_ROWS * 8 : 0));
   uint64_t *full = bars;                  // [STAGES]  TMA -> MMA
   uint64_t *empty = bars + STAGES;        // [STAGES]  MMA -> TMA
   uint64_t *a_full = bars + 2 * STAGES;   // queries landed
   uint64_t *a_empty = a_full + 1;         // queries no longer read by the tensor pipe
-  uint64_t *t_full = a_empty + 1;         // [MT] accumulators ready
-  uint64_t *t_empty = t_full + MT;        // [MT] accumulators drained
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + MT);
+  uint64_t *t_full = a_empty + 1;         // [2] accumulators ready
+  uint64_t *t_empty = t_full + 2;         // [2] accumulators drained
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
 
+  constexpr int EPI_WARPS = 4 * MT;
+  constexpr int ROWS = BM * MT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (n_dict + BN - 1) / BN;
-  const int n_qblocks = (n_q + BM * MT - 1) / (BM * MT);
+  const int n_qblocks = (n_q + ROWS - 1) / ROWS;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_full, 1);
     mbar_init(a_empty, 1);
-    for (int g = 0; g < MT; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], 4); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], 4); }
     fence_barrier_init();
   }
-  if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_d); }
+  if (warp == EPI_WARPS + 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == EPI_WARPS && lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_d); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == EPI_WARPS) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0, w = 0;
@@ -160,7 +149,7 @@ knn_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         mbar_expect_tx(a_full, MT * A_TILE);
         for (int g = 0; g < MT; ++g)
           for (int c = 0; c < 3; ++c)
-            tma_load_2d(sA + g * A_TILE + c * CHUNK_A, &tmap_q, a_full, c * 128, qb * (BM * MT) + g * BM);
+            tma_load_2d(sA + g * A_TILE + c * CHUNK_A, &tmap_q, a_full, c * 128, qb * ROWS + g * BM);
         for (int j = 0; j < n_tiles; ++j, ++it) {
           const uint32_t s = it % STAGES, r = it / STAGES;
           mbar_wait(&empty[s], (r & 1) ^ 1);
@@ -169,7 +158,7 @@ knn_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == EPI_WARPS + 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t I_SS = make_idesc(kDFmtS32, kFmtS8, kFmtS8, BM, BN);
@@ -181,7 +170,7 @@ knn_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       // K-step ks (32 bytes) of a tile lives in chunk ks/4 at byte (ks%4)*32; offsets in 16-byte units
       auto koffA = [](int ks) { return (uint64_t)(((ks >> 2) * CHUNK_A + (ks & 3) * 32) >> 4); };
       auto koffB = [](int ks) { return (uint64_t)(((ks >> 2) * CHUNK_B + (ks & 3) * 32) >> 4); };
-      uint32_t it = 0, w = 0;
+      uint32_t it = 0, u = 0, w = 0;
       for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
         mbar_wait(a_full, w & 1);
         tc_fence_after();
@@ -190,11 +179,12 @@ knn_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           mbar_wait(&full[s], r & 1);
           tc_fence_after();
           const uint64_t dB = descB0 + (uint64_t)((s * B_TILE) >> 4);
-          for (int g = 0; g < MT; ++g) {
-            mbar_wait(&t_empty[g], (it & 1) ^ 1);
+          for (int g = 0; g < MT; ++g, ++u) {
+            const uint32_t ts = u & 1;
+            mbar_wait(&t_empty[ts], ((u >> 1) & 1) ^ 1);
             tc_fence_after();
             const uint64_t dA = descA0 + (uint64_t)((g * A_TILE) >> 4);
-            const uint32_t acc = tmem_base + g * ACC_COLS;
+            const uint32_t acc = tmem_base + ts * ACC_COLS;
 #pragma unroll
             for (int t = 0; t < 6; ++t) mma_i8(acc, dA + koffA(t), dB + koffB(t), I_SS, t > 0);                 // HH
 #pragma unroll
@@ -203,7 +193,7 @@ knn_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
             for (int t = 0; t < 6; ++t) mma_i8(acc + BN, dA + koffA(6 + t), dB + koffB(t), I_US, 1);            // LH
 #pragma unroll
             for (int t = 0; t < 6; ++t) mma_i8(acc + 2 * BN, dA + koffA(6 + t), dB + koffB(6 + t), I_UU, t > 0);  // LL
-            tc_commit(&t_full[g]);
+            tc_commit(&t_full[ts]);
           }
           tc_commit(&empty[s]);
         }
@@ -211,32 +201,37 @@ knn_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue: 8 warps, thread = query row =====================
-    const int g = warp >> 2, wq = warp & 3;
-    const int row = g * BM + wq * 32 + lane;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16) + g * ACC_COLS;
-    uint2 *wbuf0 = ws + ((size_t)blockIdx.x * (BM * MT) + g * BM + wq * 32) * CAP;  // warp's 32 candidate rows
-    uint2 *mybuf = wbuf0 + (size_t)lane * CAP;
-    uint32_t it = 0;
+    // ===================== epilogue: thread = query row =====================
+    const int g = (MT == 2) ? (warp >> 2) : 0;          // M tile owned by this warp
+    const int wq = warp & 3;                            // TMEM lane quarter
+    const int row = g * BM + wq * 32 + lane;            // row within the CTA's query block
+    const int hrow = wq * 32 + lane;                    // row within the top-k state arrays
+    const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
+    uint32_t u = (MT == 2) ? (uint32_t)g : 0u;          // this warp's next unit
     for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
-      const int64_t qi = (int64_t)qb * (BM * MT) + row;
+      const int64_t qi = (int64_t)qb * ROWS + row;
       const bool valid = qi < n_q;
       const uint32_t nq = valid ? __ldg(qnorm + qi) : 0u;
       uint32_t best_d = 0xFFFFFFFFu;
       int32_t best_i = -1;
       uint32_t tau = 0xFFFFFFFFu;
-      int cnt = 0;
-      for (int j = 0; j < n_tiles; ++j, ++it) {
-        mbar_wait(&t_full[g], it & 1);
+      int qn = 0;
+      if (TOPK) {
+        for (int sl = 0; sl < k; ++sl) s_heap[sl * TK_ROWS + hrow] = ~0ull;
+      }
+      for (int j = 0; j < n_tiles; ++j, u += MT) {
+        const uint32_t ts = u & 1;
+        mbar_wait(&t_full[ts], (u >> 1) & 1);
         tc_fence_after();
+        const uint32_t t_acc = t_lane + ts * ACC_COLS;
         const int col0 = j * BN;
         const int ncol = min(BN, n_dict - col0);
 #pragma unroll 1
         for (int ch = 0; ch < BN / 16; ++ch) {
           uint32_t hh[16], xx[16], ll[16];
-          tmem_ld16(t_lane + ch * 16, hh);
-          tmem_ld16(t_lane + BN + ch * 16, xx);
-          tmem_ld16(t_lane + 2 * BN + ch * 16, ll);
+          tmem_ld16(t_acc + ch * 16, hh);
+          tmem_ld16(t_acc + BN + ch * 16, xx);
+          tmem_ld16(t_acc + 2 * BN + ch * 16, ll);
           uint32_t nd[16];
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
@@ -247,62 +242,94 @@ knn_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
           if (ch == BN / 16 - 1) {  // accumulators are in registers: hand the TMEM stage back to the tensor pipe
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[g]);
+            if (lane == 0) mbar_arrive(&t_empty[ts]);
           }
+          // d = nq + nd - 2*(65536*HH + 256*X + LL)  (mod 2^32); m = min over the 16 columns
+          uint32_t dv[16];
+          uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
-            const int c = ch * 16 + e;
-            // d = nq + nd - 2*(65536*HH + 256*X + LL)  (mod 2^32)
             uint32_t d = nq + nd[e];
             d -= hh[e] << 17;
             d -= xx[e] << 9;
             d -= ll[e] << 1;
-            if (c < ncol) {
-              if (!TOPK) {
-                if (d < best_d) { best_d = d; best_i = col0 + c; }
-              } else {
-                if (d < tau) { mybuf[cnt] = make_uint2(d, (uint32_t)(col0 + c)); ++cnt; }
-              }
+            dv[e] = d;
+            m = min(m, d);
+          }
+          const int cbase = ch * 16;
+          if (ncol < BN) {   // ragged last dictionary tile: columns beyond the dictionary never compete
+            m = 0xFFFFFFFFu;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              if (cbase + e >= ncol) dv[e] = 0xFFFFFFFFu;
+              m = min(m, dv[e]);
             }
           }
-          if (TOPK) {
-            uint32_t fullm = __ballot_sync(0xffffffffu, cnt > CAP - 16);
-            while (fullm) {
-              const int L = __ffs(fullm) - 1;
-              fullm &= fullm - 1;
-              const int nL = __shfl_sync(0xffffffffu, cnt, L);
-              const uint32_t T = select_k(wbuf0 + (size_t)L * CAP, nL, k, lane);
-              if (lane == L) { cnt = k; tau = T; }
+          if (!TOPK) {
+            if (m < best_d) {   // rare once a good candidate has been seen
+#pragma unroll
+              for (int e = 0; e < 16; ++e)
+                if (dv[e] < best_d) { best_d = dv[e]; best_i = col0 + cbase + e; }
+            }
+          } else {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint32_t mh = 0xFFFFFFFFu;
+#pragma unroll
+              for (int e = 0; e < 8; ++e) mh = min(mh, dv[half * 8 + e]);
+              if (mh < tau) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                  const uint32_t d = dv[half * 8 + e];
+                  if (d < tau) {
+                    s_queue[qn * TK_ROWS + hrow] = ((unsigned long long)d << 32) | (uint32_t)(col0 + cbase + half * 8 + e);
+                    ++qn;
+                  }
+                }
+              }
+              // a queue may receive 8 more entries before the next check: drain when any row is past half
+              if (__any_sync(0xffffffffu, qn > QCAP - 8)) {
+                const int qmax = __reduce_max_sync(0xffffffffu, qn);
+                for (int t = 0; t < qmax; ++t) {
+                  if (t < qn) {
+                    const unsigned long long key = s_queue[t * TK_ROWS + hrow];
+                    if (key < s_heap[hrow]) heap_replace_root(s_heap, hrow, k, key);
+                  }
+                }
+                qn = 0;
+                tau = (uint32_t)(s_heap[hrow] >> 32);
+              }
             }
           }
         }
       }
-      // ---- write results for this query block
+      // ---- results of this query block
       if (!TOPK) {
         if (valid) { out_idx[qi] = best_i; out_dist[qi] = best_d; }
       } else {
-        for (int L = 0; L < 32; ++L) {
-          int nL = __shfl_sync(0xffffffffu, cnt, L);
-          uint2 *b = wbuf0 + (size_t)L * CAP;
-          if (nL > k) { select_k(b, nL, k, lane); nL = k; }
-          __syncwarp();
-          const int64_t qL = (int64_t)qb * (BM * MT) + g * BM + wq * 32 + L;
-          if (qL < n_q) {
-            for (int p = lane; p < k; p += 32) {
-              uint2 v = p < nL ? b[p] : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-              out_idx[qL * k + p] = (int32_t)v.y;
-              out_dist[qL * k + p] = v.x;
-            }
-          }
-          __syncwarp();
+        for (int t = 0; t < qn; ++t) {
+          const unsigned long long key = s_queue[t * TK_ROWS + hrow];
+          if (key < s_heap[hrow]) heap_replace_root(s_heap, hrow, k, key);
         }
+        __syncwarp();
+        // coalesced write-out: the warp walks its 32 rows, lanes take heap slots
+        for (int L = 0; L < 32; ++L) {
+          const int64_t qL = (int64_t)qb * ROWS + wq * 32 + L;
+          if (qL >= n_q) break;
+          for (int p = lane; p < k; p += 32) {
+            const unsigned long long key = s_heap[p * TK_ROWS + wq * 32 + L];
+            out_idx[qL * k + p] = (int32_t)(uint32_t)key;          // empty slots: 0xFFFFFFFF = -1
+            out_dist[qL * k + p] = (uint32_t)(key >> 32);
+          }
+        }
+        __syncwarp();
       }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == EPI_WARPS + 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------ row sort: (distance, index) ascending, k <= 64
@@ -371,8 +398,8 @@ int make_tmap_rows_u8(CUtensorMap *map, const void *base, uint64_t rows, uint32_
   return r == CUDA_SUCCESS ? TM_OK : TM_ERR_DRIVER;
 }
 
-size_t knn_workspace_bytes(int num_ctas) { return (size_t)num_ctas * BM * MT * CAP * sizeof(uint2); }
-int knn_rows_per_cta() { return BM * MT; }
+size_t knn_workspace_bytes(int num_ctas) { (void)num_ctas; return 0; }   // top-k state lives in shared memory
+int knn_rows_per_cta() { return BM * 2; }
 
 int launch_limb_split(const int16_t *in, int64_t n, uint8_t *limbs, uint32_t *norms, cudaStream_t st) {
   if (n <= 0) return TM_OK;
@@ -384,26 +411,34 @@ int launch_limb_split(const int16_t *in, int64_t n, uint8_t *limbs, uint32_t *no
 int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const uint8_t *d_limbs, const uint32_t *d_norm,
                   int n_dict, int k, int32_t *out_idx, uint32_t *out_dist, void *ws, int num_ctas, int sort_rows,
                   cudaStream_t st) {
+  (void)ws;
   if (n_q <= 0) return TM_OK;
-  if (k < 1 || k > 64 || n_dict <= 0) return TM_ERR_ARG;
+  if (k < 1 || k > KMAX || n_dict <= 0) return TM_ERR_ARG;
   CUtensorMap tq, td;
   int rc = make_tmap_rows_u8(&tq, q_limbs, (uint64_t)n_q, ROWB, BM);
   if (rc != TM_OK) return rc;
   rc = make_tmap_rows_u8(&td, d_limbs, (uint64_t)n_dict, ROWB, BN);
   if (rc != TM_OK) return rc;
+  constexpr int SMEM_K1 = 2 * A_TILE + STAGES * B_TILE + 256 + 1024;
+  constexpr int SMEM_TK = 1 * A_TILE + STAGES * B_TILE + (KMAX + QCAP) * TK_ROWS * 8 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(knn_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return TM_ERR_CUDA;
-    if (cudaFuncSetAttribute(knn_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaFuncSetAttribute(knn_i8_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaFuncSetAttribute(knn_i8_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK) != cudaSuccess) return TM_ERR_CUDA;
     attr_set = true;
   }
-  const int n_qblocks = (n_q + BM * MT - 1) / (BM * MT);
-  const int grid = n_qblocks < num_ctas ? n_qblocks : num_ctas;
-  if (k == 1)
-    knn_i8_kernel<false><<<grid, KNN_THREADS, SMEM_BYTES, st>>>(tq, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, nullptr);
-  else
-    knn_i8_kernel<true><<<grid, KNN_THREADS, SMEM_BYTES, st>>>(tq, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist,
-                                                                reinterpret_cast<uint2 *>(ws));
+  {
+    ProfScope prof(k == 1 ? "knn_k1" : "knn_topk", st);
+    if (k == 1) {
+      const int n_qblocks = (n_q + 2 * BM - 1) / (2 * BM);
+      const int grid = n_qblocks < num_ctas ? n_qblocks : num_ctas;
+      knn_i8_kernel<2, false><<<grid, 64 + 256, SMEM_K1, st>>>(tq, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist);
+    } else {
+      const int n_qblocks = (n_q + BM - 1) / BM;
+      const int grid = n_qblocks < num_ctas ? n_qblocks : num_ctas;
+      knn_i8_kernel<1, true><<<grid, 64 + 128, SMEM_TK, st>>>(tq, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist);
+    }
+  }
   note_launch();
   if (cudaGetLastError() != cudaSuccess) return TM_ERR_CUDA;
   if (k > 1 && sort_rows) {

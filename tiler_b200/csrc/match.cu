@@ -170,6 +170,7 @@ int launch_match_rerank(const int16_t *q_feat, int64_t n_q, const int32_t *knn_i
   (void)dict_idx; (void)palettes; (void)pal_size;
   if (n_q <= 0) return TM_OK;
   if (k < 1 || k > 64 || !pair_feat) return TM_ERR_ARG;
+  ProfScope prof("rerank", st);
   match_rerank_kernel<<<(unsigned)((n_q + 3) / 4), 128, 0, st>>>(q_feat, n_q, knn_idx, k, dict_pal, n_dict, n_pal, pair_feat, out_tile,
                                                                  out_pal, out_err);
   note_launch();

@@ -50,8 +50,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > TM_MBAR_TIMEOUT_CYCLES) __trap();
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {   // try_wait itself suspends the thread for a hardware-bounded time
+    if ((++spins & 0x3FF) == 0 && clock64() - t0 > TM_MBAR_TIMEOUT_CYCLES) __trap();
   }
 }
 

@@ -19,6 +19,16 @@ namespace tmg {
 extern std::atomic<long long> g_launches;
 inline void note_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// Optional per-kernel timing with CUDA events on the launching stream (tm_profile_enable / tm_profile_read):
+// this is how bench.py measures the dominant kernel's duration live, outside any profiler.
+void prof_begin(const char *name, cudaStream_t st);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  ProfScope(const char *name, cudaStream_t s) : st(s) { prof_begin(name, s); }
+  ~ProfScope() { prof_end(st); }
+};
+
 // ---- knn_i8.cu
 size_t knn_workspace_bytes(int num_ctas);
 int knn_rows_per_cta();

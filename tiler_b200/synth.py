@@ -26,42 +26,50 @@ def _value_noise(rng, h, w, octaves=3):
 
 
 def make_clip(width, height, n_frames, cut_every=0, seed=SEED, n_sprites=12, noise=0.02):
-    """-> uint8 [n_frames, height, width, 3] (R, G, B).  Gradient background translating 1-3 px/frame, textured
-    sprites on linear paths, `noise` fraction of uniformly random pixels, a hard scene cut every `cut_every` frames."""
+    """-> uint8 [n_frames, height, width, 3] (R, G, B).  Per scene: a smooth colour-gradient canvas translating
+    1-3 px/frame, textured sprites (3-octave value noise) on linear paths, `noise` fraction of uniformly random pixels;
+    a hard scene cut every `cut_every` frames (0 = none)."""
     rng = np.random.default_rng(seed)
     frames = np.empty((n_frames, height, width, 3), dtype=np.uint8)
     scene = None
-    yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
     for f in range(n_frames):
         if scene is None or (cut_every and f % cut_every == 0):
+            n_left = n_frames - f if not cut_every else min(cut_every, n_frames - f)
+            vel = rng.integers(1, 4, size=2) * rng.choice([-1, 1], size=2)
+            pad_y, pad_x = abs(int(vel[1])) * n_left + 1, abs(int(vel[0])) * n_left + 1
+            ch, cw = height + pad_y, width + pad_x
+            yy, xx = np.mgrid[0:ch, 0:cw].astype(np.float32)
             base = rng.random(3) * 255
             gx, gy = (rng.random(3) - 0.5) * 300 / width, (rng.random(3) - 0.5) * 300 / height
-            vel = rng.integers(1, 4, size=2) * rng.choice([-1, 1], size=2)
+            canvas = np.empty((ch, cw, 3), dtype=np.float32)
+            for c in range(3):
+                canvas[..., c] = base[c] + gx[c] * xx + gy[c] * yy
+            canvas += (_value_noise(rng, ch, cw, 2)[..., None] - 0.5) * 40.0
+            canvas = np.mod(np.abs(canvas), 510.0)
+            canvas = np.where(canvas > 255, 510.0 - canvas, canvas).astype(np.uint8)
             sprites = []
             for _ in range(n_sprites):
                 sh, sw = int(rng.integers(16, 96)), int(rng.integers(16, 96))
-                tex = (_value_noise(rng, sh, sw)[..., None] * (rng.random(3) * 255 + 40)).clip(0, 255)
+                tex = (_value_noise(rng, sh, sw)[..., None] * (rng.random(3) * 255 + 40)).clip(0, 255).astype(np.uint8)
                 pos = rng.random(2) * [height, width]
                 sv = (rng.random(2) - 0.5) * 8
-                sprites.append((tex.astype(np.float32), pos, sv))
-            scene = (base, gx, gy, vel, sprites, f)
-        base, gx, gy, vel, sprites, f0 = scene
+                sprites.append((tex, pos, sv))
+            scene = (canvas, vel, sprites, f, pad_y, pad_x)
+        canvas, vel, sprites, f0, pad_y, pad_x = scene
         t = f - f0
-        img = np.empty((height, width, 3), dtype=np.float32)
-        for c in range(3):
-            img[..., c] = base[c] + gx[c] * (xx + vel[0] * t) + gy[c] * (yy + vel[1] * t)
+        oy = vel[1] * t if vel[1] > 0 else pad_y - 1 + vel[1] * t
+        ox = vel[0] * t if vel[0] > 0 else pad_x - 1 + vel[0] * t
+        out = canvas[oy:oy + height, ox:ox + width].copy()
         for tex, pos, sv in sprites:
             sh, sw = tex.shape[:2]
             y = int(pos[0] + sv[0] * t) % height
             x = int(pos[1] + sv[1] * t) % width
             y1, x1 = min(height, y + sh), min(width, x + sw)
-            img[y:y1, x:x1] = tex[: y1 - y, : x1 - x]
-        img = np.mod(np.abs(img), 510.0)
-        img = np.where(img > 255, 510.0 - img, img)
-        out = img.astype(np.uint8)
+            out[y:y1, x:x1] = tex[: y1 - y, : x1 - x]
         if noise > 0:
-            m = rng.random((height, width)) < noise
-            out[m] = rng.integers(0, 256, size=(int(m.sum()), 3), dtype=np.uint8)
+            n_noise = int(noise * height * width)
+            pos = rng.integers(0, height * width, size=n_noise)
+            out.reshape(-1, 3)[pos] = rng.integers(0, 256, size=(n_noise, 3), dtype=np.uint8)
         frames[f] = out
     return frames
 

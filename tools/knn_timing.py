@@ -1,0 +1,26 @@
+"""k-NN timing probe (device-resident inputs, CUDA events on torch's current stream)."""
+import sys, os, json, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from tiler_b200 import api, synth
+
+n_dict = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
+n_q = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 256 * 4
+d = torch.from_numpy(synth.random_features(n_dict, 1)).cuda()
+q = torch.from_numpy(synth.random_features(n_q, 2)).cuda()
+knn = api.KnnShort(d)
+res = {}
+for k in (1, 64):
+    for _ in range(2):
+        knn.search(q, k, sorted=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reps = 3
+    for _ in range(reps):
+        knn.search(q, k, sorted=False)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    evals = n_q * n_dict / (ms * 1e-3)
+    res[f"k{k}"] = {"ms": ms, "evals_per_s": evals, "tflops_algorithmic": evals * 384 / 1e12}
+print(json.dumps({"n_dict": n_dict, "n_q": n_q, **res}))
