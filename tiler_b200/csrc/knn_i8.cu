@@ -21,13 +21,15 @@ namespace tmg {
 
 constexpr int BM = 128;          // rows per M tile (UMMA M)
 constexpr int BN = 64;           // rows per N tile (UMMA N)
-constexpr int STAGES = 4;        // dictionary ring depth
+constexpr int STAGES = 6;        // dictionary ring depth (top-k path: the heaps take the rest of shared memory)
+constexpr int STAGES_K1 = 8;     // dictionary ring depth (k = 1 path)
 constexpr int ROWB = 384;        // bytes per limb row
 constexpr int CHUNK_A = BM * 128;  // one 128-byte-wide swizzle chunk of an A tile
 constexpr int CHUNK_B = BN * 128;
 constexpr int A_TILE = 3 * CHUNK_A;  // 49152
 constexpr int B_TILE = 3 * CHUNK_B;  // 24576
-constexpr int ACC_COLS = 3 * BN; // TMEM columns per stage
+constexpr int ACC_COLS = 3 * BN; // TMEM columns per accumulator stage
+constexpr int A_COL = 2 * ACC_COLS;  // query rows live in TMEM columns [384, 480)
 
 // ------------------------------------------------------------------ limb split + norms
 // in: [n][192] int16 -> limbs [n][384] (hi bytes then lo bytes), norms[n] = sum v^2 mod 2^32
@@ -75,184 +77,211 @@ constexpr int KMAX = 64;         // heap slots per row
 constexpr int QCAP = 16;         // queue slots per row
 constexpr int TK_ROWS = 128;     // rows per CTA on the top-k path
 
-__device__ __forceinline__ void heap_replace_root(unsigned long long *heap, int row, int k, unsigned long long key) {
-  // heap[slot * TK_ROWS + row]; root holds the largest key; key < root guaranteed by the caller
+// explicit .shared accesses (32-bit shared-window addresses): never generic LD/ST
+__device__ __forceinline__ unsigned long long lds64(uint32_t a) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;\n" ::"r"(a), "l"(v) : "memory"); }
+
+// heap element (slot, row) lives at heap + (slot * TK_ROWS + row) * 8; `hrow` = heap + row * 8
+__device__ __forceinline__ void heap_replace_root(uint32_t hrow, int k, unsigned long long key) {
+  // root holds the largest key; key < root guaranteed by the caller
   int i = 0;
   for (;;) {
     const int l = 2 * i + 1;
     if (l >= k) break;
     int c = l;
-    unsigned long long ck = heap[l * TK_ROWS + row];
+    unsigned long long ck = lds64(hrow + l * (TK_ROWS * 8));
     if (l + 1 < k) {
-      const unsigned long long rk = heap[(l + 1) * TK_ROWS + row];
+      const unsigned long long rk = lds64(hrow + (l + 1) * (TK_ROWS * 8));
       if (rk > ck) { ck = rk; c = l + 1; }
     }
     if (ck <= key) break;
-    heap[i * TK_ROWS + row] = ck;
+    sts64(hrow + i * (TK_ROWS * 8), ck);
     i = c;
   }
-  heap[i * TK_ROWS + row] = key;
+  sts64(hrow + i * (TK_ROWS * 8), key);
 }
 
 // ------------------------------------------------------------------ main kernel
-// MT = M tiles (128 query rows each) per CTA.  Work is a flat sequence of units u = (dictionary tile j, M tile g),
-// u = j*MT + g; unit u accumulates into TMEM stage u & 1.  MT = 2: epilogue warps 0-3 own M tile 0 / stage 0, warps
-// 4-7 own M tile 1 / stage 1 (k = 1 path).  MT = 1: the four epilogue warps alternate between the two stages (top-k
-// path, which needs the shared memory for the heaps).
-template <int MT, bool TOPK>
-__global__ void __launch_bounds__(64 + 128 * MT, 1)
-knn_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_d,
+// CTA (persistent, one per SM) = 128 query rows (resident in smem) x the whole dictionary streamed in 64-row tiles.
+// Tile j accumulates into TMEM stage j & 1 (3 x 64 columns: HH, X = HL + LH, LL).  The four epilogue warps pull a
+// finished stage into registers in two bursts (HH and X, folded to P = 256*HH + X, then LL), hand the stage back to
+// the tensor pipe immediately, and only then do the per-column arithmetic -- so the tensor pipe waits for TMEM reads,
+// not for ALU work.
+template <bool TOPK>
+__global__ void __launch_bounds__(224, 1)
+knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUtensorMap tmap_d,
               const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict, int k,
               int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist) {
   extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic only: an integer round trip would make every
+  // heap/queue access a generic LD/ST instead of LDS/STS
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *sA = smem;
-  uint8_t *sB = smem + MT * A_TILE;
-  uint8_t *sX = sB + STAGES * B_TILE;                                   // top-k state (TOPK only)
+  constexpr int NST = TOPK ? STAGES : STAGES_K1;
+  uint8_t *sB = smem;
+  uint8_t *sX = sB + NST * B_TILE;                                      // top-k state (TOPK only)
   unsigned long long *s_heap = reinterpret_cast<unsigned long long *>(sX);                  // [KMAX][TK_ROWS]
   unsigned long long *s_queue = s_heap + KMAX * TK_ROWS;                                     // [QCAP][TK_ROWS]
   uint64_t *bars = reinterpret_cast<uint64_t *>(sX + (TOPK ? (KMAX + QCAP) * TK_ROWS * 8 : 0));
-  uint64_t *full = bars;                  // [STAGES]  TMA -> MMA
-  uint64_t *empty = bars + STAGES;        // [STAGES]  MMA -> TMA
-  uint64_t *a_full = bars + 2 * STAGES;   // queries landed
+  uint64_t *full = bars;                  // [NST]  TMA -> MMA
+  uint64_t *empty = bars + NST;           // [NST]  MMA -> TMA
+  uint64_t *a_full = bars + 2 * NST;      // queries landed
   uint64_t *a_empty = a_full + 1;         // queries no longer read by the tensor pipe
   uint64_t *t_full = a_empty + 1;         // [2] accumulators ready
   uint64_t *t_empty = t_full + 2;         // [2] accumulators drained
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
 
-  constexpr int EPI_WARPS = 4 * MT;
-  constexpr int ROWS = BM * MT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (n_dict + BN - 1) / BN;
-  const int n_qblocks = (n_q + ROWS - 1) / ROWS;
+  const int n_qblocks = (n_q + BM - 1) / BM;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(a_full, 1);
-    mbar_init(a_empty, 1);
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(a_full, 4);
+    mbar_init(a_empty, 2);
     for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], 4); }
     fence_barrier_init();
   }
-  if (warp == EPI_WARPS + 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  if (warp == EPI_WARPS && lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_d); }
+  if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 4 && lane == 0) tma_prefetch_desc(&tmap_d);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == EPI_WARPS) {
+  if (warp == 4) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      uint32_t it = 0, w = 0;
-      for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
-        mbar_wait(a_empty, (w & 1) ^ 1);
-        mbar_expect_tx(a_full, MT * A_TILE);
-        for (int g = 0; g < MT; ++g)
-          for (int c = 0; c < 3; ++c)
-            tma_load_2d(sA + g * A_TILE + c * CHUNK_A, &tmap_q, a_full, c * 128, qb * ROWS + g * BM);
+      uint32_t it = 0;
+      for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
         for (int j = 0; j < n_tiles; ++j, ++it) {
-          const uint32_t s = it % STAGES, r = it / STAGES;
+          const uint32_t s = it % NST, r = it / NST;
           mbar_wait(&empty[s], (r & 1) ^ 1);
           mbar_expect_tx(&full[s], B_TILE);
           for (int c = 0; c < 3; ++c) tma_load_2d(sB + s * B_TILE + c * CHUNK_B, &tmap_d, &full[s], c * 128, j * BN);
         }
       }
     }
-  } else if (warp == EPI_WARPS + 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp >= 5) {
+    // ===================== two MMA issuer warps: warp 5 takes even dictionary tiles (TMEM stage 0), warp 6 odd ones
+    // (stage 1).  A single issuing thread cannot sustain one 32-cycle int8 MMA per 32 cycles; two can.  Whole warp runs
+    // the loop, one elected lane issues. =====================
+    {
+      const uint32_t my_parity = (uint32_t)(warp - 5);
       constexpr uint32_t I_SS = make_idesc(kDFmtS32, kFmtS8, kFmtS8, BM, BN);
       constexpr uint32_t I_SU = make_idesc(kDFmtS32, kFmtS8, kFmtU8, BM, BN);
       constexpr uint32_t I_US = make_idesc(kDFmtS32, kFmtU8, kFmtS8, BM, BN);
       constexpr uint32_t I_UU = make_idesc(kDFmtS32, kFmtU8, kFmtU8, BM, BN);
-      const uint64_t descA0 = umma_desc_sw128(smem_u32(sA));
+      const uint32_t tA = tmem_base + A_COL;   // query rows: lane = row, K-step ks = columns [8*ks, 8*ks + 8)
       const uint64_t descB0 = umma_desc_sw128(smem_u32(sB));
-      // K-step ks (32 bytes) of a tile lives in chunk ks/4 at byte (ks%4)*32; offsets in 16-byte units
-      auto koffA = [](int ks) { return (uint64_t)(((ks >> 2) * CHUNK_A + (ks & 3) * 32) >> 4); };
+      // K-step ks (32 bytes) of a B tile lives in chunk ks/4 at byte (ks%4)*32; offsets in 16-byte units
       auto koffB = [](int ks) { return (uint64_t)(((ks >> 2) * CHUNK_B + (ks & 3) * 32) >> 4); };
-      uint32_t it = 0, u = 0, w = 0;
+      uint32_t it = 0, w = 0;
       for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
         mbar_wait(a_full, w & 1);
         tc_fence_after();
         for (int j = 0; j < n_tiles; ++j, ++it) {
-          const uint32_t s = it % STAGES, r = it / STAGES;
+          const uint32_t s = it % NST, r = it / NST;
+          const uint32_t ts = it & 1;
+          if (ts != my_parity) continue;
           mbar_wait(&full[s], r & 1);
+          mbar_wait(&t_empty[ts], ((it >> 1) & 1) ^ 1);
           tc_fence_after();
           const uint64_t dB = descB0 + (uint64_t)((s * B_TILE) >> 4);
-          for (int g = 0; g < MT; ++g, ++u) {
-            const uint32_t ts = u & 1;
-            mbar_wait(&t_empty[ts], ((u >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint64_t dA = descA0 + (uint64_t)((g * A_TILE) >> 4);
-            const uint32_t acc = tmem_base + ts * ACC_COLS;
+          const uint32_t acc = tmem_base + ts * ACC_COLS;
 #pragma unroll
-            for (int t = 0; t < 6; ++t) mma_i8(acc, dA + koffA(t), dB + koffB(t), I_SS, t > 0);                 // HH
+          for (int t = 0; t < 6; ++t) mma_i8_ts_elect(acc, tA + 8 * t, dB + koffB(t), I_SS, t > 0);                       // HH
 #pragma unroll
-            for (int t = 0; t < 6; ++t) mma_i8(acc + BN, dA + koffA(t), dB + koffB(6 + t), I_SU, t > 0);        // HL
+          for (int t = 0; t < 6; ++t) mma_i8_ts_elect(acc + BN, tA + 8 * t, dB + koffB(6 + t), I_SU, t > 0);              // HL
 #pragma unroll
-            for (int t = 0; t < 6; ++t) mma_i8(acc + BN, dA + koffA(6 + t), dB + koffB(t), I_US, 1);            // LH
+          for (int t = 0; t < 6; ++t) mma_i8_ts_elect(acc + BN, tA + 8 * (6 + t), dB + koffB(t), I_US, 1);                // LH
 #pragma unroll
-            for (int t = 0; t < 6; ++t) mma_i8(acc + 2 * BN, dA + koffA(6 + t), dB + koffB(6 + t), I_UU, t > 0);  // LL
-            tc_commit(&t_full[ts]);
-          }
-          tc_commit(&empty[s]);
+          for (int t = 0; t < 6; ++t) mma_i8_ts_elect(acc + 2 * BN, tA + 8 * (6 + t), dB + koffB(6 + t), I_UU, t > 0);    // LL
+          tc_commit_elect(&t_full[ts]);
+          tc_commit_elect(&empty[s]);
         }
-        tc_commit(a_empty);
+        tc_commit_elect(a_empty);
       }
     }
   } else {
     // ===================== epilogue: thread = query row =====================
-    const int g = (MT == 2) ? (warp >> 2) : 0;          // M tile owned by this warp
-    const int wq = warp & 3;                            // TMEM lane quarter
-    const int row = g * BM + wq * 32 + lane;            // row within the CTA's query block
-    const int hrow = wq * 32 + lane;                    // row within the top-k state arrays
-    const uint32_t t_lane = tmem_base + ((uint32_t)(wq * 32) << 16);
-    uint32_t u = (MT == 2) ? (uint32_t)g : 0u;          // this warp's next unit
-    for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
-      const int64_t qi = (int64_t)qb * ROWS + row;
+    const int row = warp * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t it = 0, w = 0;
+    for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
+      const int64_t qi = (int64_t)qb * BM + row;
       const bool valid = qi < n_q;
       const uint32_t nq = valid ? __ldg(qnorm + qi) : 0u;
+      // this thread's query row (384 limb bytes = 96 words) -> TMEM columns [A_COL, A_COL + 96) of its lane,
+      // once the tensor pipe has finished reading the previous block's rows
+      mbar_wait(a_empty, (w & 1) ^ 1);
+      tc_fence_after();
+      {
+        const uint4 *src = reinterpret_cast<const uint4 *>(q_limbs + (valid ? qi : 0) * ROWB);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          uint32_t r[16];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint4 t4 = valid ? __ldg(src + c * 4 + v) : make_uint4(0, 0, 0, 0);
+            r[4 * v] = t4.x; r[4 * v + 1] = t4.y; r[4 * v + 2] = t4.z; r[4 * v + 3] = t4.w;
+          }
+          tmem_st16(t_lane + A_COL + c * 16, r);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full);
+      }
       uint32_t best_d = 0xFFFFFFFFu;
       int32_t best_i = -1;
       uint32_t tau = 0xFFFFFFFFu;
       int qn = 0;
+      const uint32_t hrow = smem_u32(s_heap) + row * 8, qrow = smem_u32(s_queue) + row * 8;
       if (TOPK) {
-        for (int sl = 0; sl < k; ++sl) s_heap[sl * TK_ROWS + hrow] = ~0ull;
+        for (int sl = 0; sl < k; ++sl) sts64(hrow + sl * (TK_ROWS * 8), ~0ull);
       }
-      for (int j = 0; j < n_tiles; ++j, u += MT) {
-        const uint32_t ts = u & 1;
-        mbar_wait(&t_full[ts], (u >> 1) & 1);
-        tc_fence_after();
-        const uint32_t t_acc = t_lane + ts * ACC_COLS;
+      for (int j = 0; j < n_tiles; ++j, ++it) {
+        const uint32_t ts = it & 1;
         const int col0 = j * BN;
         const int ncol = min(BN, n_dict - col0);
-#pragma unroll 1
+        mbar_wait(&t_full[ts], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_acc = t_lane + ts * ACC_COLS;
+        uint32_t pp[BN], lo[BN];
+#pragma unroll
+        for (int c = 0; c < BN / 16; ++c) {
+          tmem_ld16(t_acc + c * 16, reinterpret_cast<uint32_t(&)[16]>(pp[c * 16]));            // HH
+          tmem_ld16(t_acc + BN + c * 16, reinterpret_cast<uint32_t(&)[16]>(lo[c * 16]));       // X
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < BN; ++e) pp[e] = (pp[e] << 8) + lo[e];                              // P = 256*HH + X
+#pragma unroll
+        for (int c = 0; c < BN / 16; ++c) tmem_ld16(t_acc + 2 * BN + c * 16, reinterpret_cast<uint32_t(&)[16]>(lo[c * 16]));  // LL
+        tmem_ld_wait();
+        tc_fence_before();          // the stage is in registers: hand it back to the tensor pipe
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[ts]);
+#pragma unroll
         for (int ch = 0; ch < BN / 16; ++ch) {
-          uint32_t hh[16], xx[16], ll[16];
-          tmem_ld16(t_acc + ch * 16, hh);
-          tmem_ld16(t_acc + BN + ch * 16, xx);
-          tmem_ld16(t_acc + 2 * BN + ch * 16, ll);
           uint32_t nd[16];
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(dnorm + col0 + ch * 16) + v);
             nd[4 * v] = t4.x; nd[4 * v + 1] = t4.y; nd[4 * v + 2] = t4.z; nd[4 * v + 3] = t4.w;
           }
-          tmem_ld_wait();
-          if (ch == BN / 16 - 1) {  // accumulators are in registers: hand the TMEM stage back to the tensor pipe
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t_empty[ts]);
-          }
-          // d = nq + nd - 2*(65536*HH + 256*X + LL)  (mod 2^32); m = min over the 16 columns
+          // d = nq + nd - 2*(256*P + LL)  (mod 2^32); m = min over the 16 columns
           uint32_t dv[16];
           uint32_t m = 0xFFFFFFFFu;
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             uint32_t d = nq + nd[e];
-            d -= hh[e] << 17;
-            d -= xx[e] << 9;
-            d -= ll[e] << 1;
+            d -= pp[ch * 16 + e] << 9;
+            d -= lo[ch * 16 + e] << 1;
             dv[e] = d;
             m = min(m, d);
           }
@@ -282,7 +311,7 @@ knn_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 for (int e = 0; e < 8; ++e) {
                   const uint32_t d = dv[half * 8 + e];
                   if (d < tau) {
-                    s_queue[qn * TK_ROWS + hrow] = ((unsigned long long)d << 32) | (uint32_t)(col0 + cbase + half * 8 + e);
+                    sts64(qrow + qn * (TK_ROWS * 8), ((unsigned long long)d << 32) | (uint32_t)(col0 + cbase + half * 8 + e));
                     ++qn;
                   }
                 }
@@ -292,12 +321,12 @@ knn_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
                 const int qmax = __reduce_max_sync(0xffffffffu, qn);
                 for (int t = 0; t < qmax; ++t) {
                   if (t < qn) {
-                    const unsigned long long key = s_queue[t * TK_ROWS + hrow];
-                    if (key < s_heap[hrow]) heap_replace_root(s_heap, hrow, k, key);
+                    const unsigned long long key = lds64(qrow + t * (TK_ROWS * 8));
+                    if (key < lds64(hrow)) heap_replace_root(hrow, k, key);
                   }
                 }
                 qn = 0;
-                tau = (uint32_t)(s_heap[hrow] >> 32);
+                tau = (uint32_t)(lds64(hrow) >> 32);
               }
             }
           }
@@ -308,16 +337,16 @@ knn_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
         if (valid) { out_idx[qi] = best_i; out_dist[qi] = best_d; }
       } else {
         for (int t = 0; t < qn; ++t) {
-          const unsigned long long key = s_queue[t * TK_ROWS + hrow];
-          if (key < s_heap[hrow]) heap_replace_root(s_heap, hrow, k, key);
+          const unsigned long long key = lds64(qrow + t * (TK_ROWS * 8));
+          if (key < lds64(hrow)) heap_replace_root(hrow, k, key);
         }
         __syncwarp();
         // coalesced write-out: the warp walks its 32 rows, lanes take heap slots
         for (int L = 0; L < 32; ++L) {
-          const int64_t qL = (int64_t)qb * ROWS + wq * 32 + L;
+          const int64_t qL = (int64_t)qb * BM + warp * 32 + L;
           if (qL >= n_q) break;
           for (int p = lane; p < k; p += 32) {
-            const unsigned long long key = s_heap[p * TK_ROWS + wq * 32 + L];
+            const unsigned long long key = lds64(smem_u32(s_heap) + (p * TK_ROWS + warp * 32 + L) * 8);
             out_idx[qL * k + p] = (int32_t)(uint32_t)key;          // empty slots: 0xFFFFFFFF = -1
             out_dist[qL * k + p] = (uint32_t)(key >> 32);
           }
@@ -329,7 +358,7 @@ knn_i8_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == EPI_WARPS + 1) tmem_dealloc(tmem_base, 512);
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------ row sort: (distance, index) ascending, k <= 64
@@ -399,7 +428,7 @@ int make_tmap_rows_u8(CUtensorMap *map, const void *base, uint64_t rows, uint32_
 }
 
 size_t knn_workspace_bytes(int num_ctas) { (void)num_ctas; return 0; }   // top-k state lives in shared memory
-int knn_rows_per_cta() { return BM * 2; }
+int knn_rows_per_cta() { return BM; }
 
 int launch_limb_split(const int16_t *in, int64_t n, uint8_t *limbs, uint32_t *norms, cudaStream_t st) {
   if (n <= 0) return TM_OK;
@@ -414,30 +443,23 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
   (void)ws;
   if (n_q <= 0) return TM_OK;
   if (k < 1 || k > KMAX || n_dict <= 0) return TM_ERR_ARG;
-  CUtensorMap tq, td;
-  int rc = make_tmap_rows_u8(&tq, q_limbs, (uint64_t)n_q, ROWB, BM);
+  CUtensorMap td;
+  int rc = make_tmap_rows_u8(&td, d_limbs, (uint64_t)n_dict, ROWB, BN);
   if (rc != TM_OK) return rc;
-  rc = make_tmap_rows_u8(&td, d_limbs, (uint64_t)n_dict, ROWB, BN);
-  if (rc != TM_OK) return rc;
-  constexpr int SMEM_K1 = 2 * A_TILE + STAGES * B_TILE + 256 + 1024;
-  constexpr int SMEM_TK = 1 * A_TILE + STAGES * B_TILE + (KMAX + QCAP) * TK_ROWS * 8 + 256 + 1024;
+  constexpr int SMEM_K1 = STAGES_K1 * B_TILE + 256 + 1024;
+  constexpr int SMEM_TK = STAGES * B_TILE + (KMAX + QCAP) * TK_ROWS * 8 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(knn_i8_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
-    if (cudaFuncSetAttribute(knn_i8_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaFuncSetAttribute(knn_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaFuncSetAttribute(knn_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK) != cudaSuccess) return TM_ERR_CUDA;
     attr_set = true;
   }
   {
     ProfScope prof(k == 1 ? "knn_k1" : "knn_topk", st);
-    if (k == 1) {
-      const int n_qblocks = (n_q + 2 * BM - 1) / (2 * BM);
-      const int grid = n_qblocks < num_ctas ? n_qblocks : num_ctas;
-      knn_i8_kernel<2, false><<<grid, 64 + 256, SMEM_K1, st>>>(tq, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist);
-    } else {
-      const int n_qblocks = (n_q + BM - 1) / BM;
-      const int grid = n_qblocks < num_ctas ? n_qblocks : num_ctas;
-      knn_i8_kernel<1, true><<<grid, 64 + 128, SMEM_TK, st>>>(tq, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist);
-    }
+    const int n_qblocks = (n_q + BM - 1) / BM;
+    const int grid = n_qblocks < num_ctas ? n_qblocks : num_ctas;
+    if (k == 1) knn_i8_kernel<false><<<grid, 224, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist);
+    else knn_i8_kernel<true><<<grid, 224, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist);
   }
   note_launch();
   if (cudaGetLastError() != cudaSuccess) return TM_ERR_CUDA;
