@@ -21,7 +21,7 @@ namespace tmg {
 
 constexpr int BM = 128;          // rows per M tile (UMMA M)
 constexpr int BN = 64;           // rows per N tile (UMMA N)
-constexpr int STAGES = 6;        // dictionary ring depth (top-k path: the heaps take the rest of shared memory)
+constexpr int STAGES = 4;        // dictionary ring depth (top-k path: the candidate buffers take the rest of shared memory)
 constexpr int STAGES_K1 = 8;     // dictionary ring depth (k = 1 path)
 constexpr int ROWB = 384;        // bytes per limb row
 constexpr int CHUNK_A = BM * 128;  // one 128-byte-wide swizzle chunk of an A tile
@@ -69,13 +69,15 @@ __global__ void __launch_bounds__(192) limb_split_kernel(const int16_t *__restri
 }
 
 // ------------------------------------------------------------------ top-k state in shared memory
-// Per query row (= per epilogue thread): a max-heap of the k best (distance << 32 | index) keys and a small queue of
-// admitted-but-not-yet-inserted candidates.  Arrays are [slot][row] so a warp touches 32 consecutive words whatever
-// slot each lane is at.  Insertions are deferred and done by all lanes together (the sift-down loop is divergent:
-// batching makes every trip through it serve many rows at once).
-constexpr int KMAX = 64;         // heap slots per row
-constexpr int QCAP = 16;         // queue slots per row
-constexpr int TK_ROWS = 128;     // rows per CTA on the top-k path
+// Per query row (= per epilogue thread) a candidate buffer of CAP (distance << 32 | index) keys, row-major so that a
+// warp can read one row with consecutive lanes.  A column is admitted when its distance is below the row's threshold
+// tau (the k-th smallest distance at the last cut); when a row's buffer fills, the warp cuts it back to its k
+// smallest with a 32-step radix select on the distance (ties at the threshold keep the earliest = lowest dictionary
+// index: the buffer is always in ascending index order) and tau drops to the new k-th distance.  With a random
+// column order each cut doubles the number of columns needed to refill the buffer: ~log2(N/k) cuts per row.
+constexpr int KMAX = 64;         // largest k
+constexpr int CAP = 128;         // candidate slots per row
+constexpr int TK_ROWS = 128;     // rows per CTA
 
 // explicit .shared accesses (32-bit shared-window addresses): never generic LD/ST
 __device__ __forceinline__ unsigned long long lds64(uint32_t a) {
@@ -85,24 +87,47 @@ __device__ __forceinline__ unsigned long long lds64(uint32_t a) {
 }
 __device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;\n" ::"r"(a), "l"(v) : "memory"); }
 
-// heap element (slot, row) lives at heap + (slot * TK_ROWS + row) * 8; `hrow` = heap + row * 8
-__device__ __forceinline__ void heap_replace_root(uint32_t hrow, int k, unsigned long long key) {
-  // root holds the largest key; key < root guaranteed by the caller
-  int i = 0;
-  for (;;) {
-    const int l = 2 * i + 1;
-    if (l >= k) break;
-    int c = l;
-    unsigned long long ck = lds64(hrow + l * (TK_ROWS * 8));
-    if (l + 1 < k) {
-      const unsigned long long rk = lds64(hrow + (l + 1) * (TK_ROWS * 8));
-      if (rk > ck) { ck = rk; c = l + 1; }
-    }
-    if (ck <= key) break;
-    sts64(hrow + i * (TK_ROWS * 8), ck);
-    i = c;
+// Whole warp: cut the n (> k) candidates at shared address `buf` back to the k smallest; returns the k-th distance.
+__device__ __forceinline__ uint32_t select_k(uint32_t buf, int n, int k, int lane) {
+  __syncwarp();
+  unsigned long long e[CAP / 32];
+#pragma unroll
+  for (int i = 0; i < CAP / 32; ++i) {
+    const int p = i * 32 + lane;
+    e[i] = p < n ? lds64(buf + p * 8) : ~0ull;
   }
-  sts64(hrow + i * (TK_ROWS * 8), key);
+  uint32_t T = 0;
+#pragma unroll 4
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t trial = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < CAP / 32; ++i) c += ((uint32_t)(e[i] >> 32) < trial);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c < k) T = trial;
+  }
+  int cl = 0;
+#pragma unroll
+  for (int i = 0; i < CAP / 32; ++i) cl += ((uint32_t)(e[i] >> 32) < T);
+  cl = __reduce_add_sync(0xffffffffu, cl);
+  const int need = k - cl;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  int outp = 0, eqseen = 0;
+#pragma unroll
+  for (int i = 0; i < CAP / 32; ++i) {
+    const uint32_t d = (uint32_t)(e[i] >> 32);
+    const bool lt = d < T;
+    const bool eq = (d == T) && (i * 32 + lane < n);
+    const uint32_t em = __ballot_sync(0xffffffffu, eq);
+    const int rank = eqseen + __popc(em & lt_mask);
+    const bool keep = lt || (eq && rank < need);
+    eqseen += __popc(em);
+    const uint32_t km = __ballot_sync(0xffffffffu, keep);
+    if (keep) sts64(buf + (outp + __popc(km & lt_mask)) * 8, e[i]);
+    outp += __popc(km);
+  }
+  __syncwarp();
+  return T;
 }
 
 // ------------------------------------------------------------------ main kernel
@@ -123,9 +148,7 @@ knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUten
   constexpr int NST = TOPK ? STAGES : STAGES_K1;
   uint8_t *sB = smem;
   uint8_t *sX = sB + NST * B_TILE;                                      // top-k state (TOPK only)
-  unsigned long long *s_heap = reinterpret_cast<unsigned long long *>(sX);                  // [KMAX][TK_ROWS]
-  unsigned long long *s_queue = s_heap + KMAX * TK_ROWS;                                     // [QCAP][TK_ROWS]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sX + (TOPK ? (KMAX + QCAP) * TK_ROWS * 8 : 0));
+  uint64_t *bars = reinterpret_cast<uint64_t *>(sX + (TOPK ? CAP * TK_ROWS * 8 : 0));     // sX: candidate buffers [TK_ROWS][CAP]
   uint64_t *full = bars;                  // [NST]  TMA -> MMA
   uint64_t *empty = bars + NST;           // [NST]  MMA -> TMA
   uint64_t *a_full = bars + 2 * NST;      // queries landed
@@ -239,11 +262,9 @@ knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUten
       uint32_t best_d = 0xFFFFFFFFu;
       int32_t best_i = -1;
       uint32_t tau = 0xFFFFFFFFu;
-      int qn = 0;
-      const uint32_t hrow = smem_u32(s_heap) + row * 8, qrow = smem_u32(s_queue) + row * 8;
-      if (TOPK) {
-        for (int sl = 0; sl < k; ++sl) sts64(hrow + sl * (TK_ROWS * 8), ~0ull);
-      }
+      const uint32_t wbuf = smem_u32(sX) + warp * 32 * (CAP * 8);   // this warp's 32 candidate rows
+      const uint32_t mybuf = wbuf + lane * (CAP * 8);
+      int cnt = 0;
       for (int j = 0; j < n_tiles; ++j, ++it) {
         const uint32_t ts = it & 1;
         const int col0 = j * BN;
@@ -311,22 +332,19 @@ knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUten
                 for (int e = 0; e < 8; ++e) {
                   const uint32_t d = dv[half * 8 + e];
                   if (d < tau) {
-                    sts64(qrow + qn * (TK_ROWS * 8), ((unsigned long long)d << 32) | (uint32_t)(col0 + cbase + half * 8 + e));
-                    ++qn;
+                    sts64(mybuf + cnt * 8, ((unsigned long long)d << 32) | (uint32_t)(col0 + cbase + half * 8 + e));
+                    ++cnt;
                   }
                 }
               }
-              // a queue may receive 8 more entries before the next check: drain when any row is past half
-              if (__any_sync(0xffffffffu, qn > QCAP - 8)) {
-                const int qmax = __reduce_max_sync(0xffffffffu, qn);
-                for (int t = 0; t < qmax; ++t) {
-                  if (t < qn) {
-                    const unsigned long long key = lds64(qrow + t * (TK_ROWS * 8));
-                    if (key < lds64(hrow)) heap_replace_root(hrow, k, key);
-                  }
-                }
-                qn = 0;
-                tau = (uint32_t)(lds64(hrow) >> 32);
+              // a row may take 8 more candidates before the next check
+              uint32_t fullm = __ballot_sync(0xffffffffu, cnt > CAP - 8);
+              while (fullm) {
+                const int L = __ffs(fullm) - 1;
+                fullm &= fullm - 1;
+                const int nL = __shfl_sync(0xffffffffu, cnt, L);
+                const uint32_t T = select_k(wbuf + L * (CAP * 8), nL, k, lane);
+                if (lane == L) { cnt = k; tau = T; }
               }
             }
           }
@@ -336,22 +354,22 @@ knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUten
       if (!TOPK) {
         if (valid) { out_idx[qi] = best_i; out_dist[qi] = best_d; }
       } else {
-        for (int t = 0; t < qn; ++t) {
-          const unsigned long long key = lds64(qrow + t * (TK_ROWS * 8));
-          if (key < lds64(hrow)) heap_replace_root(hrow, k, key);
-        }
-        __syncwarp();
-        // coalesced write-out: the warp walks its 32 rows, lanes take heap slots
+        // final cut + coalesced write-out: the warp walks its 32 rows
         for (int L = 0; L < 32; ++L) {
+          int nL = __shfl_sync(0xffffffffu, cnt, L);
+          const uint32_t b = wbuf + L * (CAP * 8);
+          if (nL > k) { select_k(b, nL, k, lane); nL = k; }
+          __syncwarp();
           const int64_t qL = (int64_t)qb * BM + warp * 32 + L;
-          if (qL >= n_q) break;
-          for (int p = lane; p < k; p += 32) {
-            const unsigned long long key = lds64(smem_u32(s_heap) + (p * TK_ROWS + warp * 32 + L) * 8);
-            out_idx[qL * k + p] = (int32_t)(uint32_t)key;          // empty slots: 0xFFFFFFFF = -1
-            out_dist[qL * k + p] = (uint32_t)(key >> 32);
+          if (qL < n_q) {
+            for (int p = lane; p < k; p += 32) {
+              const unsigned long long key = p < nL ? lds64(b + p * 8) : ~0ull;
+              out_idx[qL * k + p] = (int32_t)(uint32_t)key;          // empty slots: 0xFFFFFFFF = -1
+              out_dist[qL * k + p] = (uint32_t)(key >> 32);
+            }
           }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   }
@@ -447,7 +465,7 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
   int rc = make_tmap_rows_u8(&td, d_limbs, (uint64_t)n_dict, ROWB, BN);
   if (rc != TM_OK) return rc;
   constexpr int SMEM_K1 = STAGES_K1 * B_TILE + 256 + 1024;
-  constexpr int SMEM_TK = STAGES * B_TILE + (KMAX + QCAP) * TK_ROWS * 8 + 256 + 1024;
+  constexpr int SMEM_TK = STAGES * B_TILE + CAP * TK_ROWS * 8 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(knn_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
