@@ -87,14 +87,21 @@ __device__ __forceinline__ unsigned long long lds64(uint32_t a) {
 }
 __device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;\n" ::"r"(a), "l"(v) : "memory"); }
 
-// Whole warp: cut the n (> k) candidates at shared address `buf` back to the k smallest; returns the k-th distance.
+__device__ __forceinline__ void sts_pair(uint32_t a, uint32_t lo, uint32_t hi) {
+  asm volatile("st.shared.v2.u32 [%0], {%1, %2};\n" ::"r"(a), "r"(lo), "r"(hi) : "memory");
+}
+constexpr int SLOT = TK_ROWS * 8;   // byte stride between consecutive slots of one row ([slot][row] layout)
+
+// Whole warp: cut the n (> k) candidates of the row at shared address `buf` (slot stride SLOT) back to the k smallest
+// under the (distance, index) order; returns the k-th distance.  Dictionary tiles are scanned in a scrambled order, so
+// ties at the threshold are resolved explicitly by a second radix select on the index (rare).
 __device__ __forceinline__ uint32_t select_k(uint32_t buf, int n, int k, int lane) {
   __syncwarp();
   unsigned long long e[CAP / 32];
 #pragma unroll
   for (int i = 0; i < CAP / 32; ++i) {
     const int p = i * 32 + lane;
-    e[i] = p < n ? lds64(buf + p * 8) : ~0ull;
+    e[i] = p < n ? lds64(buf + p * SLOT) : ~0ull;
   }
   uint32_t T = 0;
 #pragma unroll 4
@@ -106,24 +113,36 @@ __device__ __forceinline__ uint32_t select_k(uint32_t buf, int n, int k, int lan
     c = __reduce_add_sync(0xffffffffu, c);
     if (c < k) T = trial;
   }
-  int cl = 0;
-#pragma unroll
-  for (int i = 0; i < CAP / 32; ++i) cl += ((uint32_t)(e[i] >> 32) < T);
-  cl = __reduce_add_sync(0xffffffffu, cl);
-  const int need = k - cl;
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  int outp = 0, eqseen = 0;
+  int cl = 0, ce = 0;
 #pragma unroll
   for (int i = 0; i < CAP / 32; ++i) {
     const uint32_t d = (uint32_t)(e[i] >> 32);
-    const bool lt = d < T;
-    const bool eq = (d == T) && (i * 32 + lane < n);
-    const uint32_t em = __ballot_sync(0xffffffffu, eq);
-    const int rank = eqseen + __popc(em & lt_mask);
-    const bool keep = lt || (eq && rank < need);
-    eqseen += __popc(em);
+    cl += (d < T);
+    ce += (d == T) && (i * 32 + lane < n);
+  }
+  cl = __reduce_add_sync(0xffffffffu, cl);
+  ce = __reduce_add_sync(0xffffffffu, ce);
+  const int need = k - cl;      // how many of the distance-T entries survive (1 <= need <= ce)
+  uint32_t TI = 0xFFFFFFFFu;    // largest surviving index among them
+  if (ce > need) {              // warp-uniform, rare: need-th smallest index among the distance-T entries
+    TI = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t trial = TI | (1u << bit);
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < CAP / 32; ++i) c += ((uint32_t)(e[i] >> 32) == T) && ((uint32_t)e[i] < trial) && (i * 32 + lane < n);
+      c = __reduce_add_sync(0xffffffffu, c);
+      if (c < need) TI = trial;
+    }
+  }
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  int outp = 0;
+#pragma unroll
+  for (int i = 0; i < CAP / 32; ++i) {
+    const uint32_t d = (uint32_t)(e[i] >> 32);
+    const bool keep = (d < T) || ((d == T) && ((uint32_t)e[i] <= TI) && (i * 32 + lane < n));
     const uint32_t km = __ballot_sync(0xffffffffu, keep);
-    if (keep) sts64(buf + (outp + __popc(km & lt_mask)) * 8, e[i]);
+    if (keep) sts64(buf + (outp + __popc(km & lt_mask)) * SLOT, e[i]);
     outp += __popc(km);
   }
   __syncwarp();
@@ -140,7 +159,7 @@ template <bool TOPK>
 __global__ void __launch_bounds__(224, 1)
 knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUtensorMap tmap_d,
               const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict, int k,
-              int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist) {
+              int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist, int tile_stride) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic only: an integer round trip would make every
   // heap/queue access a generic LD/ST instead of LDS/STS
@@ -180,11 +199,14 @@ knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUten
     if (lane == 0) {
       uint32_t it = 0;
       for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
+        int jt = 0;   // scrambled scan order: jt = (j * tile_stride) mod n_tiles (see host side)
         for (int j = 0; j < n_tiles; ++j, ++it) {
           const uint32_t s = it % NST, r = it / NST;
           mbar_wait(&empty[s], (r & 1) ^ 1);
           mbar_expect_tx(&full[s], B_TILE);
-          for (int c = 0; c < 3; ++c) tma_load_2d(sB + s * B_TILE + c * CHUNK_B, &tmap_d, &full[s], c * 128, j * BN);
+          for (int c = 0; c < 3; ++c) tma_load_2d(sB + s * B_TILE + c * CHUNK_B, &tmap_d, &full[s], c * 128, jt * BN);
+          jt += tile_stride;
+          if (jt >= n_tiles) jt -= n_tiles;
         }
       }
     }
@@ -261,13 +283,16 @@ knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUten
       }
       uint32_t best_d = 0xFFFFFFFFu;
       int32_t best_i = -1;
-      uint32_t tau = 0xFFFFFFFFu;
-      const uint32_t wbuf = smem_u32(sX) + warp * 32 * (CAP * 8);   // this warp's 32 candidate rows
-      const uint32_t mybuf = wbuf + lane * (CAP * 8);
-      int cnt = 0;
+      uint32_t tau = 0xFFFFFFFEu;   // distances of 0xFFFFFFFF (masked columns) are never admitted
+      const uint32_t wbuf = smem_u32(sX) + warp * 32 * 8;   // this warp's 32 candidate rows, [slot][row] layout
+      const uint32_t mybuf = wbuf + lane * 8;
+      uint32_t waddr = mybuf;                               // next free slot of this thread's row
+      int jt = 0;
       for (int j = 0; j < n_tiles; ++j, ++it) {
         const uint32_t ts = it & 1;
-        const int col0 = j * BN;
+        const int col0 = jt * BN;
+        jt += tile_stride;
+        if (jt >= n_tiles) jt -= n_tiles;
         const int ncol = min(BN, n_dict - col0);
         mbar_wait(&t_full[ts], (it >> 1) & 1);
         tc_fence_after();
@@ -316,36 +341,29 @@ knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUten
             }
           }
           if (!TOPK) {
-            if (m < best_d) {   // rare once a good candidate has been seen
+            if (m <= best_d) {   // rare once a good candidate has been seen; ties go to the lower dictionary index
 #pragma unroll
-              for (int e = 0; e < 16; ++e)
-                if (dv[e] < best_d) { best_d = dv[e]; best_i = col0 + cbase + e; }
+              for (int e = 0; e < 16; ++e) {
+                const int32_t ci = col0 + cbase + e;
+                if (dv[e] < best_d || (dv[e] == best_d && dv[e] != 0xFFFFFFFFu && ci < best_i)) { best_d = dv[e]; best_i = ci; }
+              }
             }
           } else {
+            // branch-free admission: always store at the row's next free slot, advance it only when admitted
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              uint32_t mh = 0xFFFFFFFFu;
-#pragma unroll
-              for (int e = 0; e < 8; ++e) mh = min(mh, dv[half * 8 + e]);
-              if (mh < tau) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                  const uint32_t d = dv[half * 8 + e];
-                  if (d < tau) {
-                    sts64(mybuf + cnt * 8, ((unsigned long long)d << 32) | (uint32_t)(col0 + cbase + half * 8 + e));
-                    ++cnt;
-                  }
-                }
-              }
-              // a row may take 8 more candidates before the next check
-              uint32_t fullm = __ballot_sync(0xffffffffu, cnt > CAP - 8);
-              while (fullm) {
-                const int L = __ffs(fullm) - 1;
-                fullm &= fullm - 1;
-                const int nL = __shfl_sync(0xffffffffu, cnt, L);
-                const uint32_t T = select_k(wbuf + L * (CAP * 8), nL, k, lane);
-                if (lane == L) { cnt = k; tau = T; }
-              }
+            for (int e = 0; e < 16; ++e) {
+              const uint32_t d = dv[e];
+              sts_pair(waddr, (uint32_t)(col0 + cbase + e), d);
+              waddr += (d <= tau) ? (uint32_t)SLOT : 0u;   // <=: an equal distance with a lower index may still win
+            }
+            // the next chunk may take 16 more slots
+            uint32_t fullm = __ballot_sync(0xffffffffu, waddr > mybuf + (CAP - 17) * SLOT);
+            while (fullm) {
+              const int L = __ffs(fullm) - 1;
+              fullm &= fullm - 1;
+              const int nL = (int)((__shfl_sync(0xffffffffu, waddr, L) - (wbuf + L * 8)) / SLOT);
+              const uint32_t T = select_k(wbuf + L * 8, nL, k, lane);
+              if (lane == L) { waddr = mybuf + k * SLOT; tau = T; }
             }
           }
         }
@@ -356,14 +374,14 @@ knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUten
       } else {
         // final cut + coalesced write-out: the warp walks its 32 rows
         for (int L = 0; L < 32; ++L) {
-          int nL = __shfl_sync(0xffffffffu, cnt, L);
-          const uint32_t b = wbuf + L * (CAP * 8);
+          int nL = (int)((__shfl_sync(0xffffffffu, waddr, L) - (wbuf + L * 8)) / SLOT);
+          const uint32_t b = wbuf + L * 8;
           if (nL > k) { select_k(b, nL, k, lane); nL = k; }
           __syncwarp();
           const int64_t qL = (int64_t)qb * BM + warp * 32 + L;
           if (qL < n_q) {
             for (int p = lane; p < k; p += 32) {
-              const unsigned long long key = p < nL ? lds64(b + p * 8) : ~0ull;
+              const unsigned long long key = p < nL ? lds64(b + p * SLOT) : ~0ull;
               out_idx[qL * k + p] = (int32_t)(uint32_t)key;          // empty slots: 0xFFFFFFFF = -1
               out_dist[qL * k + p] = (uint32_t)(key >> 32);
             }
@@ -474,10 +492,18 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
   }
   {
     ProfScope prof(k == 1 ? "knn_k1" : "knn_topk", st);
+    // Dictionary tiles are visited in the order j -> (j * stride) mod n_tiles with stride ~ 0.618 n_tiles, coprime to
+    // n_tiles: a streaming top-k admits ~k ln(N/k) candidates per row when the order is uncorrelated with the distance,
+    // but nearly all N when distances fall along the scan (dictionaries built frame by frame do exactly that).
+    const int n_tiles_h = (n_dict + BN - 1) / BN;
+    int tile_stride = (int)(0.6180339887 * n_tiles_h);
+    if (tile_stride < 1) tile_stride = 1;
+    auto gcd = [](int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; };
+    while (gcd(tile_stride, n_tiles_h) != 1) ++tile_stride;
     const int n_qblocks = (n_q + BM - 1) / BM;
     const int grid = n_qblocks < num_ctas ? n_qblocks : num_ctas;
-    if (k == 1) knn_i8_kernel<false><<<grid, 224, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist);
-    else knn_i8_kernel<true><<<grid, 224, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist);
+    if (k == 1) knn_i8_kernel<false><<<grid, 224, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride);
+    else knn_i8_kernel<true><<<grid, 224, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride);
   }
   note_launch();
   if (cudaGetLastError() != cudaSuccess) return TM_ERR_CUDA;
