@@ -1,0 +1,78 @@
+"""Multi-GPU plumbing for the stages that shard: one process per GPU, torch.distributed for the only
+exchange step the path has.
+
+  * match / reconstruct : keyframe sequences are independent units (tilingencoder.pas:1496, 1668) -> whole sequences
+    per rank, dictionary and palettes replicated, NO collective; tilemaps are gathered on the host.
+  * k-means             : points sharded, centroids replicated, one all-reduce(sum) of the per-cluster sums [k, dim]
+    and counts [k] per Lloyd iteration (NCCL over NVLink on GPUs; gloo in the CPU tests).
+  * palette quantisation / dithering : palettes and (tile, palette) pairs are independent -> shard, no collective.
+"""
+import numpy as np
+
+try:
+    import torch
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    torch = None
+    dist = None
+
+
+def shard_sequences(frame_counts, world):
+    """Greedy longest-first assignment of keyframe sequences to ranks. -> list (per rank) of sequence indices."""
+    order = sorted(range(len(frame_counts)), key=lambda i: (-frame_counts[i], i))
+    load = [0] * world
+    out = [[] for _ in range(world)]
+    for i in order:
+        r = min(range(world), key=lambda j: (load[j], j))
+        out[r].append(i)
+        load[r] += frame_counts[i]
+    return [sorted(s) for s in out]
+
+
+def shard_rows(n, rank, world):
+    """Contiguous row range [lo, hi) of rank `rank` when n rows are split as evenly as possible."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_partials(sums, counts, changed, inertia):
+    """Sum the per-rank k-means partials over the default process group (no-op without one). Tensors in, tensors out."""
+    if dist is None or not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return sums, counts, changed, inertia
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    extra = torch.tensor([float(changed), float(inertia)], dtype=torch.float64, device=sums.device)
+    dist.all_reduce(extra, op=dist.ReduceOp.SUM)
+    return sums, counts, int(extra[0].item()), float(extra[1].item())
+
+
+def kmeans_fit_sharded(x_shard, init, max_iter=300, nan_empty=False):
+    """Lloyd with the points sharded over the ranks of the default process group (x_shard: this rank's CUDA rows,
+    init: the same [k, dim] on every rank).  Same stopping rule as the single-GPU tm_kmeans_fit: stop when no label
+    changed anywhere or after max_iter updates.  -> labels (this shard), centroids, inertia, iterations."""
+    from . import api
+    cent = init.clone()
+    labels = torch.full((x_shard.shape[0],), -1, dtype=torch.int32, device=x_shard.device)
+    it = 0
+    while True:
+        labels, sums, counts, changed, inertia = api.kmeans_partial_step(x_shard, cent, labels)
+        sums, counts, changed, inertia = allreduce_partials(sums, counts, changed, inertia)
+        if changed == 0 or it >= max_iter:
+            break
+        it += 1
+        cent = api.kmeans_finish_step(sums, counts, cent, nan_empty=nan_empty)
+    return labels, cent, inertia, it
+
+
+def gather_tilemaps(local, world_shards):
+    """All-gather per-rank tilemap arrays (numpy, keyed by sequence index) onto every rank via the object collective."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return dict(local)
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, local)
+    merged = {}
+    for d in out:
+        merged.update(d)
+    assert sorted(merged) == sorted(i for s in world_shards for i in s)
+    return merged
