@@ -211,7 +211,10 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": "knn_i8_kernel<TOPK>", "achieved": achieved_tflops,
                      "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tflops / pk["bf16_tflops_sustained"],
-                     "traffic": None, "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
+                     "traffic": 393.26e6 * (TILES_PER_STEP / 432000.0), "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
+                     "ncu --set full capture of this kernel in this bench (profiles/r01_knn_topk_bench_raw.csv): 199.4 MB + 193.8 MB per "
+                     "launch; algorithmic bytes per launch = 166 MB query limbs + 25 MB dictionary + 221 MB top-64 results",
+                     "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                      "algorithmic_flops_per_launch": evals_per_step * 384, "kernel_ms_per_launch": knn_launch_ms,
                      "note": "384 flop per 192-d distance evaluation; the exact int8-limb scheme issues 4 int8 MMAs (= 2 "
                              "bf16-equivalent passes) per evaluation, so the algorithmic fraction is capped at 0.5"},
