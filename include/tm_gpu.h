@@ -126,6 +126,14 @@ int tm_dither(const int32_t *rgb, const uint8_t *mirror_flags, int64_t n_tiles, 
    Stops when no label changes or after max_iter updates.  labels[n], centroids[k][dim] out; inertia/iters optional. */
 int tm_kmeans_fit(const double *x, int64_t n, int dim, int k, int max_iter, const double *init, uint64_t seed, int nan_empty,
                   int32_t *labels, double *centroids, double *inertia, int *iters);
+/* Lloyd on int16 rows x[n][192] (tile feature vectors) with f64 centroids: the nearest-centroid search runs on the tensor
+   cores (exact int8-limb k-NN against the centroids rounded to int16, 4 candidates), the label is decided by exact f64
+   distances, certified by an error bound; uncertified points fall to an exact f64 scan (count returned in *ambiguous).
+   Labels and centroids equal those of tm_kmeans_fit on the same data.  init[k][192] is required. */
+int tm_kmeans_fit_i16(const int16_t *x, int64_t n, int k, int max_iter, const double *init, int nan_empty, int32_t *labels,
+                      double *centroids, double *inertia, int *iters, int64_t *ambiguous);
+int tm_kmeans_partial_step_i16(const int16_t *x, int64_t n, int k, const double *centroids, int32_t *labels, double *partial_sums,
+                               int64_t *partial_counts, int64_t *changed, double *inertia);
 /* one Lloyd step for a SHARD of the points (multi-GPU): assignment against replicated centroids, then per-cluster
    partial sums [k][dim] and counts [k] that the caller all-reduces (NCCL) before tm_kmeans_finish_step. */
 int tm_kmeans_partial_step(const double *x, int64_t n, int dim, int k, const double *centroids, int32_t *labels,

@@ -321,3 +321,31 @@ def test_dropin_ann_double_yakmo_bico(tm, oracle):
     c, w = b.get_results()
     assert 1 <= len(c) <= 16 and abs(w.sum() - len(x)) < 1e-6
     b.destroy()
+
+
+# ---------------------------------------------------------------- k-means on int16 tile vectors (tensor-core search)
+@pytest.mark.parametrize("n,k,adv", [(6000, 96, False), (6000, 96, True), (3000, 3, False), (2500, 700, True)])
+def test_kmeans_i16_tensorcore_matches_oracle(tm, oracle, n, k, adv):
+    rng = np.random.default_rng(n + k)
+    centres = synth.random_features(k, 1000 + k, adv).astype(np.float64)
+    x = np.clip(np.rint(centres[rng.integers(0, k, size=n)] + rng.normal(0, 25, size=(n, 192))), -32768, 32767).astype(np.int16)
+    init = x[rng.permutation(n)[:k]].astype(np.float64)
+    labels, cent, inertia, iters, amb = tm.kmeans_fit_i16(x, k, init, max_iter=12, nan_empty=True)
+    ol, oc, oin, oit = oracle.kmeans_lloyd(x.astype(np.float64), init, max_iter=12, nan_empty=True)
+    assert iters == oit
+    assert np.array_equal(labels, ol)                      # exact f64 arg-min, certified or re-checked
+    assert np.array_equal(np.isnan(cent), np.isnan(oc)) and np.array_equal(np.nan_to_num(cent), np.nan_to_num(oc))
+    assert abs(inertia - oin) <= 1e-9 * max(oin, 1.0)
+    assert amb <= 0.2 * n * (iters + 1)
+
+
+def test_kmeans_i16_near_ties_fall_back(tm, oracle):
+    # centroids a fraction of an LSB apart: rounding cannot separate them, the certificate must refuse and the exact
+    # f64 fallback must decide
+    rng = np.random.default_rng(4)
+    base = synth.random_features(1, 5)[0].astype(np.float64)
+    init = np.stack([base + 0.2 * i for i in range(8)])
+    x = np.clip(np.rint(base + rng.normal(0, 3, size=(2000, 192))), -32768, 32767).astype(np.int16)
+    labels, cent, inertia, iters, amb = tm.kmeans_fit_i16(x, 8, init, max_iter=0)
+    ol, oc, oin, oit = oracle.kmeans_lloyd(x.astype(np.float64), init, max_iter=0)
+    assert np.array_equal(labels, ol) and amb > 0

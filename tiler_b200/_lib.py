@@ -46,6 +46,8 @@ SIGNATURES = {
     "tm_knn_double_batch": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _vp, _vp]),
     "tm_dither": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i64, _vp, _i32, _i32, _i32, _i32, _vp]),
     "tm_kmeans_fit": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _u64, _i32, _vp, _vp, C.POINTER(_dbl), C.POINTER(_i32)]),
+    "tm_kmeans_fit_i16": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, C.POINTER(_dbl), C.POINTER(_i32), C.POINTER(_i64)]),
+    "tm_kmeans_partial_step_i16": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_dbl)]),
     "tm_kmeans_partial_step": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_dbl)]),
     "tm_kmeans_finish_step": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "tm_palquant_kmeans": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _u64, _vp, C.POINTER(_i32)]),

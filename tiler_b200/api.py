@@ -223,6 +223,39 @@ def kmeans_fit(x, k, init=None, seed=1, max_iter=300, nan_empty=False):
     return labels, cent, inertia.value, iters.value
 
 
+def kmeans_fit_i16(x, k, init, max_iter=300, nan_empty=False):
+    """Lloyd on int16 feature rows [n,192]: tensor-core candidate search + exact f64 decision (tm_kmeans_fit_i16).
+    -> labels, centroids (f64), inertia, iterations, number of points that needed the exact f64 fallback."""
+    c = _Call(x, init)
+    n = _n_rows(x, DCT)
+    labels, pl = c.out((n,), np.int32)
+    cent, pc = c.out((k, DCT), np.float64)
+    inertia, iters, amb = C.c_double(), C.c_int(), C.c_int64()
+    check(_lib.lib().tm_kmeans_fit_i16(c.inp(x, np.int16), n, int(k), int(max_iter), c.inp(init, np.float64), int(nan_empty),
+                                       pl, pc, C.byref(inertia), C.byref(iters), C.byref(amb)))
+    return labels, cent, inertia.value, iters.value, amb.value
+
+
+def kmeans_partial_step_i16(x, centroids, labels):
+    """Sharded variant of kmeans_fit_i16's step (see kmeans_partial_step)."""
+    c = _Call(x, centroids, labels)
+    n = _n_rows(x, DCT)
+    k = centroids.shape[0]
+    sums, ps = c.out((k, DCT), np.float64)
+    counts, pc = c.out((k,), np.int64)
+    changed, inertia = C.c_int64(), C.c_double()
+    if c.dev:
+        lab = labels.contiguous()
+        c.keep.append(lab)
+        plab = C.c_void_p(lab.data_ptr())
+    else:
+        lab = np.ascontiguousarray(labels, dtype=np.int32)
+        plab = C.c_void_p(lab.ctypes.data)
+    check(_lib.lib().tm_kmeans_partial_step_i16(c.inp(x, np.int16), n, int(k), c.inp(centroids, np.float64), plab, ps, pc,
+                                                C.byref(changed), C.byref(inertia)))
+    return lab, sums, counts, changed.value, inertia.value
+
+
 def kmeans_partial_step(x, centroids, labels):
     """One Lloyd step on a shard: assignment + per-cluster partial sums/counts (to be all-reduced across GPUs)."""
     c = _Call(x, centroids, labels)

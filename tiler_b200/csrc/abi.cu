@@ -162,8 +162,6 @@ struct tm_matcher {
   tm_knn_short *knn = nullptr;
 };
 
-static void *g_knn_ws = nullptr;
-static size_t g_knn_ws_bytes = 0;
 
 // ------------------------------------------------------------------ runtime
 extern "C" int tm_version(void) { return 100; }
@@ -312,21 +310,9 @@ static int knn_short_batch_dev(tm_knn_short *h, const int16_t *d_q, int64_t n_q,
   uint8_t *q_limbs = (uint8_t *)s.temp((size_t)n_q * 384);
   uint32_t *q_norm = (uint32_t *)s.temp((size_t)n_q * 4);
   if (s.err) return s.err;
-  const int ctas = num_sms();
-  void *ws = nullptr;
-  if (k > 1) {
-    const size_t need = knn_workspace_bytes(ctas);
-    if (need > g_knn_ws_bytes) {
-      if (g_knn_ws) { cudaStreamSynchronize(s.st); cudaFree(g_knn_ws); }
-      g_knn_ws = nullptr; g_knn_ws_bytes = 0;
-      if (cudaMalloc(&g_knn_ws, need) != cudaSuccess) return TM_ERR_NOMEM;
-      g_knn_ws_bytes = need;
-    }
-    ws = g_knn_ws;
-  }
   int rc = launch_limb_split(d_q, n_q, q_limbs, q_norm, s.st);
   if (rc) return rc;
-  return launch_knn_i8(q_limbs, q_norm, (int)n_q, h->limbs, h->norms, (int)h->n, k, d_idx, d_dist, ws, ctas, sorted, s.st);
+  return launch_knn_i8(q_limbs, q_norm, (int)n_q, h->limbs, h->norms, (int)h->n, k, d_idx, d_dist, nullptr, num_sms(), sorted, s.st);
 }
 
 extern "C" int tm_knn_short_batch(tm_knn_short *h, const int16_t *q, int64_t n_q, int k, int32_t *idx, uint32_t *dist, int sorted) {
@@ -422,6 +408,120 @@ extern "C" int tm_kmeans_fit(const double *x, int64_t n, int dim, int k, int max
   int32_t *d_labels = s.out(labels, (size_t)n);
   double *d_cent = s.out(centroids, (size_t)k * dim);
   if (s.err == TM_OK) s.err = kmeans_fit_dev(d_x, nullptr, n, dim, k, max_iter, d_init, seed, nan_empty, d_labels, d_cent, nullptr, inertia, iters, s);
+  RC(s.finish(true));
+  return TM_OK;
+}
+
+// ---- int16 points: candidate search on the tensor cores, exact f64 decision (see kmeans.cu)
+struct KmI16 {   // per-fit device state
+  const int16_t *x; int64_t n; int k;
+  uint8_t *x_limbs; uint32_t *x_norm;       // points, split once
+  int16_t *rc; uint8_t *c_limbs; uint32_t *c_norm;   // rounded centroids, rebuilt every iteration
+  int32_t *cand; uint32_t *cdist; int32_t *amb_list; int32_t *counters;   // counters[0] = changed, [1] = ambiguous
+  double *dist;
+};
+static int km_i16_setup(KmI16 &w, const int16_t *d_x, int64_t n, int k, Stage &s) {
+  w.x = d_x; w.n = n; w.k = k;
+  const int64_t kpad = (k + 63) / 64 * 64;
+  w.x_limbs = (uint8_t *)s.temp((size_t)n * 384); w.x_norm = (uint32_t *)s.temp((size_t)n * 4);
+  w.rc = (int16_t *)s.temp((size_t)k * 384); w.c_limbs = (uint8_t *)s.temp((size_t)k * 384); w.c_norm = (uint32_t *)s.temp((size_t)kpad * 4);
+  w.cand = (int32_t *)s.temp((size_t)n * KMEANS_KC * 4); w.cdist = (uint32_t *)s.temp((size_t)n * KMEANS_KC * 4);
+  w.amb_list = (int32_t *)s.temp((size_t)n * 4); w.counters = (int32_t *)s.temp(8);
+  w.dist = (double *)s.temp((size_t)n * 8);
+  if (s.err) return s.err;
+  if (cudaMemsetAsync(w.c_norm, 0, (size_t)kpad * 4, s.st) != cudaSuccess) return TM_ERR_CUDA;
+  return launch_limb_split(d_x, n, w.x_limbs, w.x_norm, s.st);
+}
+// one assignment pass; *changed / *n_amb are host outputs (synchronises)
+static int km_i16_assign(KmI16 &w, const double *d_cent, int32_t *d_labels, int *changed, int *n_amb, Stage &s) {
+  int rc = launch_round_centroids(d_cent, w.k, w.rc, s.st);
+  if (rc) return rc;
+  rc = launch_limb_split(w.rc, w.k, w.c_limbs, w.c_norm, s.st);
+  if (rc) return rc;
+  const int kc = KMEANS_KC;
+  rc = launch_knn_i8(w.x_limbs, w.x_norm, (int)w.n, w.c_limbs, w.c_norm, w.k, kc, w.cand, w.cdist, nullptr, num_sms(), 1, s.st);
+  if (rc) return rc;
+  if (cudaMemsetAsync(w.counters, 0, 8, s.st) != cudaSuccess) return TM_ERR_CUDA;
+  rc = launch_kmeans_rerank_i16(w.x, w.n, w.cand, w.cdist, d_cent, w.k, d_labels, w.dist, w.counters, w.amb_list, w.counters + 1, s.st);
+  if (rc) return rc;
+  int32_t h[2] = {0, 0};
+  if (cudaMemcpyAsync(h, w.counters, 8, cudaMemcpyDeviceToHost, s.st) != cudaSuccess || cudaStreamSynchronize(s.st) != cudaSuccess) return TM_ERR_CUDA;
+  if (h[1] > 0) {
+    double *xa = (double *)s.temp((size_t)h[1] * 192 * 8), *da = (double *)s.temp((size_t)h[1] * 8);
+    int32_t *la = (int32_t *)s.temp((size_t)h[1] * 4);
+    if (s.err) return s.err;
+    rc = launch_kmeans_assign_amb(w.x, w.amb_list, h[1], d_cent, w.k, d_labels, w.dist, w.counters, xa, la, da, s.st);
+    if (rc) return rc;
+    if (cudaMemcpyAsync(h, w.counters, 4, cudaMemcpyDeviceToHost, s.st) != cudaSuccess || cudaStreamSynchronize(s.st) != cudaSuccess) return TM_ERR_CUDA;
+  }
+  *changed = h[0];
+  *n_amb = h[1];
+  return TM_OK;
+}
+static double sum_dist(const double *d_dist, int64_t n, cudaStream_t st, int *err) {
+  std::vector<double> h((size_t)n);
+  if (cudaMemcpyAsync(h.data(), d_dist, (size_t)n * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { *err = TM_ERR_CUDA; return 0.0; }
+  double t = 0.0;
+  for (double v : h) t += v;   // reporting scalar only
+  return t;
+}
+
+extern "C" int tm_kmeans_fit_i16(const int16_t *x, int64_t n, int k, int max_iter, const double *init, int nan_empty, int32_t *labels,
+                                 double *centroids, double *inertia, int *iters, int64_t *ambiguous) {
+  RC(require_gpu());
+  if (n < 1 || n > 0x7fffffff || k < 1 || max_iter < 0 || !x || !init || !labels || !centroids)
+    return fail(TM_ERR_ARG, "tm_kmeans_fit_i16: bad argument (explicit initial centroids required)");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int16_t *d_x = s.in(x, (size_t)n * 192);
+  const double *d_init = s.in(init, (size_t)k * 192);
+  int32_t *d_labels = s.out(labels, (size_t)n);
+  double *d_cent = s.out(centroids, (size_t)k * 192);
+  KmI16 w;
+  const size_t ws_bytes = kmeans_update_ws_bytes(n, k);
+  void *ws = s.temp(ws_bytes);
+  int it = 0;
+  int64_t amb_total = 0;
+  if (s.err == TM_OK) s.err = km_i16_setup(w, d_x, n, k, s);
+  if (s.err == TM_OK && cudaMemcpyAsync(d_cent, d_init, (size_t)k * 192 * 8, cudaMemcpyDeviceToDevice, s.st) != cudaSuccess) s.err = TM_ERR_CUDA;
+  if (s.err == TM_OK && cudaMemsetAsync(d_labels, 0xFF, (size_t)n * 4, s.st) != cudaSuccess) s.err = TM_ERR_CUDA;
+  while (s.err == TM_OK) {
+    int changed = 0, n_amb = 0;
+    s.err = km_i16_assign(w, d_cent, d_labels, &changed, &n_amb, s);
+    amb_total += n_amb;
+    if (s.err != TM_OK || changed == 0 || it >= max_iter) break;
+    ++it;
+    s.err = launch_kmeans_update_i16(d_x, n, d_labels, k, d_cent, nullptr, ws, ws_bytes, nan_empty, 1, s.st);
+  }
+  if (s.err == TM_OK && inertia) { int e = TM_OK; *inertia = sum_dist(w.dist, n, s.st, &e); s.err = e; }
+  if (iters) *iters = it;
+  if (ambiguous) *ambiguous = amb_total;
+  RC(s.finish(true));
+  return TM_OK;
+}
+
+// multi-GPU building block: one assignment over this rank's shard + per-cluster partial sums/counts
+extern "C" int tm_kmeans_partial_step_i16(const int16_t *x, int64_t n, int k, const double *centroids, int32_t *labels,
+                                          double *partial_sums, int64_t *partial_counts, int64_t *changed, double *inertia) {
+  RC(require_gpu());
+  if (n < 1 || n > 0x7fffffff || k < 1 || !x || !centroids || !labels || !partial_sums || !partial_counts)
+    return fail(TM_ERR_ARG, "tm_kmeans_partial_step_i16: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int16_t *d_x = s.in(x, (size_t)n * 192);
+  const double *d_cent = s.in(centroids, (size_t)k * 192);
+  int32_t *d_labels = s.inout(labels, (size_t)n);
+  double *d_sums = s.out(partial_sums, (size_t)k * 192);
+  int64_t *d_counts = s.out(partial_counts, (size_t)k);
+  KmI16 w;
+  const size_t ws_bytes = kmeans_update_ws_bytes(n, k);
+  void *ws = s.temp(ws_bytes);
+  int ch = 0, n_amb = 0;
+  if (s.err == TM_OK) s.err = km_i16_setup(w, d_x, n, k, s);
+  if (s.err == TM_OK) s.err = km_i16_assign(w, d_cent, d_labels, &ch, &n_amb, s);
+  if (s.err == TM_OK) s.err = launch_kmeans_update_i16(d_x, n, d_labels, k, d_sums, d_counts, ws, ws_bytes, 0, 0, s.st);
+  if (changed) *changed = ch;
+  if (s.err == TM_OK && inertia) { int e = TM_OK; *inertia = sum_dist(w.dist, n, s.st, &e); s.err = e; }
   RC(s.finish(true));
   return TM_OK;
 }

@@ -75,8 +75,9 @@ __global__ void hist_kernel(const int32_t *__restrict__ labels, int64_t n, int32
   if (i < n) atomicAdd(counts + labels[i], 1);
 }
 // thread = (cluster, dim); members of a cluster are contiguous in `order` and in ascending point index
+template <typename T>
 __global__ void __launch_bounds__(256)
-kmeans_update_f64_kernel(const double *__restrict__ x, const double *__restrict__ wts, int dim, const int32_t *__restrict__ order,
+kmeans_update_kernel(const T *__restrict__ x, const double *__restrict__ wts, int dim, const int32_t *__restrict__ order,
                          const int32_t *__restrict__ offs, const int32_t *__restrict__ counts, int k, int nan_empty, int divide,
                          double *__restrict__ cent, int64_t *__restrict__ counts_out, double *__restrict__ wsum_out) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -95,11 +96,11 @@ kmeans_update_f64_kernel(const double *__restrict__ x, const double *__restrict_
     for (int m = 0; m < cnt; ++m) {
       const int32_t i = order[o0 + m];
       const double w = __ldg(wts + i);
-      s = __dadd_rn(s, __dmul_rn(w, __ldg(x + (int64_t)i * dim + j)));
+      s = __dadd_rn(s, __dmul_rn(w, (double)__ldg(x + (int64_t)i * dim + j)));
       ws = __dadd_rn(ws, w);
     }
   } else {
-    for (int m = 0; m < cnt; ++m) s = __dadd_rn(s, __ldg(x + (int64_t)order[o0 + m] * dim + j));
+    for (int m = 0; m < cnt; ++m) s = __dadd_rn(s, (double)__ldg(x + (int64_t)order[o0 + m] * dim + j));
     ws = (double)cnt;
   }
   cent[t] = divide ? __ddiv_rn(s, ws) : s;
@@ -188,9 +189,10 @@ int launch_kmeans_assign_f64(const double *x, int64_t n, int dim, const double *
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }
 
-int launch_kmeans_update_f64(const double *x, const double *weights, int64_t n, int dim, const int32_t *labels, int k, double *cent,
-                             int64_t *counts_out, double *wsum_out, void *ws, size_t ws_bytes, int nan_empty, int divide,
-                             cudaStream_t st) {
+template <typename T>
+static int launch_kmeans_update_t(const T *x, const double *weights, int64_t n, int dim, const int32_t *labels, int k, double *cent,
+                                  int64_t *counts_out, double *wsum_out, void *ws, size_t ws_bytes, int nan_empty, int divide,
+                                  cudaStream_t st) {
   if (n <= 0) return TM_OK;
   if (ws_bytes < kmeans_update_ws_bytes(n, k)) return TM_ERR_ARG;
   auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
@@ -214,9 +216,134 @@ int launch_kmeans_update_f64(const double *x, const double *weights, int64_t n, 
   cub::DeviceRadixSort::SortPairs(d_tmp, sort_tmp, labels, keys_out, vals_in, vals_out, (int)n, 0, bits, st);  // stable
   cub::DeviceScan::ExclusiveSum(d_tmp, scan_tmp, counts, offs, k, st);
   const int64_t total = (int64_t)k * dim;
-  kmeans_update_f64_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, weights, dim, vals_out, offs, counts, k, nan_empty, divide,
-                                                                            cent, counts_out, wsum_out);
+  kmeans_update_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, weights, dim, vals_out, offs, counts, k, nan_empty, divide,
+                                                                           cent, counts_out, wsum_out);
   note_launch(8);
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+int launch_kmeans_update_f64(const double *x, const double *weights, int64_t n, int dim, const int32_t *labels, int k, double *cent,
+                             int64_t *counts_out, double *wsum_out, void *ws, size_t ws_bytes, int nan_empty, int divide,
+                             cudaStream_t st) {
+  return launch_kmeans_update_t<double>(x, weights, n, dim, labels, k, cent, counts_out, wsum_out, ws, ws_bytes, nan_empty, divide, st);
+}
+int launch_kmeans_update_i16(const int16_t *x, int64_t n, const int32_t *labels, int k, double *cent, int64_t *counts_out, void *ws,
+                             size_t ws_bytes, int nan_empty, int divide, cudaStream_t st) {
+  return launch_kmeans_update_t<int16_t>(x, nullptr, n, 192, labels, k, cent, counts_out, nullptr, ws, ws_bytes, nan_empty, divide, st);
+}
+
+// ------------------------------------------------------------------ tensor-core assignment for int16 points
+// The candidate search runs on the exact int8-limb k-NN kernel against the centroids ROUNDED to int16; the exact f64
+// distances to the KC nearest rounded centroids then decide the label.  With c = r + delta, |delta_i| <= 1/2:
+//   |d_true - d_round| <= 2 sqrt(d_round) sqrt(192/4) + 192/4 = sqrt(192 d_round) + 48 =: eps(d_round),
+// and d - eps(d) is increasing, so every centroid outside the candidates has d_true >= g(d_round of the KC-th candidate).
+// If that exceeds the best exact candidate distance the label is certified; otherwise the point is queued for the
+// brute-force f64 kernel.  Labels are therefore exactly the f64 arg-min (first minimum), like the oracle's.
+__global__ void round_centroids_kernel(const double *__restrict__ cent, int64_t total, int16_t *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const double c = cent[i];
+  // empty clusters (NaN) are parked far away; they can never be the exact arg-min either (NaN compares false)
+  out[i] = isnan(c) ? (int16_t)32767 : (int16_t)max(-32768, min(32767, __double2int_rn(c)));
+}
+
+template <int KC>
+__global__ void __launch_bounds__(256)
+kmeans_rerank_i16_kernel(const int16_t *__restrict__ x, int64_t n, const int32_t *__restrict__ cand, const uint32_t *__restrict__ cdist,
+                         const double *__restrict__ cent, int k, int32_t *__restrict__ labels, double *__restrict__ dist,
+                         int32_t *__restrict__ changed, int32_t *__restrict__ amb_list, int32_t *__restrict__ amb_count) {
+  // KC threads per point (one candidate each): sequential 192-term f64 sums in the oracle's order
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p = t / KC;
+  const int c = (int)(t % KC);
+  const bool live = p < n;
+  const int32_t ci = live ? cand[p * KC + c] : -1;
+  double s = INFINITY;
+  if (ci >= 0 && ci < k) {
+    const int16_t *xv = x + p * 192;
+    const double *cv = cent + (int64_t)ci * 192;
+    s = 0.0;
+    for (int j = 0; j < 192; ++j) {
+      const double df = __dsub_rn((double)__ldg(xv + j), __ldg(cv + j));
+      s = __dadd_rn(s, __dmul_rn(df, df));
+    }
+    if (isnan(s)) s = INFINITY;
+  }
+  // arg-min over the KC lanes of this point: (distance, centroid index) lexicographic = first minimum in index order
+  double bs = s;
+  int32_t bi = (s < INFINITY) ? ci : 0x7fffffff;
+#pragma unroll
+  for (int o = KC / 2; o >= 1; o >>= 1) {
+    const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+    const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+  }
+  if (live && c == 0) {
+    // certificate from the largest rounded distance among the candidates (the list is sorted ascending)
+    const int32_t last = cand[p * KC + KC - 1];
+    bool certified;
+    if (last < 0) certified = true;   // fewer than KC centroids exist: the candidates are all of them
+    else {
+      const double dl = (double)cdist[p * KC + KC - 1];
+      certified = (dl - sqrt(192.0 * dl) - 48.0) > bs;
+    }
+    if (bi == 0x7fffffff) certified = false;
+    if (certified) {
+      if (labels[p] != bi) { labels[p] = bi; atomicAdd(changed, 1); }
+      if (dist) dist[p] = bs;
+    } else {
+      amb_list[atomicAdd(amb_count, 1)] = (int32_t)p;
+    }
+  }
+}
+
+// queued (uncertified) points: gathered into a dense f64 matrix, assigned by the exact f64 kernel (32 points per block
+// share every centroid load), scattered back
+__global__ void amb_gather_kernel(const int16_t *__restrict__ x, const int32_t *__restrict__ amb_list, int n_amb,
+                                  const int32_t *__restrict__ labels, double *__restrict__ xa, int32_t *__restrict__ la) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (int64_t)n_amb * 192) return;
+  const int i = (int)(t / 192), j = (int)(t % 192);
+  const int64_t p = amb_list[i];
+  xa[t] = (double)x[p * 192 + j];
+  if (j == 0) la[i] = labels[p];
+}
+__global__ void amb_scatter_kernel(const int32_t *__restrict__ amb_list, int n_amb, const int32_t *__restrict__ la,
+                                   const double *__restrict__ da, int32_t *__restrict__ labels, double *__restrict__ dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_amb) return;
+  const int64_t p = amb_list[i];
+  labels[p] = la[i];
+  if (dist) dist[p] = da[i];
+}
+
+int launch_round_centroids(const double *cent, int k, int16_t *out, cudaStream_t st) {
+  const int64_t total = (int64_t)k * 192;
+  round_centroids_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cent, total, out);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+int launch_kmeans_rerank_i16(const int16_t *x, int64_t n, const int32_t *cand, const uint32_t *cdist, const double *cent, int k,
+                             int32_t *labels, double *dist, int32_t *changed, int32_t *amb_list, int32_t *amb_count, cudaStream_t st) {
+  if (n <= 0) return TM_OK;
+  const int64_t threads = n * KMEANS_KC;
+  kmeans_rerank_i16_kernel<KMEANS_KC><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, n, cand, cdist, cent, k, labels, dist, changed,
+                                                                                        amb_list, amb_count);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+int launch_kmeans_assign_amb(const int16_t *x, const int32_t *amb_list, int n_amb, const double *cent, int k, int32_t *labels,
+                             double *dist, int32_t *changed, double *xa, int32_t *la, double *da, cudaStream_t st) {
+  if (n_amb <= 0) return TM_OK;
+  const int64_t total = (int64_t)n_amb * 192;
+  amb_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, amb_list, n_amb, labels, xa, la);
+  note_launch();
+  int rc = launch_kmeans_assign_f64(xa, n_amb, 192, cent, k, la, da, changed, st);
+  if (rc) return rc;
+  amb_scatter_kernel<<<(n_amb + 255) / 256, 256, 0, st>>>(amb_list, n_amb, la, da, labels, dist);
+  note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }
 

@@ -69,6 +69,15 @@ int launch_kmeans_assign_f64(const double *x, int64_t n, int dim, const double *
 int launch_kmeans_update_f64(const double *x, const double *weights, int64_t n, int dim, const int32_t *labels, int k, double *cent,
                              int64_t *counts, double *wsum_out, void *ws, size_t ws_bytes, int nan_empty, int divide,
                              cudaStream_t st);
+// int16 points: tensor-core candidate search + exact f64 decision (kmeans.cu)
+#define KMEANS_KC 4
+int launch_kmeans_update_i16(const int16_t *x, int64_t n, const int32_t *labels, int k, double *cent, int64_t *counts_out, void *ws,
+                             size_t ws_bytes, int nan_empty, int divide, cudaStream_t st);
+int launch_round_centroids(const double *cent, int k, int16_t *out, cudaStream_t st);
+int launch_kmeans_rerank_i16(const int16_t *x, int64_t n, const int32_t *cand, const uint32_t *cdist, const double *cent, int k,
+                             int32_t *labels, double *dist, int32_t *changed, int32_t *amb_list, int32_t *amb_count, cudaStream_t st);
+int launch_kmeans_assign_amb(const int16_t *x, const int32_t *amb_list, int n_amb, const double *cent, int k, int32_t *labels,
+                             double *dist, int32_t *changed, double *xa, int32_t *la, double *da, cudaStream_t st);
 int launch_kmeanspp_f64(const double *x, int64_t n, int dim, int k, unsigned long long seed, double *d2_ws, double *cent,
                         cudaStream_t st);
 int launch_kmeans_finish(const double *sums, const int64_t *counts, int k, int dim, int nan_empty, double *cent, cudaStream_t st);
