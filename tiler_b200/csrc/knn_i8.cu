@@ -193,6 +193,7 @@ knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUten
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tmem_base != 0) __trap();   // the MMA issue code addresses TMEM with immediates
 
   if (warp == 4) {
     // ===================== TMA producer =====================
@@ -237,14 +238,7 @@ knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUten
           tc_fence_after();
           const uint64_t dB = descB0 + (uint64_t)((s * B_TILE) >> 4);
           const uint32_t acc = tmem_base + ts * ACC_COLS;
-#pragma unroll
-          for (int t = 0; t < 6; ++t) mma_i8_ts_elect(acc, tA + 8 * t, dB + koffB(t), I_SS, t > 0);                       // HH
-#pragma unroll
-          for (int t = 0; t < 6; ++t) mma_i8_ts_elect(acc + BN, tA + 8 * t, dB + koffB(6 + t), I_SU, t > 0);              // HL
-#pragma unroll
-          for (int t = 0; t < 6; ++t) mma_i8_ts_elect(acc + BN, tA + 8 * (6 + t), dB + koffB(t), I_US, 1);                // LH
-#pragma unroll
-          for (int t = 0; t < 6; ++t) mma_i8_ts_elect(acc + 2 * BN, tA + 8 * (6 + t), dB + koffB(6 + t), I_UU, t > 0);    // LL
+          if (my_parity == 0) mma_i8_tile_elect<0>((uint32_t)dB); else mma_i8_tile_elect<1>((uint32_t)dB);   // HH, HL, LH, LL: 24 MMAs
           tc_commit_elect(&t_full[ts]);
           tc_commit_elect(&empty[s]);
         }
@@ -397,6 +391,202 @@ knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUten
   if (warp == 5) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------ k = 1 kernel: 8 epilogue warps
+// Same pipeline as above, but every TMEM lane quarter is drained by TWO warps (w and w + 4 may both address quarter
+// w % 4), each taking half of the tile's 64 columns.  One warp per scheduler issues ~1 instruction every 3 cycles on
+// this dependent integer code; two warps per scheduler hide each other's latencies.  A query row therefore has two
+// threads, each with its own running arg-min; they are merged through shared memory at the end of the query block.
+constexpr int K1_THREADS = 352;   // 8 epilogue warps + TMA warp + 2 MMA issuer warps
+__global__ void __launch_bounds__(K1_THREADS, 1)
+knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUtensorMap tmap_d,
+                 const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict,
+                 int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist, int tile_stride) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NST = STAGES_K1;
+  uint8_t *sB = smem;
+  unsigned long long *s_merge = reinterpret_cast<unsigned long long *>(sB + NST * B_TILE);   // [128]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_merge + BM);
+  uint64_t *full = bars, *empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + 1, *t_full = a_empty + 1,
+           *t_empty = t_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (n_dict + BN - 1) / BN;
+  const int n_qblocks = (n_q + BM - 1) / BM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(a_full, 4);
+    mbar_init(a_empty, 2);
+    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 8 && lane == 0) tma_prefetch_desc(&tmap_d);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tmem_base != 0) __trap();   // the MMA issue code addresses TMEM with immediates
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
+        int jt = 0;
+        for (int j = 0; j < n_tiles; ++j, ++it) {
+          const uint32_t s = it % NST, r = it / NST;
+          mbar_wait(&empty[s], (r & 1) ^ 1);
+          mbar_expect_tx(&full[s], B_TILE);
+          for (int c = 0; c < 3; ++c) tma_load_2d(sB + s * B_TILE + c * CHUNK_B, &tmap_d, &full[s], c * 128, jt * BN);
+          jt += tile_stride;
+          if (jt >= n_tiles) jt -= n_tiles;
+        }
+      }
+    }
+  } else if (warp >= 9) {
+    // ===================== two MMA issuer warps (even / odd tiles) =====================
+    const uint32_t my_parity = (uint32_t)(warp - 9);
+    constexpr uint32_t I_SS = make_idesc(kDFmtS32, kFmtS8, kFmtS8, BM, BN);
+    constexpr uint32_t I_SU = make_idesc(kDFmtS32, kFmtS8, kFmtU8, BM, BN);
+    constexpr uint32_t I_US = make_idesc(kDFmtS32, kFmtU8, kFmtS8, BM, BN);
+    constexpr uint32_t I_UU = make_idesc(kDFmtS32, kFmtU8, kFmtU8, BM, BN);
+    const uint32_t tA = tmem_base + A_COL;
+    const uint64_t descB0 = umma_desc_sw128(smem_u32(sB));
+    auto koffB = [](int ks) { return (uint64_t)(((ks >> 2) * CHUNK_B + (ks & 3) * 32) >> 4); };
+    uint32_t it = 0, w = 0;
+    for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
+      mbar_wait(a_full, w & 1);
+      tc_fence_after();
+      for (int j = 0; j < n_tiles; ++j, ++it) {
+        const uint32_t s = it % NST, r = it / NST;
+        const uint32_t ts = it & 1;
+        if (ts != my_parity) continue;
+        mbar_wait(&full[s], r & 1);
+        mbar_wait(&t_empty[ts], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t dB = descB0 + (uint64_t)((s * B_TILE) >> 4);
+        const uint32_t acc = tmem_base + ts * ACC_COLS;
+        if (my_parity == 0) mma_i8_tile_elect<0>((uint32_t)dB); else mma_i8_tile_elect<1>((uint32_t)dB);
+        tc_commit_elect(&t_full[ts]);
+        tc_commit_elect(&empty[s]);
+      }
+      tc_commit_elect(a_empty);
+    }
+  } else {
+    // ===================== epilogue: thread = (query row, column half) =====================
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int HN = BN / 2;   // 32 columns per thread and tile
+    uint32_t it = 0, w = 0;
+    for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
+      const int64_t qi = (int64_t)qb * BM + row;
+      const bool valid = qi < n_q;
+      const uint32_t nq = valid ? __ldg(qnorm + qi) : 0u;
+      if (h == 0) {   // warps 0-3 also store the query rows into TMEM
+        mbar_wait(a_empty, (w & 1) ^ 1);
+        tc_fence_after();
+        const uint4 *src = reinterpret_cast<const uint4 *>(q_limbs + (valid ? qi : 0) * ROWB);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          uint32_t r[16];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint4 t4 = valid ? __ldg(src + c * 4 + v) : make_uint4(0, 0, 0, 0);
+            r[4 * v] = t4.x; r[4 * v + 1] = t4.y; r[4 * v + 2] = t4.z; r[4 * v + 3] = t4.w;
+          }
+          tmem_st16(t_lane + A_COL + c * 16, r);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full);
+      }
+      uint32_t best_d = 0xFFFFFFFFu;
+      int32_t best_i = -1;
+      int jt = 0;
+      for (int j = 0; j < n_tiles; ++j, ++it) {
+        const uint32_t ts = it & 1;
+        const int col0 = jt * BN + h * HN;
+        jt += tile_stride;
+        if (jt >= n_tiles) jt -= n_tiles;
+        const int ncol = min(HN, n_dict - col0);   // may be <= 0 on the ragged last tile
+        // dictionary norms of this tile half: independent of the MMA, so fetched before waiting for it
+        uint32_t nd[HN];
+#pragma unroll
+        for (int v = 0; v < HN / 4; ++v) {
+          const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(dnorm + col0) + v);
+          nd[4 * v] = t4.x + nq; nd[4 * v + 1] = t4.y + nq; nd[4 * v + 2] = t4.z + nq; nd[4 * v + 3] = t4.w + nq;
+        }
+        mbar_wait(&t_full[ts], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_acc = t_lane + ts * ACC_COLS + h * HN;
+        // one burst: all three accumulators of this thread's 32 columns, then the stage goes straight back to the tensor
+        // pipe (the TMEM hand-off chain, not the MMA rate, bounds a 2-stage ping-pong with K = 192)
+        uint32_t pp[HN], xx[HN], lo[HN];
+#pragma unroll
+        for (int c = 0; c < HN / 16; ++c) {
+          tmem_ld16(t_acc + c * 16, reinterpret_cast<uint32_t(&)[16]>(pp[c * 16]));
+          tmem_ld16(t_acc + BN + c * 16, reinterpret_cast<uint32_t(&)[16]>(xx[c * 16]));
+          tmem_ld16(t_acc + 2 * BN + c * 16, reinterpret_cast<uint32_t(&)[16]>(lo[c * 16]));
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[ts]);
+#pragma unroll
+        for (int e = 0; e < HN; ++e) pp[e] = (pp[e] << 8) + xx[e];
+#pragma unroll
+        for (int ch = 0; ch < HN / 16; ++ch) {
+          uint32_t dv[16];
+          uint32_t m = 0xFFFFFFFFu;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            uint32_t d = nd[ch * 16 + e];          // nq + nd
+            d -= pp[ch * 16 + e] << 9;
+            d -= lo[ch * 16 + e] << 1;
+            dv[e] = d;
+            m = min(m, d);
+          }
+          const int cbase = ch * 16;
+          if (ncol < HN) {
+            m = 0xFFFFFFFFu;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              if (cbase + e >= ncol) dv[e] = 0xFFFFFFFFu;
+              m = min(m, dv[e]);
+            }
+          }
+          if (m <= best_d) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const int32_t ci = col0 + cbase + e;
+              if (dv[e] < best_d || (dv[e] == best_d && dv[e] != 0xFFFFFFFFu && ci < best_i)) { best_d = dv[e]; best_i = ci; }
+            }
+          }
+        }
+      }
+      // merge the two column halves of each row: (distance, index) lexicographic minimum
+      const unsigned long long key = ((unsigned long long)best_d << 32) | (uint32_t)best_i;
+      if (h == 1) s_merge[row] = key;
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      if (h == 0 && valid) {
+        const unsigned long long other = s_merge[row];
+        const unsigned long long best = other < key ? other : key;
+        out_idx[qi] = (int32_t)(uint32_t)best;
+        out_dist[qi] = (uint32_t)(best >> 32);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------ row sort: (distance, index) ascending, k <= 64
 __global__ void __launch_bounds__(256) knn_sort_rows_kernel(int32_t *__restrict__ idx, uint32_t *__restrict__ dist, int64_t n_q, int k) {
   const int lane = threadIdx.x & 31;
@@ -482,11 +672,11 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
   CUtensorMap td;
   int rc = make_tmap_rows_u8(&td, d_limbs, (uint64_t)n_dict, ROWB, BN);
   if (rc != TM_OK) return rc;
-  constexpr int SMEM_K1 = STAGES_K1 * B_TILE + 256 + 1024;
+  constexpr int SMEM_K1 = STAGES_K1 * B_TILE + BM * 8 + 256 + 1024;
   constexpr int SMEM_TK = STAGES * B_TILE + CAP * TK_ROWS * 8 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(knn_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaFuncSetAttribute(knn_i8_k1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
     if (cudaFuncSetAttribute(knn_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK) != cudaSuccess) return TM_ERR_CUDA;
     attr_set = true;
   }
@@ -502,7 +692,7 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
     while (gcd(tile_stride, n_tiles_h) != 1) ++tile_stride;
     const int n_qblocks = (n_q + BM - 1) / BM;
     const int grid = n_qblocks < num_ctas ? n_qblocks : num_ctas;
-    if (k == 1) knn_i8_kernel<false><<<grid, 224, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride);
+    if (k == 1) knn_i8_k1_kernel<<<grid, K1_THREADS, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride);
     else knn_i8_kernel<true><<<grid, 224, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride);
   }
   note_launch();

@@ -117,6 +117,24 @@ __device__ __forceinline__ void mma_i8_ts_elect(uint32_t d_tmem, uint32_t a_tmem
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// All 24 MMAs of one 128x64 int8-limb tile (HH, HL, LH, LL x 6 K-steps) under ONE elect.  The kernel owns the whole
+// TMEM (512 columns, base 0 -- checked at run time), so accumulator / query-row addresses and instruction descriptors
+// are immediates; only the low word of the dictionary tile's shared-memory descriptor is a register.  This takes the
+// issue cost from ~12 to ~4 SASS instructions per MMA (a 128x64x32 int8 MMA occupies the tensor pipe for 32 cycles).
+template <int PARITY>
+__device__ __forceinline__ void mma_i8_tile_elect(uint32_t b_desc_lo) {
+  if (PARITY == 0) {
+    asm volatile(
+#include "knn_mma_tile_p0.inc"
+        ::"r"(b_desc_lo)
+        : "memory");
+  } else {
+    asm volatile(
+#include "knn_mma_tile_p1.inc"
+        ::"r"(b_desc_lo)
+        : "memory");
+  }
+}
 __device__ __forceinline__ void tc_commit_elect(uint64_t *bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"
