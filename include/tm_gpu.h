@@ -92,6 +92,17 @@ void bico_set_rebuild_properties(tm_bico *b, uint32_t interval, double initial, 
 void bico_insert_line(tm_bico *b, const double *row, double weight);
 int64_t bico_get_results(tm_bico *b, double *centroids, double *weights);
 
+/* ---------------------------------------------------------------- drop-in: dlquant_dll.dll (extern.pas:195-196; dlquant/quantizer.h:16-20) */
+/* rgb888 image -> palette, planar R/G/B rows of 65536; 0 = ok, 1 = failure.  Bit-exact against dlquant/quantizer.c
+   built with MSVC type widths (32-bit `ulong`).  lookup_bpc in 1..5. */
+int dl1quant(uint8_t *inbuf, int width, int height, int quant_to, int lookup_bpc, uint8_t *userpal /* [3][65536] */);
+int dl3quant(uint8_t *inbuf, int width, int height, int quant_to, int lookup_bpc, uint8_t *userpal /* [3][65536] */);
+/* batched: n_img images concatenated (img_off[n_img+1] in pixels) -> palettes[n_img][quant_to][3] (R,G,B), counts[n_img] */
+int tm_dl3quant_batch(const uint8_t *rgb888, const int64_t *img_off, int n_img, int quant_to, int lookup_bpc, uint8_t *palettes,
+                      int32_t *counts);
+int tm_dl1quant_batch(const uint8_t *rgb888, const int64_t *img_off, int n_img, int quant_to, int lookup_bpc, uint8_t *palettes,
+                      int32_t *counts);
+
 /* ---------------------------------------------------------------- batched: features (tilingencoder.pas:3049-3182) */
 /* RGB tiles [n][64] -> int16 features [n][192] (ConvertToCpnPixels + ComputeCpnPixelsPsyVisFeatures, pvsWeightedDCT, YUV) */
 int tm_features_from_rgb(const int32_t *rgb, int64_t n, int16_t *out);

@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared_symbols():
     src = open(os.path.join(ROOT, "include", "tm_gpu.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"\b((?:tm|ann_kdtree|yakmo|bico)_[a-z0-9_]+)\s*\(", src)
+    names = re.findall(r"\b((?:tm|ann_kdtree|yakmo|bico)_[a-z0-9_]+|dl[13]quant)\s*\(", src)
     return sorted(set(names))
 
 
@@ -35,7 +35,7 @@ def test_drop_in_names_match_extern_pas():
                  "ann_kdtree_short_destroy", "ann_kdtree_short_search", "ann_kdtree_short_search_multi", "yakmo_create",
                  "yakmo_destroy", "yakmo_set_num_threads", "yakmo_load_train_data", "yakmo_train_on_data",
                  "yakmo_get_centroids", "bico_create", "bico_destroy", "bico_set_num_threads",
-                 "bico_set_rebuild_properties", "bico_insert_line", "bico_get_results"]:
+                 "bico_set_rebuild_properties", "bico_insert_line", "bico_get_results", "dl1quant", "dl3quant"]:
         assert hasattr(_lib.lib(), name)
 
 

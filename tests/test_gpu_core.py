@@ -349,3 +349,36 @@ def test_kmeans_i16_near_ties_fall_back(tm, oracle):
     labels, cent, inertia, iters, amb = tm.kmeans_fit_i16(x, 8, init, max_iter=0)
     ol, oc, oin, oit = oracle.kmeans_lloyd(x.astype(np.float64), init, max_iter=0)
     assert np.array_equal(labels, ol) and amb > 0
+
+
+# ---------------------------------------------------------------- dlquant: against the REFERENCE's own C code (oracle/_ref)
+def _dl_images():
+    rng = np.random.default_rng(77)
+    imgs = []
+    a = rng.integers(0, 256, size=(64 * 64, 3), dtype=np.uint8); imgs.append(a)                       # noise: many cells
+    b = rand_tiles(96, 5).reshape(-1); imgs.append(np.stack([b & 255, (b >> 8) & 255, (b >> 16) & 255], 1).astype(np.uint8))
+    c = rng.integers(0, 256, size=(40, 3), dtype=np.uint8); imgs.append(np.repeat(c, 30, axis=0))      # few distinct colours
+    g = np.load(os.path.join(GOLD, "dlquant_ref.npz"))["img"]; imgs.append(g)
+    return imgs
+
+
+@pytest.mark.parametrize("which", [3, 1])
+def test_dlquant_matches_reference_c(tm, oracle, which):
+    if oracle.ref_dlquant() is None:
+        pytest.skip("oracle/_ref not built")
+    imgs = _dl_images()
+    name = "dl3quant" if which == 3 else "dl1quant"
+    for quant_to, bpc in ((16, 5), (64, 5), (5, 4)):
+        pal, cnt = tm.dlquant_batch(imgs, quant_to, bpc, which=which)
+        for i, im in enumerate(imgs):
+            rc, want = oracle.ref_dl3quant(im, len(im), 1, quant_to, bpc, which=name)
+            assert rc == 0
+            assert np.array_equal(pal[i], want), (name, i, quant_to, bpc)
+
+
+def test_dlquant_golden_and_dropin(tm):
+    g = np.load(os.path.join(GOLD, "dlquant_ref.npz"))
+    rc, pal, full = tm.dlquant_dropin(g["img"], 48, 48, 16, 5, which=3)
+    assert rc == 0 and np.array_equal(pal, g["dl3_16"]) and not full[:, 16:].any()
+    rc, pal, full = tm.dlquant_dropin(g["img"], 48, 48, 16, 5, which=1)
+    assert rc == 0 and np.array_equal(pal, g["dl1_16"])

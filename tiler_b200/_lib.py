@@ -51,6 +51,10 @@ SIGNATURES = {
     "tm_kmeans_partial_step": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_dbl)]),
     "tm_kmeans_finish_step": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "tm_palquant_kmeans": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _u64, _vp, C.POINTER(_i32)]),
+    "tm_dl3quant_batch": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "tm_dl1quant_batch": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
+    "dl3quant": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp]),
+    "dl1quant": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp]),
     "tm_matcher_create": (C.c_int, [_vp, _vp, _i64, _vp, _i32, _i32, _i32, C.POINTER(_vp)]),
     "tm_matcher_destroy": (C.c_int, [_vp]),
     "tm_match_tiles_rgb": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),

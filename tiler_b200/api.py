@@ -302,6 +302,31 @@ def palquant_kmeans(rgb, tile_pal, n_pal, pal_size, init=None, seed=1):
     return out, iters.value
 
 
+# ------------------------------------------------------------------ dlquant (dlquant/quantizer.c; extern.pas:195-196)
+def dlquant_batch(images, quant_to, lookup_bpc=5, which=3):
+    """images: list of uint8 arrays [n_px, 3] (R,G,B).  -> palettes uint8 [n_img, quant_to, 3], counts int32 [n_img]."""
+    imgs = [np.ascontiguousarray(im, dtype=np.uint8).reshape(-1, 3) for im in images]
+    off = np.zeros(len(imgs) + 1, dtype=np.int64)
+    off[1:] = np.cumsum([len(im) for im in imgs])
+    flat = np.concatenate(imgs, axis=0)
+    pal = np.empty((len(imgs), quant_to, 3), dtype=np.uint8)
+    cnt = np.empty(len(imgs), dtype=np.int32)
+    check(_lib.lib().tm_set_stream(None))
+    fn = _lib.lib().tm_dl3quant_batch if which == 3 else _lib.lib().tm_dl1quant_batch
+    check(fn(C.c_void_p(flat.ctypes.data), C.c_void_p(off.ctypes.data), len(imgs), int(quant_to), int(lookup_bpc),
+             C.c_void_p(pal.ctypes.data), C.c_void_p(cnt.ctypes.data)))
+    return pal, cnt
+
+
+def dlquant_dropin(rgb888, width, height, quant_to, lookup_bpc=5, which=3):
+    """dl3quant / dl1quant with the DLL's own signature -> (return code, palette [quant_to, 3])."""
+    buf = np.ascontiguousarray(rgb888, dtype=np.uint8).reshape(-1).copy()
+    userpal = np.full((3, 65536), 255, dtype=np.uint8)
+    fn = _lib.lib().dl3quant if which == 3 else _lib.lib().dl1quant
+    rc = fn(C.c_void_p(buf.ctypes.data), int(width), int(height), int(quant_to), int(lookup_bpc), C.c_void_p(userpal.ctypes.data))
+    return rc, userpal[:, :quant_to].T.copy(), userpal
+
+
 # ------------------------------------------------------------------ matcher (tilingencoder.pas:4566-4613, 1464-1659)
 class Matcher:
     """PrepareReconstruct + the k-NN / extended-palette part of TFrame.Reconstruct.DoXY."""

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <cstdio>
 #include <cmath>
+#include <algorithm>
 
 namespace tmg {
 std::atomic<long long> g_launches{0};
@@ -593,6 +594,59 @@ extern "C" int tm_palquant_kmeans(const int32_t *rgb, const int32_t *tile_pal, i
   if (iters) *iters = it;
   RC(s.finish(true));
   return TM_OK;
+}
+
+// ------------------------------------------------------------------ dlquant (quantizer.c; extern.pas:195-196)
+static int dlquant_batch(int which, const uint8_t *rgb888, const int64_t *img_off, int n_img, int quant_to, int bpc, uint8_t *palettes,
+                         int32_t *counts) {
+  RC(require_gpu());
+  if (n_img < 1 || !rgb888 || !img_off || !palettes || quant_to < 1 || quant_to > 65536 || bpc < 1 || bpc > 5)
+    return fail(TM_ERR_ARG, "tm_dlNquant_batch: bad argument (1 <= lookup_bpc <= 5)");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  // image offsets are needed on both sides: bring them to the host if they live on the device
+  std::vector<int64_t> h_off((size_t)n_img + 1);
+  if (cudaMemcpyAsync(h_off.data(), img_off, h_off.size() * 8, cudaMemcpyDefault, s.st) != cudaSuccess || cudaStreamSynchronize(s.st) != cudaSuccess)
+    return fail(TM_ERR_CUDA, "tm_dlNquant_batch: offsets");
+  int64_t max_px = 0;
+  for (int i = 0; i < n_img; ++i) {
+    if (h_off[i + 1] <= h_off[i]) return fail(TM_ERR_ARG, "tm_dlNquant_batch: empty image");
+    max_px = std::max(max_px, h_off[i + 1] - h_off[i]);
+  }
+  const uint8_t *d_rgb = s.in(rgb888, (size_t)h_off[n_img] * 3);
+  const int64_t *d_off = s.in(img_off, (size_t)n_img + 1);
+  uint8_t *d_pal = s.out(palettes, (size_t)n_img * quant_to * 3);
+  int32_t *d_cnt = s.out(counts, (size_t)n_img);
+  if (s.err == TM_OK)
+    s.err = which == 3 ? run_dl3quant(d_rgb, d_off, n_img, max_px, quant_to, bpc, d_pal, d_cnt, s.st)
+                       : run_dl1quant(d_rgb, d_off, n_img, max_px, quant_to, bpc, d_pal, d_cnt, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+extern "C" int tm_dl3quant_batch(const uint8_t *rgb888, const int64_t *img_off, int n_img, int quant_to, int lookup_bpc, uint8_t *palettes,
+                                 int32_t *counts) {
+  return dlquant_batch(3, rgb888, img_off, n_img, quant_to, lookup_bpc, palettes, counts);
+}
+extern "C" int tm_dl1quant_batch(const uint8_t *rgb888, const int64_t *img_off, int n_img, int quant_to, int lookup_bpc, uint8_t *palettes,
+                                 int32_t *counts) {
+  return dlquant_batch(1, rgb888, img_off, n_img, quant_to, lookup_bpc, palettes, counts);
+}
+// drop-in: int dlNquant(uchar *inbuf, int width, int height, int quant_to, int lookup_bpc, uchar userpal[3][65536])
+static int dlquant_dropin(int which, uint8_t *inbuf, int width, int height, int quant_to, int lookup_bpc, uint8_t *userpal) {
+  if (!inbuf || !userpal || width < 1 || height < 1 || quant_to < 1 || quant_to > 65536) return 1;
+  const int64_t off[2] = {0, (int64_t)width * height};
+  std::vector<uint8_t> pal((size_t)quant_to * 3);
+  if (dlquant_batch(which, inbuf, off, 1, quant_to, lookup_bpc, pal.data(), nullptr) != TM_OK) return 1;
+  memset(userpal, 0, 3 * 65536);   // the DLL's context is calloc'ed: unused entries read 0
+  for (int i = 0; i < quant_to; ++i)
+    for (int c = 0; c < 3; ++c) userpal[c * 65536 + i] = pal[(size_t)i * 3 + c];
+  return 0;
+}
+extern "C" int dl3quant(uint8_t *inbuf, int width, int height, int quant_to, int lookup_bpc, uint8_t *userpal) {
+  return dlquant_dropin(3, inbuf, width, height, quant_to, lookup_bpc, userpal);
+}
+extern "C" int dl1quant(uint8_t *inbuf, int width, int height, int quant_to, int lookup_bpc, uint8_t *userpal) {
+  return dlquant_dropin(1, inbuf, width, height, quant_to, lookup_bpc, userpal);
 }
 
 // ------------------------------------------------------------------ matcher

@@ -87,4 +87,10 @@ size_t kmeans_update_ws_bytes(int64_t n, int k);
 int run_palette_quantise(const int32_t *rgb, const int32_t *tile_pal, int64_t n_tiles, int n_pal, int pal_size, const double *init,
                          unsigned long long seed, int max_iter, int32_t *palettes_out, int32_t *iters_out, cudaStream_t st);
 
+// ---- dlquant.cu
+int run_dl3quant(const uint8_t *rgb, const int64_t *img_off, int n_img, int64_t max_pixels, int quant_to, int bpc, uint8_t *pal_out,
+                 int32_t *count_out, cudaStream_t st);
+int run_dl1quant(const uint8_t *rgb, const int64_t *img_off, int n_img, int64_t max_pixels, int quant_to, int bpc, uint8_t *pal_out,
+                 int32_t *count_out, cudaStream_t st);
+
 }  // namespace tmg
