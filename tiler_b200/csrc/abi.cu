@@ -447,16 +447,35 @@ static int km_i16_assign(KmI16 &w, const double *d_cent, int32_t *d_labels, int 
   if (rc) return rc;
   int32_t h[2] = {0, 0};
   if (cudaMemcpyAsync(h, w.counters, 8, cudaMemcpyDeviceToHost, s.st) != cudaSuccess || cudaStreamSynchronize(s.st) != cudaSuccess) return TM_ERR_CUDA;
+  int n_bf = 0;
   if (h[1] > 0) {
-    double *xa = (double *)s.temp((size_t)h[1] * 192 * 8), *da = (double *)s.temp((size_t)h[1] * 8);
-    int32_t *la = (int32_t *)s.temp((size_t)h[1] * 4);
+    // level 2: the uncertified points again on the tensor cores with 64 candidates
+    const int na = h[1];
+    uint8_t *al = (uint8_t *)s.temp((size_t)na * 384);
+    uint32_t *an = (uint32_t *)s.temp((size_t)na * 4), *ad = (uint32_t *)s.temp((size_t)na * 64 * 4);
+    int32_t *ac = (int32_t *)s.temp((size_t)na * 64 * 4), *a2 = (int32_t *)s.temp((size_t)na * 4), *a2n = (int32_t *)s.temp(4);
     if (s.err) return s.err;
-    rc = launch_kmeans_assign_amb(w.x, w.amb_list, h[1], d_cent, w.k, d_labels, w.dist, w.counters, xa, la, da, s.st);
+    if (cudaMemsetAsync(a2n, 0, 4, s.st) != cudaSuccess) return TM_ERR_CUDA;
+    rc = launch_amb_gather_limbs(w.x_limbs, w.x_norm, w.amb_list, na, al, an, s.st);
     if (rc) return rc;
+    rc = launch_knn_i8(al, an, na, w.c_limbs, w.c_norm, w.k, 64, ac, ad, nullptr, num_sms(), 1, s.st);
+    if (rc) return rc;
+    rc = launch_kmeans_rerank64(w.x, w.amb_list, na, ac, ad, d_cent, w.k, d_labels, w.dist, w.counters, a2, a2n, s.st);
+    if (rc) return rc;
+    int32_t h2 = 0;
+    if (cudaMemcpyAsync(&h2, a2n, 4, cudaMemcpyDeviceToHost, s.st) != cudaSuccess || cudaStreamSynchronize(s.st) != cudaSuccess) return TM_ERR_CUDA;
+    n_bf = h2;
+    if (h2 > 0) {   // level 3: exact f64 scan of the residue
+      double *xa = (double *)s.temp((size_t)h2 * 192 * 8), *da = (double *)s.temp((size_t)h2 * 8);
+      int32_t *la = (int32_t *)s.temp((size_t)h2 * 4);
+      if (s.err) return s.err;
+      rc = launch_kmeans_assign_amb(w.x, a2, h2, d_cent, w.k, d_labels, w.dist, w.counters, xa, la, da, s.st);
+      if (rc) return rc;
+    }
     if (cudaMemcpyAsync(h, w.counters, 4, cudaMemcpyDeviceToHost, s.st) != cudaSuccess || cudaStreamSynchronize(s.st) != cudaSuccess) return TM_ERR_CUDA;
   }
   *changed = h[0];
-  *n_amb = h[1];
+  *n_amb = n_bf;   // points that needed the brute-force scan
   return TM_OK;
 }
 static double sum_dist(const double *d_dist, int64_t n, cudaStream_t st, int *err) {

@@ -208,6 +208,7 @@ static int launch_kmeans_update_t(const T *x, const double *weights, int64_t n, 
   int32_t *vals_out = (int32_t *)p; p += al((size_t)n * 4);
   int32_t *counts = (int32_t *)p; p += al((size_t)k * 4);
   int32_t *offs = (int32_t *)p;
+  ProfScope prof("km_update", st);
   int bits = 1;
   while ((1ll << bits) < k) ++bits;
   iota_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(vals_in, n);
@@ -297,6 +298,67 @@ kmeans_rerank_i16_kernel(const int16_t *__restrict__ x, int64_t n, const int32_t
   }
 }
 
+// second level for the uncertified points: their limb rows are gathered, the tensor-core search is repeated with 64
+// candidates, and a warp per point evaluates the 64 exact f64 distances; the same bound with the 64th rounded distance
+// certifies almost all of them.  Only the residue goes to the brute-force f64 kernel.
+__global__ void amb_gather_limbs_kernel(const uint8_t *__restrict__ limbs, const uint32_t *__restrict__ norms,
+                                        const int32_t *__restrict__ amb_list, int n_amb, uint8_t *__restrict__ out_limbs,
+                                        uint32_t *__restrict__ out_norms) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one uint4 (16 bytes) per thread, 24 per row
+  if (t >= (int64_t)n_amb * 24) return;
+  const int i = (int)(t / 24), c = (int)(t % 24);
+  const int64_t p = amb_list[i];
+  reinterpret_cast<uint4 *>(out_limbs)[t] = reinterpret_cast<const uint4 *>(limbs + p * 384)[c];
+  if (c == 0) out_norms[i] = norms[p];
+}
+
+__global__ void __launch_bounds__(256)
+kmeans_rerank64_kernel(const int16_t *__restrict__ x, const int32_t *__restrict__ amb_list, int n_amb, const int32_t *__restrict__ cand,
+                       const uint32_t *__restrict__ cdist, const double *__restrict__ cent, int k, int32_t *__restrict__ labels,
+                       double *__restrict__ dist, int32_t *__restrict__ changed, int32_t *__restrict__ amb2_list,
+                       int32_t *__restrict__ amb2_count) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n_amb) return;
+  const int64_t p = amb_list[i];
+  const int16_t *xv = x + p * 192;
+  double bs = INFINITY;
+  int32_t bi = 0x7fffffff;
+  for (int c = lane; c < 64; c += 32) {
+    const int32_t ci = cand[(int64_t)i * 64 + c];
+    if (ci < 0 || ci >= k) continue;
+    const double *cv = cent + (int64_t)ci * 192;
+    double s = 0.0;
+    for (int j = 0; j < 192; ++j) {
+      const double df = __dsub_rn((double)__ldg(xv + j), __ldg(cv + j));
+      s = __dadd_rn(s, __dmul_rn(df, df));
+    }
+    if (s < bs || (s == bs && ci < bi)) { bs = s; bi = ci; }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+    const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (os < bs || (os == bs && oi < bi)) { bs = os; bi = oi; }
+  }
+  if (lane == 0) {
+    const int32_t last = cand[(int64_t)i * 64 + 63];
+    bool certified;
+    if (last < 0) certified = true;   // fewer than 64 centroids: the candidates are all of them
+    else {
+      const double dl = (double)cdist[(int64_t)i * 64 + 63];
+      certified = (dl - sqrt(192.0 * dl) - 48.0) > bs;
+    }
+    if (bi == 0x7fffffff) certified = false;
+    if (certified) {
+      if (labels[p] != bi) { labels[p] = bi; atomicAdd(changed, 1); }
+      if (dist) dist[p] = bs;
+    } else {
+      amb2_list[atomicAdd(amb2_count, 1)] = (int32_t)p;
+    }
+  }
+}
+
 // queued (uncertified) points: gathered into a dense f64 matrix, assigned by the exact f64 kernel (32 points per block
 // share every centroid load), scattered back
 __global__ void amb_gather_kernel(const int16_t *__restrict__ x, const int32_t *__restrict__ amb_list, int n_amb,
@@ -317,6 +379,24 @@ __global__ void amb_scatter_kernel(const int32_t *__restrict__ amb_list, int n_a
   if (dist) dist[p] = da[i];
 }
 
+int launch_amb_gather_limbs(const uint8_t *limbs, const uint32_t *norms, const int32_t *amb_list, int n_amb, uint8_t *out_limbs,
+                            uint32_t *out_norms, cudaStream_t st) {
+  if (n_amb <= 0) return TM_OK;
+  const int64_t total = (int64_t)n_amb * 24;
+  amb_gather_limbs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(limbs, norms, amb_list, n_amb, out_limbs, out_norms);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+int launch_kmeans_rerank64(const int16_t *x, const int32_t *amb_list, int n_amb, const int32_t *cand, const uint32_t *cdist,
+                           const double *cent, int k, int32_t *labels, double *dist, int32_t *changed, int32_t *amb2_list,
+                           int32_t *amb2_count, cudaStream_t st) {
+  if (n_amb <= 0) return TM_OK;
+  ProfScope prof("km_rerank64", st);
+  kmeans_rerank64_kernel<<<(n_amb + 7) / 8, 256, 0, st>>>(x, amb_list, n_amb, cand, cdist, cent, k, labels, dist, changed, amb2_list, amb2_count);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
 int launch_round_centroids(const double *cent, int k, int16_t *out, cudaStream_t st) {
   const int64_t total = (int64_t)k * 192;
   round_centroids_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(cent, total, out);
@@ -327,6 +407,7 @@ int launch_round_centroids(const double *cent, int k, int16_t *out, cudaStream_t
 int launch_kmeans_rerank_i16(const int16_t *x, int64_t n, const int32_t *cand, const uint32_t *cdist, const double *cent, int k,
                              int32_t *labels, double *dist, int32_t *changed, int32_t *amb_list, int32_t *amb_count, cudaStream_t st) {
   if (n <= 0) return TM_OK;
+  ProfScope prof("km_rerank", st);
   const int64_t threads = n * KMEANS_KC;
   kmeans_rerank_i16_kernel<KMEANS_KC><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(x, n, cand, cdist, cent, k, labels, dist, changed,
                                                                                         amb_list, amb_count);
@@ -337,6 +418,7 @@ int launch_kmeans_rerank_i16(const int16_t *x, int64_t n, const int32_t *cand, c
 int launch_kmeans_assign_amb(const int16_t *x, const int32_t *amb_list, int n_amb, const double *cent, int k, int32_t *labels,
                              double *dist, int32_t *changed, double *xa, int32_t *la, double *da, cudaStream_t st) {
   if (n_amb <= 0) return TM_OK;
+  ProfScope prof("km_amb", st);
   const int64_t total = (int64_t)n_amb * 192;
   amb_gather_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, amb_list, n_amb, labels, xa, la);
   note_launch();

@@ -397,6 +397,8 @@ knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUten
 // this dependent integer code; two warps per scheduler hide each other's latencies.  A query row therefore has two
 // threads, each with its own running arg-min; they are merged through shared memory at the end of the query block.
 constexpr int K1_THREADS = 352;   // 8 epilogue warps + TMA warp + 2 MMA issuer warps
+// KS = 1: arg-min.  KS = 4: the four nearest, kept sorted in registers (k-means candidate search).
+template <int KS>
 __global__ void __launch_bounds__(K1_THREADS, 1)
 knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUtensorMap tmap_d,
                  const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict,
@@ -405,8 +407,8 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int NST = STAGES_K1;
   uint8_t *sB = smem;
-  unsigned long long *s_merge = reinterpret_cast<unsigned long long *>(sB + NST * B_TILE);   // [128]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_merge + BM);
+  unsigned long long *s_merge = reinterpret_cast<unsigned long long *>(sB + NST * B_TILE);   // [KS][128]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_merge + BM * KS);
   uint64_t *full = bars, *empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + 1, *t_full = a_empty + 1,
            *t_empty = t_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
@@ -505,8 +507,11 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full);
       }
-      uint32_t best_d = 0xFFFFFFFFu;
-      int32_t best_i = -1;
+      // the KS best (distance << 32 | index) keys of this thread's column half, ascending
+      unsigned long long bk[KS];
+#pragma unroll
+      for (int r = 0; r < KS; ++r) bk[r] = ~0ull;
+      uint32_t best_d = 0xFFFFFFFFu;   // distance of bk[KS - 1]: the admission threshold
       int jt = 0;
       for (int j = 0; j < n_tiles; ++j, ++it) {
         const uint32_t ts = it & 1;
@@ -560,25 +565,47 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
               m = min(m, dv[e]);
             }
           }
-          if (m <= best_d) {
+          if (m <= best_d) {   // rare once good candidates have been seen; ties go to the lower dictionary index
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-              const int32_t ci = col0 + cbase + e;
-              if (dv[e] < best_d || (dv[e] == best_d && dv[e] != 0xFFFFFFFFu && ci < best_i)) { best_d = dv[e]; best_i = ci; }
+              if (dv[e] == 0xFFFFFFFFu) continue;
+              unsigned long long key = ((unsigned long long)dv[e] << 32) | (uint32_t)(col0 + cbase + e);
+              if (key < bk[KS - 1]) {   // sorted insertion
+#pragma unroll
+                for (int r = 0; r < KS; ++r) {
+                  if (key < bk[r]) { const unsigned long long t = bk[r]; bk[r] = key; key = t; }
+                }
+                best_d = (uint32_t)(bk[KS - 1] >> 32);
+              }
             }
           }
         }
       }
-      // merge the two column halves of each row: (distance, index) lexicographic minimum
-      const unsigned long long key = ((unsigned long long)best_d << 32) | (uint32_t)best_i;
-      if (h == 1) s_merge[row] = key;
+      // merge the two column halves of each row: the KS smallest of two ascending lists
+      if (h == 1) {
+#pragma unroll
+        for (int r = 0; r < KS; ++r) s_merge[r * BM + row] = bk[r];
+      }
       asm volatile("bar.sync 1, 256;\n" ::: "memory");
       if (h == 0 && valid) {
-        const unsigned long long other = s_merge[row];
-        const unsigned long long best = other < key ? other : key;
-        out_idx[qi] = (int32_t)(uint32_t)best;
-        out_dist[qi] = (uint32_t)(best >> 32);
+        unsigned long long ok[KS];
+#pragma unroll
+        for (int r = 0; r < KS; ++r) ok[r] = s_merge[r * BM + row];
+        int ia = 0, ib = 0;
+#pragma unroll
+        for (int r = 0; r < KS; ++r) {
+          // ia, ib <= r: static indexing through a small select keeps the lists in registers
+          unsigned long long a = ~0ull, b = ~0ull;
+#pragma unroll
+          for (int u = 0; u < KS; ++u) { if (u == ia) a = bk[u]; if (u == ib) b = ok[u]; }
+          const bool ta = a <= b;
+          const unsigned long long v = ta ? a : b;
+          ia += ta; ib += !ta;
+          out_idx[qi * KS + r] = (int32_t)(uint32_t)v;        // 0xFFFFFFFF = -1 when fewer than KS rows exist
+          out_dist[qi * KS + r] = (uint32_t)(v >> 32);
+        }
       }
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");   // s_merge is rewritten by the next query block
     }
   }
 
@@ -672,16 +699,17 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
   CUtensorMap td;
   int rc = make_tmap_rows_u8(&td, d_limbs, (uint64_t)n_dict, ROWB, BN);
   if (rc != TM_OK) return rc;
-  constexpr int SMEM_K1 = STAGES_K1 * B_TILE + BM * 8 + 256 + 1024;
+  constexpr int SMEM_K1 = STAGES_K1 * B_TILE + BM * 8 * 4 + 256 + 1024;
   constexpr int SMEM_TK = STAGES * B_TILE + CAP * TK_ROWS * 8 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(knn_i8_k1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaFuncSetAttribute(knn_i8_k1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaFuncSetAttribute(knn_i8_k1_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
     if (cudaFuncSetAttribute(knn_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK) != cudaSuccess) return TM_ERR_CUDA;
     attr_set = true;
   }
   {
-    ProfScope prof(k == 1 ? "knn_k1" : "knn_topk", st);
+    ProfScope prof(k == 1 ? "knn_k1" : (k == 4 ? "knn_k4" : "knn_topk"), st);
     // Dictionary tiles are visited in the order j -> (j * stride) mod n_tiles with stride ~ 0.618 n_tiles, coprime to
     // n_tiles: a streaming top-k admits ~k ln(N/k) candidates per row when the order is uncorrelated with the distance,
     // but nearly all N when distances fall along the scan (dictionaries built frame by frame do exactly that).
@@ -692,12 +720,13 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
     while (gcd(tile_stride, n_tiles_h) != 1) ++tile_stride;
     const int n_qblocks = (n_q + BM - 1) / BM;
     const int grid = n_qblocks < num_ctas ? n_qblocks : num_ctas;
-    if (k == 1) knn_i8_k1_kernel<<<grid, K1_THREADS, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride);
+    if (k == 1) knn_i8_k1_kernel<1><<<grid, K1_THREADS, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride);
+    else if (k == 4) knn_i8_k1_kernel<4><<<grid, K1_THREADS, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride);
     else knn_i8_kernel<true><<<grid, 224, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride);
   }
   note_launch();
   if (cudaGetLastError() != cudaSuccess) return TM_ERR_CUDA;
-  if (k > 1 && sort_rows) {
+  if (k > 1 && k != 4 && sort_rows) {   // the k = 4 kernel emits sorted rows
     note_launch();
     knn_sort_rows_kernel<<<(unsigned)((n_q + 7) / 8), 256, 0, st>>>(out_idx, out_dist, n_q, k);
     if (cudaGetLastError() != cudaSuccess) return TM_ERR_CUDA;

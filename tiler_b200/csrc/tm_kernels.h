@@ -78,6 +78,11 @@ int launch_kmeans_rerank_i16(const int16_t *x, int64_t n, const int32_t *cand, c
                              int32_t *labels, double *dist, int32_t *changed, int32_t *amb_list, int32_t *amb_count, cudaStream_t st);
 int launch_kmeans_assign_amb(const int16_t *x, const int32_t *amb_list, int n_amb, const double *cent, int k, int32_t *labels,
                              double *dist, int32_t *changed, double *xa, int32_t *la, double *da, cudaStream_t st);
+int launch_amb_gather_limbs(const uint8_t *limbs, const uint32_t *norms, const int32_t *amb_list, int n_amb, uint8_t *out_limbs,
+                            uint32_t *out_norms, cudaStream_t st);
+int launch_kmeans_rerank64(const int16_t *x, const int32_t *amb_list, int n_amb, const int32_t *cand, const uint32_t *cdist,
+                           const double *cent, int k, int32_t *labels, double *dist, int32_t *changed, int32_t *amb2_list,
+                           int32_t *amb2_count, cudaStream_t st);
 int launch_kmeanspp_f64(const double *x, int64_t n, int dim, int k, unsigned long long seed, double *d2_ws, double *cent,
                         cudaStream_t st);
 int launch_kmeans_finish(const double *sums, const int64_t *counts, int k, int dim, int nan_empty, double *cent, cudaStream_t st);

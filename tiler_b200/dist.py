@@ -65,6 +65,23 @@ def kmeans_fit_sharded(x_shard, init, max_iter=300, nan_empty=False):
     return labels, cent, inertia, it
 
 
+def kmeans_fit_i16_sharded(x_shard, init, max_iter=300, nan_empty=False):
+    """Same as kmeans_fit_sharded for int16 tile vectors: the assignment of every shard runs on the tensor cores
+    (tm_kmeans_partial_step_i16), the [k,192] sums and [k] counts are all-reduced, centroids stay replicated."""
+    from . import api
+    cent = init.clone()
+    labels = torch.full((x_shard.shape[0],), -1, dtype=torch.int32, device=x_shard.device)
+    it = 0
+    while True:
+        labels, sums, counts, changed, inertia = api.kmeans_partial_step_i16(x_shard, cent, labels)
+        sums, counts, changed, inertia = allreduce_partials(sums, counts, changed, inertia)
+        if changed == 0 or it >= max_iter:
+            break
+        it += 1
+        cent = api.kmeans_finish_step(sums, counts, cent, nan_empty=nan_empty)
+    return labels, cent, inertia, it
+
+
 def gather_tilemaps(local, world_shards):
     """All-gather per-rank tilemap arrays (numpy, keyed by sequence index) onto every rank via the object collective."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:

@@ -36,4 +36,22 @@ if rank == 0:
     print(json.dumps({"world": world, "n": n, "k": k, "iters": iters, "iters_1gpu": it1, "label_agreement": agree,
                       "max_rel_centroid_err": rel, "inertia_rel_err": abs(inertia - in1) / in1, "sharded_s": dt, "single_s": dt1}))
     assert agree > 0.9999 and rel < 1e-9 and iters == it1
+# ---- config-C style run on int16 tile vectors: tensor-core assignment, points sharded, NCCL all-reduce of sums/counts
+n2, k2 = int(os.environ.get("KM_N2", 1 << 21)), int(os.environ.get("KM_K2", 1 << 16))
+g = torch.Generator(device=dev); g.manual_seed(5)
+cen = torch.randint(-3000, 3000, (k2, 192), generator=g, device=dev, dtype=torch.int32).to(torch.float32)
+lo2, hi2 = tdist.shard_rows(n2, rank, world)
+g2 = torch.Generator(device=dev); g2.manual_seed(100 + rank)
+own = torch.randint(0, k2, (hi2 - lo2,), generator=g2, device=dev)
+xs2 = (cen[own] + 25.0 * torch.randn(hi2 - lo2, 192, generator=g2, device=dev)).round().clamp(-32768, 32767).to(torch.int16)
+init2 = cen.to(torch.float64) + 3.0
+tdist.kmeans_fit_i16_sharded(xs2, init2, max_iter=0)           # warm-up
+dist.barrier(); torch.cuda.synchronize()
+t0 = time.perf_counter()
+lab2, cent2, inertia2, it2 = tdist.kmeans_fit_i16_sharded(xs2, init2, max_iter=3)
+torch.cuda.synchronize(); dist.barrier()
+dt2 = time.perf_counter() - t0
+if rank == 0:
+    print(json.dumps({"i16_config_c": {"world": world, "n": n2, "k": k2, "lloyd_updates": it2, "seconds": dt2,
+                                       "evals_per_s": n2 * k2 * (it2 + 1) / dt2, "inertia": inertia2}}))
 dist.destroy_process_group()

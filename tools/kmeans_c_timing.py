@@ -13,15 +13,16 @@ centres = synth.random_features(k, 3, adversarial=True).astype(np.float32)
 x = torch.from_numpy(centres).cuda()[torch.from_numpy(rng.integers(0, k, size=n)).cuda()]
 x = (x + 25.0 * torch.randn(n, 192, device="cuda")).round().clamp(-32768, 32767).to(torch.int16)
 init = x[torch.randperm(n, device="cuda")[:k]].to(torch.float64)
-api.kmeans_fit_i16(x[:4096], 64, init[:64].contiguous(), max_iter=1)
+api.kmeans_fit_i16(x, k, init, max_iter=1)      # warm-up: grows the allocation pool, loads the kernels
 torch.cuda.synchronize()
 api.profile_enable(True)
 t0 = time.perf_counter()
 labels, cent, inertia, it, amb = api.kmeans_fit_i16(x, k, init, max_iter=iters)
 torch.cuda.synchronize()
 dt = time.perf_counter() - t0
-knn_ms, knn_n = api.profile_read("knn_topk")
+knn_ms, knn_n = api.profile_read("knn_k4")
+parts = {nm: api.profile_read(nm)[0] for nm in ("km_rerank", "knn_topk", "km_rerank64", "km_amb", "km_update")}
 evals = n * k * (it + 1)
 print(json.dumps({"n": n, "k": k, "lloyd_updates": it, "assign_passes": it + 1, "seconds": dt, "ambiguous_points": amb,
                   "knn_kernel_ms_per_pass": knn_ms / max(knn_n, 1), "evals_per_s_total": evals / dt,
-                  "evals_per_s_knn_kernel": n * k / (knn_ms / max(knn_n, 1) * 1e-3), "inertia": inertia}))
+                  "evals_per_s_knn_kernel": n * k / (knn_ms / max(knn_n, 1) * 1e-3), "inertia": inertia, "ms_total_by_kernel": {"knn_k4": knn_ms, **parts}}))
