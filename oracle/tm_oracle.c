@@ -626,6 +626,7 @@ void tmo_dither_batch(const int32_t *rgb, const uint8_t *mirror_flags, const int
 }
 
 /* ------------------------------------------------------------------ k-means */
+#define TMO_KM_BLOCK 128
 
 static inline uint64_t xorshift64s(uint64_t *s) {
   uint64_t x = *s; x ^= x >> 12; x ^= x << 25; x ^= x >> 27; *s = x; return x * 0x2545F4914F6CDD1DULL;
@@ -662,6 +663,7 @@ void tmo_kmeanspp_init(const double *x, int64_t n, int dim, int k, uint64_t seed
 int tmo_kmeans_lloyd(const double *x, int64_t n, int dim, int k, int max_iter, double *cent,
                      int32_t *labels, double *inertia, int nan_empty) {
   double *sums = (double *)malloc(sizeof(double) * (size_t)k * dim);
+  double *blk = (double *)malloc(sizeof(double) * (size_t)k * dim);
   int64_t *cnt = (int64_t *)malloc(sizeof(int64_t) * (size_t)k);
   for (int64_t i = 0; i < n; ++i) labels[i] = -1;
   int it = 0;
@@ -682,20 +684,34 @@ int tmo_kmeans_lloyd(const double *x, int64_t n, int dim, int k, int max_iter, d
     }
     if (changed == 0 || it >= max_iter) break;
     ++it;
+    /* per-cluster sums in a FIXED blocked order: members in ascending point index, consecutive blocks of
+       TMO_KM_BLOCK members summed sequentially from 0, block sums added sequentially from 0.  (yakmo's own summation
+       order is unknowable; this one is parallel-friendly and is what the GPU update kernel reproduces bit for bit.
+       For clusters of <= TMO_KM_BLOCK members it is the plain sequential sum.) */
     memset(sums, 0, sizeof(double) * (size_t)k * dim);
     memset(cnt, 0, sizeof(int64_t) * (size_t)k);
+    memset(blk, 0, sizeof(double) * (size_t)k * dim);
     for (int64_t i = 0; i < n; ++i) {
-      double *sv = sums + (int64_t)labels[i] * dim; const double *xv = x + i * dim;
-      for (int j = 0; j < dim; ++j) sv[j] += xv[j];
-      ++cnt[labels[i]];
+      const int32_t c = labels[i];
+      double *bv = blk + (int64_t)c * dim; const double *xv = x + i * dim;
+      for (int j = 0; j < dim; ++j) bv[j] += xv[j];
+      if (++cnt[c] % TMO_KM_BLOCK == 0) {
+        double *sv = sums + (int64_t)c * dim;
+        for (int j = 0; j < dim; ++j) { sv[j] += bv[j]; bv[j] = 0.0; }
+      }
     }
+    for (int c = 0; c < k; ++c)
+      if (cnt[c] % TMO_KM_BLOCK != 0) {
+        double *sv = sums + (int64_t)c * dim, *bv = blk + (int64_t)c * dim;
+        for (int j = 0; j < dim; ++j) sv[j] += bv[j];
+      }
     for (int c = 0; c < k; ++c) {
       if (cnt[c] > 0) for (int j = 0; j < dim; ++j) cent[(int64_t)c * dim + j] = sums[(int64_t)c * dim + j] / (double)cnt[c];
       else if (nan_empty) for (int j = 0; j < dim; ++j) cent[(int64_t)c * dim + j] = NAN;
     }
   }
   if (inertia) *inertia = total;
-  free(sums); free(cnt);
+  free(sums); free(blk); free(cnt);
   return it;
 }
 

@@ -340,15 +340,26 @@ def test_kmeans_i16_tensorcore_matches_oracle(tm, oracle, n, k, adv):
 
 
 def test_kmeans_i16_near_ties_fall_back(tm, oracle):
-    # centroids a fraction of an LSB apart: rounding cannot separate them, the certificate must refuse and the exact
-    # f64 fallback must decide
+    # 80 centroids a fraction of an LSB apart: they all round to the same int16 vector, so neither the 4-candidate nor the
+    # 64-candidate certificate can separate them and the brute-force f64 kernel must decide
     rng = np.random.default_rng(4)
     base = synth.random_features(1, 5)[0].astype(np.float64)
-    init = np.stack([base + 0.2 * i for i in range(8)])
+    init = np.stack([base + 0.005 * i for i in range(80)])
     x = np.clip(np.rint(base + rng.normal(0, 3, size=(2000, 192))), -32768, 32767).astype(np.int16)
-    labels, cent, inertia, iters, amb = tm.kmeans_fit_i16(x, 8, init, max_iter=0)
+    labels, cent, inertia, iters, amb = tm.kmeans_fit_i16(x, 80, init, max_iter=0)
     ol, oc, oin, oit = oracle.kmeans_lloyd(x.astype(np.float64), init, max_iter=0)
     assert np.array_equal(labels, ol) and amb > 0
+
+
+def test_kmeans_update_blocked_order_large_clusters(tm, oracle):
+    # clusters far above the 128-member block of the oracle's fixed summation order: centroids must still be bit-identical
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.normal(m, 40.0, size=(1500, 192)) for m in (0.0, 300.0, -250.0)]) + rng.random((4500, 192)) * 1e-3
+    init = x[[10, 1600, 3100]].copy()
+    labels, cent, inertia, iters = tm.kmeans_fit(x, 3, init, max_iter=25)[:4]
+    ol, oc, oin, oit = oracle.kmeans_lloyd(x, init, max_iter=25)
+    assert iters == oit and np.array_equal(labels, ol) and np.array_equal(cent, oc)
+    assert np.bincount(labels).max() > 1000
 
 
 # ---------------------------------------------------------------- dlquant: against the REFERENCE's own C code (oracle/_ref)

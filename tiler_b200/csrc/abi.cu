@@ -367,7 +367,7 @@ static int kmeans_fit_dev(const double *d_x, const double *d_w, int64_t n, int d
                           int nan_empty, int32_t *d_labels, double *d_cent, double *d_wsum, double *inertia, int *iters, Stage &s) {
   int32_t *d_changed = (int32_t *)s.temp(4);
   double *d_dist = (double *)s.temp((size_t)n * 8);
-  const size_t ws_bytes = kmeans_update_ws_bytes(n, k);
+  const size_t ws_bytes = kmeans_update_ws_bytes(n, k, dim);
   void *ws = s.temp(ws_bytes);
   if (s.err) return s.err;
   if (d_init) { if (cudaMemcpyAsync(d_cent, d_init, (size_t)k * dim * 8, cudaMemcpyDeviceToDevice, s.st) != cudaSuccess) return TM_ERR_CUDA; }
@@ -559,7 +559,7 @@ extern "C" int tm_kmeans_partial_step(const double *x, int64_t n, int dim, int k
   int64_t *d_counts = s.out(partial_counts, (size_t)k);
   int32_t *d_changed = (int32_t *)s.temp(4);
   double *d_dist = (double *)s.temp((size_t)(n > 0 ? n : 1) * 8);
-  const size_t ws_bytes = kmeans_update_ws_bytes(n > 0 ? n : 1, k);
+  const size_t ws_bytes = kmeans_update_ws_bytes(n > 0 ? n : 1, k, dim);
   void *ws = s.temp(ws_bytes);
   int32_t h_changed = 0;
   if (s.err == TM_OK) {

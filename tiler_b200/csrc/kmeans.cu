@@ -74,11 +74,64 @@ __global__ void hist_kernel(const int32_t *__restrict__ labels, int64_t n, int32
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) atomicAdd(counts + labels[i], 1);
 }
-// thread = (cluster, dim); members of a cluster are contiguous in `order` and in ascending point index
+// Per-cluster sums in the oracle's FIXED blocked order (tmo_kmeans_lloyd): members in ascending point index, consecutive
+// blocks of KM_BLOCK members summed sequentially from 0, block sums added sequentially from 0.  A cluster of <= KM_BLOCK
+// members is the plain sequential sum.  Members of a cluster are contiguous in `order` (stable sort by label).
+constexpr int KM_BLOCK = 128;
+
+// blocks of the clusters with more than KM_BLOCK members (they are the only ones that need partial sums)
+__global__ void kmeans_nblk_kernel(const int32_t *__restrict__ counts, int k, int32_t *__restrict__ nb) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < k) nb[c] = counts[c] > KM_BLOCK ? (counts[c] + KM_BLOCK - 1) / KM_BLOCK : 0;
+}
+
+// CTA = one member block of one large cluster; thread = dimension (strided).  partial[b][j] (and pw[b] for weights)
+template <typename T>
+__global__ void __launch_bounds__(256)
+kmeans_partial_kernel(const T *__restrict__ x, const double *__restrict__ wts, int dim, const int32_t *__restrict__ order,
+                      const int32_t *__restrict__ offs, const int32_t *__restrict__ counts, const int32_t *__restrict__ nb,
+                      const int32_t *__restrict__ poffs, int k, double *__restrict__ partial, double *__restrict__ pw) {
+  const int b = blockIdx.x;
+  // last cluster c with poffs[c] <= b: zero-width (small) clusters share their successor's offset, so this is the owner
+  int lo = 0, hi = k - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (poffs[mid] <= b) lo = mid; else hi = mid - 1;
+  }
+  const int c = lo;
+  const int rel = b - poffs[c];
+  if (rel >= nb[c]) return;   // beyond the last block (the grid is an upper bound)
+  const int cnt = counts[c], o0 = offs[c] + rel * KM_BLOCK;
+  const int m1 = min(KM_BLOCK, cnt - rel * KM_BLOCK);
+  __shared__ int32_t s_idx[KM_BLOCK];
+  for (int m = threadIdx.x; m < m1; m += blockDim.x) s_idx[m] = order[o0 + m];
+  __syncthreads();
+  for (int j = threadIdx.x; j < dim; j += blockDim.x) {
+    double s = 0.0;
+    if (wts) {
+      for (int m = 0; m < m1; ++m) {
+        const int32_t i = s_idx[m];
+        s = __dadd_rn(s, __dmul_rn(__ldg(wts + i), (double)__ldg(x + (int64_t)i * dim + j)));
+      }
+    } else {
+      for (int m = 0; m < m1; ++m) s = __dadd_rn(s, (double)__ldg(x + (int64_t)s_idx[m] * dim + j));
+    }
+    partial[(int64_t)b * dim + j] = s;
+  }
+  if (wts && threadIdx.x == 0) {
+    double ws = 0.0;
+    for (int m = 0; m < m1; ++m) ws = __dadd_rn(ws, __ldg(wts + s_idx[m]));
+    pw[b] = ws;
+  }
+}
+
+// thread = (cluster, dim): small clusters are summed here, large ones add up their block sums
 template <typename T>
 __global__ void __launch_bounds__(256)
 kmeans_update_kernel(const T *__restrict__ x, const double *__restrict__ wts, int dim, const int32_t *__restrict__ order,
-                         const int32_t *__restrict__ offs, const int32_t *__restrict__ counts, int k, int nan_empty, int divide,
+                         const int32_t *__restrict__ offs, const int32_t *__restrict__ counts, const int32_t *__restrict__ nb,
+                         const int32_t *__restrict__ poffs, const double *__restrict__ partial, const double *__restrict__ pw,
+                         int k, int nan_empty, int divide,
                          double *__restrict__ cent, int64_t *__restrict__ counts_out, double *__restrict__ wsum_out) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (int64_t)k * dim) return;
@@ -92,7 +145,12 @@ kmeans_update_kernel(const T *__restrict__ x, const double *__restrict__ wts, in
     return;
   }
   double s = 0.0, ws = 0.0;
-  if (wts) {
+  if (cnt > KM_BLOCK) {
+    const int b0 = poffs[c], n_b = nb[c];
+    for (int b = 0; b < n_b; ++b) s = __dadd_rn(s, partial[(int64_t)(b0 + b) * dim + j]);
+    if (wts) { for (int b = 0; b < n_b; ++b) ws = __dadd_rn(ws, pw[b0 + b]); }
+    else ws = (double)cnt;
+  } else if (wts) {
     for (int m = 0; m < cnt; ++m) {
       const int32_t i = order[o0 + m];
       const double w = __ldg(wts + i);
@@ -166,14 +224,17 @@ kmeanspp_f64_kernel(const double *__restrict__ x, int64_t n, int dim, int k, uns
   }
 }
 
-size_t kmeans_update_ws_bytes(int64_t n, int k) {
+static inline size_t km_al(size_t v) { return (v + 255) & ~(size_t)255; }
+// member blocks of large clusters: each has > KM_BLOCK members, so there are at most 2n / KM_BLOCK of them
+static inline int64_t km_max_blocks(int64_t n) { return 2 * (n / KM_BLOCK) + 1; }
+size_t kmeans_update_ws_bytes(int64_t n, int k, int dim) {
   size_t sort_tmp = 0, scan_tmp = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const int32_t *)nullptr, (int32_t *)nullptr, (const int32_t *)nullptr,
                                   (int32_t *)nullptr, (int)n);
   cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const int32_t *)nullptr, (int32_t *)nullptr, k);
   size_t tmp = sort_tmp > scan_tmp ? sort_tmp : scan_tmp;
-  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-  return al(tmp) + 3 * al((size_t)n * 4) + 2 * al((size_t)k * 4);
+  return km_al(tmp) + 3 * km_al((size_t)n * 4) + 4 * km_al((size_t)k * 4) + km_al((size_t)km_max_blocks(n) * dim * 8) +
+         km_al((size_t)km_max_blocks(n) * 8);
 }
 
 int launch_kmeans_assign_f64(const double *x, int64_t n, int dim, const double *cent, int k, int32_t *labels, double *dist,
@@ -194,20 +255,24 @@ static int launch_kmeans_update_t(const T *x, const double *weights, int64_t n, 
                                   int64_t *counts_out, double *wsum_out, void *ws, size_t ws_bytes, int nan_empty, int divide,
                                   cudaStream_t st) {
   if (n <= 0) return TM_OK;
-  if (ws_bytes < kmeans_update_ws_bytes(n, k)) return TM_ERR_ARG;
-  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  if (ws_bytes < kmeans_update_ws_bytes(n, k, dim)) return TM_ERR_ARG;
   size_t sort_tmp = 0, scan_tmp = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const int32_t *)nullptr, (int32_t *)nullptr, (const int32_t *)nullptr,
                                   (int32_t *)nullptr, (int)n);
   cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (const int32_t *)nullptr, (int32_t *)nullptr, k);
   size_t tmp = sort_tmp > scan_tmp ? sort_tmp : scan_tmp;
+  const int64_t max_blocks = km_max_blocks(n);
   uint8_t *p = (uint8_t *)ws;
-  void *d_tmp = p; p += al(tmp);
-  int32_t *keys_out = (int32_t *)p; p += al((size_t)n * 4);
-  int32_t *vals_in = (int32_t *)p; p += al((size_t)n * 4);
-  int32_t *vals_out = (int32_t *)p; p += al((size_t)n * 4);
-  int32_t *counts = (int32_t *)p; p += al((size_t)k * 4);
-  int32_t *offs = (int32_t *)p;
+  void *d_tmp = p; p += km_al(tmp);
+  int32_t *keys_out = (int32_t *)p; p += km_al((size_t)n * 4);
+  int32_t *vals_in = (int32_t *)p; p += km_al((size_t)n * 4);
+  int32_t *vals_out = (int32_t *)p; p += km_al((size_t)n * 4);
+  int32_t *counts = (int32_t *)p; p += km_al((size_t)k * 4);
+  int32_t *offs = (int32_t *)p; p += km_al((size_t)k * 4);
+  int32_t *nb = (int32_t *)p; p += km_al((size_t)k * 4);
+  int32_t *poffs = (int32_t *)p; p += km_al((size_t)k * 4);
+  double *partial = (double *)p; p += km_al((size_t)max_blocks * dim * 8);
+  double *pw = (double *)p;
   ProfScope prof("km_update", st);
   int bits = 1;
   while ((1ll << bits) < k) ++bits;
@@ -216,10 +281,15 @@ static int launch_kmeans_update_t(const T *x, const double *weights, int64_t n, 
   hist_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(labels, n, counts);
   cub::DeviceRadixSort::SortPairs(d_tmp, sort_tmp, labels, keys_out, vals_in, vals_out, (int)n, 0, bits, st);  // stable
   cub::DeviceScan::ExclusiveSum(d_tmp, scan_tmp, counts, offs, k, st);
+  kmeans_nblk_kernel<<<(unsigned)((k + 255) / 256), 256, 0, st>>>(counts, k, nb);
+  cub::DeviceScan::ExclusiveSum(d_tmp, scan_tmp, nb, poffs, k, st);
+  if (n > KM_BLOCK)   // otherwise no cluster can be large
+    kmeans_partial_kernel<T><<<(unsigned)max_blocks, dim >= 256 ? 256 : ((dim + 31) / 32) * 32, 0, st>>>(
+        x, weights, dim, vals_out, offs, counts, nb, poffs, k, partial, pw);
   const int64_t total = (int64_t)k * dim;
-  kmeans_update_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, weights, dim, vals_out, offs, counts, k, nan_empty, divide,
-                                                                           cent, counts_out, wsum_out);
-  note_launch(8);
+  kmeans_update_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, weights, dim, vals_out, offs, counts, nb, poffs, partial, pw,
+                                                                           k, nan_empty, divide, cent, counts_out, wsum_out);
+  note_launch(11);
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }
 

@@ -88,7 +88,7 @@ int launch_kmeanspp_f64(const double *x, int64_t n, int dim, int k, unsigned lon
 int launch_kmeans_finish(const double *sums, const int64_t *counts, int k, int dim, int nan_empty, double *cent, cudaStream_t st);
 int launch_match_plain(const int32_t *knn_idx, const uint32_t *knn_dist, int64_t n_q, const int32_t *dict_pal, int64_t n_dict,
                        int32_t *out_tile, int32_t *out_pal, uint32_t *out_err, cudaStream_t st);
-size_t kmeans_update_ws_bytes(int64_t n, int k);
+size_t kmeans_update_ws_bytes(int64_t n, int k, int dim = 192);
 int run_palette_quantise(const int32_t *rgb, const int32_t *tile_pal, int64_t n_tiles, int n_pal, int pal_size, const double *init,
                          unsigned long long seed, int max_iter, int32_t *palettes_out, int32_t *iters_out, cudaStream_t st);
 
