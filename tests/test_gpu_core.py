@@ -82,7 +82,8 @@ def test_knn_k1_exact(tm, oracle, n_dict, n_q, adv):
 
 
 @pytest.mark.parametrize("n_dict,n_q,k,adv", [(1000, 300, 64, False), (1000, 300, 64, True), (5000, 600, 8, True),
-                                              (40, 50, 64, False), (9000, 513, 33, False)])
+                                              (40, 50, 64, False), (9000, 513, 33, False), (30000, 700, 64, True),
+                                              (20011, 300, 2, False), (70, 129, 64, True)])
 def test_knn_topk_exact(tm, oracle, n_dict, n_q, k, adv):
     d = synth.random_features(n_dict, 30 + n_dict, adv)
     q = synth.random_features(n_q, 40 + n_q, adv)
@@ -101,6 +102,20 @@ def test_knn_ties_and_duplicates(tm, oracle):
     q = np.concatenate([d[:64], synth.random_features(64, 6)])
     knn = tm.KnnShort(d)
     for k in (1, 4, 64):
+        idx, dist = knn.search(q, k)
+        oi, od = oracle.knn_short(d, q, k)
+        assert np.array_equal(_u32(dist), od) and np.array_equal(idx, oi)
+    knn.close()
+
+
+def test_knn_topk_heavy_ties_across_cuts(tm, oracle):
+    # 40 distinct rows repeated 150 times each: every distance value occurs 150 times, so the streaming cuts and the
+    # final selection all have to split ties by dictionary index, exactly like the oracle's (distance, index) order
+    base = synth.random_features(40, 17)
+    d = np.tile(base, (150, 1))
+    q = np.concatenate([base[:20], synth.random_features(200, 18)])
+    knn = tm.KnnShort(d)
+    for k in (64, 7):
         idx, dist = knn.search(q, k)
         oi, od = oracle.knn_short(d, q, k)
         assert np.array_equal(_u32(dist), od) and np.array_equal(idx, oi)

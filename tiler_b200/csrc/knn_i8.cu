@@ -614,6 +614,332 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
   if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------ top-k kernel (2 <= k <= 64): 8 epilogue warps
+// Same pipeline as the k = 1 kernel: every TMEM lane quarter is drained by two warps, each taking 32 of a tile's 64
+// columns.  A thread = (query row, column half) runs its own streaming top-k over its 32 768-odd columns:
+//   * admission is branch-free and PREDICATED: `d <= tau` guards one 8-byte store and one pointer bump, nothing else
+//     (7-8 SASS instructions per distance, no shared-memory traffic, no serial select/move chain);
+//   * the candidate list of a thread is a private 2 KB strip of a global workspace that stays in L2 (148 CTAs x 256
+//     threads x 2 KB = 78 MB allocated, only admitted entries ever written);
+//   * when a strip is nearly full the warp cuts it back with a LOOSE selection: bisection on the distance value until
+//     between k and k + TK_SLACK entries survive (any threshold that keeps >= k entries is a valid tau).  That takes
+//     ~6 warp reductions instead of the 32 of an exact radix select, and with TK_CAP = 256 a row is cut ~5 times per
+//     scan instead of ~11;
+//   * at the end of the query block the two strips of a row are merged by one exact selection under the
+//     (distance, index) order -- the same order the oracle's brute force uses.
+constexpr int TK_CAP = 256;      // candidate slots per (query row, column half)
+constexpr int TK_SLACK = 32;     // a loose cut keeps between k and k + TK_SLACK candidates
+constexpr int TK_THREADS = 352;  // 8 epilogue warps + TMA warp + 2 MMA issuer warps
+
+__device__ __forceinline__ unsigned long long ldg_key(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void stg_key(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+// if (d <= tau) { *(uint2 *)waddr = {idx, d}; waddr += 8; }   -- predicated, never a branch.  Only the low word of the
+// pointer is bumped (a strip never straddles a 4 GB boundary), in place, so the pointer stays in one register pair.
+__device__ __forceinline__ void tk_admit(unsigned long long &waddr, uint32_t idx, uint32_t d, uint32_t tau) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 lo, hi;\n\t"
+      "setp.ls.u32 p, %2, %3;\n\t"
+      "@p st.global.v2.u32 [%0], {%1, %2};\n\t"
+      "mov.b64 {lo, hi}, %0;\n\t"
+      "@p add.u32 lo, lo, 8;\n\t"
+      "mov.b64 %0, {lo, hi};\n\t}\n"
+      : "+l"(waddr)
+      : "r"(idx), "r"(d), "r"(tau)
+      : "memory");
+}
+// d = nqnd - 2 (65536 HH + 256 X + LL)  (mod 2^32)
+__device__ __forceinline__ uint32_t tk_dist(uint32_t nqnd, uint32_t hh, uint32_t xx, uint32_t ll) {
+  const uint32_t a = hh * 256u + xx;
+  const uint32_t b = a * 0xFFFFFE00u + nqnd;   // - 512 a
+  return b - ll - ll;
+}
+
+// Whole warp; every lane holds NE (distance, index) entries, invalid ones as (0xFFFFFFFF, 0xFFFFFFFF); n_valid >= k.
+// Finds T, TI such that the entries with  d < T  or  (d == T and index <= TI)  number between k and k + slack
+// (exactly k when slack == 0) and contain the k smallest under the (distance, index) order.  Returns their count.
+template <int NE>
+__device__ __forceinline__ int tk_threshold(const uint32_t (&dd)[NE], const uint32_t (&ii)[NE], int n_valid, int k, int slack,
+                                            uint32_t &T_out, uint32_t &TI_out) {
+  uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    mn = min(mn, dd[i]);
+    mx = max(mx, dd[i] == 0xFFFFFFFFu ? 0u : dd[i]);
+  }
+  uint32_t lo = __reduce_min_sync(0xffffffffu, mn), hi = __reduce_max_sync(0xffffffffu, mx);
+  int c_hi = n_valid;   // invariant: count(d <= hi) == c_hi >= k
+  while (lo < hi && c_hi > k + slack) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) c += (dd[i] <= mid);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c < k) lo = mid + 1;
+    else { hi = mid; c_hi = c; }
+  }
+  T_out = hi;
+  TI_out = 0xFFFFFFFFu;
+  if (c_hi <= k + slack) return c_hi;
+  // ties at the threshold distance: keep the (k - #{d < T}) lowest indices among them (rare)
+  int cl = 0;
+#pragma unroll
+  for (int i = 0; i < NE; ++i) cl += (dd[i] < hi);
+  cl = __reduce_add_sync(0xffffffffu, cl);
+  const int need = k - cl;   // >= 1
+  uint32_t TI = 0;
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t trial = TI | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int i = 0; i < NE; ++i) c += (dd[i] == hi) && (ii[i] < trial);
+    c = __reduce_add_sync(0xffffffffu, c);
+    if (c < need) TI = trial;
+  }
+  TI_out = TI;   // need-th smallest index among the ties
+  return k;
+}
+
+// Whole warp: cut the n candidates of the strip `buf` back to between k and k + TK_SLACK; returns the new count and
+// the new admission threshold.
+__device__ __forceinline__ int tk_cut(unsigned long long *buf, int n, int k, int lane, uint32_t &tau_out) {
+  constexpr int NE = TK_CAP / 32;
+  __syncwarp();
+  uint32_t dd[NE], ii[NE];
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    const int p = i * 32 + lane;
+    const unsigned long long key = p < n ? ldg_key(buf + p) : ~0ull;
+    dd[i] = (uint32_t)(key >> 32);
+    ii[i] = (uint32_t)key;
+  }
+  uint32_t T, TI;
+  const int kept = tk_threshold<NE>(dd, ii, n, k, TK_SLACK, T, TI);
+  __syncwarp();   // every lane has its entries in registers before the strip is rewritten
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  int outp = 0;
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    const bool keep = (dd[i] < T) || (dd[i] == T && ii[i] <= TI && dd[i] != 0xFFFFFFFFu);
+    const uint32_t km = __ballot_sync(0xffffffffu, keep);
+    if (keep) stg_key(buf + outp + __popc(km & lt_mask), ((unsigned long long)dd[i] << 32) | ii[i]);
+    outp += __popc(km);
+  }
+  __syncwarp();
+  (void)kept;
+  tau_out = T;
+  return outp;
+}
+
+__global__ void __launch_bounds__(TK_THREADS, 1)
+knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUtensorMap tmap_d,
+                   const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict, int k,
+                   int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist, int tile_stride,
+                   unsigned long long *ws /* [gridDim.x][256][TK_CAP], 2 KB aligned */) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  constexpr int NST = STAGES_K1;
+  uint8_t *sB = smem;
+  int32_t *s_cnt = reinterpret_cast<int32_t *>(sB + NST * B_TILE);   // [256] candidates per thread at the end of a query block
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_cnt + 256);
+  uint64_t *full = bars, *empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + 1, *t_full = a_empty + 1,
+           *t_empty = t_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (n_dict + BN - 1) / BN;
+  const int n_qblocks = (n_q + BM - 1) / BM;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(a_full, 4);
+    mbar_init(a_empty, 2);
+    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], 8); }
+    fence_barrier_init();
+  }
+  if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == 8 && lane == 0) tma_prefetch_desc(&tmap_d);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (tmem_base != 0) __trap();   // the MMA issue code addresses TMEM with immediates
+
+  if (warp == 8) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
+        int jt = 0;
+        for (int j = 0; j < n_tiles; ++j, ++it) {
+          const uint32_t s = it % NST, r = it / NST;
+          mbar_wait(&empty[s], (r & 1) ^ 1);
+          mbar_expect_tx(&full[s], B_TILE);
+          for (int c = 0; c < 3; ++c) tma_load_2d(sB + s * B_TILE + c * CHUNK_B, &tmap_d, &full[s], c * 128, jt * BN);
+          jt += tile_stride;
+          if (jt >= n_tiles) jt -= n_tiles;
+        }
+      }
+    }
+  } else if (warp >= 9) {
+    // ===================== two MMA issuer warps (even / odd tiles) =====================
+    const uint32_t my_parity = (uint32_t)(warp - 9);
+    const uint64_t descB0 = umma_desc_sw128(smem_u32(sB));
+    uint32_t it = 0, w = 0;
+    for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
+      mbar_wait(a_full, w & 1);
+      tc_fence_after();
+      for (int j = 0; j < n_tiles; ++j, ++it) {
+        const uint32_t s = it % NST, r = it / NST;
+        const uint32_t ts = it & 1;
+        if (ts != my_parity) continue;
+        mbar_wait(&full[s], r & 1);
+        mbar_wait(&t_empty[ts], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t dB = descB0 + (uint64_t)((s * B_TILE) >> 4);
+        if (my_parity == 0) mma_i8_tile_elect<0>((uint32_t)dB); else mma_i8_tile_elect<1>((uint32_t)dB);
+        tc_commit_elect(&t_full[ts]);
+        tc_commit_elect(&empty[s]);
+      }
+      tc_commit_elect(a_empty);
+    }
+  } else {
+    // ===================== epilogue: thread = (query row, column half) =====================
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int HN = BN / 2;   // 32 columns per thread and tile
+    unsigned long long *cta_ws = ws + (size_t)blockIdx.x * 256 * TK_CAP;
+    unsigned long long *wbuf = cta_ws + (size_t)(warp * 32) * TK_CAP;   // this warp's 32 strips
+    unsigned long long *mybuf = wbuf + (size_t)lane * TK_CAP;
+    const uint32_t base_lo = (uint32_t)(uintptr_t)mybuf;
+    uint32_t it = 0, w = 0;
+    for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
+      const int64_t qi = (int64_t)qb * BM + row;
+      const bool valid = qi < n_q;
+      const uint32_t nq = valid ? __ldg(qnorm + qi) : 0u;
+      if (h == 0) {   // warps 0-3 also store the query rows into TMEM
+        mbar_wait(a_empty, (w & 1) ^ 1);
+        tc_fence_after();
+        const uint4 *src = reinterpret_cast<const uint4 *>(q_limbs + (valid ? qi : 0) * ROWB);
+#pragma unroll
+        for (int c = 0; c < 6; ++c) {
+          uint32_t r[16];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint4 t4 = valid ? __ldg(src + c * 4 + v) : make_uint4(0, 0, 0, 0);
+            r[4 * v] = t4.x; r[4 * v + 1] = t4.y; r[4 * v + 2] = t4.z; r[4 * v + 3] = t4.w;
+          }
+          tmem_st16(t_lane + A_COL + c * 16, r);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full);
+      }
+      uint32_t tau = 0xFFFFFFFEu;   // distances of 0xFFFFFFFF (masked columns) are never admitted
+      unsigned long long waddr = (unsigned long long)(uintptr_t)mybuf;   // next free slot of this thread's strip
+      int jt = 0;
+      for (int j = 0; j < n_tiles; ++j, ++it) {
+        const uint32_t ts = it & 1;
+        const int col0 = jt * BN + h * HN;
+        jt += tile_stride;
+        if (jt >= n_tiles) jt -= n_tiles;
+        const int ncol = min(HN, n_dict - col0);   // may be <= 0 on the ragged last tile
+        // dictionary norms of this tile half: independent of the MMA, so fetched before waiting for it
+        uint32_t nd[HN];
+#pragma unroll
+        for (int v = 0; v < HN / 4; ++v) {
+          const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(dnorm + col0) + v);
+          nd[4 * v] = t4.x + nq; nd[4 * v + 1] = t4.y + nq; nd[4 * v + 2] = t4.z + nq; nd[4 * v + 3] = t4.w + nq;
+        }
+        mbar_wait(&t_full[ts], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t t_acc = t_lane + ts * ACC_COLS + h * HN;
+        uint32_t pp[HN], xx[HN], lo[HN];
+#pragma unroll
+        for (int c = 0; c < HN / 16; ++c) {
+          tmem_ld16(t_acc + c * 16, reinterpret_cast<uint32_t(&)[16]>(pp[c * 16]));
+          tmem_ld16(t_acc + BN + c * 16, reinterpret_cast<uint32_t(&)[16]>(xx[c * 16]));
+          tmem_ld16(t_acc + 2 * BN + c * 16, reinterpret_cast<uint32_t(&)[16]>(lo[c * 16]));
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[ts]);
+        if (ncol >= HN) {
+#pragma unroll
+          for (int e = 0; e < HN; ++e) tk_admit(waddr, (uint32_t)(col0 + e), tk_dist(nd[e], pp[e], xx[e], lo[e]), tau);
+        } else {   // ragged last dictionary tile: columns beyond the dictionary never compete
+#pragma unroll
+          for (int e = 0; e < HN; ++e)
+            tk_admit(waddr, (uint32_t)(col0 + e), e >= ncol ? 0xFFFFFFFFu : tk_dist(nd[e], pp[e], xx[e], lo[e]), tau);
+        }
+        // the next tile may take HN more slots
+        const uint32_t wlo = (uint32_t)waddr;
+        uint32_t fullm = __ballot_sync(0xffffffffu, wlo - base_lo > (uint32_t)((TK_CAP - HN) * 8));
+        while (fullm) {
+          const int L = __ffs(fullm) - 1;
+          fullm &= fullm - 1;
+          const int nL = (int)((__shfl_sync(0xffffffffu, wlo, L) - __shfl_sync(0xffffffffu, base_lo, L)) >> 3);
+          uint32_t T;
+          const int kept = tk_cut(wbuf + (size_t)L * TK_CAP, nL, k, lane, T);
+          if (lane == L) { waddr = (unsigned long long)(uintptr_t)(mybuf + kept); tau = T; }
+        }
+      }
+      // ---- results of this query block: merge the two column halves of every row
+      s_cnt[warp * 32 + lane] = (int)(((uint32_t)waddr - base_lo) >> 3);
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      {
+        constexpr int NE = 2 * TK_CAP / 32;
+        const uint32_t lt_mask = (1u << lane) - 1u;
+        for (int L = 16 * h; L < 16 * h + 16; ++L) {   // warp (q, h) merges rows [16 h, 16 h + 16) of quarter q
+          const int64_t qL = (int64_t)qb * BM + q * 32 + L;
+          if (qL >= n_q) break;
+          const int n0 = s_cnt[q * 32 + L], n1 = s_cnt[128 + q * 32 + L];
+          const unsigned long long *b0 = cta_ws + (size_t)(q * 32 + L) * TK_CAP, *b1 = cta_ws + (size_t)(128 + q * 32 + L) * TK_CAP;
+          uint32_t dd[NE], ii[NE];
+#pragma unroll
+          for (int i = 0; i < NE / 2; ++i) {
+            const int p = i * 32 + lane;
+            const unsigned long long k0 = p < n0 ? ldg_key(b0 + p) : ~0ull, k1 = p < n1 ? ldg_key(b1 + p) : ~0ull;
+            dd[i] = (uint32_t)(k0 >> 32); ii[i] = (uint32_t)k0;
+            dd[NE / 2 + i] = (uint32_t)(k1 >> 32); ii[NE / 2 + i] = (uint32_t)k1;
+          }
+          uint32_t T = 0xFFFFFFFEu, TI = 0xFFFFFFFFu;
+          if (n0 + n1 > k) tk_threshold<NE>(dd, ii, n0 + n1, k, 0, T, TI);
+          int outp = 0;
+#pragma unroll
+          for (int i = 0; i < NE; ++i) {
+            const bool keep = (dd[i] < T) || (dd[i] == T && ii[i] <= TI && dd[i] != 0xFFFFFFFFu);
+            const uint32_t km = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+              const int pos = outp + __popc(km & lt_mask);
+              out_idx[qL * k + pos] = (int32_t)ii[i];
+              out_dist[qL * k + pos] = dd[i];
+            }
+            outp += __popc(km);
+          }
+          for (int pos = outp + lane; pos < k; pos += 32) {   // fewer than k dictionary rows: empty slots are (-1, 0xFFFFFFFF)
+            out_idx[qL * k + pos] = -1;
+            out_dist[qL * k + pos] = 0xFFFFFFFFu;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");   // strips and s_cnt are reused by the next query block
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, 512);
+}
+
 // ------------------------------------------------------------------ row sort: (distance, index) ascending, k <= 64
 __global__ void __launch_bounds__(256) knn_sort_rows_kernel(int32_t *__restrict__ idx, uint32_t *__restrict__ dist, int64_t n_q, int k) {
   const int lane = threadIdx.x & 31;
@@ -700,12 +1026,12 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
   int rc = make_tmap_rows_u8(&td, d_limbs, (uint64_t)n_dict, ROWB, BN);
   if (rc != TM_OK) return rc;
   constexpr int SMEM_K1 = STAGES_K1 * B_TILE + BM * 8 * 4 + 256 + 1024;
-  constexpr int SMEM_TK = STAGES * B_TILE + CAP * TK_ROWS * 8 + 256 + 1024;
+  constexpr int SMEM_TK = STAGES_K1 * B_TILE + 256 * 4 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(knn_i8_k1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
     if (cudaFuncSetAttribute(knn_i8_k1_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
-    if (cudaFuncSetAttribute(knn_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaFuncSetAttribute(knn_i8_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK) != cudaSuccess) return TM_ERR_CUDA;
     attr_set = true;
   }
   {
@@ -722,7 +1048,16 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
     const int grid = n_qblocks < num_ctas ? n_qblocks : num_ctas;
     if (k == 1) knn_i8_k1_kernel<1><<<grid, K1_THREADS, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride);
     else if (k == 4) knn_i8_k1_kernel<4><<<grid, K1_THREADS, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride);
-    else knn_i8_kernel<true><<<grid, 224, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride);
+    else {
+      // candidate strips: stream-ordered scratch (the pool keeps it cached between calls); 2 KB alignment keeps every
+      // strip inside one 4 GB window, so the kernel bumps only the low word of its write pointer
+      void *raw = nullptr;
+      const size_t strips = (size_t)grid * 256 * TK_CAP * 8;
+      if (cudaMallocAsync(&raw, strips + 2048, st) != cudaSuccess) return TM_ERR_NOMEM;
+      unsigned long long *strip_ws = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(raw) + 2047) & ~uintptr_t(2047));
+      knn_i8_topk_kernel<<<grid, TK_THREADS, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride, strip_ws);
+      cudaFreeAsync(raw, st);
+    }
   }
   note_launch();
   if (cudaGetLastError() != cudaSuccess) return TM_ERR_CUDA;
