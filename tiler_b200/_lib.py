@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtm_gpu.so")
+LIB_PATH = os.environ.get("TM_LIB_PATH") or os.path.join(_HERE, "libtm_gpu.so")   # TM_LIB_PATH: another build of the same library
 
 TM_OK = 0
 ERR_NAMES = {1: "TM_ERR_ARG", 2: "TM_ERR_CUDA", 3: "TM_ERR_DRIVER", 4: "TM_ERR_NOGPU", 5: "TM_ERR_NOMEM"}

@@ -16,6 +16,8 @@
 // (k = 1) or a thresholded candidate list that is cut back to the k best by a warp-cooperative radix select.
 #include "tc_common.cuh"
 #include "tm_kernels.h"
+#include <cstdlib>
+#include <cstdio>
 
 namespace tmg {
 
@@ -68,328 +70,7 @@ __global__ void __launch_bounds__(192) limb_split_kernel(const int16_t *__restri
   }
 }
 
-// ------------------------------------------------------------------ top-k state in shared memory
-// Per query row (= per epilogue thread) a candidate buffer of CAP (distance << 32 | index) keys, row-major so that a
-// warp can read one row with consecutive lanes.  A column is admitted when its distance is below the row's threshold
-// tau (the k-th smallest distance at the last cut); when a row's buffer fills, the warp cuts it back to its k
-// smallest with a 32-step radix select on the distance (ties at the threshold keep the earliest = lowest dictionary
-// index: the buffer is always in ascending index order) and tau drops to the new k-th distance.  With a random
-// column order each cut doubles the number of columns needed to refill the buffer: ~log2(N/k) cuts per row.
 constexpr int KMAX = 64;         // largest k
-constexpr int CAP = 128;         // candidate slots per row
-constexpr int TK_ROWS = 128;     // rows per CTA
-
-// explicit .shared accesses (32-bit shared-window addresses): never generic LD/ST
-__device__ __forceinline__ unsigned long long lds64(uint32_t a) {
-  unsigned long long v;
-  asm volatile("ld.shared.u64 %0, [%1];\n" : "=l"(v) : "r"(a));
-  return v;
-}
-__device__ __forceinline__ void sts64(uint32_t a, unsigned long long v) { asm volatile("st.shared.u64 [%0], %1;\n" ::"r"(a), "l"(v) : "memory"); }
-
-__device__ __forceinline__ void sts_pair(uint32_t a, uint32_t lo, uint32_t hi) {
-  asm volatile("st.shared.v2.u32 [%0], {%1, %2};\n" ::"r"(a), "r"(lo), "r"(hi) : "memory");
-}
-constexpr int SLOT = TK_ROWS * 8;   // byte stride between consecutive slots of one row ([slot][row] layout)
-
-// Whole warp: cut the n (> k) candidates of the row at shared address `buf` (slot stride SLOT) back to the k smallest
-// under the (distance, index) order; returns the k-th distance.  Dictionary tiles are scanned in a scrambled order, so
-// ties at the threshold are resolved explicitly by a second radix select on the index (rare).
-__device__ __forceinline__ uint32_t select_k(uint32_t buf, int n, int k, int lane) {
-  __syncwarp();
-  unsigned long long e[CAP / 32];
-#pragma unroll
-  for (int i = 0; i < CAP / 32; ++i) {
-    const int p = i * 32 + lane;
-    e[i] = p < n ? lds64(buf + p * SLOT) : ~0ull;
-  }
-  uint32_t T = 0;
-#pragma unroll 4
-  for (int bit = 31; bit >= 0; --bit) {
-    const uint32_t trial = T | (1u << bit);
-    int c = 0;
-#pragma unroll
-    for (int i = 0; i < CAP / 32; ++i) c += ((uint32_t)(e[i] >> 32) < trial);
-    c = __reduce_add_sync(0xffffffffu, c);
-    if (c < k) T = trial;
-  }
-  int cl = 0, ce = 0;
-#pragma unroll
-  for (int i = 0; i < CAP / 32; ++i) {
-    const uint32_t d = (uint32_t)(e[i] >> 32);
-    cl += (d < T);
-    ce += (d == T) && (i * 32 + lane < n);
-  }
-  cl = __reduce_add_sync(0xffffffffu, cl);
-  ce = __reduce_add_sync(0xffffffffu, ce);
-  const int need = k - cl;      // how many of the distance-T entries survive (1 <= need <= ce)
-  uint32_t TI = 0xFFFFFFFFu;    // largest surviving index among them
-  if (ce > need) {              // warp-uniform, rare: need-th smallest index among the distance-T entries
-    TI = 0;
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t trial = TI | (1u << bit);
-      int c = 0;
-#pragma unroll
-      for (int i = 0; i < CAP / 32; ++i) c += ((uint32_t)(e[i] >> 32) == T) && ((uint32_t)e[i] < trial) && (i * 32 + lane < n);
-      c = __reduce_add_sync(0xffffffffu, c);
-      if (c < need) TI = trial;
-    }
-  }
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  int outp = 0;
-#pragma unroll
-  for (int i = 0; i < CAP / 32; ++i) {
-    const uint32_t d = (uint32_t)(e[i] >> 32);
-    const bool keep = (d < T) || ((d == T) && ((uint32_t)e[i] <= TI) && (i * 32 + lane < n));
-    const uint32_t km = __ballot_sync(0xffffffffu, keep);
-    if (keep) sts64(buf + (outp + __popc(km & lt_mask)) * SLOT, e[i]);
-    outp += __popc(km);
-  }
-  __syncwarp();
-  return T;
-}
-
-// ------------------------------------------------------------------ main kernel
-// CTA (persistent, one per SM) = 128 query rows (resident in smem) x the whole dictionary streamed in 64-row tiles.
-// Tile j accumulates into TMEM stage j & 1 (3 x 64 columns: HH, X = HL + LH, LL).  The four epilogue warps pull a
-// finished stage into registers in two bursts (HH and X, folded to P = 256*HH + X, then LL), hand the stage back to
-// the tensor pipe immediately, and only then do the per-column arithmetic -- so the tensor pipe waits for TMEM reads,
-// not for ALU work.
-template <bool TOPK>
-__global__ void __launch_bounds__(224, 1)
-knn_i8_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUtensorMap tmap_d,
-              const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict, int k,
-              int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist, int tile_stride) {
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment (SWIZZLE_128B atoms) by pointer arithmetic only: an integer round trip would make every
-  // heap/queue access a generic LD/ST instead of LDS/STS
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int NST = TOPK ? STAGES : STAGES_K1;
-  uint8_t *sB = smem;
-  uint8_t *sX = sB + NST * B_TILE;                                      // top-k state (TOPK only)
-  uint64_t *bars = reinterpret_cast<uint64_t *>(sX + (TOPK ? CAP * TK_ROWS * 8 : 0));     // sX: candidate buffers [TK_ROWS][CAP]
-  uint64_t *full = bars;                  // [NST]  TMA -> MMA
-  uint64_t *empty = bars + NST;           // [NST]  MMA -> TMA
-  uint64_t *a_full = bars + 2 * NST;      // queries landed
-  uint64_t *a_empty = a_full + 1;         // queries no longer read by the tensor pipe
-  uint64_t *t_full = a_empty + 1;         // [2] accumulators ready
-  uint64_t *t_empty = t_full + 2;         // [2] accumulators drained
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_tiles = (n_dict + BN - 1) / BN;
-  const int n_qblocks = (n_q + BM - 1) / BM;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(a_full, 4);
-    mbar_init(a_empty, 2);
-    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], 4); }
-    fence_barrier_init();
-  }
-  if (warp == 5) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  if (warp == 4 && lane == 0) tma_prefetch_desc(&tmap_d);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (tmem_base != 0) __trap();   // the MMA issue code addresses TMEM with immediates
-
-  if (warp == 4) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x) {
-        int jt = 0;   // scrambled scan order: jt = (j * tile_stride) mod n_tiles (see host side)
-        for (int j = 0; j < n_tiles; ++j, ++it) {
-          const uint32_t s = it % NST, r = it / NST;
-          mbar_wait(&empty[s], (r & 1) ^ 1);
-          mbar_expect_tx(&full[s], B_TILE);
-          for (int c = 0; c < 3; ++c) tma_load_2d(sB + s * B_TILE + c * CHUNK_B, &tmap_d, &full[s], c * 128, jt * BN);
-          jt += tile_stride;
-          if (jt >= n_tiles) jt -= n_tiles;
-        }
-      }
-    }
-  } else if (warp >= 5) {
-    // ===================== two MMA issuer warps: warp 5 takes even dictionary tiles (TMEM stage 0), warp 6 odd ones
-    // (stage 1).  A single issuing thread cannot sustain one 32-cycle int8 MMA per 32 cycles; two can.  Whole warp runs
-    // the loop, one elected lane issues. =====================
-    {
-      const uint32_t my_parity = (uint32_t)(warp - 5);
-      constexpr uint32_t I_SS = make_idesc(kDFmtS32, kFmtS8, kFmtS8, BM, BN);
-      constexpr uint32_t I_SU = make_idesc(kDFmtS32, kFmtS8, kFmtU8, BM, BN);
-      constexpr uint32_t I_US = make_idesc(kDFmtS32, kFmtU8, kFmtS8, BM, BN);
-      constexpr uint32_t I_UU = make_idesc(kDFmtS32, kFmtU8, kFmtU8, BM, BN);
-      const uint32_t tA = tmem_base + A_COL;   // query rows: lane = row, K-step ks = columns [8*ks, 8*ks + 8)
-      const uint64_t descB0 = umma_desc_sw128(smem_u32(sB));
-      // K-step ks (32 bytes) of a B tile lives in chunk ks/4 at byte (ks%4)*32; offsets in 16-byte units
-      auto koffB = [](int ks) { return (uint64_t)(((ks >> 2) * CHUNK_B + (ks & 3) * 32) >> 4); };
-      uint32_t it = 0, w = 0;
-      for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
-        mbar_wait(a_full, w & 1);
-        tc_fence_after();
-        for (int j = 0; j < n_tiles; ++j, ++it) {
-          const uint32_t s = it % NST, r = it / NST;
-          const uint32_t ts = it & 1;
-          if (ts != my_parity) continue;
-          mbar_wait(&full[s], r & 1);
-          mbar_wait(&t_empty[ts], ((it >> 1) & 1) ^ 1);
-          tc_fence_after();
-          const uint64_t dB = descB0 + (uint64_t)((s * B_TILE) >> 4);
-          const uint32_t acc = tmem_base + ts * ACC_COLS;
-          if (my_parity == 0) mma_i8_tile_elect<0>((uint32_t)dB); else mma_i8_tile_elect<1>((uint32_t)dB);   // HH, HL, LH, LL: 24 MMAs
-          tc_commit_elect(&t_full[ts]);
-          tc_commit_elect(&empty[s]);
-        }
-        tc_commit_elect(a_empty);
-      }
-    }
-  } else {
-    // ===================== epilogue: thread = query row =====================
-    const int row = warp * 32 + lane;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-    uint32_t it = 0, w = 0;
-    for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
-      const int64_t qi = (int64_t)qb * BM + row;
-      const bool valid = qi < n_q;
-      const uint32_t nq = valid ? __ldg(qnorm + qi) : 0u;
-      // this thread's query row (384 limb bytes = 96 words) -> TMEM columns [A_COL, A_COL + 96) of its lane,
-      // once the tensor pipe has finished reading the previous block's rows
-      mbar_wait(a_empty, (w & 1) ^ 1);
-      tc_fence_after();
-      {
-        const uint4 *src = reinterpret_cast<const uint4 *>(q_limbs + (valid ? qi : 0) * ROWB);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          uint32_t r[16];
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const uint4 t4 = valid ? __ldg(src + c * 4 + v) : make_uint4(0, 0, 0, 0);
-            r[4 * v] = t4.x; r[4 * v + 1] = t4.y; r[4 * v + 2] = t4.z; r[4 * v + 3] = t4.w;
-          }
-          tmem_st16(t_lane + A_COL + c * 16, r);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full);
-      }
-      uint32_t best_d = 0xFFFFFFFFu;
-      int32_t best_i = -1;
-      uint32_t tau = 0xFFFFFFFEu;   // distances of 0xFFFFFFFF (masked columns) are never admitted
-      const uint32_t wbuf = smem_u32(sX) + warp * 32 * 8;   // this warp's 32 candidate rows, [slot][row] layout
-      const uint32_t mybuf = wbuf + lane * 8;
-      uint32_t waddr = mybuf;                               // next free slot of this thread's row
-      int jt = 0;
-      for (int j = 0; j < n_tiles; ++j, ++it) {
-        const uint32_t ts = it & 1;
-        const int col0 = jt * BN;
-        jt += tile_stride;
-        if (jt >= n_tiles) jt -= n_tiles;
-        const int ncol = min(BN, n_dict - col0);
-        mbar_wait(&t_full[ts], (it >> 1) & 1);
-        tc_fence_after();
-        const uint32_t t_acc = t_lane + ts * ACC_COLS;
-        uint32_t pp[BN], lo[BN];
-#pragma unroll
-        for (int c = 0; c < BN / 16; ++c) {
-          tmem_ld16(t_acc + c * 16, reinterpret_cast<uint32_t(&)[16]>(pp[c * 16]));            // HH
-          tmem_ld16(t_acc + BN + c * 16, reinterpret_cast<uint32_t(&)[16]>(lo[c * 16]));       // X
-        }
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < BN; ++e) pp[e] = (pp[e] << 8) + lo[e];                              // P = 256*HH + X
-#pragma unroll
-        for (int c = 0; c < BN / 16; ++c) tmem_ld16(t_acc + 2 * BN + c * 16, reinterpret_cast<uint32_t(&)[16]>(lo[c * 16]));  // LL
-        tmem_ld_wait();
-        tc_fence_before();          // the stage is in registers: hand it back to the tensor pipe
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[ts]);
-#pragma unroll
-        for (int ch = 0; ch < BN / 16; ++ch) {
-          uint32_t nd[16];
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(dnorm + col0 + ch * 16) + v);
-            nd[4 * v] = t4.x; nd[4 * v + 1] = t4.y; nd[4 * v + 2] = t4.z; nd[4 * v + 3] = t4.w;
-          }
-          // d = nq + nd - 2*(256*P + LL)  (mod 2^32); m = min over the 16 columns
-          uint32_t dv[16];
-          uint32_t m = 0xFFFFFFFFu;
-#pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            uint32_t d = nq + nd[e];
-            d -= pp[ch * 16 + e] << 9;
-            d -= lo[ch * 16 + e] << 1;
-            dv[e] = d;
-            m = min(m, d);
-          }
-          const int cbase = ch * 16;
-          if (ncol < BN) {   // ragged last dictionary tile: columns beyond the dictionary never compete
-            m = 0xFFFFFFFFu;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              if (cbase + e >= ncol) dv[e] = 0xFFFFFFFFu;
-              m = min(m, dv[e]);
-            }
-          }
-          if (!TOPK) {
-            if (m <= best_d) {   // rare once a good candidate has been seen; ties go to the lower dictionary index
-#pragma unroll
-              for (int e = 0; e < 16; ++e) {
-                const int32_t ci = col0 + cbase + e;
-                if (dv[e] < best_d || (dv[e] == best_d && dv[e] != 0xFFFFFFFFu && ci < best_i)) { best_d = dv[e]; best_i = ci; }
-              }
-            }
-          } else {
-            // branch-free admission: always store at the row's next free slot, advance it only when admitted
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const uint32_t d = dv[e];
-              sts_pair(waddr, (uint32_t)(col0 + cbase + e), d);
-              waddr += (d <= tau) ? (uint32_t)SLOT : 0u;   // <=: an equal distance with a lower index may still win
-            }
-            // the next chunk may take 16 more slots
-            uint32_t fullm = __ballot_sync(0xffffffffu, waddr > mybuf + (CAP - 17) * SLOT);
-            while (fullm) {
-              const int L = __ffs(fullm) - 1;
-              fullm &= fullm - 1;
-              const int nL = (int)((__shfl_sync(0xffffffffu, waddr, L) - (wbuf + L * 8)) / SLOT);
-              const uint32_t T = select_k(wbuf + L * 8, nL, k, lane);
-              if (lane == L) { waddr = mybuf + k * SLOT; tau = T; }
-            }
-          }
-        }
-      }
-      // ---- results of this query block
-      if (!TOPK) {
-        if (valid) { out_idx[qi] = best_i; out_dist[qi] = best_d; }
-      } else {
-        // final cut + coalesced write-out: the warp walks its 32 rows
-        for (int L = 0; L < 32; ++L) {
-          int nL = (int)((__shfl_sync(0xffffffffu, waddr, L) - (wbuf + L * 8)) / SLOT);
-          const uint32_t b = wbuf + L * 8;
-          if (nL > k) { select_k(b, nL, k, lane); nL = k; }
-          __syncwarp();
-          const int64_t qL = (int64_t)qb * BM + warp * 32 + L;
-          if (qL < n_q) {
-            for (int p = lane; p < k; p += 32) {
-              const unsigned long long key = p < nL ? lds64(b + p * SLOT) : ~0ull;
-              out_idx[qL * k + p] = (int32_t)(uint32_t)key;          // empty slots: 0xFFFFFFFF = -1
-              out_dist[qL * k + p] = (uint32_t)(key >> 32);
-            }
-          }
-          __syncwarp();
-        }
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, 512);
-}
 
 // ------------------------------------------------------------------ k = 1 kernel: 8 epilogue warps
 // Same pipeline as above, but every TMEM lane quarter is drained by TWO warps (w and w + 4 may both address quarter
@@ -628,7 +309,7 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
 //   * at the end of the query block the two strips of a row are merged by one exact selection under the
 //     (distance, index) order -- the same order the oracle's brute force uses.
 constexpr int TK_CAP = 256;      // candidate slots per (query row, column half)
-constexpr int TK_SLACK = 32;     // a loose cut keeps between k and k + TK_SLACK candidates
+constexpr int TK_SLACK = 16;     // a loose cut keeps between k and k + TK_SLACK candidates
 constexpr int TK_THREADS = 352;  // 8 epilogue warps + TMA warp + 2 MMA issuer warps
 
 __device__ __forceinline__ unsigned long long ldg_key(const unsigned long long *p) {
@@ -663,6 +344,38 @@ __device__ __forceinline__ uint32_t tk_dist(uint32_t nqnd, uint32_t hh, uint32_t
 // Whole warp; every lane holds NE (distance, index) entries, invalid ones as (0xFFFFFFFF, 0xFFFFFFFF); n_valid >= k.
 // Finds T, TI such that the entries with  d < T  or  (d == T and index <= TI)  number between k and k + slack
 // (exactly k when slack == 0) and contain the k smallest under the (distance, index) order.  Returns their count.
+#ifdef TM_TK_TIMING
+#define TKT_DECL long long tkt[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tkt_t = clock64_volatile();
+#define TKT(i) { const long long t_ = clock64_volatile(); tkt[i] += t_ - tkt_t; tkt_t = t_; }
+#define TKT_PRINT(role, n) if (blockIdx.x == 1 && lane == 0) printf("%s warp %d tiles %d: %lld %lld %lld %lld %lld %lld %lld %lld\n", role, warp, n, tkt[0] / (n), tkt[1] / (n), tkt[2] / (n), tkt[3] / (n), tkt[4] / (n), tkt[5] / (n), tkt[6] / (n), tkt[7] / (n));
+#else
+#define TKT_DECL
+#define TKT(i)
+#define TKT_PRINT(role, n)
+#endif
+
+// One 16-column unit of a tile: distances first (pure arithmetic, full ILP), then admission PAIR by PAIR behind a warp
+// vote.  A memory instruction costs LSU issue bandwidth even when its predicate is false (32 predicated stores per
+// tile and warp were ~40 % of the kernel), so the predicated store pair is only ISSUED when some lane of the warp
+// admits one of the two columns -- late in the scan that is one pair in three.
+__device__ __forceinline__ void tk_unit(unsigned long long &waddr, uint32_t tau, uint32_t nq, int col, int nvalid, const uint32_t (&nd)[16],
+                                        uint32_t (&pp)[16], const uint32_t (&xx)[16], const uint32_t (&lo)[16]) {
+#pragma unroll
+  for (int e = 0; e < 16; ++e) pp[e] = tk_dist(nd[e] + nq, pp[e], xx[e], lo[e]);
+  if (nvalid < 16) {   // ragged last dictionary tile: columns beyond the dictionary never compete
+#pragma unroll
+    for (int e = 0; e < 16; ++e) if (e >= nvalid) pp[e] = 0xFFFFFFFFu;
+  }
+#pragma unroll
+  for (int e = 0; e < 16; e += 2) {
+    const uint32_t m = min(pp[e], pp[e + 1]);
+    if (__builtin_expect(__any_sync(0xffffffffu, m <= tau), 0)) {
+      tk_admit(waddr, (uint32_t)(col + e), pp[e], tau);
+      tk_admit(waddr, (uint32_t)(col + e + 1), pp[e + 1], tau);
+    }
+  }
+}
+
 template <int NE>
 __device__ __forceinline__ int tk_threshold(const uint32_t (&dd)[NE], const uint32_t (&ii)[NE], int n_valid, int k, int slack,
                                             uint32_t &T_out, uint32_t &TI_out) {
@@ -707,7 +420,7 @@ __device__ __forceinline__ int tk_threshold(const uint32_t (&dd)[NE], const uint
 
 // Whole warp: cut the n candidates of the strip `buf` back to between k and k + TK_SLACK; returns the new count and
 // the new admission threshold.
-__device__ __forceinline__ int tk_cut(unsigned long long *buf, int n, int k, int lane, uint32_t &tau_out) {
+__device__ __forceinline__ int tk_cut(unsigned long long *buf, int n, int k, int slack, int lane, uint32_t &tau_out) {
   constexpr int NE = TK_CAP / 32;
   __syncwarp();
   uint32_t dd[NE], ii[NE];
@@ -719,7 +432,7 @@ __device__ __forceinline__ int tk_cut(unsigned long long *buf, int n, int k, int
     ii[i] = (uint32_t)key;
   }
   uint32_t T, TI;
-  const int kept = tk_threshold<NE>(dd, ii, n, k, TK_SLACK, T, TI);
+  const int kept = tk_threshold<NE>(dd, ii, n, k, slack, T, TI);
   __syncwarp();   // every lane has its entries in registers before the strip is rewritten
   const uint32_t lt_mask = (1u << lane) - 1u;
   int outp = 0;
@@ -740,7 +453,7 @@ __global__ void __launch_bounds__(TK_THREADS, 1)
 knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUtensorMap tmap_d,
                    const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict, int k,
                    int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist, int tile_stride,
-                   unsigned long long *ws /* [gridDim.x][256][TK_CAP], 2 KB aligned */) {
+                   unsigned long long *ws /* [gridDim.x][256][TK_CAP], 2 KB aligned */, int slack, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int NST = STAGES_K1;
@@ -748,8 +461,8 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
   int32_t *s_cnt = reinterpret_cast<int32_t *>(sB + NST * B_TILE);   // [256] candidates per thread at the end of a query block
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_cnt + 256);
   uint64_t *full = bars, *empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + 1, *t_full = a_empty + 1,
-           *t_empty = t_full + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+           *t_empty = t_full + 2, *issued = t_empty + 2;   // issued[2]: the MMAs of a tile have been handed to the tensor pipe
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(issued + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (n_dict + BN - 1) / BN;
@@ -759,7 +472,7 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_full, 4);
     mbar_init(a_empty, 2);
-    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], 8); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], 8); mbar_init(&issued[g], 1); }
     fence_barrier_init();
   }
   if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -779,6 +492,7 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         for (int j = 0; j < n_tiles; ++j, ++it) {
           const uint32_t s = it % NST, r = it / NST;
           mbar_wait(&empty[s], (r & 1) ^ 1);
+          if (dbg == 7) { mbar_arrive(&full[s]); continue; }   // timing experiment: no dictionary traffic
           mbar_expect_tx(&full[s], B_TILE);
           for (int c = 0; c < 3; ++c) tma_load_2d(sB + s * B_TILE + c * CHUNK_B, &tmap_d, &full[s], c * 128, jt * BN);
           jt += tile_stride;
@@ -791,23 +505,31 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
     const uint32_t my_parity = (uint32_t)(warp - 9);
     const uint64_t descB0 = umma_desc_sw128(smem_u32(sB));
     uint32_t it = 0, w = 0;
+    TKT_DECL
     for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
       mbar_wait(a_full, w & 1);
       tc_fence_after();
+      TKT(0)
       for (int j = 0; j < n_tiles; ++j, ++it) {
         const uint32_t s = it % NST, r = it / NST;
         const uint32_t ts = it & 1;
         if (ts != my_parity) continue;
         mbar_wait(&full[s], r & 1);
+        TKT(1)
         mbar_wait(&t_empty[ts], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
+        TKT(2)
         const uint64_t dB = descB0 + (uint64_t)((s * B_TILE) >> 4);
         if (my_parity == 0) mma_i8_tile_elect<0>((uint32_t)dB); else mma_i8_tile_elect<1>((uint32_t)dB);
         tc_commit_elect(&t_full[ts]);
         tc_commit_elect(&empty[s]);
+        if (lane == 0) mbar_arrive(&issued[ts]);
+        __syncwarp();
+        TKT(3)
       }
       tc_commit_elect(a_empty);
     }
+    TKT_PRINT("mma [a_full, full, t_empty, issue]", (int)(it / 2))
   } else {
     // ===================== epilogue: thread = (query row, column half) =====================
     const int q = warp & 3, h = warp >> 2;
@@ -819,6 +541,7 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
     unsigned long long *mybuf = wbuf + (size_t)lane * TK_CAP;
     const uint32_t base_lo = (uint32_t)(uintptr_t)mybuf;
     uint32_t it = 0, w = 0;
+    TKT_DECL
     for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
       const int64_t qi = (int64_t)qb * BM + row;
       const bool valid = qi < n_q;
@@ -842,45 +565,47 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full);
       }
-      uint32_t tau = 0xFFFFFFFEu;   // distances of 0xFFFFFFFF (masked columns) are never admitted
+      uint32_t tau = (dbg == 1 || dbg >= 5) ? 0u : 0xFFFFFFFEu;
+   // distances of 0xFFFFFFFF (masked columns) are never admitted
       unsigned long long waddr = (unsigned long long)(uintptr_t)mybuf;   // next free slot of this thread's strip
       int jt = 0;
+      TKT(0)
       for (int j = 0; j < n_tiles; ++j, ++it) {
         const uint32_t ts = it & 1;
         const int col0 = jt * BN + h * HN;
         jt += tile_stride;
         if (jt >= n_tiles) jt -= n_tiles;
-        const int ncol = min(HN, n_dict - col0);   // may be <= 0 on the ragged last tile
         // dictionary norms of this tile half: independent of the MMA, so fetched before waiting for it
-        uint32_t nd[HN];
+        uint32_t ndA[16], ndB[16];
 #pragma unroll
-        for (int v = 0; v < HN / 4; ++v) {
+        for (int v = 0; v < 4; ++v) {
           const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(dnorm + col0) + v);
-          nd[4 * v] = t4.x + nq; nd[4 * v + 1] = t4.y + nq; nd[4 * v + 2] = t4.z + nq; nd[4 * v + 3] = t4.w + nq;
+          ndA[4 * v] = t4.x; ndA[4 * v + 1] = t4.y; ndA[4 * v + 2] = t4.z; ndA[4 * v + 3] = t4.w;
+          const uint4 u4 = __ldg(reinterpret_cast<const uint4 *>(dnorm + col0 + 16) + v);
+          ndB[4 * v] = u4.x; ndB[4 * v + 1] = u4.y; ndB[4 * v + 2] = u4.z; ndB[4 * v + 3] = u4.w;
         }
+        TKT(1)
         mbar_wait(&t_full[ts], (it >> 1) & 1);
         tc_fence_after();
+        TKT(2)
         const uint32_t t_acc = t_lane + ts * ACC_COLS + h * HN;
-        uint32_t pp[HN], xx[HN], lo[HN];
-#pragma unroll
-        for (int c = 0; c < HN / 16; ++c) {
-          tmem_ld16(t_acc + c * 16, reinterpret_cast<uint32_t(&)[16]>(pp[c * 16]));
-          tmem_ld16(t_acc + BN + c * 16, reinterpret_cast<uint32_t(&)[16]>(xx[c * 16]));
-          tmem_ld16(t_acc + 2 * BN + c * 16, reinterpret_cast<uint32_t(&)[16]>(lo[c * 16]));
-        }
+        uint32_t ppA[16], xxA[16], loA[16], ppB[16], xxB[16], loB[16];
+        tmem_ld16(t_acc, ppA);
+        tmem_ld16(t_acc + BN, xxA);
+        tmem_ld16(t_acc + 2 * BN, loA);
+        tmem_ld16(t_acc + 16, ppB);
+        tmem_ld16(t_acc + BN + 16, xxB);
+        tmem_ld16(t_acc + 2 * BN + 16, loB);
         tmem_ld_wait();
-        tc_fence_before();
+        tc_fence_before();          // the whole tile is in registers: hand the stage back to the tensor pipe
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[ts]);
-        if (ncol >= HN) {
-#pragma unroll
-          for (int e = 0; e < HN; ++e) tk_admit(waddr, (uint32_t)(col0 + e), tk_dist(nd[e], pp[e], xx[e], lo[e]), tau);
-        } else {   // ragged last dictionary tile: columns beyond the dictionary never compete
-#pragma unroll
-          for (int e = 0; e < HN; ++e)
-            tk_admit(waddr, (uint32_t)(col0 + e), e >= ncol ? 0xFFFFFFFFu : tk_dist(nd[e], pp[e], xx[e], lo[e]), tau);
-        }
-        // the next tile may take HN more slots
+        TKT(3)
+        tk_unit(waddr, tau, nq, col0, n_dict - col0, ndA, ppA, xxA, loA);
+        TKT(4)
+        tk_unit(waddr, tau, nq, col0 + 16, n_dict - col0 - 16, ndB, ppB, xxB, loB);
+        TKT(5)
+        // the next check is a tile (HN admissions at most) away
         const uint32_t wlo = (uint32_t)waddr;
         uint32_t fullm = __ballot_sync(0xffffffffu, wlo - base_lo > (uint32_t)((TK_CAP - HN) * 8));
         while (fullm) {
@@ -888,9 +613,10 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
           fullm &= fullm - 1;
           const int nL = (int)((__shfl_sync(0xffffffffu, wlo, L) - __shfl_sync(0xffffffffu, base_lo, L)) >> 3);
           uint32_t T;
-          const int kept = tk_cut(wbuf + (size_t)L * TK_CAP, nL, k, lane, T);
+          const int kept = tk_cut(wbuf + (size_t)L * TK_CAP, nL, k, slack, lane, T);
           if (lane == L) { waddr = (unsigned long long)(uintptr_t)(mybuf + kept); tau = T; }
         }
+        TKT(6)
       }
       // ---- results of this query block: merge the two column halves of every row
       s_cnt[warp * 32 + lane] = (int)(((uint32_t)waddr - base_lo) >> 3);
@@ -932,7 +658,9 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         }
       }
       asm volatile("bar.sync 1, 256;\n" ::: "memory");   // strips and s_cnt are reused by the next query block
+      TKT(7)
     }
+    TKT_PRINT("epi [qblock setup, nd loads, t_full wait, ld+release, unit A, unit B, cuts, merge]", (int)it)
   }
 
   tc_fence_before();
@@ -1026,7 +754,7 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
   int rc = make_tmap_rows_u8(&td, d_limbs, (uint64_t)n_dict, ROWB, BN);
   if (rc != TM_OK) return rc;
   constexpr int SMEM_K1 = STAGES_K1 * B_TILE + BM * 8 * 4 + 256 + 1024;
-  constexpr int SMEM_TK = STAGES_K1 * B_TILE + 256 * 4 + 256 + 1024;
+  constexpr int SMEM_TK = STAGES_K1 * B_TILE + 256 * 4 + 512 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(knn_i8_k1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
@@ -1055,7 +783,12 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
       const size_t strips = (size_t)grid * 256 * TK_CAP * 8;
       if (cudaMallocAsync(&raw, strips + 2048, st) != cudaSuccess) return TM_ERR_NOMEM;
       unsigned long long *strip_ws = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(raw) + 2047) & ~uintptr_t(2047));
-      knn_i8_topk_kernel<<<grid, TK_THREADS, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride, strip_ws);
+      static int slack = -1, dbg = 0;   // TM_TK_SLACK / TM_TK_DBG: tuning and timing experiments (dbg = 1 admits nothing)
+      if (slack < 0) {
+        slack = getenv("TM_TK_SLACK") ? atoi(getenv("TM_TK_SLACK")) : TK_SLACK;
+        dbg = getenv("TM_TK_DBG") ? atoi(getenv("TM_TK_DBG")) : 0;
+      }
+      knn_i8_topk_kernel<<<grid, TK_THREADS, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride, strip_ws, slack, dbg);
       cudaFreeAsync(raw, st);
     }
   }

@@ -43,16 +43,46 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the hardware parks the thread until the phase flips or the hint expires, so a
+// waiting warp does not burn issue slots that the arithmetic warps of the same scheduler need.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t *bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ long long clock64_volatile() {
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;\n" : "=l"(t));
+  return t;
+}
 // Bounded wait: a protocol bug must fault the kernel (trap -> launch error the host reports), never hang the GPU.
+// The spin loop is three instructions; the clock is read only once every 256 failed probes.
 #ifndef TM_MBAR_TIMEOUT_CYCLES
 #define TM_MBAR_TIMEOUT_CYCLES (8ll * 1000 * 1000 * 1000)
 #endif
+#ifndef TM_WAIT_HINT
+#define TM_WAIT_HINT 1
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  long long t0 = 0;
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {   // try_wait itself suspends the thread for a hardware-bounded time
-    if ((++spins & 0x3FF) == 0 && clock64() - t0 > TM_MBAR_TIMEOUT_CYCLES) __trap();
+#if TM_WAIT_HINT
+  while (!mbar_try_wait_hint(bar, parity, 100000u)) {
+#else
+  while (!mbar_try_wait(bar, parity)) {
+#endif
+    if ((++spins & 0xFF) == 0) {
+      const long long t = clock64_volatile();
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > TM_MBAR_TIMEOUT_CYCLES) __trap();
+    }
   }
 }
 
