@@ -83,7 +83,7 @@ template <int KS>
 __global__ void __launch_bounds__(K1_THREADS, 1)
 knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUtensorMap tmap_d,
                  const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict,
-                 int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist, int tile_stride) {
+                 int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist, int tile_stride, int dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int NST = STAGES_K1;
@@ -122,6 +122,7 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
         for (int j = 0; j < n_tiles; ++j, ++it) {
           const uint32_t s = it % NST, r = it / NST;
           mbar_wait(&empty[s], (r & 1) ^ 1);
+          if (dbg & 2) { mbar_arrive(&full[s]); jt += tile_stride; if (jt >= n_tiles) jt -= n_tiles; continue; }   // timing experiment: no dictionary traffic
           mbar_expect_tx(&full[s], B_TILE);
           for (int c = 0; c < 3; ++c) tma_load_2d(sB + s * B_TILE + c * CHUNK_B, &tmap_d, &full[s], c * 128, jt * BN);
           jt += tile_stride;
@@ -151,8 +152,7 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
         mbar_wait(&t_empty[ts], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint64_t dB = descB0 + (uint64_t)((s * B_TILE) >> 4);
-        const uint32_t acc = tmem_base + ts * ACC_COLS;
-        if (my_parity == 0) mma_i8_tile_elect<0>((uint32_t)dB); else mma_i8_tile_elect<1>((uint32_t)dB);
+        if (!(dbg & 4)) { if (my_parity == 0) mma_i8_tile_elect<0>((uint32_t)dB); else mma_i8_tile_elect<1>((uint32_t)dB); }
         tc_commit_elect(&t_full[ts]);
         tc_commit_elect(&empty[s]);
       }
@@ -366,12 +366,19 @@ __device__ __forceinline__ void tk_unit(unsigned long long &waddr, uint32_t tau,
 #pragma unroll
     for (int e = 0; e < 16; ++e) if (e >= nvalid) pp[e] = 0xFFFFFFFFu;
   }
+  // The eight "does any lane admit pair e" questions of a unit are answered by ONE warp reduction (per-lane bit mask,
+  // OR-reduced): eight vote -> branch chains in a row cost ~35 cycles of latency each.
+  uint32_t mine = 0;
 #pragma unroll
-  for (int e = 0; e < 16; e += 2) {
-    const uint32_t m = min(pp[e], pp[e + 1]);
-    if (__builtin_expect(__any_sync(0xffffffffu, m <= tau), 0)) {
-      tk_admit(waddr, (uint32_t)(col + e), pp[e], tau);
-      tk_admit(waddr, (uint32_t)(col + e + 1), pp[e + 1], tau);
+  for (int e = 0; e < 8; ++e) mine |= (min(pp[2 * e], pp[2 * e + 1]) <= tau) ? (1u << e) : 0u;
+  const uint32_t any = __reduce_or_sync(0xffffffffu, mine);
+  if (any != 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (any & (1u << e)) {
+        tk_admit(waddr, (uint32_t)(col + 2 * e), pp[2 * e], tau);
+        tk_admit(waddr, (uint32_t)(col + 2 * e + 1), pp[2 * e + 1], tau);
+      }
     }
   }
 }
@@ -461,8 +468,8 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
   int32_t *s_cnt = reinterpret_cast<int32_t *>(sB + NST * B_TILE);   // [256] candidates per thread at the end of a query block
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_cnt + 256);
   uint64_t *full = bars, *empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + 1, *t_full = a_empty + 1,
-           *t_empty = t_full + 2, *issued = t_empty + 2;   // issued[2]: the MMAs of a tile have been handed to the tensor pipe
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(issued + 2);
+           *t_empty = t_full + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (n_dict + BN - 1) / BN;
@@ -472,7 +479,7 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_full, 4);
     mbar_init(a_empty, 2);
-    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], 8); mbar_init(&issued[g], 1); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], 8); }
     fence_barrier_init();
   }
   if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -492,7 +499,7 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         for (int j = 0; j < n_tiles; ++j, ++it) {
           const uint32_t s = it % NST, r = it / NST;
           mbar_wait(&empty[s], (r & 1) ^ 1);
-          if (dbg == 7) { mbar_arrive(&full[s]); continue; }   // timing experiment: no dictionary traffic
+          if (dbg & 2) { mbar_arrive(&full[s]); jt += tile_stride; if (jt >= n_tiles) jt -= n_tiles; continue; }   // timing experiment: no dictionary traffic
           mbar_expect_tx(&full[s], B_TILE);
           for (int c = 0; c < 3; ++c) tma_load_2d(sB + s * B_TILE + c * CHUNK_B, &tmap_d, &full[s], c * 128, jt * BN);
           jt += tile_stride;
@@ -520,11 +527,9 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         tc_fence_after();
         TKT(2)
         const uint64_t dB = descB0 + (uint64_t)((s * B_TILE) >> 4);
-        if (my_parity == 0) mma_i8_tile_elect<0>((uint32_t)dB); else mma_i8_tile_elect<1>((uint32_t)dB);
+        if (!(dbg & 4)) { if (my_parity == 0) mma_i8_tile_elect<0>((uint32_t)dB); else mma_i8_tile_elect<1>((uint32_t)dB); }
         tc_commit_elect(&t_full[ts]);
         tc_commit_elect(&empty[s]);
-        if (lane == 0) mbar_arrive(&issued[ts]);
-        __syncwarp();
         TKT(3)
       }
       tc_commit_elect(a_empty);
@@ -565,7 +570,7 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full);
       }
-      uint32_t tau = (dbg == 1 || dbg >= 5) ? 0u : 0xFFFFFFFEu;
+      uint32_t tau = (dbg & 1) ? 0u : 0xFFFFFFFEu;
    // distances of 0xFFFFFFFF (masked columns) are never admitted
       unsigned long long waddr = (unsigned long long)(uintptr_t)mybuf;   // next free slot of this thread's strip
       int jt = 0;
@@ -601,9 +606,9 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[ts]);
         TKT(3)
-        tk_unit(waddr, tau, nq, col0, n_dict - col0, ndA, ppA, xxA, loA);
+        if (!(dbg & 8)) tk_unit(waddr, tau, nq, col0, n_dict - col0, ndA, ppA, xxA, loA);
         TKT(4)
-        tk_unit(waddr, tau, nq, col0 + 16, n_dict - col0 - 16, ndB, ppB, xxB, loB);
+        if (!(dbg & 8)) tk_unit(waddr, tau, nq, col0 + 16, n_dict - col0 - 16, ndB, ppB, xxB, loB);
         TKT(5)
         // the next check is a tile (HN admissions at most) away
         const uint32_t wlo = (uint32_t)waddr;
@@ -774,8 +779,10 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
     while (gcd(tile_stride, n_tiles_h) != 1) ++tile_stride;
     const int n_qblocks = (n_q + BM - 1) / BM;
     const int grid = n_qblocks < num_ctas ? n_qblocks : num_ctas;
-    if (k == 1) knn_i8_k1_kernel<1><<<grid, K1_THREADS, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride);
-    else if (k == 4) knn_i8_k1_kernel<4><<<grid, K1_THREADS, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride);
+    static int kdbg = -1;   // TM_TK_DBG bits: 1 admit nothing (top-k), 2 no dictionary loads, 4 no MMAs, 8 no epilogue arithmetic
+    if (kdbg < 0) kdbg = getenv("TM_TK_DBG") ? atoi(getenv("TM_TK_DBG")) : 0;
+    if (k == 1) knn_i8_k1_kernel<1><<<grid, K1_THREADS, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride, kdbg);
+    else if (k == 4) knn_i8_k1_kernel<4><<<grid, K1_THREADS, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride, kdbg);
     else {
       // candidate strips: stream-ordered scratch (the pool keeps it cached between calls); 2 KB alignment keeps every
       // strip inside one 4 GB window, so the kernel bumps only the low word of its write pointer
