@@ -173,6 +173,31 @@ int tm_match_tiles_feat(tm_matcher *m, const int16_t *feat, int64_t n_q, int k, 
 /* the dictionary's own features (device pointer, [n_dict][192]) for inspection/tests */
 int tm_matcher_dict_features(tm_matcher *m, int16_t *out);
 
+
+/* ---------------------------------------------------------------- batched: motion search + Reconstruct
+   (TFrame.PredictMotion :1154-1282, TFrame.Reconstruct :1430-1679, TTilingEncoder.Reconstruct :1928-1962) */
+/* DoDCTs: features of the 8x8 window at every pixel offset of a frame buffer [h][w] -> [(h-7)*(w-7)][192] */
+int tm_sliding_features(const int32_t *frame, int w, int h, int16_t *out);
+/* the window scan of DoXY: cur_feat [th*tw][192] (tiles in natural orientation) against the sliding features of the
+   previous frame buffer; radius = MotionPredictRadius setting (window dy-radius .. dy+radius-1).  err includes the
+   Manhattan penalty; first strict minimum of the row-major scan; err = 0xFFFFFFFF if nothing was accepted. */
+int tm_motion_search(const int16_t *cur_feat, int tw, int th, const int16_t *dcts, int radius, int32_t *pred_x, int32_t *pred_y,
+                     uint32_t *err);
+/* one frame of TTilingEncoder.PredictMotion: prev_frame [th*8][tw*8] pixels, this frame's stored (canonicalised) tiles
+   [th*tw][64] + mirror flags -> motion vector and error per tile */
+int tm_predict_motion_frame(const int32_t *prev_frame, const int32_t *canon_tiles, const uint8_t *flags, int tw, int th, int radius,
+                            int32_t *pred_x, int32_t *pred_y, uint32_t *err);
+/* TTilingEncoder.Reconstruct for ONE keyframe sequence (frame 0 = the sequence's start frame): canon_tiles
+   [n_frames][th*tw][64], flags [n_frames][th*tw] (bit 0 HMirror, bit 1 VMirror).  Per tile: TileIdx / PalIdx / PredictedX /
+   PredictedY / IsPredicted as TFrame.Reconstruct leaves them, err = the error whose PSNR it accumulates, psnr (optional)
+   = EuclideanToPSNR(err), recon (optional) = the reconstructed frames [n_frames][th*8][tw*8].  The frame chain
+   (sliding features of the previous reconstruction -> motion search -> decision -> draw) stays on the device. */
+int tm_reconstruct_sequence(tm_matcher *m, const int32_t *canon_tiles, const uint8_t *flags, int n_frames, int tw, int th, int radius,
+                            int k, int32_t *tile_idx, int32_t *pal_idx, int32_t *pred_x, int32_t *pred_y, uint8_t *is_pred,
+                            uint32_t *err, float *psnr, int32_t *recon);
+/* mean squared error over the three colour channels of two packed-RGB buffers of n pixels */
+int tm_mse_rgb(const int32_t *a, const int32_t *b, int64_t n, double *mse);
+
 #ifdef __cplusplus
 }
 #endif

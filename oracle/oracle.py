@@ -280,6 +280,59 @@ def match_tiles(q_feat, dict_feat, dict_idx, dict_pal, palettes, k=64, extended=
     return out[:, 0].copy(), out[:, 1].copy(), out[:, 2].view(np.uint32).copy()
 
 
+def sliding_features(frame):
+    f = np.ascontiguousarray(frame, dtype=np.int32)
+    h, w = f.shape
+    out = np.empty(((h - 7) * (w - 7), DCT), dtype=np.int16)
+    lib().tmo_sliding_features(_p(f, C.c_int32), int(w), int(h), _p(out, C.c_int16))
+    return out
+
+
+def motion_search(cur_feat, tw, th, dcts, radius=32):
+    cf = np.ascontiguousarray(cur_feat, dtype=np.int16)
+    d = np.ascontiguousarray(dcts, dtype=np.int16)
+    nt = tw * th
+    px, py, err = np.empty(nt, np.int32), np.empty(nt, np.int32), np.empty(nt, np.uint32)
+    lib().tmo_motion_search(_p(cf, C.c_int16), int(tw), int(th), _p(d, C.c_int16), int(radius), _p(px, C.c_int32), _p(py, C.c_int32),
+                            _p(err, C.c_uint32))
+    return px, py, err
+
+
+def features_from_rgb_mirrored(rgb, flags):
+    """Features of stored tiles read through their mirror flags (ConvertToCpnPixels with AHMirror/AVMirror)."""
+    t = np.ascontiguousarray(rgb, dtype=np.int32).reshape(-1, 64)
+    fl = np.ascontiguousarray(flags, dtype=np.uint8).reshape(-1)
+    out = np.empty((t.shape[0], DCT), dtype=np.int16)
+    L = lib()
+    for i in range(t.shape[0]):
+        L.tmo_tile_features_i16(_p(t[i], C.c_int32), None, None, 0, int(fl[i] & 1), int((fl[i] >> 1) & 1),
+                                out[i].ctypes.data_as(C.POINTER(C.c_int16)))
+    return out
+
+
+def reconstruct_sequence(canon_tiles, flags, tw, th, dict_feat, dict_idx, dict_pal, palettes, radius=32, extended=True):
+    t = np.ascontiguousarray(canon_tiles, dtype=np.int32)
+    n_frames = t.shape[0]
+    nt = tw * th
+    fl = np.ascontiguousarray(flags, dtype=np.uint8)
+    d = np.ascontiguousarray(dict_feat, dtype=np.int16).reshape(-1, DCT)
+    di = np.ascontiguousarray(dict_idx, dtype=np.uint8).reshape(-1, 64)
+    dp = np.ascontiguousarray(dict_pal, dtype=np.int32)
+    pal = np.ascontiguousarray(palettes, dtype=np.int32)
+    shp = (n_frames, nt)
+    r = {"tile_idx": np.empty(shp, np.int32), "pal_idx": np.empty(shp, np.int32), "pred_x": np.empty(shp, np.int32),
+         "pred_y": np.empty(shp, np.int32), "is_pred": np.empty(shp, np.uint8), "err": np.empty(shp, np.uint32),
+         "recon": np.empty((n_frames, th * 8, tw * 8), np.int32)}
+    ps = C.c_double()
+    lib().tmo_reconstruct_sequence(_p(t, C.c_int32), _p(fl, C.c_uint8), int(n_frames), int(tw), int(th), _p(d, C.c_int16),
+                                   _p(di, C.c_uint8), _p(dp, C.c_int32), C.c_int64(d.shape[0]), _p(pal, C.c_int32),
+                                   int(pal.shape[1]), int(pal.shape[0]), int(radius), int(extended), _p(r["tile_idx"], C.c_int32),
+                                   _p(r["pal_idx"], C.c_int32), _p(r["pred_x"], C.c_int32), _p(r["pred_y"], C.c_int32),
+                                   _p(r["is_pred"], C.c_uint8), _p(r["err"], C.c_uint32), _p(r["recon"], C.c_int32), C.byref(ps))
+    r["psnr_sum"] = ps.value
+    return r
+
+
 # ---- reference dlquant (oracle/_ref) ----
 def ref_dl3quant(rgb888, w, h, quant_to, lookup_bpc=5, which="dl3quant"):
     r = ref_dlquant()

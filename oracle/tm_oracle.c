@@ -822,3 +822,123 @@ void tmo_match_tiles(const int16_t *q_feat, int64_t n_q, const int16_t *dict_fea
   }
   free(idx); free(dist);
 }
+
+/* ------------------------------------------------------------------ motion search + Reconstruct */
+
+/* TFrame.Reconstruct.DoDCTs / TFrame.PredictMotion.DoDCTs (tilingencoder.pas:1437-1462, 1157-1181): weighted-DCT YUV
+   features of the 8x8 window at every pixel offset of a frame buffer, row-major [(h-7)][(w-7)][192]. */
+void tmo_sliding_features(const int32_t *frame, int w, int h, int16_t *out) {
+  init_luts();
+  const int pw = w - 7, ph = h - 7;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int oy = 0; oy < ph; ++oy)
+    for (int ox = 0; ox < pw; ++ox) {
+      int32_t px[64];
+      for (int y = 0; y < 8; ++y) memcpy(px + y * 8, frame + (int64_t)(oy + y) * w + ox, 8 * sizeof(int32_t));
+      tmo_tile_features_i16(px, NULL, NULL, 0, 0, 0, out + ((int64_t)oy * pw + ox) * TMO_DCT);
+    }
+}
+
+/* The motion search of TFrame.PredictMotion.DoXY / TFrame.Reconstruct.DoXY (tilingencoder.pas:1213-1244, 1496-1532):
+   cur_feat [th*tw][192] = features of the frame's tiles in NATURAL orientation, dcts = sliding features of the previous
+   (source or reconstructed) frame buffer.  radius_setting is MotionPredictRadius (the callers Dec() it, :1275, :1666).
+   Row-major scan, Manhattan penalty added to the error (:1236, :1519), strict '<' keeps the first minimum.
+   err = 0xFFFFFFFF and pred = (0,0) when no position was accepted. */
+void tmo_motion_search(const int16_t *cur_feat, int tw, int th, const int16_t *dcts, int radius_setting,
+                       int32_t *pred_x, int32_t *pred_y, uint32_t *err_out) {
+  const int w = tw * 8, h = th * 8, pw = w - 7;
+  const int R = radius_setting - 1;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int t = 0; t < tw * th; ++t) {
+    const int sy = t / tw, sx = t % tw, dx = sx * 8, dy = sy * 8;
+    const int16_t *cur = cur_feat + (int64_t)t * TMO_DCT;
+    uint32_t best = 0xFFFFFFFFu; int bx = 0, by = 0;
+    const int oymn = dy - R - 1 > 0 ? dy - R - 1 : 0, oymx = dy + R < h - 8 ? dy + R : h - 8;
+    const int oxmn = dx - R - 1 > 0 ? dx - R - 1 : 0, oxmx = dx + R < w - 8 ? dx + R : w - 8;
+    for (int oy = oymn; oy <= oymx; ++oy)
+      for (int ox = oxmn; ox <= oxmx; ++ox) {
+        const int16_t *p = dcts + ((int64_t)oy * pw + ox) * TMO_DCT;
+        if (tmo_quick_test(cur, p, best)) {
+          uint32_t e = tmo_compare_euclidean_dct(cur, p);
+          e += (uint32_t)(abs(ox - dx) + abs(oy - dy));
+          if (e < best) { best = e; bx = ox - dx; by = oy - dy; }
+        }
+      }
+    pred_x[t] = bx; pred_y[t] = by; err_out[t] = best;
+  }
+}
+
+/* TTilingEncoder.Reconstruct over ONE keyframe sequence (tilingencoder.pas:1928-1962 driver, 1430-1679 per frame).
+   canon_tiles [n_frames][th*tw][64]: frame tiles as stored (mirror-canonicalised at load, :1393-1411), flags bit0 =
+   HMirror, bit1 = VMirror.  Frame 0 is the sequence's StartFrame (no motion search, :1496).  Outputs per tile:
+   tile_idx / pal_idx as the reference leaves them in the TTileMapItem (-1/-1 when the motion error is inside the dead
+   band, :1534-1541), pred_x / pred_y, is_pred, err (the error whose PSNR the reference accumulates, :1614-1653), and
+   optionally the reconstructed frames recon [n_frames][h][w].  CompareValue(knnErr, mpErr, 192) is restated on exact
+   integers (the FPC overload taken for Cardinal arguments is not pinned by any reference test). */
+void tmo_reconstruct_sequence(const int32_t *canon_tiles, const uint8_t *flags, int n_frames, int tw, int th,
+                              const int16_t *dict_feat, const uint8_t *dict_idx, const int32_t *dict_pal, int64_t n_dict,
+                              const int32_t *palettes, int pal_size, int n_pal, int radius_setting, int extended,
+                              int32_t *tile_idx, int32_t *pal_idx, int32_t *pred_x, int32_t *pred_y, uint8_t *is_pred,
+                              uint32_t *err_out, int32_t *recon, double *psnr_sum) {
+  init_luts();
+  const int nt = tw * th, w = tw * 8, h = th * 8;
+  const int64_t npos = (int64_t)(w - 7) * (h - 7);
+  int32_t *buf[2];
+  buf[0] = (int32_t *)calloc((size_t)w * h, 4);
+  buf[1] = (int32_t *)calloc((size_t)w * h, 4);
+  int16_t *dcts = (int16_t *)malloc((size_t)npos * TMO_DCT * 2);
+  int16_t *ft = (int16_t *)malloc((size_t)nt * TMO_DCT * 2), *cur = (int16_t *)malloc((size_t)nt * TMO_DCT * 2);
+  tmo_match *knn = (tmo_match *)malloc(sizeof(tmo_match) * (size_t)nt);
+  int32_t *mx = (int32_t *)malloc(4 * (size_t)nt), *my = (int32_t *)malloc(4 * (size_t)nt);
+  uint32_t *me = (uint32_t *)malloc(4 * (size_t)nt);
+  double psum = 0;
+  for (int f = 0; f < n_frames; ++f) {
+    const int32_t *tiles = canon_tiles + (int64_t)f * nt * 64;
+    const uint8_t *fl = flags + (int64_t)f * nt;
+    int32_t *front = buf[(f + 1) & 1], *back = buf[f & 1];
+    tmo_features_from_rgb_batch(tiles, nt, ft);                               /* FTDCT, :1481-1482 */
+    const int motion = f > 0 && radius_setting - 1 >= 0;
+    if (motion) {
+      tmo_sliding_features(back, w, h, dcts);
+#pragma omp parallel for schedule(static)
+      for (int t = 0; t < nt; ++t)                                             /* CurDCT, :1498-1499 */
+        tmo_tile_features_i16(tiles + (int64_t)t * 64, NULL, NULL, 0, fl[t] & 1, (fl[t] >> 1) & 1, cur + (int64_t)t * TMO_DCT);
+      tmo_motion_search(cur, tw, th, dcts, radius_setting, mx, my, me);
+    }
+    tmo_match_tiles(ft, nt, dict_feat, dict_idx, dict_pal, n_dict, palettes, pal_size, n_pal, 64, extended, knn);
+    for (int t = 0; t < nt; ++t) {
+      const int64_t o = (int64_t)f * nt + t;
+      const int sy = t / tw, sx = t % tw, dx = sx * 8, dy = sy * 8;
+      const uint32_t mp = motion ? me[t] : 0xFFFFFFFFu;
+      uint32_t ke; int32_t ti, pi;
+      if (mp <= TMO_DCT) { ti = -1; pi = -1; ke = 0xFFFFFFFFu; }               /* IsZero(mpErr, cTileDCTSize), :1534 */
+      else { ti = knn[t].tile_idx; pi = knn[t].pal_idx; ke = knn[t].err; if (ti < 0) { pi = -1; ke = 0xFFFFFFFFu; } }
+      const int knn_best = (uint64_t)ke + TMO_DCT < (uint64_t)mp;              /* CompareValue = LessThanValue, :1614 */
+      tile_idx[o] = ti; pal_idx[o] = pi;
+      pred_x[o] = motion ? mx[t] : 0; pred_y[o] = motion ? my[t] : 0;
+      is_pred[o] = (uint8_t)!knn_best;
+      const uint32_t e = knn_best ? ke : mp;
+      err_out[o] = e;
+      psum += (double)tmo_euclidean_to_psnr(e);
+      if (knn_best) {                                                          /* draw fb (pal tile), :1623-1637 */
+        const uint8_t *pp = dict_idx + (int64_t)ti * 64;
+        const int32_t *pal = palettes + (int64_t)pi * pal_size;
+        for (int ty = 0; ty < 8; ++ty) {
+          const int tym = (fl[t] & 2) ? 7 - ty : ty;
+          for (int tx = 0; tx < 8; ++tx) {
+            const int txm = (fl[t] & 1) ? 7 - tx : tx;
+            front[(int64_t)(dy + ty) * w + dx + tx] = pal[pp[tym * 8 + txm]];
+          }
+        }
+      } else if (motion) {                                                     /* draw fb (motion predicted tile), :1646-1651 */
+        for (int ty = 0; ty < 8; ++ty)
+          memcpy(front + (int64_t)(dy + ty) * w + dx, back + (int64_t)(dy + ty + my[t]) * w + dx + mx[t], 8 * sizeof(int32_t));
+      } else {
+        for (int ty = 0; ty < 8; ++ty) memset(front + (int64_t)(dy + ty) * w + dx, 0, 8 * sizeof(int32_t));
+      }
+    }
+    if (recon) memcpy(recon + (int64_t)f * w * h, front, (size_t)w * h * 4);
+  }
+  if (psnr_sum) *psnr_sum = psum;
+  free(buf[0]); free(buf[1]); free(dcts); free(ft); free(cur); free(knn); free(mx); free(my); free(me);
+}

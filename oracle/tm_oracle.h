@@ -126,6 +126,16 @@ void tmo_match_tiles(const int16_t *q_feat, int64_t n_q, const int16_t *dict_fea
                      const int32_t *dict_pal, int64_t n_dict, const int32_t *palettes, int pal_size, int n_pal,
                      int k, int extended, tmo_match *out);
 
+/* ---- motion search + Reconstruct (tilingencoder.pas:1154-1282, 1430-1679, 1928-1962) ---- */
+void tmo_sliding_features(const int32_t *frame, int w, int h, int16_t *out /* [(h-7)*(w-7)][192] */);
+void tmo_motion_search(const int16_t *cur_feat, int tw, int th, const int16_t *dcts, int radius_setting,
+                       int32_t *pred_x, int32_t *pred_y, uint32_t *err_out);
+void tmo_reconstruct_sequence(const int32_t *canon_tiles, const uint8_t *flags, int n_frames, int tw, int th,
+                              const int16_t *dict_feat, const uint8_t *dict_idx, const int32_t *dict_pal, int64_t n_dict,
+                              const int32_t *palettes, int pal_size, int n_pal, int radius_setting, int extended,
+                              int32_t *tile_idx, int32_t *pal_idx, int32_t *pred_x, int32_t *pred_y, uint8_t *is_pred,
+                              uint32_t *err_out, int32_t *recon, double *psnr_sum);
+
 int tmo_num_threads(void);
 
 #ifdef __cplusplus

@@ -408,3 +408,96 @@ def test_dlquant_golden_and_dropin(tm):
     assert rc == 0 and np.array_equal(pal, g["dl3_16"]) and not full[:, 16:].any()
     rc, pal, full = tm.dlquant_dropin(g["img"], 48, 48, 16, 5, which=1)
     assert rc == 0 and np.array_equal(pal, g["dl1_16"])
+
+
+# ---------------------------------------------------------------- motion search + Reconstruct
+def _small_clip(w, h, n, seed):
+    clip = synth.make_clip(w, h, n, cut_every=0, seed=seed, n_sprites=6)
+    return synth.pack_rgb(clip)          # [n, h, w] int32
+
+
+def test_sliding_features_bit_exact(tm, oracle):
+    frame = _small_clip(96, 64, 1, 11)[0]
+    got = tm.sliding_features(frame)
+    want = oracle.sliding_features(frame)
+    assert got.shape == ((64 - 7) * (96 - 7), 192)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("w,h,radius", [(96, 64, 32), (160, 96, 32), (64, 64, 5)])
+def test_motion_search_bit_exact(tm, oracle, w, h, radius):
+    frames = _small_clip(w, h, 2, 12)
+    tw, th = w // 8, h // 8
+    tiles = synth.frame_to_tiles(frames[1])
+    cur = oracle.features_from_rgb(tiles)
+    dcts = oracle.sliding_features(frames[0])
+    gx, gy, ge = tm.motion_search(cur, tw, th, dcts, radius)
+    ox, oy, oe = oracle.motion_search(cur, tw, th, dcts, radius)
+    assert np.array_equal(_u32(ge), oe)
+    assert np.array_equal(gx, ox) and np.array_equal(gy, oy)
+    # a static region must be found at (0, 0) with error 0 when the frame repeats
+    gx0, gy0, ge0 = tm.motion_search(oracle.features_from_rgb(synth.frame_to_tiles(frames[0])), tw, th, dcts, radius)
+    assert np.all(_u32(ge0) == 0) and np.all(gx0 == 0) and np.all(gy0 == 0)
+
+
+def test_predict_motion_frame_uses_natural_orientation(tm, oracle):
+    frames = _small_clip(96, 64, 2, 13)
+    tw, th = 12, 8
+    canon, flags = tm.mirror_canonicalise(synth.frame_to_tiles(frames[1]))
+    gx, gy, ge = tm.predict_motion_frame(frames[0], canon, flags, tw, th, 32)
+    cur = oracle.features_from_rgb_mirrored(canon, flags)
+    assert np.array_equal(cur, oracle.features_from_rgb(synth.frame_to_tiles(frames[1])))   # un-mirroring restores the source tile
+    ox, oy, oe = oracle.motion_search(cur, tw, th, oracle.sliding_features(frames[0]), 32)
+    assert np.array_equal(_u32(ge), oe) and np.array_equal(gx, ox) and np.array_equal(gy, oy)
+
+
+def _build_small_dictionary(tm, oracle, frames, n_dict, n_pal, pal_size, seed):
+    """Dictionary + palettes for a small clip through the library's own stages (their parity is tested above)."""
+    tiles = np.concatenate([synth.frame_to_tiles(f) for f in frames])
+    canon, flags = tm.mirror_canonicalise(tiles)
+    sel = np.linspace(0, len(canon) - 1, n_dict).astype(np.int64)
+    dt, dfl = np.ascontiguousarray(canon[sel]), np.ascontiguousarray(flags[sel])
+    rng = np.random.default_rng(seed)
+    dpal = rng.integers(0, n_pal, size=n_dict).astype(np.int32)
+    pal, _ = tm.palquant_kmeans(dt, dpal, n_pal, pal_size, seed=seed)
+    didx = tm.dither(dt, dfl, dpal, pal)
+    return canon.reshape(len(frames), -1, 64), flags.reshape(len(frames), -1), didx, dpal, pal
+
+
+@pytest.mark.parametrize("extended", [True, False])
+def test_reconstruct_sequence_bit_exact(tm, oracle, extended):
+    w, h, n_frames = 96, 64, 4
+    frames = _small_clip(w, h, n_frames, 14)
+    tw, th = w // 8, h // 8
+    canon, flags, didx, dpal, pal = _build_small_dictionary(tm, oracle, frames, 160, 4, 16, 5)
+    m = tm.Matcher(didx, dpal, pal, extended=extended)
+    got = m.reconstruct_sequence(canon, flags, tw, th, radius=32)
+    dict_feat = oracle.features_from_pal(didx, dpal, pal)
+    want = oracle.reconstruct_sequence(canon, flags, tw, th, dict_feat, didx, dpal, pal, radius=32, extended=extended)
+    for key in ("is_pred", "pred_x", "pred_y", "tile_idx", "pal_idx"):
+        assert np.array_equal(got[key], want[key]), key
+    assert np.array_equal(_u32(got["err"]), want["err"])
+    assert np.array_equal(got["recon"], want["recon"])
+    assert got["is_pred"][0].sum() == 0            # first frame of the sequence: no motion prediction (:1496)
+    assert got["is_pred"][1:].sum() > 0            # a translating clip must predict some tiles
+    psnr = np.array([oracle.euclidean_to_psnr(int(e)) for e in want["err"].reshape(-1)], dtype=np.float32)
+    assert np.allclose(got["psnr"].reshape(-1), psnr, rtol=1e-6, atol=1e-5)
+    # decoded-frame PSNR of the reconstruction against the source, GPU reduction vs numpy
+    src = np.stack([synth.tiles_to_frame(synth.frame_to_tiles(f), h, w) for f in frames])
+    a, b = src.astype(np.int64), want["recon"].astype(np.int64)
+    se = sum((((a >> s) & 255) - ((b >> s) & 255)) ** 2 for s in (0, 8, 16)).sum()
+    assert abs(tm.mse_rgb(src, got["recon"]) - se / (3.0 * a.size)) < 1e-9
+    m.close()
+
+
+def test_reconstruct_sequence_device_tensors(tm, oracle):
+    import torch
+    w, h, n_frames = 64, 64, 3
+    frames = _small_clip(w, h, n_frames, 15)
+    canon, flags, didx, dpal, pal = _build_small_dictionary(tm, oracle, frames, 100, 2, 16, 6)
+    m = tm.Matcher(didx, dpal, pal, extended=True)
+    host = m.reconstruct_sequence(canon, flags, 8, 8)
+    dev = m.reconstruct_sequence(torch.from_numpy(canon).cuda(), torch.from_numpy(flags).cuda(), 8, 8)
+    for key in ("is_pred", "pred_x", "pred_y", "tile_idx", "pal_idx", "recon"):
+        assert np.array_equal(dev[key].cpu().numpy(), host[key]), key
+    m.close()

@@ -150,3 +150,57 @@ def test_oracle_against_committed_golden(oracle):
     assert np.array_equal(oracle.dither(g["tiles"], g["flags"], g["tile_pal"], g["palettes"], use_tk=False), g["pal_idx_yl"])
     idx, dist = oracle.knn_short(g["feat_pal"], g["feat_rgb"], 8)
     assert np.array_equal(idx, g["knn_idx"]) and np.array_equal(dist, g["knn_dist"])
+
+
+# ---------------------------------------------------------------- motion search + Reconstruct restatement
+def test_motion_search_properties(oracle):
+    from tiler_b200 import synth
+    rng = np.random.default_rng(3)
+    w, h = 64, 48
+    base = rng.integers(0, 256, size=(h + 16, w + 16, 3)).astype(np.uint8)
+    prev = synth.pack_rgb(base[8:8 + h, 8:8 + w])
+    cur = synth.pack_rgb(base[8 + 2:8 + 2 + h, 8 - 3:8 - 3 + w])   # cur(y, x) = prev(y + 2, x - 3)
+    dcts = oracle.sliding_features(prev)
+    assert dcts.shape == ((h - 7) * (w - 7), 192)
+    # sliding features at tile-aligned offsets are the tile features
+    tiles_prev = synth.frame_to_tiles(prev)
+    f_prev = oracle.features_from_rgb(tiles_prev)
+    pw = w - 7
+    for t in (0, 5, 13):
+        ty, tx = divmod(t, w // 8)
+        assert np.array_equal(dcts[ty * 8 * pw + tx * 8], f_prev[t])
+    px, py, err = oracle.motion_search(oracle.features_from_rgb(synth.frame_to_tiles(cur)), w // 8, h // 8, dcts, 32)
+    inner = [t for t in range((w // 8) * (h // 8)) if 1 <= t % (w // 8) < w // 8 - 1 and 1 <= t // (w // 8) < h // 8 - 1]
+    assert all(px[t] == -3 and py[t] == 2 and err[t] == 5 for t in inner)   # exact match, error = Manhattan penalty only
+    # identical frame: zero vector, zero error everywhere
+    px0, py0, err0 = oracle.motion_search(f_prev, w // 8, h // 8, dcts, 32)
+    assert not px0.any() and not py0.any() and not err0.any()
+    # radius 1 -> window dy-1 .. dy+0 (tilingencoder.pas:1213-1216 after Dec(ARadius))
+    px1, py1, _ = oracle.motion_search(oracle.features_from_rgb(synth.frame_to_tiles(cur)), w // 8, h // 8, dcts, 1)
+    assert px1.min() >= -1 and px1.max() <= 0 and py1.min() >= -1 and py1.max() <= 0
+
+
+def test_reconstruct_sequence_oracle_semantics(oracle):
+    from tiler_b200 import synth
+    frames = synth.pack_rgb(synth.make_clip(64, 48, 3, seed=21, n_sprites=3, noise=0.0))
+    tw, th = 8, 6
+    tiles = np.stack([synth.frame_to_tiles(f) for f in frames])
+    flags = np.zeros(tiles.shape[:2], np.uint8)
+    # dictionary = 80 tiles of frame 0 "dithered" to 16 grey levels
+    pal = np.array([[(v * 17) * 0x010101 for v in range(16)]], dtype=np.int32)
+    sel = tiles[0][:48]
+    luma = ((sel & 255) * 299 + ((sel >> 8) & 255) * 587 + ((sel >> 16) & 255) * 114) // 1000
+    didx = np.clip((luma + 8) // 17, 0, 15).astype(np.uint8)
+    dpal = np.zeros(len(didx), np.int32)
+    dfeat = oracle.features_from_pal(didx, dpal, pal)
+    r = oracle.reconstruct_sequence(tiles, flags, tw, th, dfeat, didx, dpal, pal, radius=32, extended=True)
+    assert not r["is_pred"][0].any() and (r["tile_idx"][0] >= 0).all()        # start frame: k-NN only (:1496)
+    # every reconstructed pixel of frame 0 is a palette colour; predicted tiles of later frames copy the previous recon
+    assert np.isin(r["recon"][0], pal).all()
+    for f in (1, 2):
+        for t in np.nonzero(r["is_pred"][f])[0][:10]:
+            y, x = (t // tw) * 8, (t % tw) * 8
+            sy, sx = y + r["pred_y"][f, t], x + r["pred_x"][f, t]
+            assert np.array_equal(r["recon"][f, y:y + 8, x:x + 8], r["recon"][f - 1, sy:sy + 8, sx:sx + 8])
+        dead = r["is_pred"][f].astype(bool) & (r["tile_idx"][f] < 0)
+        assert (r["err"][f][dead] <= 192).all()                                # dead band: mpErr <= cTileDCTSize (:1534)

@@ -60,6 +60,11 @@ SIGNATURES = {
     "tm_match_tiles_rgb": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "tm_match_tiles_feat": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "tm_matcher_dict_features": (C.c_int, [_vp, _vp]),
+    "tm_sliding_features": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "tm_motion_search": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
+    "tm_predict_motion_frame": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "tm_reconstruct_sequence": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tm_mse_rgb": (C.c_int, [_vp, _vp, _i64, C.POINTER(_dbl)]),
     # drop-in exports (extern.pas:178-223)
     "ann_kdtree_short_create": (_vp, [_vp, _i32, _i32, _i32, _i32]),
     "ann_kdtree_short_destroy": (None, [_vp]),

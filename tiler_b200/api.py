@@ -25,7 +25,8 @@ except Exception:  # pragma: no cover
 _NP2T = {}
 if torch is not None:
     _NP2T = {np.dtype(np.int16): torch.int16, np.dtype(np.int32): torch.int32, np.dtype(np.uint8): torch.uint8,
-             np.dtype(np.float64): torch.float64, np.dtype(np.int64): torch.int64, np.dtype(np.uint32): torch.int32}
+             np.dtype(np.float64): torch.float64, np.dtype(np.int64): torch.int64, np.dtype(np.uint32): torch.int32,
+             np.dtype(np.float32): torch.float32}
 
 
 def _is_dev(x):
@@ -360,6 +361,27 @@ class Matcher:
     def match_feat(self, feat, k=None):
         return self._run(_lib.lib().tm_match_tiles_feat, feat, DCT, np.int16, k or (self.K_EPU if self.extended else 1))
 
+    def reconstruct_sequence(self, canon_tiles, flags, tw, th, radius=32, k=None, want_recon=True):
+        """TTilingEncoder.Reconstruct over one keyframe sequence (tilingencoder.pas:1928-1962, 1430-1679).
+        canon_tiles [n_frames, th*tw, 64] stored (canonicalised) tiles, flags [n_frames, th*tw].
+        -> dict(tile_idx, pal_idx, pred_x, pred_y, is_pred, err, psnr, recon [n_frames, th*8, tw*8])."""
+        c = _Call(canon_tiles, flags)
+        n_frames = int(canon_tiles.shape[0])
+        nt = tw * th
+        shp = (n_frames, nt)
+        tile, p_tile = c.out(shp, np.int32)
+        pal, p_pal = c.out(shp, np.int32)
+        px, p_px = c.out(shp, np.int32)
+        py, p_py = c.out(shp, np.int32)
+        isp, p_isp = c.out(shp, np.uint8)
+        err, p_err = c.out(shp, np.uint32)
+        psnr, p_psnr = c.out(shp, np.float32)
+        recon, p_recon = c.out((n_frames, th * 8, tw * 8), np.int32) if want_recon else (None, None)
+        check(_lib.lib().tm_reconstruct_sequence(self._h, c.inp(canon_tiles, np.int32), c.inp(flags, np.uint8), n_frames, int(tw), int(th),
+                                                 int(radius), int(k or (self.K_EPU if self.extended else 1)), p_tile, p_pal, p_px, p_py,
+                                                 p_isp, p_err, p_psnr, p_recon))
+        return {"tile_idx": tile, "pal_idx": pal, "pred_x": px, "pred_y": py, "is_pred": isp, "err": err, "psnr": psnr, "recon": recon}
+
     def dict_features(self):
         out = np.empty((self.n_dict, DCT), dtype=np.int16)
         check(_lib.lib().tm_matcher_dict_features(self._h, C.c_void_p(out.ctypes.data)))
@@ -375,6 +397,47 @@ class Matcher:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------ motion search (tilingencoder.pas:1154-1282, 1496-1532)
+def sliding_features(frame):
+    """DoDCTs: frame buffer [h, w] packed RGB -> features of every 8x8 window, int16 [(h-7)*(w-7), 192]."""
+    c = _Call(frame)
+    h, w = int(frame.shape[0]), int(frame.shape[1])
+    out, po = c.out(((h - 7) * (w - 7), DCT), np.int16)
+    check(_lib.lib().tm_sliding_features(c.inp(frame, np.int32), w, h, po))
+    return out
+
+
+def motion_search(cur_feat, tw, th, dcts, radius=32):
+    """Window scan of DoXY -> (pred_x, pred_y, err) per tile; err carries the Manhattan penalty."""
+    c = _Call(cur_feat, dcts)
+    nt = tw * th
+    px, ppx = c.out((nt,), np.int32)
+    py, ppy = c.out((nt,), np.int32)
+    err, pe = c.out((nt,), np.uint32)
+    check(_lib.lib().tm_motion_search(c.inp(cur_feat, np.int16), int(tw), int(th), c.inp(dcts, np.int16), int(radius), ppx, ppy, pe))
+    return px, py, err
+
+
+def predict_motion_frame(prev_frame, canon_tiles, flags, tw, th, radius=32):
+    """One frame of TTilingEncoder.PredictMotion: previous frame pixels [th*8, tw*8] + this frame's stored tiles."""
+    c = _Call(prev_frame, canon_tiles, flags)
+    nt = tw * th
+    px, ppx = c.out((nt,), np.int32)
+    py, ppy = c.out((nt,), np.int32)
+    err, pe = c.out((nt,), np.uint32)
+    check(_lib.lib().tm_predict_motion_frame(c.inp(prev_frame, np.int32), c.inp(canon_tiles, np.int32), c.inp(flags, np.uint8), int(tw),
+                                             int(th), int(radius), ppx, ppy, pe))
+    return px, py, err
+
+
+def mse_rgb(a, b):
+    c = _Call(a, b)
+    n = int(np.prod(a.shape))
+    out = C.c_double()
+    check(_lib.lib().tm_mse_rgb(c.inp(a, np.int32), c.inp(b, np.int32), n, C.byref(out)))
+    return out.value
 
 
 # ------------------------------------------------------------------ drop-in symbols, exercised the way extern.pas binds them

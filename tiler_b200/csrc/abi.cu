@@ -765,6 +765,128 @@ extern "C" int tm_matcher_dict_features(tm_matcher *m, int16_t *out) {
   return TM_OK;
 }
 
+// ------------------------------------------------------------------ motion search + Reconstruct
+extern "C" int tm_sliding_features(const int32_t *frame, int w, int h, int16_t *out) {
+  RC(require_gpu());
+  if (!frame || !out || w < 8 || h < 8) return fail(TM_ERR_ARG, "tm_sliding_features: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int32_t *d_frame = s.in(frame, (size_t)w * h);
+  int16_t *d_out = s.out(out, (size_t)(w - 7) * (h - 7) * 192);
+  if (s.err == TM_OK) s.err = launch_features_sliding(d_frame, w, h, d_out, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+extern "C" int tm_motion_search(const int16_t *cur_feat, int tw, int th, const int16_t *dcts, int radius, int32_t *pred_x, int32_t *pred_y,
+                                uint32_t *err) {
+  RC(require_gpu());
+  if (!cur_feat || !dcts || !pred_x || !pred_y || !err || tw < 1 || th < 1 || radius < 1 || radius > 128)
+    return fail(TM_ERR_ARG, "tm_motion_search: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const size_t nt = (size_t)tw * th;
+  const int16_t *d_cur = s.in(cur_feat, nt * 192);
+  const int16_t *d_dcts = s.in(dcts, (size_t)(tw * 8 - 7) * (th * 8 - 7) * 192);
+  int32_t *d_px = s.out(pred_x, nt), *d_py = s.out(pred_y, nt);
+  uint32_t *d_err = s.out(err, nt);
+  if (s.err == TM_OK) s.err = launch_motion_search(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+extern "C" int tm_predict_motion_frame(const int32_t *prev_frame, const int32_t *canon_tiles, const uint8_t *flags, int tw, int th, int radius,
+                                       int32_t *pred_x, int32_t *pred_y, uint32_t *err) {
+  RC(require_gpu());
+  if (!prev_frame || !canon_tiles || !flags || !pred_x || !pred_y || !err || tw < 1 || th < 1 || radius < 1 || radius > 128)
+    return fail(TM_ERR_ARG, "tm_predict_motion_frame: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const size_t nt = (size_t)tw * th;
+  const int w = tw * 8, h = th * 8;
+  const int32_t *d_prev = s.in(prev_frame, (size_t)w * h);
+  const int32_t *d_tiles = s.in(canon_tiles, nt * 64);
+  const uint8_t *d_flags = s.in(flags, nt);
+  int32_t *d_px = s.out(pred_x, nt), *d_py = s.out(pred_y, nt);
+  uint32_t *d_err = s.out(err, nt);
+  int16_t *d_cur = (int16_t *)s.temp(nt * 384);
+  int16_t *d_dcts = (int16_t *)s.temp((size_t)(w - 7) * (h - 7) * 384);
+  if (s.err == TM_OK) s.err = launch_features_rgb_mirrored(d_tiles, d_flags, (int64_t)nt, d_cur, s.st);
+  if (s.err == TM_OK) s.err = launch_features_sliding(d_prev, w, h, d_dcts, s.st);
+  if (s.err == TM_OK) s.err = launch_motion_search(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+extern "C" int tm_reconstruct_sequence(tm_matcher *m, const int32_t *canon_tiles, const uint8_t *flags, int n_frames, int tw, int th, int radius,
+                                       int k, int32_t *tile_idx, int32_t *pal_idx, int32_t *pred_x, int32_t *pred_y, uint8_t *is_pred,
+                                       uint32_t *err, float *psnr, int32_t *recon) {
+  RC(require_gpu());
+  if (!m || !canon_tiles || !flags || n_frames < 1 || tw < 1 || th < 1 || radius < 0 || radius > 128 || k < 1 || k > 64 || !tile_idx ||
+      !pal_idx || !pred_x || !pred_y || !is_pred || !err)
+    return fail(TM_ERR_ARG, "tm_reconstruct_sequence: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const size_t nt = (size_t)tw * th, n_all = nt * (size_t)n_frames;
+  const int w = tw * 8, h = th * 8;
+  const size_t fpx = (size_t)w * h;
+  if (n_all > 0x7fffffff) return fail(TM_ERR_ARG, "tm_reconstruct_sequence: too many tiles in one call");
+  const int32_t *d_tiles = s.in(canon_tiles, n_all * 64);
+  const uint8_t *d_flags = s.in(flags, n_all);
+  int32_t *d_tile = s.out(tile_idx, n_all), *d_pal = s.out(pal_idx, n_all), *d_px = s.out(pred_x, n_all), *d_py = s.out(pred_y, n_all);
+  uint8_t *d_isp = s.out(is_pred, n_all);
+  uint32_t *d_err = s.out(err, n_all);
+  float *d_psnr = psnr ? s.out(psnr, n_all) : nullptr;
+  int32_t *d_recon = recon ? s.out(recon, fpx * n_frames) : nullptr;
+  int32_t *pp[2] = {nullptr, nullptr};
+  if (!d_recon) { pp[0] = (int32_t *)s.temp(fpx * 4); pp[1] = (int32_t *)s.temp(fpx * 4); }
+  const bool motion = radius - 1 >= 0 && n_frames > 1;
+  int16_t *d_ft = (int16_t *)s.temp(n_all * 384);
+  int16_t *d_cur = motion ? (int16_t *)s.temp(n_all * 384) : nullptr;
+  int16_t *d_dcts = motion ? (int16_t *)s.temp((size_t)(w - 7) * (h - 7) * 384) : nullptr;
+  int32_t *k_tile = (int32_t *)s.temp(n_all * 4), *k_pal = (int32_t *)s.temp(n_all * 4);
+  uint32_t *k_err = (uint32_t *)s.temp(n_all * 4);
+  int32_t *mx = (int32_t *)s.temp(nt * 4), *my = (int32_t *)s.temp(nt * 4);
+  uint32_t *me = (uint32_t *)s.temp(nt * 4);
+  // the k-NN + re-rank candidates do not depend on the reconstructed frames: one batched pass over the whole sequence
+  if (s.err == TM_OK) s.err = launch_features_rgb(d_tiles, (int64_t)n_all, d_ft, s.st);
+  if (s.err == TM_OK) s.err = match_feat_dev(m, d_ft, (int64_t)n_all, k, k_tile, k_pal, k_err, s);
+  if (s.err == TM_OK && motion) s.err = launch_features_rgb_mirrored(d_tiles, d_flags, (int64_t)n_all, d_cur, s.st);
+  for (int f = 0; f < n_frames && s.err == TM_OK; ++f) {
+    int32_t *front = d_recon ? d_recon + fpx * f : pp[(f + 1) & 1];
+    const int32_t *back = d_recon ? (f > 0 ? d_recon + fpx * (f - 1) : nullptr) : pp[f & 1];
+    const bool mo = motion && f > 0;
+    if (mo) {
+      s.err = launch_features_sliding(back, w, h, d_dcts, s.st);
+      if (s.err == TM_OK) s.err = launch_motion_search(d_cur + nt * 192 * f, tw, th, d_dcts, radius, mx, my, me, s.st);
+    }
+    const size_t o = nt * f;
+    if (s.err == TM_OK)
+      s.err = launch_reconstruct_decide(d_flags + o, tw, th, mo ? mx : nullptr, mo ? my : nullptr, mo ? me : nullptr, k_tile + o, k_pal + o,
+                                        k_err + o, m->dict_idx, m->palettes, m->pal_size, back, front, d_tile + o, d_pal + o, d_px + o,
+                                        d_py + o, d_isp + o, d_err + o, d_psnr ? d_psnr + o : nullptr, s.st);
+  }
+  RC(s.finish());
+  return TM_OK;
+}
+
+/* mean squared error over the three colour channels of two packed-RGB buffers */
+extern "C" int tm_mse_rgb(const int32_t *a, const int32_t *b, int64_t n, double *mse) {
+  RC(require_gpu());
+  if (!a || !b || n < 1 || !mse) return fail(TM_ERR_ARG, "tm_mse_rgb: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int32_t *da = s.in(a, (size_t)n), *db = s.in(b, (size_t)n);
+  unsigned long long *acc = (unsigned long long *)s.temp(8);
+  unsigned long long host = 0;
+  if (s.err == TM_OK && cudaMemsetAsync(acc, 0, 8, s.st) != cudaSuccess) s.err = TM_ERR_CUDA;
+  if (s.err == TM_OK) s.err = launch_sq_err_rgb(da, db, n, acc, s.st);
+  if (s.err == TM_OK && cudaMemcpyAsync(&host, acc, 8, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.err = TM_ERR_CUDA;
+  RC(s.finish(true));
+  *mse = (double)host / (3.0 * (double)n);
+  return TM_OK;
+}
+
 // ================================================================== drop-in exports (extern.pas:178-223)
 extern "C" tm_knn_short *ann_kdtree_short_create(int16_t **rows, int n, int dim, int bucket, int split) {
   (void)bucket; (void)split;

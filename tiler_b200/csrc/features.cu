@@ -130,12 +130,14 @@ __device__ __forceinline__ double dct_inner(const float *__restrict__ s_c, const
   return __dadd_rn(acc0, acc1);
 }
 
-// MODE 0: RGB tiles; 1: palette indices with per-tile palette; 2: every (tile, palette) pair, item = tile*n_pal + pal
+// MODE 0: RGB tiles; 1: palette indices with per-tile palette; 2: every (tile, palette) pair, item = tile*n_pal + pal;
+// 3: RGB tiles read through their mirror flags (pal_idx = flags[n]: ConvertToCpnPixels with AHMirror / AVMirror, :3049-3101);
+// 4: sliding window over a frame buffer (rgb = frame [h][fw], item = oy * pw + ox: DoDCTs, :1437-1462)
 template <int MODE>
 __global__ void __launch_bounds__(192, 4)
 features_i16_kernel(const int32_t *__restrict__ rgb, const uint8_t *__restrict__ pal_idx, int n_pal_all,
                     const int32_t *__restrict__ sel_pal, const int32_t *__restrict__ palettes, int pal_size, int64_t n,
-                    const float *__restrict__ lutT, int16_t *__restrict__ out) {
+                    const float *__restrict__ lutT, int16_t *__restrict__ out, int fw = 0, int pw = 0) {
   extern __shared__ float s_lut[];       // 4096 floats
   __shared__ float s_cpn[3][64];
   __shared__ int16_t s_out[192];
@@ -150,6 +152,13 @@ features_i16_kernel(const int32_t *__restrict__ rgb, const uint8_t *__restrict__
       int32_t col;
       if (MODE == 0) {
         col = __ldg(rgb + tile * 64 + t);
+      } else if (MODE == 3) {
+        const int fl = __ldg(pal_idx + tile);
+        const int x = (fl & 1) ? 7 - (t & 7) : (t & 7), y = (fl & 2) ? 7 - (t >> 3) : (t >> 3);
+        col = __ldg(rgb + tile * 64 + y * 8 + x);
+      } else if (MODE == 4) {
+        const int64_t oy = tile / pw, ox = tile - oy * pw;
+        col = __ldg(rgb + (oy + (t >> 3)) * fw + ox + (t & 7));
       } else {
         const int64_t src = (MODE == 2) ? tile / n_pal_all : tile;
         const int32_t p = (MODE == 2) ? (int32_t)(tile % n_pal_all) : __ldg(sel_pal + tile);
@@ -233,6 +242,28 @@ int launch_features_rgb(const int32_t *rgb, int64_t n, int16_t *out, cudaStream_
   if (rc) return rc;
   ProfScope prof("features_rgb", st);
   features_i16_kernel<0><<<grid_for(n, 4), 192, 4096 * sizeof(float), st>>>(rgb, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+int launch_features_rgb_mirrored(const int32_t *rgb, const uint8_t *flags, int64_t n, int16_t *out, cudaStream_t st) {
+  if (n <= 0) return TM_OK;
+  int rc = features_init(st);
+  if (rc) return rc;
+  features_i16_kernel<3><<<grid_for(n, 4), 192, 4096 * sizeof(float), st>>>(rgb, flags, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+// frame [h][w] packed RGB -> features of the 8x8 window at every pixel offset, [(h-7)][(w-7)][192]
+int launch_features_sliding(const int32_t *frame, int w, int h, int16_t *out, cudaStream_t st) {
+  if (w < 8 || h < 8) return TM_ERR_ARG;
+  int rc = features_init(st);
+  if (rc) return rc;
+  const int64_t n = (int64_t)(w - 7) * (h - 7);
+  ProfScope prof("features_sliding", st);
+  features_i16_kernel<4><<<grid_for(n, 4), 192, 4096 * sizeof(float), st>>>(frame, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out, w,
+                                                                             w - 7);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }

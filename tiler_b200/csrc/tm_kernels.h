@@ -45,6 +45,21 @@ int launch_features_pal(const uint8_t *pal_idx, const int32_t *tile_pal, const i
 int launch_features_allpairs(const uint8_t *pal_idx, int64_t n_tiles, const int32_t *palettes, int pal_size, int n_pal,
                              int16_t *out, cudaStream_t st);
 int launch_features_f64(const int32_t *rgb, int64_t n, int mode, int use_lab, double *out, cudaStream_t st);
+int launch_features_rgb_mirrored(const int32_t *rgb, const uint8_t *flags, int64_t n, int16_t *out, cudaStream_t st);
+int launch_features_sliding(const int32_t *frame, int w, int h, int16_t *out, cudaStream_t st);
+
+// ---- motion.cu
+// motion search of every tile of a frame against the sliding features of the previous frame buffer
+int launch_motion_search(const int16_t *cur_feat, int tw, int th, const int16_t *dcts, int radius_setting, int32_t *pred_x,
+                         int32_t *pred_y, uint32_t *err, cudaStream_t st);
+// TFrame.Reconstruct's decision + frame-buffer draw for one frame; motion arrays null on the first frame of a sequence
+int launch_reconstruct_decide(const uint8_t *flags, int tw, int th, const int32_t *mp_x, const int32_t *mp_y, const uint32_t *mp_err,
+                              const int32_t *knn_tile, const int32_t *knn_pal, const uint32_t *knn_err, const uint8_t *dict_idx,
+                              const int32_t *palettes, int pal_size, const int32_t *back, int32_t *front, int32_t *tile_idx,
+                              int32_t *pal_idx, int32_t *pred_x, int32_t *pred_y, uint8_t *is_pred, uint32_t *err, float *psnr,
+                              cudaStream_t st);
+// RGB PSNR accumulators: sum of squared channel differences between two packed-RGB buffers
+int launch_sq_err_rgb(const int32_t *a, const int32_t *b, int64_t n, unsigned long long *acc, cudaStream_t st);
 int launch_mirror_canonicalise(int32_t *rgb, int64_t n, uint8_t *flags, cudaStream_t st);
 int features_init(cudaStream_t st);
 
