@@ -100,7 +100,7 @@ def build_dictionary(enc, canon_tiles, canon_flags, stages):
         stages[name + "_ms"] = round((time.perf_counter() - t0) * 1e3, 2)
         return r
 
-    enc.reduce(canon_tiles, canon_flags, N_DICT)
+    enc.reduce_sample(canon_tiles, canon_flags, N_DICT)
     timed("prepare_palettes", enc.prepare_palettes)
     timed("dither", enc.dither)
     timed("prepare_reconstruct", enc.prepare_reconstruct)

@@ -195,6 +195,12 @@ int tm_predict_motion_frame(const int32_t *prev_frame, const int32_t *canon_tile
 int tm_reconstruct_sequence(tm_matcher *m, const int32_t *canon_tiles, const uint8_t *flags, int n_frames, int tw, int th, int radius,
                             int k, int32_t *tile_idx, int32_t *pal_idx, int32_t *pred_x, int32_t *pred_y, uint8_t *is_pred,
                             uint32_t *err, float *psnr, int32_t *recon);
+/* ---------------------------------------------------------------- batched: Reduce (tilingencoder.pas:4014-4103, 4720-4781)
+   Exact equivalence classes of n RGB tiles [n][64] (MakeTilesUnique on RGB pixels): class_id[n] in [0, *n_classes),
+   equal ids <=> all 64 pixels equal.  The numbering is arbitrary (hash order); the host orders the chosen dictionary
+   (ReindexTiles, :4626-4696). */
+int tm_tile_classes(const int32_t *rgb, int64_t n, int32_t *class_id, int32_t *n_classes);
+
 /* mean squared error over the three colour channels of two packed-RGB buffers of n pixels */
 int tm_mse_rgb(const int32_t *a, const int32_t *b, int64_t n, double *mse);
 

@@ -501,3 +501,60 @@ def test_reconstruct_sequence_device_tensors(tm, oracle):
     for key in ("is_pred", "pred_x", "pred_y", "tile_idx", "pal_idx", "recon"):
         assert np.array_equal(dev[key].cpu().numpy(), host[key]), key
     m.close()
+
+
+# ---------------------------------------------------------------- Reduce and the whole encode
+def test_tile_classes_exact(tm):
+    rng = np.random.default_rng(9)
+    base = rand_tiles(5000, 31)
+    tiles = base[rng.integers(0, 5000, size=60000)]            # heavy duplication
+    tiles[::7, 63] ^= 1                                         # near-duplicates differing in the last pixel only
+    cls, n_cls = tm.tile_classes(tiles)
+    rows = np.ascontiguousarray(tiles).view(np.dtype((np.void, 256))).reshape(-1)
+    uniq, inv = np.unique(rows, return_inverse=True)
+    assert n_cls == len(uniq)
+    # same partition: class ids are a relabelling of numpy's
+    pairs = np.unique(np.stack([cls, inv.reshape(-1)], axis=1), axis=0)
+    assert len(pairs) == n_cls and len(np.unique(pairs[:, 0])) == n_cls and len(np.unique(pairs[:, 1])) == n_cls
+    assert cls.min() == 0 and cls.max() == n_cls - 1
+
+
+def test_encode_end_to_end_small_clip(tm, oracle):
+    from tiler_b200 import gtm
+    from tiler_b200.encoder import TilingEncoder, euclidean_to_psnr, psnr_rgb
+    w, h, n = 96, 64, 6
+    frames = synth.pack_rgb(synth.make_clip(w, h, n, cut_every=3, seed=33, n_sprites=4))
+    tw, th = w // 8, h // 8
+    seqs = [(0, 2), (3, 5)]
+    enc = TilingEncoder(palette_size=16, palette_count=2)
+    res = enc.encode(frames, seqs, tile_count=150, radius=32)
+    # --- PredictMotion + Reduce against a numpy/oracle restatement
+    tiles = np.stack([synth.frame_to_tiles(f) for f in frames])
+    canon, flags = tm.mirror_canonicalise(tiles.reshape(-1, 64))
+    canon, flags = canon.reshape(n, -1, 64), flags.reshape(n, -1)
+    psnr = np.empty((n, tw * th), np.float32)
+    for f in range(n):
+        prev = frames[f - 1] if f > 0 else frames[1]
+        cur = oracle.features_from_rgb_mirrored(canon[f], flags[f])
+        _, _, e = oracle.motion_search(cur, tw, th, oracle.sliding_features(prev), 32)
+        psnr[f] = [oracle.euclidean_to_psnr(int(v)) for v in e]
+    got_psnr, _, _ = enc.predict_motion(frames, canon, flags, tw, th, 32)
+    assert np.array_equal(got_psnr, psnr)
+    eff = psnr.copy(); eff[0] /= np.float32(10); eff[3] /= np.float32(10)
+    unpred = ~(eff.reshape(-1) > np.float32(enc.reduce_threshold))
+    rows = np.ascontiguousarray(canon.reshape(-1, 64)).view(np.dtype((np.void, 256))).reshape(-1)
+    assert len(enc.tiles) == len(np.unique(rows[unpred]))                       # MakeTilesUnique(True) count at the chosen threshold
+    assert abs(len(enc.tiles) - 150) <= 12                                      # the search lands near the requested tile count
+    uc = enc.use_count
+    assert (np.diff(uc) <= 0).all() and uc.sum() == unpred.sum()                # ReindexTiles(True): use count descending
+    # --- the stream decodes to exactly the frames Reconstruct drew, and they resemble the source
+    decoded, hdr = gtm.decode_gtm(res["gtm"])
+    assert hdr["frame_count"] == n and hdr["kf_count"] == 2 and (hdr["width"], hdr["height"]) == (w, h)
+    assert np.array_equal(decoded, res["recon"])
+    assert psnr_rgb(decoded, frames) > 18.0
+    assert abs(psnr_rgb(decoded, frames) - 10 * np.log10(255.0 ** 2 / tm.mse_rgb(frames, decoded))) < 1e-9
+    tmap = res["tilemap"]
+    assert not tmap["is_pred"][0].any() and not tmap["is_pred"][3].any()        # first frame of each keyframe sequence
+    assert tmap["is_pred"][[1, 2, 4, 5]].any()
+    used = tmap["tile_idx"][tmap["tile_idx"] >= 0]
+    assert used.max() == len(res["tiles"]) - 1 and np.array_equal(np.bincount(used, minlength=len(res["tiles"])), res["use_count"])

@@ -432,6 +432,16 @@ def predict_motion_frame(prev_frame, canon_tiles, flags, tw, th, radius=32):
     return px, py, err
 
 
+def tile_classes(rgb):
+    """Exact duplicate classes of RGB tiles [n,64] (MakeTilesUnique(True), tilingencoder.pas:4720-4781) -> (class_id [n], n_classes)."""
+    c = _Call(rgb)
+    n = _n_rows(rgb, 64)
+    cls, pc = c.out((n,), np.int32)
+    cnt = C.c_int()
+    check(_lib.lib().tm_tile_classes(c.inp(rgb, np.int32), n, pc, C.byref(cnt)))
+    return cls, cnt.value
+
+
 def mse_rgb(a, b):
     c = _Call(a, b)
     n = int(np.prod(a.shape))

@@ -887,6 +887,25 @@ extern "C" int tm_mse_rgb(const int32_t *a, const int32_t *b, int64_t n, double 
   return TM_OK;
 }
 
+// ------------------------------------------------------------------ Reduce: exact duplicate classes of RGB tiles
+extern "C" int tm_tile_classes(const int32_t *rgb, int64_t n, int32_t *class_id, int32_t *n_classes) {
+  RC(require_gpu());
+  if (!rgb || !class_id || !n_classes || n < 1 || n > 0x7fffffff) return fail(TM_ERR_ARG, "tm_tile_classes: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int32_t *d_rgb = s.in(rgb, (size_t)n * 64);
+  int32_t *d_cls = s.out(class_id, (size_t)n);
+  const size_t wsb = tile_classes_ws_bytes(n);
+  void *ws = s.temp(wsb);
+  int32_t *d_cnt = (int32_t *)s.temp(4);
+  int32_t host_cnt = 0;
+  if (s.err == TM_OK) s.err = run_tile_classes(d_rgb, n, d_cls, d_cnt, ws, wsb, s.st);
+  if (s.err == TM_OK && cudaMemcpyAsync(&host_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.err = TM_ERR_CUDA;
+  RC(s.finish(true));
+  *n_classes = host_cnt;
+  return TM_OK;
+}
+
 // ================================================================== drop-in exports (extern.pas:178-223)
 extern "C" tm_knn_short *ann_kdtree_short_create(int16_t **rows, int n, int dim, int bucket, int split) {
   (void)bucket; (void)split;

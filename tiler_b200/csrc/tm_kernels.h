@@ -107,6 +107,10 @@ size_t kmeans_update_ws_bytes(int64_t n, int k, int dim = 192);
 int run_palette_quantise(const int32_t *rgb, const int32_t *tile_pal, int64_t n_tiles, int n_pal, int pal_size, const double *init,
                          unsigned long long seed, int max_iter, int32_t *palettes_out, int32_t *iters_out, cudaStream_t st);
 
+// ---- reduce.cu: exact equivalence classes of 256-byte tiles (MakeTilesUnique on RGB pixels)
+size_t tile_classes_ws_bytes(int64_t n);
+int run_tile_classes(const int32_t *rgb, int64_t n, int32_t *class_id, int32_t *n_classes_dev, void *ws, size_t ws_bytes, cudaStream_t st);
+
 // ---- dlquant.cu
 int run_dl3quant(const uint8_t *rgb, const int64_t *img_off, int n_img, int64_t max_pixels, int quant_to, int bpc, uint8_t *pal_out,
                  int32_t *count_out, cudaStream_t st);

@@ -2,14 +2,46 @@
 (tilingencoder.pas:1843-1962): PreparePalettes -> Dither -> PrepareReconstruct -> Reconstruct, each one a handful of
 batched calls into libtm_gpu.so instead of the per-tile DLL calls of the reference.
 
-What is NOT here (kept by the FreePascal host, out of this tier's scope): video loading, keyframe
-detection, motion prediction, the PSNR-threshold dictionary selection (TransferTiles), OptimizePalettes, reindexing
-and the GTM bitstream writer.  `reduce()` below is a stand-in that picks dictionary tiles so the four stages can run
-end to end on a synthetic clip.
+`encode()` chains every step of TTilingEncoder.Run (Load -> PredictMotion -> Reduce -> PreparePalettes -> Dither ->
+Reconstruct -> Reindex -> Save, tilingencoder.pas:5530-5552) on a clip already in memory; the heavy steps are library
+calls, the bookkeeping between them (threshold search over per-class PSNRs, dictionary ordering, stream writing) is
+host code as it is in the reference.  Not here: video decoding (FFmpeg), keyframe detection (sequences are an input)
+and OptimizePalettes (it only permutes colour order).  `reduce_sample()` is the old stand-in that samples dictionary
+tiles without the motion pass; bench.py's match-stage step still uses it.
 """
 import numpy as np
 
 from . import api
+from . import gtm as gtm_io
+
+C_PSNR_MAX = np.float64(10.0 * np.log(255.0 * 255.0 / 0.5) / np.log(10.0))   # cPsnrMaxValue, utils.pas:111
+C_INV_PHI = 2.0 / (1.0 + np.sqrt(5.0))                                         # cInvPhi, utils.pas:42-43
+
+
+def euclidean_to_psnr(err):
+    """EuclideanToPSNR (utils.pas:1074-1078), vectorised: Single(d / 192) -> max 0.5 -> 10 log10(255^2 / x) -> Single."""
+    r = (np.asarray(err).astype(np.float64) * (1.0 / 192.0)).astype(np.float32)
+    m = np.maximum(r.astype(np.float64), 0.5)
+    return (10.0 * np.log10(255.0 * 255.0 / m)).astype(np.float32)
+
+
+def golden_ratio_search(func, min_x, max_x, objective_y, eps_x=1e-6, eps_y=0.5):
+    """GoldenRatioSearch (utils.pas:1044-1072).  Returns (result x, last evaluated x): the encoder state after the search
+    is the one left by the LAST evaluation, not by the returned abscissa."""
+    last = None
+    while True:
+        if abs(min_x - max_x) <= eps_x:
+            return min_x, last
+        t = (1.0 - C_INV_PHI) if min_x < max_x else C_INV_PHI
+        x = min_x + (max_x - min_x) * t
+        y = func(x)
+        last = x
+        if abs(y - objective_y) <= eps_y:
+            return x, last
+        if y < objective_y:
+            min_x = x
+        else:
+            max_x = x
 
 try:
     import torch
@@ -37,6 +69,8 @@ class TilingEncoder:
         self.palettes = None    # [palette_count, palette_size] int32
         self.tile_idx = None    # dithered palette indices [n,64]
         self.matcher = None
+        self.use_count = None
+        self.reduce_threshold = None
 
     def _to(self, x):
         if self.device is None or x is None:
@@ -51,8 +85,132 @@ class TilingEncoder:
         tiles, flags = api.mirror_canonicalise(ft.reshape(-1, 64))
         return tiles.reshape(shape), flags.reshape(shape[:2])
 
-    # --- Reduce stand-in (the reference's TransferTiles is next-tier work)
-    def reduce(self, canon_tiles, canon_flags, tile_count):
+    # --- PredictMotion (tilingencoder.pas:1964-1991, 1154-1282): every tile against the previous SOURCE frame
+    def predict_motion(self, frames_packed, canon_tiles, canon_flags, tw, th, radius=32):
+        """frames_packed [n, th*8, tw*8] source pixels; -> (psnr f32 [n, nt], pred_x, pred_y) on the host.
+        Frame 0 is predicted from frame 1 (:1982-1984); a one-frame clip is predicted from a black buffer."""
+        n = int(frames_packed.shape[0])
+        nt = tw * th
+        psnr = np.empty((n, nt), np.float32)
+        px = np.empty((n, nt), np.int32)
+        py = np.empty((n, nt), np.int32)
+        fr = self._to(frames_packed)
+        for f in range(n):
+            if f > 0:
+                prev = fr[f - 1]
+            elif n > 1:
+                prev = fr[1]
+            else:
+                prev = fr[0] * 0
+            x, y, e = api.predict_motion_frame(prev, canon_tiles[f], canon_flags[f], tw, th, radius)
+            e = e.cpu().numpy() if api._is_dev(e) else e
+            psnr[f] = euclidean_to_psnr(np.asarray(e).view(np.uint32))
+            px[f] = x.cpu().numpy() if api._is_dev(x) else x
+            py[f] = y.cpu().numpy() if api._is_dev(y) else y
+        return psnr, px, py
+
+    # --- Reduce (tilingencoder.pas:1908-1926, 4014-4103, 4626-4696, 4720-4781)
+    def reduce(self, canon_tiles, canon_flags, psnr, seq_start_frames, tile_count):
+        """SolveTileCount: golden-ratio search of the PSNR threshold x for which the number of distinct unpredicted tiles
+        equals tile_count.  A tile is predicted when its motion PSNR > x (PSNR / 10 > x on the first frame of a keyframe
+        sequence, :4028-4031).  The distinct-tile count of MakeTilesUnique(True) comes from exact duplicate classes computed
+        once on the GPU; the count for a threshold is then the number of classes whose smallest effective PSNR is <= x.
+        -> tilemap TileIdx [n, nt] (-1 = predicted), and fills self.tiles / tile_flags / use_count in ReindexTiles(True)
+        order (use count descending, then RGB pixels as unsigned dwords ascending)."""
+        shape = tuple(canon_tiles.shape[:2])
+        flat = canon_tiles.reshape(-1, 64)
+        cls, n_cls = api.tile_classes(flat)
+        cls = cls.cpu().numpy() if api._is_dev(cls) else np.asarray(cls)
+        eff = np.asarray(psnr, dtype=np.float32).copy()
+        for f in seq_start_frames:
+            eff[f] = eff[f] / np.float32(10.0)
+        eff = eff.reshape(-1)
+        cls_min = np.full(n_cls, np.inf, dtype=np.float32)
+        np.minimum.at(cls_min, cls, eff)
+        sorted_min = np.sort(cls_min)
+        target = min(int(tile_count), int(flat.shape[0]))
+        x_res, x_last = golden_ratio_search(lambda x: float(np.searchsorted(sorted_min, np.float32(x), side="right")), 0.0,
+                                            float(C_PSNR_MAX), float(target))
+        x = np.float32(x_last if x_last is not None else x_res)
+        unpred = ~(eff > x)                                   # IsPredicted := PSNR > x
+        idx_all = np.arange(flat.shape[0])
+        use = np.bincount(cls[unpred], minlength=n_cls)
+        rep = np.full(n_cls, flat.shape[0], dtype=np.int64)
+        np.minimum.at(rep, cls[unpred], idx_all[unpred])      # representative = first unpredicted member
+        chosen = np.nonzero(use > 0)[0]
+        rep_idx = rep[chosen]
+        if api._is_dev(flat):
+            rep_t = torch.as_tensor(rep_idx, device=flat.device)
+            rep_tiles_host = flat[rep_t].cpu().numpy()
+        else:
+            rep_tiles_host = flat[rep_idx]
+        # ReindexTiles(True): (use count desc, CompareDWord on the 64 pixels asc)
+        keys = [rep_tiles_host[:, c].astype(np.uint32) for c in range(63, -1, -1)] + [-use[chosen].astype(np.int64)]
+        order = np.lexsort(keys)
+        chosen, rep_idx = chosen[order], rep_idx[order]
+        new_of_cls = np.full(n_cls, -1, dtype=np.int32)
+        new_of_cls[chosen] = np.arange(len(chosen), dtype=np.int32)
+        tile_idx = np.where(unpred, new_of_cls[cls], -1).astype(np.int32).reshape(shape)
+        fl = canon_flags.reshape(-1)
+        if api._is_dev(flat):
+            rep_t = torch.as_tensor(rep_idx, device=flat.device)
+            self.tiles, self.tile_flags = flat[rep_t].contiguous(), fl[rep_t].contiguous()
+        else:
+            self.tiles, self.tile_flags = np.ascontiguousarray(flat[rep_idx]), np.ascontiguousarray(fl[rep_idx])
+        self.use_count = use[chosen].astype(np.int32)
+        self.reduce_threshold = float(x)
+        return tile_idx
+
+    # --- whole pipeline (TTilingEncoder.Run, tilingencoder.pas:5530-5552)
+    def encode(self, frames_packed, sequences, tile_count, radius=32, fps=24.0, out_path=None, emit_skip_blocks=True):
+        """frames_packed [n, H, W] int32 0x00BBGGRR with H, W multiples of 8; sequences = [(start, end)] inclusive.
+        -> dict(gtm bytes, tilemap, recon frames, dictionary, timings)."""
+        import time
+        n, H, W = (int(v) for v in frames_packed.shape)
+        assert H % 8 == 0 and W % 8 == 0
+        tw, th = W // 8, H // 8
+        nt = tw * th
+        t = {}
+        t0 = time.perf_counter()
+        tiles = np.ascontiguousarray(np.asarray(frames_packed).reshape(n, th, 8, tw, 8).transpose(0, 1, 3, 2, 4).reshape(n, nt, 64))
+        canon, flags = self.load_tiles(tiles)
+        t["load"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        psnr, _, _ = self.predict_motion(frames_packed, canon, flags, tw, th, radius)
+        t["predict_motion"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        self.reduce(canon, flags, psnr, [s for s, _ in sequences], tile_count)
+        t["reduce"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        self.prepare_palettes()
+        t["prepare_palettes"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        self.dither()
+        t["dither"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        self.prepare_reconstruct()
+        keys = ("tile_idx", "pal_idx", "pred_x", "pred_y", "is_pred", "err", "psnr", "recon")
+        parts = {k: [] for k in keys}
+        for s0, s1 in sequences:
+            r = self.matcher.reconstruct_sequence(canon[s0:s1 + 1], flags[s0:s1 + 1], tw, th, radius=radius)
+            for k in keys:
+                v = r[k]
+                parts[k].append(v.cpu().numpy() if api._is_dev(v) else v)
+        tm = {k: np.concatenate(parts[k]) for k in keys}
+        tm["err"] = tm["err"].view(np.uint32)
+        tm["mirror"] = flags.cpu().numpy() if api._is_dev(flags) else np.asarray(flags)
+        self.finish_reconstruct()
+        t["reconstruct"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        didx = self.tile_idx.cpu().numpy() if api._is_dev(self.tile_idx) else np.asarray(self.tile_idx)
+        pal = self.palettes.cpu().numpy() if api._is_dev(self.palettes) else np.asarray(self.palettes)
+        final_tiles, use_count, tile_map = gtm_io.reindex(didx, tm["tile_idx"])
+        tm_out = dict(tm)
+        tm_out["tile_idx"] = tile_map
+        t["reindex"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        data = gtm_io.write_gtm(out_path, tm_out, final_tiles, use_count, pal, tw, th, sequences, fps=fps,
+                                settings_text=f"tiler_b200 PaletteSize={self.palette_size} PaletteCount={self.palette_count}",
+                                emit_skip_blocks=emit_skip_blocks)
+        t["save"] = time.perf_counter() - t0
+        return {"gtm": data, "tilemap": tm_out, "recon": tm["recon"], "tiles": final_tiles, "use_count": use_count, "palettes": pal,
+                "timings": t, "mean_tile_psnr": float(tm["psnr"].mean()), "dictionary_before_reindex": int(didx.shape[0])}
+
+    # --- Reduce stand-in used by bench.py's match-stage step: samples dictionary tiles, no motion pass
+    def reduce_sample(self, canon_tiles, canon_flags, tile_count):
         flat = canon_tiles.reshape(-1, 64)
         fl = canon_flags.reshape(-1)
         n = flat.shape[0]

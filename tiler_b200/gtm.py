@@ -1,0 +1,212 @@
+"""GTM stream I/O for verification: writes what TTilingEncoder.SaveStream writes
+(tilingencoder.pas:5177-5482) and decodes it the way LoadStream (:4880-5175) / gtm.player.js do, so that an encode can
+be checked end to end (decoded-frame PSNR) without the FreePascal host or a browser.
+
+Host-side CPU code over libtm_gtm.so (csrc/gtm_host.cpp).  It is not on the GPU product path: in the reference the
+bitstream writer stays in the Pascal host and the decoder is the player.
+"""
+import ctypes as C
+import os
+import struct
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+GTM_LC, GTM_LP, GTM_PB, GTM_DICT = 8, 0, 2, 1 << 22      # LZCompress, extern.pas:420-440 (props byte 0x62, 4 MiB)
+ENCODER_VERSION = 4                                        # tilingencoder.pas:5343
+NULL_COLOR = -65281                                        # cDitheringNullColor
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "libtm_gtm.so")
+        if not os.path.exists(path):
+            raise RuntimeError(f"{path} not built: run `make -C tiler_b200/csrc`")
+        L = C.CDLL(path)
+        L.tmh_lzma_encode.restype = C.c_int64
+        L.tmh_lzma_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_int64]
+        L.tmh_lzma_decode.restype = C.c_int64
+        L.tmh_lzma_decode.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
+        L.tmh_gtm_write_frames.restype = C.c_int64
+        L.tmh_gtm_write_frames.argtypes = [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                                              C.c_void_p, C.c_int64]
+        L.tmh_gtm_decoder_create.restype = C.c_void_p
+        L.tmh_gtm_decoder_create.argtypes = []
+        L.tmh_gtm_decoder_destroy.argtypes = [C.c_void_p]
+        L.tmh_gtm_decoder_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
+        L.tmh_gtm_decode.restype = C.c_int64
+        L.tmh_gtm_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        _LIB = L
+    return _LIB
+
+
+# ------------------------------------------------------------------ LZMA ("alone" container, end marker)
+def lzma_encode(data, lc=GTM_LC, lp=GTM_LP, pb=GTM_PB, dict_size=GTM_DICT):
+    src = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+    cap = int(src.size + src.size // 4 + 1024)
+    out = np.empty(cap, dtype=np.uint8)
+    n = lib().tmh_lzma_encode(src.ctypes.data, src.size, lc, lp, pb, dict_size, out.ctypes.data, cap)
+    if n < 0:
+        raise RuntimeError(f"tmh_lzma_encode failed ({n})")
+    return out[:n].tobytes()
+
+
+def lzma_decode(data, offset=0, max_out=None):
+    """Decodes one stream starting at data[offset] -> (bytes, input bytes consumed)."""
+    src = np.frombuffer(data, dtype=np.uint8)[offset:]
+    cap = int(max_out or max(1 << 20, 16 * src.size))
+    while True:
+        out = np.empty(cap, dtype=np.uint8)
+        used = C.c_int64()
+        n = lib().tmh_lzma_decode(src.ctypes.data, src.size, out.ctypes.data, cap, C.byref(used))
+        if n == -1 and max_out is None:
+            cap *= 4
+            continue
+        if n < 0:
+            raise RuntimeError(f"tmh_lzma_decode failed ({n})")
+        return out[:n].tobytes(), used.value
+
+
+# ------------------------------------------------------------------ dictionary bookkeeping (Reindex, tilingencoder.pas:1992-2040)
+def reindex(tiles_idx, tile_idx_map):
+    """MakeTilesUnique(False) + use counts + ReindexTiles(False) (tilingencoder.pas:2010-2037, 4720-4781, 4626-4696):
+    merges dictionary tiles with identical palette indices, counts how often each is referenced by a tilemap item
+    (TileIdx >= 0, predicted items included, as the reference does), drops unused tiles, orders by (use count descending,
+    palette-index bytes ascending) and remaps the tilemap.  -> (tiles [n,64] uint8, use_count [n], remapped tile_idx)."""
+    tiles_idx = np.ascontiguousarray(tiles_idx, dtype=np.uint8).reshape(-1, 64)
+    tmap = np.asarray(tile_idx_map, dtype=np.int64)
+    as_rows = tiles_idx.view(np.dtype((np.void, 64))).reshape(-1)
+    uniq, inverse = np.unique(as_rows, return_inverse=True)            # lexicographic on bytes = CompareByte order
+    valid = tmap >= 0
+    cls = np.full(tmap.shape, -1, dtype=np.int64)
+    cls[valid] = inverse[tmap[valid]]
+    use = np.bincount(cls[valid].reshape(-1), minlength=len(uniq))
+    keep = np.nonzero(use > 0)[0]
+    order = keep[np.lexsort((keep, -use[keep]))]                         # keep is already in byte order
+    new_of_cls = np.full(len(uniq), -1, dtype=np.int64)
+    new_of_cls[order] = np.arange(len(order))
+    out_map = np.full(tmap.shape, -1, dtype=np.int32)
+    out_map[valid] = new_of_cls[cls[valid]].astype(np.int32)
+    tiles_out = np.frombuffer(uniq[order].tobytes(), dtype=np.uint8).reshape(-1, 64).copy()
+    return tiles_out, use[order].astype(np.int32), out_map
+
+
+# ------------------------------------------------------------------ writer (SaveStream)
+def _cmd(code, data):
+    return struct.pack("<H", ((data << 4) | code) & 0xFFFF)
+
+
+def write_gtm(path_or_none, tm, tiles_idx, use_count, palettes, tw, th, sequences, fps=24.0, settings_text="",
+              emit_skip_blocks=True):
+    """tm: dict of per-frame arrays [n_frames, th*tw] (tile_idx, pal_idx, pred_x, pred_y, is_pred, mirror) with tile_idx
+    already re-indexed; tiles_idx / use_count: the final dictionary; palettes [n_pal, pal_size] int32; sequences: list of
+    (start_frame, end_frame) inclusive.  Returns the file bytes (and writes them when a path is given)."""
+    n_frames = int(tm["tile_idx"].shape[0])
+    nt = tw * th
+    L = lib()
+    arr = {k: np.ascontiguousarray(tm[k], dtype=dt) for k, dt in (("tile_idx", np.int32), ("pal_idx", np.int32), ("pred_x", np.int32),
+                                                                  ("pred_y", np.int32), ("is_pred", np.uint8), ("mirror", np.uint8))}
+    tiles_idx = np.ascontiguousarray(tiles_idx, dtype=np.uint8).reshape(-1, 64)
+    use_count = np.ascontiguousarray(use_count, dtype=np.int32)
+    n_tiles = len(tiles_idx)
+    pal_size = int(palettes.shape[1])
+    # ---- first chunk preamble: settings, dimensions, tile set, palettes (:5331-5335, 5318-5329, 5292-5316, 5270-5290)
+    pre = bytearray()
+    txt = settings_text.encode("latin-1")
+    pre += _cmd(15, 0) + struct.pack("<I", len(txt)) + txt
+    pre += _cmd(14, 0) + struct.pack("<HHII", tw, th, int(round(1e9 / fps)), n_tiles)
+    reused = 0
+    ones = np.nonzero(use_count == 1)[0]
+    if len(ones):
+        reused = int(ones[0])                     # tiles are sorted by use count: everything before the first single-use tile
+    if reused > 0:
+        pre += _cmd(13, pal_size) + struct.pack("<II", 0, reused - 1) + tiles_idx[:reused].tobytes()
+    for p in range(palettes.shape[0]):
+        cols = np.asarray(palettes[p], dtype=np.int64).copy()
+        cols[cols == NULL_COLOR] = 0xFFFFFF
+        cols = (cols & 0xFFFFFF) | 0xFF000000
+        pre += _cmd(12, 0) + struct.pack("<H", p) + cols.astype("<u4").tobytes()
+    # ---- chunks
+    chunks, kf_info = [], []
+    for ki, (f0, f1) in enumerate(sequences):
+        nf = f1 - f0 + 1
+        cap = nf * nt * 70 + 64
+        buf = np.empty(cap, dtype=np.uint8)
+        sl = slice(f0, f1 + 1)
+        views = [np.ascontiguousarray(arr[k][sl]) for k in ("tile_idx", "pal_idx", "pred_x", "pred_y", "is_pred", "mirror")]
+        n = L.tmh_gtm_write_frames(*[v.ctypes.data for v in views], nf, nt, tiles_idx.ctypes.data, use_count.ctypes.data, n_tiles,
+                                   int(emit_skip_blocks), 1, buf.ctypes.data, cap)
+        assert 0 < n <= cap
+        raw = (bytes(pre) if ki == 0 else b"") + buf[:n].tobytes()
+        comp = lzma_encode(raw)
+        chunks.append(comp)
+        kf_info.append((ki, f0, len(raw), len(comp), int(round(1000.0 * f0 / fps))))
+    # ---- header (TGTMHeader, TGTMKeyFrameInfo: tilingencoder.pas:30-51, 5338-5370, 5470-5476)
+    whole_header = 40 + 28 * len(sequences)
+    total = sum(len(c) for c in chunks)
+    avg_bps = int(round(total * fps / n_frames))
+    max_bps = 0
+    last = 0
+    for ki, (f0, f1) in enumerate(sequences):
+        cnt = f1 - last + 1
+        last = f1 + 1
+        if ki > 0 or len(sequences) == 1:
+            max_bps = max(max_bps, int(round(len(chunks[ki]) * fps / cnt)))
+    out = bytearray()
+    out += b"GTMv" + struct.pack("<9I", 32, whole_header, ENCODER_VERSION, tw * 8, th * 8, len(sequences), n_frames, avg_bps, max_bps)
+    for ki, f0, raw_n, comp_n, ms in kf_info:
+        out += b"GTMk" + struct.pack("<6I", 20, ki, f0, raw_n, comp_n, ms)
+    for c in chunks:
+        out += c
+    if path_or_none:
+        with open(path_or_none, "wb") as fh:
+            fh.write(out)
+    return bytes(out)
+
+
+# ------------------------------------------------------------------ reader / decoder (LoadStream, gtm.player.js)
+def parse_header(data):
+    if data[:4] != b"GTMv":
+        raise ValueError("not a GTM stream")
+    riff, whole, ver, pw, ph, kfc, fc, avg, mx = struct.unpack_from("<9I", data, 4)
+    kfs = []
+    off = 8 + riff
+    for _ in range(kfc):
+        if data[off:off + 4] != b"GTMk":
+            raise ValueError("bad keyframe info")
+        rs, ki, fi, raw_n, comp_n, ms = struct.unpack_from("<6I", data, off + 4)
+        kfs.append({"kf_index": ki, "frame_index": fi, "raw_size": raw_n, "compressed_size": comp_n, "timecode_ms": ms})
+        off += 8 + rs
+    return {"whole_header_size": whole, "encoder_version": ver, "width": pw, "height": ph, "kf_count": kfc, "frame_count": fc,
+            "avg_bytes_per_sec": avg, "kf_max_bytes_per_sec": mx, "keyframes": kfs, "data_offset": off}
+
+
+def decode_gtm(data, max_frames=None):
+    """-> (frames int32 [n, H, W] packed 0x00BBGGRR, header dict).  Chunks are decompressed back to back (each ends with its
+    own end marker, wlzma.wrk.js:50-63) and played through one decoder state."""
+    hdr = parse_header(data)
+    L = lib()
+    dec = L.tmh_gtm_decoder_create()
+    try:
+        off = hdr["data_offset"]
+        n_total = hdr["frame_count"] if max_frames is None else min(max_frames, hdr["frame_count"])
+        frames = np.zeros((n_total, hdr["height"], hdr["width"]), dtype=np.int32)
+        done = 0
+        ki = 0
+        while off < len(data) and done < n_total:
+            raw_hint = hdr["keyframes"][ki]["raw_size"] if ki < len(hdr["keyframes"]) else None
+            raw, used = lzma_decode(data, off, max_out=None if not raw_hint else raw_hint + 16)
+            off += used
+            ki += 1
+            rb = np.frombuffer(raw, dtype=np.uint8)
+            room = n_total - done
+            got = L.tmh_gtm_decode(dec, rb.ctypes.data, rb.size, frames[done:].ctypes.data, room)
+            if got < 0:
+                raise ValueError("malformed GTM command stream")
+            done += min(got, room)
+        return frames[:done], hdr
+    finally:
+        L.tmh_gtm_decoder_destroy(dec)

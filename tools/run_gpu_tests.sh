@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
-GROUPS_DEFAULT="features mirror distance knn dither kmeans palquant matcher dropin sliding motion reconstruct"
+GROUPS_DEFAULT="features mirror distance knn dither kmeans palquant matcher dropin sliding motion reconstruct tile_classes encode"
 GROUPS_RUN="${@:-$GROUPS_DEFAULT}"
 : > gpurun_out/summary.txt
 for g in $GROUPS_RUN; do
