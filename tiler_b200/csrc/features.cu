@@ -112,14 +112,23 @@ __device__ void rgb_to_lab(int ir, int ig, int ib, float &ol, float &oa, float &
   ob = (float)(200 * ((double)y - (double)z));
 }
 
-// DCTInner_asm order for coefficient `co` of the plane s_c[64], basis transposed in s_lut[pixel*64 + co]
-__device__ __forceinline__ double dct_inner(const float *__restrict__ s_c, const float *__restrict__ s_lut, int co) {
+// DCTInner_asm order for one coefficient of the plane s_c[64] (shared memory, read as broadcast float4); lut[64] is the
+// coefficient's own column of the DCT basis, held in REGISTERS: a thread computes the same coefficient for every tile, and
+// fetching the basis from shared memory for every tile (64 loads per thread and tile, 768 wavefronts per tile) made the
+// kernel shared-memory-bandwidth bound at 3x its arithmetic time.
+__device__ __forceinline__ double dct_inner(const float *__restrict__ s_c, const float (&lut)[64]) {
   double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
     float p[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) p[i] = __fmul_rn(s_c[s * 16 + i], s_lut[(s * 16 + i) * 64 + co]);
+    for (int v = 0; v < 4; ++v) {
+      const float4 c4 = *reinterpret_cast<const float4 *>(s_c + s * 16 + v * 4);
+      p[v * 4 + 0] = __fmul_rn(c4.x, lut[s * 16 + v * 4 + 0]);
+      p[v * 4 + 1] = __fmul_rn(c4.y, lut[s * 16 + v * 4 + 1]);
+      p[v * 4 + 2] = __fmul_rn(c4.z, lut[s * 16 + v * 4 + 2]);
+      p[v * 4 + 3] = __fmul_rn(c4.w, lut[s * 16 + v * 4 + 3]);
+    }
     const float a0 = __fadd_rn(p[0], p[4]), a1 = __fadd_rn(p[1], p[5]), a2 = __fadd_rn(p[2], p[6]), a3 = __fadd_rn(p[3], p[7]);
     const float b0 = __fadd_rn(p[8], p[12]), b1 = __fadd_rn(p[9], p[13]), b2 = __fadd_rn(p[10], p[14]), b3 = __fadd_rn(p[11], p[15]);
     const double l0 = __dadd_rn(__dadd_rn((double)a0, (double)b0), __dadd_rn((double)a2, (double)b2));
@@ -134,47 +143,61 @@ __device__ __forceinline__ double dct_inner(const float *__restrict__ s_c, const
 // 3: RGB tiles read through their mirror flags (pal_idx = flags[n]: ConvertToCpnPixels with AHMirror / AVMirror, :3049-3101);
 // 4: sliding window over a frame buffer (rgb = frame [h][fw], item = oy * pw + ox: DoDCTs, :1437-1462)
 template <int MODE>
-__global__ void __launch_bounds__(192, 4)
+__global__ void __launch_bounds__(192, 3)
 features_i16_kernel(const int32_t *__restrict__ rgb, const uint8_t *__restrict__ pal_idx, int n_pal_all,
                     const int32_t *__restrict__ sel_pal, const int32_t *__restrict__ palettes, int pal_size, int64_t n,
                     const float *__restrict__ lutT, int16_t *__restrict__ out, int fw = 0, int pw = 0) {
-  extern __shared__ float s_lut[];       // 4096 floats
-  __shared__ float s_cpn[3][64];
-  __shared__ int16_t s_out[192];
-  for (int i = threadIdx.x; i < 4096; i += 192) s_lut[i] = lutT[i];
+  __shared__ __align__(16) float s_cpn[2][3][64];   // double-buffered colour planes: one barrier per tile
+  __shared__ __align__(16) int16_t s_out[2][192];
   const int t = threadIdx.x;
   const int c = t >> 6, vu = t & 63;
+  float lut[64];
+#pragma unroll
+  for (int i = 0; i < 64; ++i) lut[i] = __ldg(lutT + i * 64 + vu);
   const double wgt = c_weights[t];
   const int dst = c * 64 + c_snake[vu];
-  for (int64_t tile = blockIdx.x; tile < n; tile += gridDim.x) {
-    __syncthreads();  // previous s_cpn / s_out consumed (and s_lut ready on the first pass)
+  // pixel of tile `tile` that thread t (< 64) converts
+  auto fetch = [&](int64_t tile) -> int32_t {
+    if (MODE == 0) return __ldg(rgb + tile * 64 + t);
+    if (MODE == 3) {
+      const int fl = __ldg(pal_idx + tile);
+      const int x = (fl & 1) ? 7 - (t & 7) : (t & 7), y = (fl & 2) ? 7 - (t >> 3) : (t >> 3);
+      return __ldg(rgb + tile * 64 + y * 8 + x);
+    }
+    if (MODE == 4) {
+      const int64_t oy = tile / pw, ox = tile - oy * pw;
+      return __ldg(rgb + (oy + (t >> 3)) * fw + ox + (t & 7));
+    }
+    const int64_t src = (MODE == 2) ? tile / n_pal_all : tile;
+    const int32_t p = (MODE == 2) ? (int32_t)(tile % n_pal_all) : __ldg(sel_pal + tile);
+    return __ldg(palettes + (int64_t)p * pal_size + __ldg(pal_idx + src * 64 + t));
+  };
+  // Software pipeline: the pixels of the NEXT tile are requested before the current tile's 64-term sums, so the global
+  // load latency never sits between two barriers; the previous tile's coefficients leave through shared memory as
+  // coalesced 4-byte stores while the current tile is being computed.
+  int64_t tile = blockIdx.x;
+  int32_t col = (t < 64 && tile < n) ? fetch(tile) : 0;
+  int buf = 0;
+  int64_t prev_tile = -1;
+  for (; tile < n; tile += gridDim.x, buf ^= 1) {
     if (t < 64) {
-      int32_t col;
-      if (MODE == 0) {
-        col = __ldg(rgb + tile * 64 + t);
-      } else if (MODE == 3) {
-        const int fl = __ldg(pal_idx + tile);
-        const int x = (fl & 1) ? 7 - (t & 7) : (t & 7), y = (fl & 2) ? 7 - (t >> 3) : (t >> 3);
-        col = __ldg(rgb + tile * 64 + y * 8 + x);
-      } else if (MODE == 4) {
-        const int64_t oy = tile / pw, ox = tile - oy * pw;
-        col = __ldg(rgb + (oy + (t >> 3)) * fw + ox + (t & 7));
-      } else {
-        const int64_t src = (MODE == 2) ? tile / n_pal_all : tile;
-        const int32_t p = (MODE == 2) ? (int32_t)(tile % n_pal_all) : __ldg(sel_pal + tile);
-        col = __ldg(palettes + (int64_t)p * pal_size + __ldg(pal_idx + src * 64 + t));
-      }
       float y, u, v;
       rgb_to_yuv(col & 255, (col >> 8) & 255, (col >> 16) & 255, y, u, v);
-      s_cpn[0][t] = y; s_cpn[1][t] = u; s_cpn[2][t] = v;
+      s_cpn[buf][0][t] = y; s_cpn[buf][1][t] = u; s_cpn[buf][2][t] = v;
     }
-    __syncthreads();
-    double z = dct_inner(s_cpn[c], s_lut, vu);
+    __syncthreads();   // planes of this tile visible; coefficients of the previous tile complete in s_out[buf ^ 1]
+    const int64_t next = tile + gridDim.x;
+    if (t < 64 && next < n) col = fetch(next);
+    if (t < 96 && prev_tile >= 0)
+      reinterpret_cast<uint32_t *>(out + prev_tile * 192)[t] = reinterpret_cast<const uint32_t *>(s_out[buf ^ 1])[t];
+    double z = dct_inner(s_cpn[buf][c], lut);
     z = __dmul_rn(z, wgt);
-    s_out[dst] = (int16_t)__double2int_rn(z);
-    __syncthreads();
-    if (t < 96) reinterpret_cast<uint32_t *>(out + tile * 192)[t] = reinterpret_cast<const uint32_t *>(s_out)[t];
+    s_out[buf][dst] = (int16_t)__double2int_rn(z);
+    prev_tile = tile;
   }
+  __syncthreads();
+  if (t < 96 && prev_tile >= 0)
+    reinterpret_cast<uint32_t *>(out + prev_tile * 192)[t] = reinterpret_cast<const uint32_t *>(s_out[buf ^ 1])[t];
 }
 
 // ComputeTilePsyVisFeatures: f64, sequential 64-term sums (DCTInner<PDouble>, utils.pas:782-872)
@@ -241,7 +264,7 @@ int launch_features_rgb(const int32_t *rgb, int64_t n, int16_t *out, cudaStream_
   int rc = features_init(st);
   if (rc) return rc;
   ProfScope prof("features_rgb", st);
-  features_i16_kernel<0><<<grid_for(n, 4), 192, 4096 * sizeof(float), st>>>(rgb, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
+  features_i16_kernel<0><<<grid_for(n, 4), 192, 0, st>>>(rgb, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }
@@ -250,7 +273,7 @@ int launch_features_rgb_mirrored(const int32_t *rgb, const uint8_t *flags, int64
   if (n <= 0) return TM_OK;
   int rc = features_init(st);
   if (rc) return rc;
-  features_i16_kernel<3><<<grid_for(n, 4), 192, 4096 * sizeof(float), st>>>(rgb, flags, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
+  features_i16_kernel<3><<<grid_for(n, 4), 192, 0, st>>>(rgb, flags, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }
@@ -262,7 +285,7 @@ int launch_features_sliding(const int32_t *frame, int w, int h, int16_t *out, cu
   if (rc) return rc;
   const int64_t n = (int64_t)(w - 7) * (h - 7);
   ProfScope prof("features_sliding", st);
-  features_i16_kernel<4><<<grid_for(n, 4), 192, 4096 * sizeof(float), st>>>(frame, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out, w,
+  features_i16_kernel<4><<<grid_for(n, 4), 192, 0, st>>>(frame, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out, w,
                                                                              w - 7);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
@@ -273,7 +296,7 @@ int launch_features_pal(const uint8_t *pal_idx, const int32_t *tile_pal, const i
   if (n <= 0) return TM_OK;
   int rc = features_init(st);
   if (rc) return rc;
-  features_i16_kernel<1><<<grid_for(n, 4), 192, 4096 * sizeof(float), st>>>(nullptr, pal_idx, 0, tile_pal, palettes, pal_size, n,
+  features_i16_kernel<1><<<grid_for(n, 4), 192, 0, st>>>(nullptr, pal_idx, 0, tile_pal, palettes, pal_size, n,
                                                                              g_lutT_f32, out);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
@@ -285,7 +308,7 @@ int launch_features_allpairs(const uint8_t *pal_idx, int64_t n_tiles, const int3
   if (n_pairs <= 0) return TM_OK;
   int rc = features_init(st);
   if (rc) return rc;
-  features_i16_kernel<2><<<grid_for(n_pairs, 4), 192, 4096 * sizeof(float), st>>>(nullptr, pal_idx, n_pal, nullptr, palettes, pal_size,
+  features_i16_kernel<2><<<grid_for(n_pairs, 4), 192, 0, st>>>(nullptr, pal_idx, n_pal, nullptr, palettes, pal_size,
                                                                                    n_pairs, g_lutT_f32, out);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;

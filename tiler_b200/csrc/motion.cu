@@ -7,7 +7,10 @@
 //       sum (a-b)^2 (uint32, wraps like the reference's Cardinal) + the Manhattan penalty (:1236, :1519).  The
 //       reference keeps the FIRST strict minimum of a row-major scan: every thread scans its offsets in increasing
 //       scan order, the block reduces on (error, scan index).  QuickTest (utils.pas:755-759) is an optimisation only
-//       (partial sum >= best implies full error >= best) and is applied against the thread's own best.
+//       (the sum over the first 8 coefficients bounds the full error from below); here it prunes against the best
+//       error found so far by ANY warp of the block (shared-memory atomicMin), with a STRICT comparison so that a
+//       candidate that could still tie -- and win on scan order -- is always evaluated: the result does not depend on
+//       thread timing.  A pruned candidate costs one 32-byte sector instead of twelve.
 //   reconstruct_decide_kernel : one 64-thread group per tile: dead band on the motion error (:1534), KNN vs motion with the
 //       192 tolerance (:1614), draw into the front buffer (:1623-1651), error -> PSNR (utils.pas:1074-1078).
 #include "tm_kernels.h"
@@ -27,44 +30,85 @@ __device__ __forceinline__ uint32_t sq_diff8(const uint4 a, const uint4 b, uint3
   return acc;
 }
 
+// Warp-cooperative scan.  A warp takes 32 consecutive candidates of the row-major scan at a time:
+//   phase A  lane l reads the first 8 coefficients (one 32-byte sector) of candidate base + l and applies QuickTest
+//            against the block-wide best error (strict, so a candidate that could tie is never dropped);
+//   phase B  the survivors are evaluated four at a time in scan order, one per 8-lane group: a lane loads three 16-byte
+//            chunks (each group load is one 128-byte line), square-differences them against its own three chunks of the
+//            tile's vector, and three shuffles sum the group.  The tile's vector costs 16 registers per lane, not 96.
+// The zero-motion candidate is evaluated first to seed the block-wide best: it is a real candidate, so pruning against
+// its error is exact, and on real clips it removes most of the window after 8 coefficients.
 __global__ void __launch_bounds__(256) motion_search_kernel(const int16_t *__restrict__ cur_feat, int tw, int th,
                                                             const int16_t *__restrict__ dcts, int R, int32_t *__restrict__ pred_x,
                                                             int32_t *__restrict__ pred_y, uint32_t *__restrict__ err_out) {
-  __shared__ uint4 s_cur[24];
   __shared__ unsigned long long s_best[8];
-  const int t = blockIdx.x;
+  __shared__ uint32_t s_min;
+  const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sy = t / tw, sx = t - sy * tw, dx = sx * 8, dy = sy * 8;
   const int w = tw * 8, h = th * 8, pw = w - 7;
-  if (threadIdx.x < 24) s_cur[threadIdx.x] = __ldg(reinterpret_cast<const uint4 *>(cur_feat + (int64_t)t * 192) + threadIdx.x);
-  __syncthreads();
-  uint4 cur[24];
-#pragma unroll
-  for (int i = 0; i < 24; ++i) cur[i] = s_cur[i];
+  const uint4 *curp = reinterpret_cast<const uint4 *>(cur_feat + (int64_t)t * 192);
+  const int g = lane >> 3, j = lane & 7;            // phase B: 8 lanes per candidate, 3 chunks per lane
+  const uint4 cur0 = __ldg(curp);
+  const uint4 cj0 = __ldg(curp + j), cj1 = __ldg(curp + j + 8), cj2 = __ldg(curp + j + 16);
   const int oymn = max(0, dy - R - 1), oymx = min(h - 8, dy + R);
   const int oxmn = max(0, dx - R - 1), oxmx = min(w - 8, dx + R);
   const int ww = oxmx - oxmn + 1, wh = oymx - oymn + 1, np = ww * wh;
-  uint32_t best = 0xFFFFFFFFu, best_p = 0xFFFFFFFFu;
-  for (int p = threadIdx.x; p < np; p += 256) {
-    const int wy = p / ww, wx = p - wy * ww;
-    const int oy = oymn + wy, ox = oxmn + wx;
-    const uint4 *src = reinterpret_cast<const uint4 *>(dcts + ((int64_t)oy * pw + ox) * 192);
-    uint32_t e = sq_diff8(cur[0], __ldg(src), 0u);
-    if (e >= best) continue;   // QuickTestEuclideanDCTPtr: the first 8 coefficients already exceed the best error
+  // full error of scan position q (< 0: none) computed by the 8 lanes of a group; every lane of the group gets the sum
+  auto group_error = [&](int q) -> uint32_t {
+    uint32_t e = 0;
+    int oy = 0, ox = 0;
+    if (q >= 0) {
+      const int wy = q / ww, wx = q - wy * ww;
+      oy = oymn + wy; ox = oxmn + wx;
+      const uint4 *src = reinterpret_cast<const uint4 *>(dcts + ((int64_t)oy * pw + ox) * 192);
+      const uint4 v0 = __ldg(src + j), v1 = __ldg(src + j + 8), v2 = __ldg(src + j + 16);   // 8 lanes x 16 B = one 128-byte line each
+      e = sq_diff8(cj0, v0, 0u);
+      e = sq_diff8(cj1, v1, e);
+      e = sq_diff8(cj2, v2, e);
+    }
+    e += __shfl_xor_sync(0xffffffffu, e, 4);
+    e += __shfl_xor_sync(0xffffffffu, e, 2);
+    e += __shfl_xor_sync(0xffffffffu, e, 1);
+    return q >= 0 ? e + (uint32_t)(abs(ox - dx) + abs(oy - dy)) : 0xFFFFFFFFu;
+  };
+  if (warp == 0) {   // seed: the zero-motion candidate
+    const int qc = (dy - oymn) * ww + (dx - oxmn);
+    const uint32_t e = group_error(g == 0 ? qc : -1);
+    if (lane == 0) s_min = e;
+  }
+  __syncthreads();
+  uint32_t best = 0xFFFFFFFFu, best_p = 0xFFFFFFFFu;   // warp-uniform
+  for (int base = warp * 32; base < np; base += 256) {
+    const int p = base + lane;
+    bool alive = false;
+    if (p < np) {
+      const int wy = p / ww, wx = p - wy * ww;
+      const uint4 v = __ldg(reinterpret_cast<const uint4 *>(dcts + ((int64_t)(oymn + wy) * pw + oxmn + wx) * 192));
+      alive = sq_diff8(cur0, v, 0u) <= *(volatile uint32_t *)&s_min;   // QuickTestEuclideanDCTPtr (strict prune: ties are evaluated)
+    }
+    uint32_t m = __ballot_sync(0xffffffffu, alive);
+    while (m) {   // four survivors per pass, one per 8-lane group, taken in scan order
+      const int cnt = __popc(m);
+      const int b = g < cnt ? (int)__fns(m, 0, g + 1) : -1;
+      const int q = b >= 0 ? base + b : -1;
+      const uint32_t e = group_error(q);
+      bool improved = false;
 #pragma unroll
-    for (int i = 1; i < 24; ++i) e = sq_diff8(cur[i], __ldg(src + i), e);
-    e += (uint32_t)(abs(ox - dx) + abs(oy - dy));
-    if (e < best) { best = e; best_p = (uint32_t)p; }
+      for (int gg = 0; gg < 4; ++gg) {
+        const uint32_t eg = __shfl_sync(0xffffffffu, e, gg * 8);
+        const int qg = __shfl_sync(0xffffffffu, q, gg * 8);
+        if (qg >= 0 && eg < best) { best = eg; best_p = (uint32_t)qg; improved = true; }
+      }
+      if (improved && lane == 0) atomicMin(&s_min, best);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) m &= m - 1;   // m - 1 on 0 wraps, and 0 & x = 0
+    }
   }
   // block arg-min on (error, scan index): the first strict minimum of the row-major scan
-  unsigned long long key = ((unsigned long long)best << 32) | best_p;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-    key = other < key ? other : key;
-  }
-  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = key;
+  if (lane == 0) s_best[warp] = ((unsigned long long)best << 32) | best_p;
   __syncthreads();
   if (threadIdx.x == 0) {
+    unsigned long long key = s_best[0];
     for (int i = 1; i < 8; ++i) key = s_best[i] < key ? s_best[i] : key;
     const uint32_t e = (uint32_t)(key >> 32), p = (uint32_t)key;
     int bx = 0, by = 0;
