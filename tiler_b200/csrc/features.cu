@@ -156,38 +156,43 @@ features_i16_kernel(const int32_t *__restrict__ rgb, const uint8_t *__restrict__
   for (int i = 0; i < 64; ++i) lut[i] = __ldg(lutT + i * 64 + vu);
   const double wgt = c_weights[t];
   const int dst = c * 64 + c_snake[vu];
-  // pixel of tile `tile` that thread t (< 64) converts
+  // Colour conversion is spread over all 192 threads: thread t converts component t / 64 of pixel t % 64 (the luma every
+  // component needs is recomputed, 5 double operations) instead of 64 threads converting while 128 wait at the barrier.
+  const int px = t & 63;
   auto fetch = [&](int64_t tile) -> int32_t {
-    if (MODE == 0) return __ldg(rgb + tile * 64 + t);
+    if (MODE == 0) return __ldg(rgb + tile * 64 + px);
     if (MODE == 3) {
       const int fl = __ldg(pal_idx + tile);
-      const int x = (fl & 1) ? 7 - (t & 7) : (t & 7), y = (fl & 2) ? 7 - (t >> 3) : (t >> 3);
+      const int x = (fl & 1) ? 7 - (px & 7) : (px & 7), y = (fl & 2) ? 7 - (px >> 3) : (px >> 3);
       return __ldg(rgb + tile * 64 + y * 8 + x);
     }
     if (MODE == 4) {
-      const int64_t oy = tile / pw, ox = tile - oy * pw;
-      return __ldg(rgb + (oy + (t >> 3)) * fw + ox + (t & 7));
+      const int oy = (int)tile / pw, ox = (int)tile - oy * pw;
+      return __ldg(rgb + (int64_t)(oy + (px >> 3)) * fw + ox + (px & 7));
     }
     const int64_t src = (MODE == 2) ? tile / n_pal_all : tile;
     const int32_t p = (MODE == 2) ? (int32_t)(tile % n_pal_all) : __ldg(sel_pal + tile);
-    return __ldg(palettes + (int64_t)p * pal_size + __ldg(pal_idx + src * 64 + t));
+    return __ldg(palettes + (int64_t)p * pal_size + __ldg(pal_idx + src * 64 + px));
   };
   // Software pipeline: the pixels of the NEXT tile are requested before the current tile's 64-term sums, so the global
   // load latency never sits between two barriers; the previous tile's coefficients leave through shared memory as
   // coalesced 4-byte stores while the current tile is being computed.
   int64_t tile = blockIdx.x;
-  int32_t col = (t < 64 && tile < n) ? fetch(tile) : 0;
+  int32_t col = tile < n ? fetch(tile) : 0;
   int buf = 0;
   int64_t prev_tile = -1;
   for (; tile < n; tile += gridDim.x, buf ^= 1) {
-    if (t < 64) {
-      float y, u, v;
-      rgb_to_yuv(col & 255, (col >> 8) & 255, (col >> 16) & 255, y, u, v);
-      s_cpn[buf][0][t] = y; s_cpn[buf][1][t] = u; s_cpn[buf][2][t] = v;
+    {   // RGBToYUV (utils.pas:478-490), component c only (c is warp-uniform)
+      const int r = col & 255, g = (col >> 8) & 255, b = (col >> 16) & 255;
+      const float y = (float)__dadd_rn(__dadd_rn(__dmul_rn((double)r, 299.0 / 1000.0), __dmul_rn((double)g, 587.0 / 1000.0)),
+                                       __dmul_rn((double)b, 114.0 / 1000.0));
+      float val = y;
+      if (c != 0) val = (float)__dmul_rn(__dsub_rn((double)(c == 1 ? b : r), (double)y), c == 1 ? 0.492 : 0.877);
+      s_cpn[buf][c][px] = val;
     }
     __syncthreads();   // planes of this tile visible; coefficients of the previous tile complete in s_out[buf ^ 1]
     const int64_t next = tile + gridDim.x;
-    if (t < 64 && next < n) col = fetch(next);
+    if (next < n) col = fetch(next);
     if (t < 96 && prev_tile >= 0)
       reinterpret_cast<uint32_t *>(out + prev_tile * 192)[t] = reinterpret_cast<const uint32_t *>(s_out[buf ^ 1])[t];
     double z = dct_inner(s_cpn[buf][c], lut);
