@@ -71,16 +71,20 @@ __global__ void __launch_bounds__(192) limb_split_kernel(const int16_t *__restri
 }
 
 constexpr int KMAX = 64;         // largest k
+#ifndef TM_K1_NH
+#define TM_K1_NH 2
+#endif
 
 // ------------------------------------------------------------------ k = 1 kernel: 8 epilogue warps
 // Same pipeline as above, but every TMEM lane quarter is drained by TWO warps (w and w + 4 may both address quarter
 // w % 4), each taking half of the tile's 64 columns.  One warp per scheduler issues ~1 instruction every 3 cycles on
 // this dependent integer code; two warps per scheduler hide each other's latencies.  A query row therefore has two
 // threads, each with its own running arg-min; they are merged through shared memory at the end of the query block.
-constexpr int K1_THREADS = 352;   // 8 epilogue warps + TMA warp + 2 MMA issuer warps
+// NH column splits per tile: 4 NH epilogue warps + TMA warp + 2 MMA issuer warps
+constexpr int k1_threads(int nh) { return (4 * nh + 3) * 32; }
 // KS = 1: arg-min.  KS = 4: the four nearest, kept sorted in registers (k-means candidate search).
-template <int KS>
-__global__ void __launch_bounds__(K1_THREADS, 1)
+template <int KS, int NH>
+__global__ void __launch_bounds__(k1_threads(NH), 1)
 knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUtensorMap tmap_d,
                  const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict,
                  int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist, int tile_stride, int dbg) {
@@ -88,8 +92,9 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int NST = STAGES_K1;
   uint8_t *sB = smem;
-  unsigned long long *s_merge = reinterpret_cast<unsigned long long *>(sB + NST * B_TILE);   // [KS][128]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_merge + BM * KS);
+  constexpr int NEW = 4 * NH;   // epilogue warps; warp NEW = TMA producer, NEW + 1 / NEW + 2 = MMA issuers
+  unsigned long long *s_merge = reinterpret_cast<unsigned long long *>(sB + NST * B_TILE);   // [NH - 1][KS][128]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_merge + BM * KS * (NH - 1));
   uint64_t *full = bars, *empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + 1, *t_full = a_empty + 1,
            *t_empty = t_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
@@ -102,18 +107,18 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_full, 4);
     mbar_init(a_empty, 2);
-    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], 8); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], NEW); }
     fence_barrier_init();
   }
-  if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  if (warp == 8 && lane == 0) tma_prefetch_desc(&tmap_d);
+  if (warp == NEW + 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == NEW && lane == 0) tma_prefetch_desc(&tmap_d);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (tmem_base != 0) __trap();   // the MMA issue code addresses TMEM with immediates
 
-  if (warp == 8) {
+  if (warp == NEW) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
@@ -130,9 +135,9 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
         }
       }
     }
-  } else if (warp >= 9) {
+  } else if (warp > NEW) {
     // ===================== two MMA issuer warps (even / odd tiles) =====================
-    const uint32_t my_parity = (uint32_t)(warp - 9);
+    const uint32_t my_parity = (uint32_t)(warp - NEW - 1);
     constexpr uint32_t I_SS = make_idesc(kDFmtS32, kFmtS8, kFmtS8, BM, BN);
     constexpr uint32_t I_SU = make_idesc(kDFmtS32, kFmtS8, kFmtU8, BM, BN);
     constexpr uint32_t I_US = make_idesc(kDFmtS32, kFmtU8, kFmtS8, BM, BN);
@@ -159,11 +164,11 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
       tc_commit_elect(a_empty);
     }
   } else {
-    // ===================== epilogue: thread = (query row, column half) =====================
+    // ===================== epilogue: thread = (query row, column split h of NH) =====================
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    constexpr int HN = BN / 2;   // 32 columns per thread and tile
+    constexpr int HN = BN / NH;   // columns per thread and tile
     uint32_t it = 0, w = 0;
     for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
       const int64_t qi = (int64_t)qb * BM + row;
@@ -262,37 +267,45 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
           }
         }
       }
-      // merge the two column halves of each row: the KS smallest of two ascending lists
-      if (h == 1) {
+      // merge the NH column splits of each row: the KS smallest of NH ascending lists
+      if (h > 0) {
 #pragma unroll
-        for (int r = 0; r < KS; ++r) s_merge[r * BM + row] = bk[r];
+        for (int r = 0; r < KS; ++r) s_merge[((h - 1) * KS + r) * BM + row] = bk[r];
       }
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      asm volatile("bar.sync 1, %0;\n" ::"n"(NEW * 32) : "memory");
       if (h == 0 && valid) {
-        unsigned long long ok[KS];
 #pragma unroll
-        for (int r = 0; r < KS; ++r) ok[r] = s_merge[r * BM + row];
-        int ia = 0, ib = 0;
+        for (int o = 0; o < NH - 1; ++o) {
+          unsigned long long ok[KS], mg[KS];
+#pragma unroll
+          for (int r = 0; r < KS; ++r) ok[r] = s_merge[(o * KS + r) * BM + row];
+          int ia = 0, ib = 0;
+#pragma unroll
+          for (int r = 0; r < KS; ++r) {
+            // ia, ib <= r: static indexing through a small select keeps the lists in registers
+            unsigned long long a = ~0ull, b = ~0ull;
+#pragma unroll
+            for (int u = 0; u < KS; ++u) { if (u == ia) a = bk[u]; if (u == ib) b = ok[u]; }
+            const bool ta = a <= b;
+            mg[r] = ta ? a : b;
+            ia += ta; ib += !ta;
+          }
+#pragma unroll
+          for (int r = 0; r < KS; ++r) bk[r] = mg[r];
+        }
 #pragma unroll
         for (int r = 0; r < KS; ++r) {
-          // ia, ib <= r: static indexing through a small select keeps the lists in registers
-          unsigned long long a = ~0ull, b = ~0ull;
-#pragma unroll
-          for (int u = 0; u < KS; ++u) { if (u == ia) a = bk[u]; if (u == ib) b = ok[u]; }
-          const bool ta = a <= b;
-          const unsigned long long v = ta ? a : b;
-          ia += ta; ib += !ta;
-          out_idx[qi * KS + r] = (int32_t)(uint32_t)v;        // 0xFFFFFFFF = -1 when fewer than KS rows exist
-          out_dist[qi * KS + r] = (uint32_t)(v >> 32);
+          out_idx[qi * KS + r] = (int32_t)(uint32_t)bk[r];        // 0xFFFFFFFF = -1 when fewer than KS rows exist
+          out_dist[qi * KS + r] = (uint32_t)(bk[r] >> 32);
         }
       }
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");   // s_merge is rewritten by the next query block
+      asm volatile("bar.sync 1, %0;\n" ::"n"(NEW * 32) : "memory");   // s_merge is rewritten by the next query block
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == NEW + 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------ top-k kernel (2 <= k <= 64): 8 epilogue warps
@@ -758,12 +771,13 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
   CUtensorMap td;
   int rc = make_tmap_rows_u8(&td, d_limbs, (uint64_t)n_dict, ROWB, BN);
   if (rc != TM_OK) return rc;
-  constexpr int SMEM_K1 = STAGES_K1 * B_TILE + BM * 8 * 4 + 256 + 1024;
+  constexpr int K1_NH = TM_K1_NH;   // column splits per tile in the k = 1 / k = 4 kernels (2: 8 epilogue warps, 4: 16)
+  constexpr int SMEM_K1 = STAGES_K1 * B_TILE + BM * 8 * 4 * (K1_NH - 1) + 256 + 1024;
   constexpr int SMEM_TK = STAGES_K1 * B_TILE + 256 * 4 + 512 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(knn_i8_k1_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
-    if (cudaFuncSetAttribute(knn_i8_k1_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaFuncSetAttribute(knn_i8_k1_kernel<1, K1_NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaFuncSetAttribute(knn_i8_k1_kernel<4, K1_NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
     if (cudaFuncSetAttribute(knn_i8_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK) != cudaSuccess) return TM_ERR_CUDA;
     attr_set = true;
   }
@@ -781,8 +795,8 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
     const int grid = n_qblocks < num_ctas ? n_qblocks : num_ctas;
     static int kdbg = -1;   // TM_TK_DBG bits: 1 admit nothing (top-k), 2 no dictionary loads, 4 no MMAs, 8 no epilogue arithmetic
     if (kdbg < 0) kdbg = getenv("TM_TK_DBG") ? atoi(getenv("TM_TK_DBG")) : 0;
-    if (k == 1) knn_i8_k1_kernel<1><<<grid, K1_THREADS, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride, kdbg);
-    else if (k == 4) knn_i8_k1_kernel<4><<<grid, K1_THREADS, SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride, kdbg);
+    if (k == 1) knn_i8_k1_kernel<1, K1_NH><<<grid, k1_threads(K1_NH), SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride, kdbg);
+    else if (k == 4) knn_i8_k1_kernel<4, K1_NH><<<grid, k1_threads(K1_NH), SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride, kdbg);
     else {
       // candidate strips: stream-ordered scratch (the pool keeps it cached between calls); 2 KB alignment keeps every
       // strip inside one 4 GB window, so the kernel bumps only the low word of its write pointer
