@@ -267,6 +267,7 @@ def cpu_baseline_sample(enc, canon_tiles_host, n_sample=24576):
     """The oracle (CPU restatement of the reference's per-tile path: features, brute-force 64-NN with the SSE distance,
     extended-palette re-rank), OpenMP over tiles like MTProcs, on a bounded sample of the step's tiles."""
     from oracle import oracle as O
+    O.set_num_threads(os.cpu_count() or 1)
     pal = enc.palettes.cpu().numpy()
     didx = enc.tile_idx.cpu().numpy()
     dpal = enc.tile_pal.cpu().numpy()
@@ -291,6 +292,7 @@ def run_reference(args):
         return
     from oracle import oracle as O
     from tiler_b200 import synth
+    O.set_num_threads(os.cpu_count() or 1)   # torchrun exports OMP_NUM_THREADS=1; the reference uses every core (MTProcs, :3824)
     rng = np.random.default_rng(5)
     # same shapes as our arm: 65536-tile dictionary of dithered tiles, 16x16 palettes (built with the oracle itself)
     clip = synth.make_clip(W, H, 6, cut_every=0, seed=synth.SEED)

@@ -68,6 +68,10 @@ def ref_dlquant():
     return _REF
 
 
+def set_num_threads(n):
+    lib().tmo_set_num_threads(int(n))
+
+
 def num_threads():
     return int(lib().tmo_num_threads())
 

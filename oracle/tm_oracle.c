@@ -126,6 +126,9 @@ int tmo_num_threads(void) {
   return 1;
 #endif
 }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: the reference arm of bench.py asks for all host cores explicitly */
+void tmo_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
 
 /* ------------------------------------------------------------------ colour */
 

@@ -137,6 +137,7 @@ void tmo_reconstruct_sequence(const int32_t *canon_tiles, const uint8_t *flags, 
                               uint32_t *err_out, int32_t *recon, double *psnr_sum);
 
 int tmo_num_threads(void);
+void tmo_set_num_threads(int n);
 
 #ifdef __cplusplus
 }
