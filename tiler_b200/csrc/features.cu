@@ -147,8 +147,8 @@ __global__ void __launch_bounds__(192, 3)
 features_i16_kernel(const int32_t *__restrict__ rgb, const uint8_t *__restrict__ pal_idx, int n_pal_all,
                     const int32_t *__restrict__ sel_pal, const int32_t *__restrict__ palettes, int pal_size, int64_t n,
                     const float *__restrict__ lutT, int16_t *__restrict__ out, int fw = 0, int pw = 0) {
-  __shared__ __align__(16) float s_cpn[2][3][64];   // double-buffered colour planes: one barrier per tile
-  __shared__ __align__(16) int16_t s_out[2][192];
+  __shared__ __align__(16) float s_cpn[2][2][3][64];   // [buffer][tile of the pair][plane][pixel]: one barrier per PAIR of tiles
+  __shared__ __align__(16) int16_t s_out[2][2][192];
   const int t = threadIdx.x;
   const int c = t >> 6, vu = t & 63;
   float lut[64];
@@ -160,6 +160,7 @@ features_i16_kernel(const int32_t *__restrict__ rgb, const uint8_t *__restrict__
   // component needs is recomputed, 5 double operations) instead of 64 threads converting while 128 wait at the barrier.
   const int px = t & 63;
   auto fetch = [&](int64_t tile) -> int32_t {
+    if (tile >= n) return 0;
     if (MODE == 0) return __ldg(rgb + tile * 64 + px);
     if (MODE == 3) {
       const int fl = __ldg(pal_idx + tile);
@@ -174,35 +175,46 @@ features_i16_kernel(const int32_t *__restrict__ rgb, const uint8_t *__restrict__
     const int32_t p = (MODE == 2) ? (int32_t)(tile % n_pal_all) : __ldg(sel_pal + tile);
     return __ldg(palettes + (int64_t)p * pal_size + __ldg(pal_idx + src * 64 + px));
   };
-  // Software pipeline: the pixels of the NEXT tile are requested before the current tile's 64-term sums, so the global
-  // load latency never sits between two barriers; the previous tile's coefficients leave through shared memory as
-  // coalesced 4-byte stores while the current tile is being computed.
-  int64_t tile = blockIdx.x;
-  int32_t col = tile < n ? fetch(tile) : 0;
+  auto convert = [&](int32_t col) -> float {   // RGBToYUV (utils.pas:478-490), component c only (c is warp-uniform)
+    const int r = col & 255, g = (col >> 8) & 255, b = (col >> 16) & 255;
+    const float y = (float)__dadd_rn(__dadd_rn(__dmul_rn((double)r, 299.0 / 1000.0), __dmul_rn((double)g, 587.0 / 1000.0)),
+                                     __dmul_rn((double)b, 114.0 / 1000.0));
+    float val = y;
+    if (c != 0) val = (float)__dmul_rn(__dsub_rn((double)(c == 1 ? b : r), (double)y), c == 1 ? 0.492 : 0.877);
+    return val;
+  };
+  // A block works on PAIRS of consecutive tiles (2 i, 2 i + 1): two independent 64-term sums per thread share the basis
+  // registers and double the instruction-level parallelism, and the pair's 768 output bytes leave as one coalesced store.
+  // Software pipeline: the pixels of the NEXT pair are requested before the current pair's sums, so the global load
+  // latency never sits between two barriers; the previous pair's coefficients are stored while the current one is computed.
+  const int64_t n_pairs = (n + 1) >> 1;
+  int64_t pair = blockIdx.x;
+  int32_t col0 = pair < n_pairs ? fetch(2 * pair) : 0, col1 = pair < n_pairs ? fetch(2 * pair + 1) : 0;
   int buf = 0;
-  int64_t prev_tile = -1;
-  for (; tile < n; tile += gridDim.x, buf ^= 1) {
-    {   // RGBToYUV (utils.pas:478-490), component c only (c is warp-uniform)
-      const int r = col & 255, g = (col >> 8) & 255, b = (col >> 16) & 255;
-      const float y = (float)__dadd_rn(__dadd_rn(__dmul_rn((double)r, 299.0 / 1000.0), __dmul_rn((double)g, 587.0 / 1000.0)),
-                                       __dmul_rn((double)b, 114.0 / 1000.0));
-      float val = y;
-      if (c != 0) val = (float)__dmul_rn(__dsub_rn((double)(c == 1 ? b : r), (double)y), c == 1 ? 0.492 : 0.877);
-      s_cpn[buf][c][px] = val;
-    }
-    __syncthreads();   // planes of this tile visible; coefficients of the previous tile complete in s_out[buf ^ 1]
-    const int64_t next = tile + gridDim.x;
-    if (next < n) col = fetch(next);
-    if (t < 96 && prev_tile >= 0)
-      reinterpret_cast<uint32_t *>(out + prev_tile * 192)[t] = reinterpret_cast<const uint32_t *>(s_out[buf ^ 1])[t];
-    double z = dct_inner(s_cpn[buf][c], lut);
-    z = __dmul_rn(z, wgt);
-    s_out[buf][dst] = (int16_t)__double2int_rn(z);
-    prev_tile = tile;
+  int64_t prev_pair = -1;
+  auto flush = [&](int64_t pp, int b) {
+    const int64_t t0 = 2 * pp;
+    uint32_t *o = reinterpret_cast<uint32_t *>(out + t0 * 192);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(&s_out[b][0][0]);
+    if (t < 96 || t0 + 1 < n) o[t] = src[t];   // words 0..95 = tile 2 pp, 96..191 = tile 2 pp + 1
+  };
+  for (; pair < n_pairs; pair += gridDim.x, buf ^= 1) {
+    s_cpn[buf][0][c][px] = convert(col0);
+    s_cpn[buf][1][c][px] = convert(col1);
+    __syncthreads();   // planes of this pair visible; coefficients of the previous pair complete in s_out[buf ^ 1]
+    const int64_t next = pair + gridDim.x;
+    if (next < n_pairs) { col0 = fetch(2 * next); col1 = fetch(2 * next + 1); }
+    if (prev_pair >= 0) flush(prev_pair, buf ^ 1);
+    double z0 = dct_inner(s_cpn[buf][0][c], lut);
+    double z1 = dct_inner(s_cpn[buf][1][c], lut);
+    z0 = __dmul_rn(z0, wgt);
+    z1 = __dmul_rn(z1, wgt);
+    s_out[buf][0][dst] = (int16_t)__double2int_rn(z0);
+    s_out[buf][1][dst] = (int16_t)__double2int_rn(z1);
+    prev_pair = pair;
   }
   __syncthreads();
-  if (t < 96 && prev_tile >= 0)
-    reinterpret_cast<uint32_t *>(out + prev_tile * 192)[t] = reinterpret_cast<const uint32_t *>(s_out[buf ^ 1])[t];
+  if (prev_pair >= 0) flush(prev_pair, buf ^ 1);
 }
 
 // ComputeTilePsyVisFeatures: f64, sequential 64-term sums (DCTInner<PDouble>, utils.pas:782-872)
@@ -269,7 +281,7 @@ int launch_features_rgb(const int32_t *rgb, int64_t n, int16_t *out, cudaStream_
   int rc = features_init(st);
   if (rc) return rc;
   ProfScope prof("features_rgb", st);
-  features_i16_kernel<0><<<grid_for(n, 4), 192, 0, st>>>(rgb, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
+  features_i16_kernel<0><<<grid_for((n + 1) / 2, 3), 192, 0, st>>>(rgb, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }
@@ -278,7 +290,7 @@ int launch_features_rgb_mirrored(const int32_t *rgb, const uint8_t *flags, int64
   if (n <= 0) return TM_OK;
   int rc = features_init(st);
   if (rc) return rc;
-  features_i16_kernel<3><<<grid_for(n, 4), 192, 0, st>>>(rgb, flags, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
+  features_i16_kernel<3><<<grid_for((n + 1) / 2, 3), 192, 0, st>>>(rgb, flags, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }
@@ -290,7 +302,7 @@ int launch_features_sliding(const int32_t *frame, int w, int h, int16_t *out, cu
   if (rc) return rc;
   const int64_t n = (int64_t)(w - 7) * (h - 7);
   ProfScope prof("features_sliding", st);
-  features_i16_kernel<4><<<grid_for(n, 4), 192, 0, st>>>(frame, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out, w,
+  features_i16_kernel<4><<<grid_for((n + 1) / 2, 3), 192, 0, st>>>(frame, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out, w,
                                                                              w - 7);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
@@ -301,7 +313,7 @@ int launch_features_pal(const uint8_t *pal_idx, const int32_t *tile_pal, const i
   if (n <= 0) return TM_OK;
   int rc = features_init(st);
   if (rc) return rc;
-  features_i16_kernel<1><<<grid_for(n, 4), 192, 0, st>>>(nullptr, pal_idx, 0, tile_pal, palettes, pal_size, n,
+  features_i16_kernel<1><<<grid_for((n + 1) / 2, 3), 192, 0, st>>>(nullptr, pal_idx, 0, tile_pal, palettes, pal_size, n,
                                                                              g_lutT_f32, out);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
@@ -313,7 +325,7 @@ int launch_features_allpairs(const uint8_t *pal_idx, int64_t n_tiles, const int3
   if (n_pairs <= 0) return TM_OK;
   int rc = features_init(st);
   if (rc) return rc;
-  features_i16_kernel<2><<<grid_for(n_pairs, 4), 192, 0, st>>>(nullptr, pal_idx, n_pal, nullptr, palettes, pal_size,
+  features_i16_kernel<2><<<grid_for((n_pairs + 1) / 2, 3), 192, 0, st>>>(nullptr, pal_idx, n_pal, nullptr, palettes, pal_size,
                                                                                    n_pairs, g_lutT_f32, out);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
