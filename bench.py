@@ -107,7 +107,7 @@ def encode_leg(dev, frames):
     res = enc.encode(frames, seqs, tile_count=N_DICT)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
-    mse = api.mse_rgb(torch.from_numpy(frames).to(dev), torch.from_numpy(res["recon"]).to(dev))
+    mse = api.mse_rgb(torch.from_numpy(frames).to(dev), res["recon"])
     return {"frames_per_sec": n / dt, "seconds": dt, "frames": int(n), "sequences": len(seqs),
             "stage_seconds": {k: round(v, 3) for k, v in res["timings"].items()},
             "dictionary_tiles_final": int(len(res["tiles"])), "gtm_bytes": len(res["gtm"]),

@@ -120,14 +120,20 @@ class TilingEncoder:
         shape = tuple(canon_tiles.shape[:2])
         flat = canon_tiles.reshape(-1, 64)
         cls, n_cls = api.tile_classes(flat)
-        cls = cls.cpu().numpy() if api._is_dev(cls) else np.asarray(cls)
         eff = np.asarray(psnr, dtype=np.float32).copy()
         for f in seq_start_frames:
             eff[f] = eff[f] / np.float32(10.0)
         eff = eff.reshape(-1)
-        cls_min = np.full(n_cls, np.inf, dtype=np.float32)
-        np.minimum.at(cls_min, cls, eff)
-        sorted_min = np.sort(cls_min)
+        if api._is_dev(cls):   # segmented minimum over 3.4 M tiles: a scatter-reduce on the device instead of np.minimum.at
+            cls_min_t = torch.full((n_cls,), float("inf"), dtype=torch.float32, device=cls.device)
+            cls_min_t.scatter_reduce_(0, cls.long(), torch.from_numpy(eff).to(cls.device), reduce="amin")
+            sorted_min = np.sort(cls_min_t.cpu().numpy())
+            cls = cls.cpu().numpy()
+        else:
+            cls = np.asarray(cls)
+            order0 = np.argsort(cls, kind="stable")
+            starts = np.flatnonzero(np.r_[True, np.diff(cls[order0]) != 0])
+            sorted_min = np.sort(np.minimum.reduceat(eff[order0], starts))
         target = min(int(tile_count), int(flat.shape[0]))
         x_res, x_last = golden_ratio_search(lambda x: float(np.searchsorted(sorted_min, np.float32(x), side="right")), 0.0,
                                             float(C_PSNR_MAX), float(target))
@@ -135,8 +141,13 @@ class TilingEncoder:
         unpred = ~(eff > x)                                   # IsPredicted := PSNR > x
         idx_all = np.arange(flat.shape[0])
         use = np.bincount(cls[unpred], minlength=n_cls)
+        # representative = first unpredicted member of the class
+        ui = idx_all[unpred]
+        uc = cls[unpred]
+        o2 = np.argsort(uc, kind="stable")                    # ui is ascending, the sort is stable: first of each run = smallest index
+        first = np.flatnonzero(np.r_[True, np.diff(uc[o2]) != 0])
         rep = np.full(n_cls, flat.shape[0], dtype=np.int64)
-        np.minimum.at(rep, cls[unpred], idx_all[unpred])      # representative = first unpredicted member
+        rep[uc[o2][first]] = ui[o2][first]
         chosen = np.nonzero(use > 0)[0]
         rep_idx = rep[chosen]
         if api._is_dev(flat):
@@ -172,7 +183,12 @@ class TilingEncoder:
         nt = tw * th
         t = {}
         t0 = time.perf_counter()
-        tiles = np.ascontiguousarray(np.asarray(frames_packed).reshape(n, th, 8, tw, 8).transpose(0, 1, 3, 2, 4).reshape(n, nt, 64))
+        if self.device is not None:   # frames -> tiles is a pure layout change: done on the device (torch = memory plumbing)
+            fr_dev = frames_packed if api._is_dev(frames_packed) else torch.from_numpy(np.ascontiguousarray(frames_packed)).to(self.device)
+            tiles = fr_dev.view(n, th, 8, tw, 8).permute(0, 1, 3, 2, 4).contiguous().view(n, nt, 64)
+            frames_packed = fr_dev
+        else:
+            tiles = np.ascontiguousarray(np.asarray(frames_packed).reshape(n, th, 8, tw, 8).transpose(0, 1, 3, 2, 4).reshape(n, nt, 64))
         canon, flags = self.load_tiles(tiles)
         t["load"] = time.perf_counter() - t0; t0 = time.perf_counter()
         psnr, _, _ = self.predict_motion(frames_packed, canon, flags, tw, th, radius)
@@ -184,14 +200,17 @@ class TilingEncoder:
         self.dither()
         t["dither"] = time.perf_counter() - t0; t0 = time.perf_counter()
         self.prepare_reconstruct()
-        keys = ("tile_idx", "pal_idx", "pred_x", "pred_y", "is_pred", "err", "psnr", "recon")
+        keys = ("tile_idx", "pal_idx", "pred_x", "pred_y", "is_pred", "err", "psnr")
         parts = {k: [] for k in keys}
+        recon_parts = []
         for s0, s1 in sequences:
             r = self.matcher.reconstruct_sequence(canon[s0:s1 + 1], flags[s0:s1 + 1], tw, th, radius=radius)
             for k in keys:
                 v = r[k]
                 parts[k].append(v.cpu().numpy() if api._is_dev(v) else v)
+            recon_parts.append(r["recon"])   # stays on the device when the encoder is device-resident
         tm = {k: np.concatenate(parts[k]) for k in keys}
+        recon = torch.cat(recon_parts) if api._is_dev(recon_parts[0]) else np.concatenate(recon_parts)
         tm["err"] = tm["err"].view(np.uint32)
         tm["mirror"] = flags.cpu().numpy() if api._is_dev(flags) else np.asarray(flags)
         self.finish_reconstruct()
@@ -206,7 +225,7 @@ class TilingEncoder:
                                 settings_text=f"tiler_b200 PaletteSize={self.palette_size} PaletteCount={self.palette_count}",
                                 emit_skip_blocks=emit_skip_blocks)
         t["save"] = time.perf_counter() - t0
-        return {"gtm": data, "tilemap": tm_out, "recon": tm["recon"], "tiles": final_tiles, "use_count": use_count, "palettes": pal,
+        return {"gtm": data, "tilemap": tm_out, "recon": recon, "tiles": final_tiles, "use_count": use_count, "palettes": pal,
                 "timings": t, "mean_tile_psnr": float(tm["psnr"].mean()), "dictionary_before_reindex": int(didx.shape[0])}
 
     # --- Reduce stand-in used by bench.py's match-stage step: samples dictionary tiles, no motion pass

@@ -129,9 +129,9 @@ def write_gtm(path_or_none, tm, tiles_idx, use_count, palettes, tw, th, sequence
         cols[cols == NULL_COLOR] = 0xFFFFFF
         cols = (cols & 0xFFFFFF) | 0xFF000000
         pre += _cmd(12, 0) + struct.pack("<H", p) + cols.astype("<u4").tobytes()
-    # ---- chunks
-    chunks, kf_info = [], []
-    for ki, (f0, f1) in enumerate(sequences):
+    # ---- chunks: one LZMA stream per keyframe sequence, compressed in parallel (the C calls release the GIL)
+    def one_chunk(job):
+        ki, (f0, f1) = job
         nf = f1 - f0 + 1
         cap = nf * nt * 70 + 64
         buf = np.empty(cap, dtype=np.uint8)
@@ -142,8 +142,13 @@ def write_gtm(path_or_none, tm, tiles_idx, use_count, palettes, tw, th, sequence
         assert 0 < n <= cap
         raw = (bytes(pre) if ki == 0 else b"") + buf[:n].tobytes()
         comp = lzma_encode(raw)
-        chunks.append(comp)
-        kf_info.append((ki, f0, len(raw), len(comp), int(round(1000.0 * f0 / fps))))
+        return comp, (ki, f0, len(raw), len(comp), int(round(1000.0 * f0 / fps)))
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(sequences)))) as pool:
+        done = list(pool.map(one_chunk, list(enumerate(sequences))))
+    chunks = [d[0] for d in done]
+    kf_info = [d[1] for d in done]
     # ---- header (TGTMHeader, TGTMKeyFrameInfo: tilingencoder.pas:30-51, 5338-5370, 5470-5476)
     whole_header = 40 + 28 * len(sequences)
     total = sum(len(c) for c in chunks)

@@ -44,6 +44,6 @@ if a.decode:
     t0 = time.perf_counter()
     dec, hdr = gtm.decode_gtm(res["gtm"])
     out["decode_s"] = round(time.perf_counter() - t0, 2)
-    out["decoded_equals_reconstruction"] = bool(np.array_equal(dec, res["recon"]))
+    out["decoded_equals_reconstruction"] = bool(np.array_equal(dec, res["recon"].cpu().numpy()))
     out["psnr_rgb_db"] = round(psnr_rgb(dec, frames), 4)
 print(json.dumps(out))
