@@ -68,6 +68,10 @@ def _worker(rank, world, port, q):
     shards = tdist.shard_sequences([3, 5, 2, 4], world)
     local = {i: np.full(4, i, np.int32) for i in shards[rank]}
     merged = tdist.gather_tilemaps(local, shards)
+    # per-frame rows sharded like PredictMotion in TilingEncoder.encode(sharded=True): 7 frames x 3 tiles over 2 ranks
+    flo, fhi = tdist.shard_rows(7, rank, world)
+    rows = tdist.gather_rows(np.arange(7 * 3, dtype=np.float32).reshape(7, 3)[flo:fhi], 7)
+    assert tdist.world_info() == (rank, world) and np.array_equal(rows, np.arange(21, dtype=np.float32).reshape(7, 3))
     q.put((rank, cent, changed, inertia, sorted(merged)))
     dist.destroy_process_group()
 

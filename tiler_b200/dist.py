@@ -93,3 +93,21 @@ def gather_tilemaps(local, world_shards):
         merged.update(d)
     assert sorted(merged) == sorted(i for s in world_shards for i in s)
     return merged
+
+
+def gather_rows(local_rows, n_total):
+    """All-gather row shards produced by shard_rows (numpy [hi - lo, ...]) into the full [n_total, ...] array on every rank."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        assert local_rows.shape[0] == n_total
+        return local_rows
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, local_rows)
+    full = np.concatenate(out, axis=0)
+    assert full.shape[0] == n_total
+    return full
+
+
+def world_info():
+    if dist is None or not dist.is_available() or not dist.is_initialized():
+        return 0, 1
+    return dist.get_rank(), dist.get_world_size()

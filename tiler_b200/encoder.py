@@ -86,16 +86,19 @@ class TilingEncoder:
         return tiles.reshape(shape), flags.reshape(shape[:2])
 
     # --- PredictMotion (tilingencoder.pas:1964-1991, 1154-1282): every tile against the previous SOURCE frame
-    def predict_motion(self, frames_packed, canon_tiles, canon_flags, tw, th, radius=32):
+    def predict_motion(self, frames_packed, canon_tiles, canon_flags, tw, th, radius=32, frame_range=None):
         """frames_packed [n, th*8, tw*8] source pixels; -> (psnr f32 [n, nt], pred_x, pred_y) on the host.
-        Frame 0 is predicted from frame 1 (:1982-1984); a one-frame clip is predicted from a black buffer."""
+        Frame 0 is predicted from frame 1 (:1982-1984); a one-frame clip is predicted from a black buffer.
+        frame_range = (lo, hi) restricts the work to those frames (multi-GPU sharding by frame): rows [lo, hi) are returned."""
         n = int(frames_packed.shape[0])
         nt = tw * th
-        psnr = np.empty((n, nt), np.float32)
-        px = np.empty((n, nt), np.int32)
-        py = np.empty((n, nt), np.int32)
+        lo, hi = frame_range if frame_range is not None else (0, n)
+        psnr_all = np.empty((n, nt), np.float32)
+        px_all = np.empty((n, nt), np.int32)
+        py_all = np.empty((n, nt), np.int32)
+        psnr, px, py = psnr_all, px_all, py_all
         fr = self._to(frames_packed)
-        for f in range(n):
+        for f in range(lo, hi):
             if f > 0:
                 prev = fr[f - 1]
             elif n > 1:
@@ -107,7 +110,7 @@ class TilingEncoder:
             psnr[f] = euclidean_to_psnr(np.asarray(e).view(np.uint32))
             px[f] = x.cpu().numpy() if api._is_dev(x) else x
             py[f] = y.cpu().numpy() if api._is_dev(y) else y
-        return psnr, px, py
+        return psnr_all[lo:hi], px_all[lo:hi], py_all[lo:hi]
 
     # --- Reduce (tilingencoder.pas:1908-1926, 4014-4103, 4626-4696, 4720-4781)
     def reduce(self, canon_tiles, canon_flags, psnr, seq_start_frames, tile_count):
@@ -173,10 +176,16 @@ class TilingEncoder:
         return tile_idx
 
     # --- whole pipeline (TTilingEncoder.Run, tilingencoder.pas:5530-5552)
-    def encode(self, frames_packed, sequences, tile_count, radius=32, fps=24.0, out_path=None, emit_skip_blocks=True):
+    def encode(self, frames_packed, sequences, tile_count, radius=32, fps=24.0, out_path=None, emit_skip_blocks=True, sharded=False):
         """frames_packed [n, H, W] int32 0x00BBGGRR with H, W multiples of 8; sequences = [(start, end)] inclusive.
-        -> dict(gtm bytes, tilemap, recon frames, dictionary, timings)."""
+        -> dict(gtm bytes, tilemap, recon frames, dictionary, timings).
+        sharded=True (inside an initialised torch.distributed group, one process per GPU, every rank holding the clip):
+        PredictMotion is sharded by frame and Reconstruct by keyframe sequence (no data-path collective, the
+        per-tile PSNRs and the tilemaps are gathered on the host); Reduce, palettes and dithering are deterministic and run
+        replicated; rank 0 writes the stream.  The bytes equal the single-GPU encode's."""
         import time
+        from . import dist as tdist
+        rank, world = tdist.world_info() if sharded else (0, 1)
         n, H, W = (int(v) for v in frames_packed.shape)
         assert H % 8 == 0 and W % 8 == 0
         tw, th = W // 8, H // 8
@@ -191,7 +200,12 @@ class TilingEncoder:
             tiles = np.ascontiguousarray(np.asarray(frames_packed).reshape(n, th, 8, tw, 8).transpose(0, 1, 3, 2, 4).reshape(n, nt, 64))
         canon, flags = self.load_tiles(tiles)
         t["load"] = time.perf_counter() - t0; t0 = time.perf_counter()
-        psnr, _, _ = self.predict_motion(frames_packed, canon, flags, tw, th, radius)
+        if world > 1:
+            lo, hi = tdist.shard_rows(n, rank, world)
+            psnr_loc, _, _ = self.predict_motion(frames_packed, canon, flags, tw, th, radius, frame_range=(lo, hi))
+            psnr = tdist.gather_rows(psnr_loc, n)
+        else:
+            psnr, _, _ = self.predict_motion(frames_packed, canon, flags, tw, th, radius)
         t["predict_motion"] = time.perf_counter() - t0; t0 = time.perf_counter()
         self.reduce(canon, flags, psnr, [s for s, _ in sequences], tile_count)
         t["reduce"] = time.perf_counter() - t0; t0 = time.perf_counter()
@@ -201,16 +215,17 @@ class TilingEncoder:
         t["dither"] = time.perf_counter() - t0; t0 = time.perf_counter()
         self.prepare_reconstruct()
         keys = ("tile_idx", "pal_idx", "pred_x", "pred_y", "is_pred", "err", "psnr")
-        parts = {k: [] for k in keys}
-        recon_parts = []
-        for s0, s1 in sequences:
+        mine = tdist.shard_sequences([s1 - s0 + 1 for s0, s1 in sequences], world)
+        local, recon_of = {}, {}
+        for si in mine[rank]:
+            s0, s1 = sequences[si]
             r = self.matcher.reconstruct_sequence(canon[s0:s1 + 1], flags[s0:s1 + 1], tw, th, radius=radius)
-            for k in keys:
-                v = r[k]
-                parts[k].append(v.cpu().numpy() if api._is_dev(v) else v)
-            recon_parts.append(r["recon"])   # stays on the device when the encoder is device-resident
-        tm = {k: np.concatenate(parts[k]) for k in keys}
-        recon = torch.cat(recon_parts) if api._is_dev(recon_parts[0]) else np.concatenate(recon_parts)
+            local[si] = {k: (r[k].cpu().numpy() if api._is_dev(r[k]) else r[k]) for k in keys}
+            recon_of[si] = r["recon"]        # stays on the device when the encoder is device-resident
+        merged = tdist.gather_tilemaps(local, mine) if world > 1 else local
+        tm = {k: np.concatenate([merged[si][k] for si in range(len(sequences))]) for k in keys}
+        own = [recon_of[si] for si in sorted(recon_of)]
+        recon = (torch.cat(own) if api._is_dev(own[0]) else np.concatenate(own)) if own else None   # this rank's sequences only
         tm["err"] = tm["err"].view(np.uint32)
         tm["mirror"] = flags.cpu().numpy() if api._is_dev(flags) else np.asarray(flags)
         self.finish_reconstruct()
@@ -221,12 +236,14 @@ class TilingEncoder:
         tm_out = dict(tm)
         tm_out["tile_idx"] = tile_map
         t["reindex"] = time.perf_counter() - t0; t0 = time.perf_counter()
-        data = gtm_io.write_gtm(out_path, tm_out, final_tiles, use_count, pal, tw, th, sequences, fps=fps,
-                                settings_text=f"tiler_b200 PaletteSize={self.palette_size} PaletteCount={self.palette_count}",
-                                emit_skip_blocks=emit_skip_blocks)
+        data = b""
+        if rank == 0:
+            data = gtm_io.write_gtm(out_path, tm_out, final_tiles, use_count, pal, tw, th, sequences, fps=fps,
+                                    settings_text=f"tiler_b200 PaletteSize={self.palette_size} PaletteCount={self.palette_count}",
+                                    emit_skip_blocks=emit_skip_blocks)
         t["save"] = time.perf_counter() - t0
         return {"gtm": data, "tilemap": tm_out, "recon": recon, "tiles": final_tiles, "use_count": use_count, "palettes": pal,
-                "timings": t, "mean_tile_psnr": float(tm["psnr"].mean()), "dictionary_before_reindex": int(didx.shape[0])}
+                "recon_sequences": sorted(recon_of), "timings": t, "mean_tile_psnr": float(tm["psnr"].mean()), "dictionary_before_reindex": int(didx.shape[0])}
 
     # --- Reduce stand-in used by bench.py's match-stage step: samples dictionary tiles, no motion pass
     def reduce_sample(self, canon_tiles, canon_flags, tile_count):
