@@ -1,2 +1,3 @@
-python tools/encode_clip.py --decode 0 2>&1 | tail -1 | cut -c1-420
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 tools/encode_clip.py --sharded 1 2>&1 | tail -1 | cut -c1-700
+python bench.py --steps 3 --warmup 3 2> gpurun_out/bench1.err | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['encode'], d['cpu_baseline'])"
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus 2 --steps 3 --warmup 3 2> gpurun_out/bench2.err | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','n_gpus')}, d['encode'])"
+tail -3 gpurun_out/bench2.err
