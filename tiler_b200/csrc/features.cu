@@ -139,6 +139,9 @@ __device__ __forceinline__ double dct_inner(const float *__restrict__ s_c, const
   return __dadd_rn(acc0, acc1);
 }
 
+#ifndef FEAT_NP
+#define FEAT_NP 2
+#endif
 // MODE 0: RGB tiles; 1: palette indices with per-tile palette; 2: every (tile, palette) pair, item = tile*n_pal + pal;
 // 3: RGB tiles read through their mirror flags (pal_idx = flags[n]: ConvertToCpnPixels with AHMirror / AVMirror, :3049-3101);
 // 4: sliding window over a frame buffer (rgb = frame [h][fw], item = oy * pw + ox: DoDCTs, :1437-1462)
@@ -147,8 +150,9 @@ __global__ void __launch_bounds__(192, 3)
 features_i16_kernel(const int32_t *__restrict__ rgb, const uint8_t *__restrict__ pal_idx, int n_pal_all,
                     const int32_t *__restrict__ sel_pal, const int32_t *__restrict__ palettes, int pal_size, int64_t n,
                     const float *__restrict__ lutT, int16_t *__restrict__ out, int fw = 0, int pw = 0) {
-  __shared__ __align__(16) float s_cpn[2][2][3][64];   // [buffer][tile of the pair][plane][pixel]: one barrier per PAIR of tiles
-  __shared__ __align__(16) int16_t s_out[2][2][192];
+  constexpr int NP = FEAT_NP;   // tiles per block iteration
+  __shared__ __align__(16) float s_cpn[2][NP][3][64];   // [buffer][tile of the group][plane][pixel]: one barrier per GROUP of tiles
+  __shared__ __align__(16) int16_t s_out[2][NP][192];
   const int t = threadIdx.x;
   const int c = t >> 6, vu = t & 63;
   float lut[64];
@@ -183,38 +187,45 @@ features_i16_kernel(const int32_t *__restrict__ rgb, const uint8_t *__restrict__
     if (c != 0) val = (float)__dmul_rn(__dsub_rn((double)(c == 1 ? b : r), (double)y), c == 1 ? 0.492 : 0.877);
     return val;
   };
-  // A block works on PAIRS of consecutive tiles (2 i, 2 i + 1): two independent 64-term sums per thread share the basis
-  // registers and double the instruction-level parallelism, and the pair's 768 output bytes leave as one coalesced store.
-  // Software pipeline: the pixels of the NEXT pair are requested before the current pair's sums, so the global load
-  // latency never sits between two barriers; the previous pair's coefficients are stored while the current one is computed.
-  const int64_t n_pairs = (n + 1) >> 1;
-  int64_t pair = blockIdx.x;
-  int32_t col0 = pair < n_pairs ? fetch(2 * pair) : 0, col1 = pair < n_pairs ? fetch(2 * pair + 1) : 0;
+  // A block works on GROUPS of NP consecutive tiles: NP independent 64-term sums per thread share the basis registers and
+  // multiply the instruction-level parallelism, and the group's NP x 384 output bytes leave as coalesced 4-byte stores.
+  // Software pipeline: the pixels of the NEXT group are requested before the current group's sums, so the global load
+  // latency never sits between two barriers; the previous group's coefficients are stored while the current one is computed.
+  const int64_t n_groups = (n + NP - 1) / NP;
+  int64_t grp = blockIdx.x;
+  int32_t col[NP];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) col[k] = grp < n_groups ? fetch(NP * grp + k) : 0;
   int buf = 0;
-  int64_t prev_pair = -1;
-  auto flush = [&](int64_t pp, int b) {
-    const int64_t t0 = 2 * pp;
+  int64_t prev_grp = -1;
+  auto flush = [&](int64_t pg, int b) {
+    const int64_t t0 = NP * pg;
     uint32_t *o = reinterpret_cast<uint32_t *>(out + t0 * 192);
     const uint32_t *src = reinterpret_cast<const uint32_t *>(&s_out[b][0][0]);
-    if (t < 96 || t0 + 1 < n) o[t] = src[t];   // words 0..95 = tile 2 pp, 96..191 = tile 2 pp + 1
+#pragma unroll
+    for (int w = t; w < NP * 96; w += 192)
+      if (t0 + w / 96 < n) o[w] = src[w];   // words [96 k, 96 k + 96) = tile NP pg + k
   };
-  for (; pair < n_pairs; pair += gridDim.x, buf ^= 1) {
-    s_cpn[buf][0][c][px] = convert(col0);
-    s_cpn[buf][1][c][px] = convert(col1);
-    __syncthreads();   // planes of this pair visible; coefficients of the previous pair complete in s_out[buf ^ 1]
-    const int64_t next = pair + gridDim.x;
-    if (next < n_pairs) { col0 = fetch(2 * next); col1 = fetch(2 * next + 1); }
-    if (prev_pair >= 0) flush(prev_pair, buf ^ 1);
-    double z0 = dct_inner(s_cpn[buf][0][c], lut);
-    double z1 = dct_inner(s_cpn[buf][1][c], lut);
-    z0 = __dmul_rn(z0, wgt);
-    z1 = __dmul_rn(z1, wgt);
-    s_out[buf][0][dst] = (int16_t)__double2int_rn(z0);
-    s_out[buf][1][dst] = (int16_t)__double2int_rn(z1);
-    prev_pair = pair;
+  for (; grp < n_groups; grp += gridDim.x, buf ^= 1) {
+#pragma unroll
+    for (int k = 0; k < NP; ++k) s_cpn[buf][k][c][px] = convert(col[k]);
+    __syncthreads();   // planes of this group visible; coefficients of the previous group complete in s_out[buf ^ 1]
+    const int64_t next = grp + gridDim.x;
+    if (next < n_groups) {
+#pragma unroll
+      for (int k = 0; k < NP; ++k) col[k] = fetch(NP * next + k);
+    }
+    if (prev_grp >= 0) flush(prev_grp, buf ^ 1);
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+      double z = dct_inner(s_cpn[buf][k][c], lut);
+      z = __dmul_rn(z, wgt);
+      s_out[buf][k][dst] = (int16_t)__double2int_rn(z);
+    }
+    prev_grp = grp;
   }
   __syncthreads();
-  if (prev_pair >= 0) flush(prev_pair, buf ^ 1);
+  if (prev_grp >= 0) flush(prev_grp, buf ^ 1);
 }
 
 // ComputeTilePsyVisFeatures: f64, sequential 64-term sums (DCTInner<PDouble>, utils.pas:782-872)
@@ -281,7 +292,7 @@ int launch_features_rgb(const int32_t *rgb, int64_t n, int16_t *out, cudaStream_
   int rc = features_init(st);
   if (rc) return rc;
   ProfScope prof("features_rgb", st);
-  features_i16_kernel<0><<<grid_for((n + 1) / 2, 3), 192, 0, st>>>(rgb, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
+  features_i16_kernel<0><<<grid_for((n + FEAT_NP - 1) / FEAT_NP, 3), 192, 0, st>>>(rgb, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }
@@ -290,7 +301,7 @@ int launch_features_rgb_mirrored(const int32_t *rgb, const uint8_t *flags, int64
   if (n <= 0) return TM_OK;
   int rc = features_init(st);
   if (rc) return rc;
-  features_i16_kernel<3><<<grid_for((n + 1) / 2, 3), 192, 0, st>>>(rgb, flags, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
+  features_i16_kernel<3><<<grid_for((n + FEAT_NP - 1) / FEAT_NP, 3), 192, 0, st>>>(rgb, flags, 0, nullptr, nullptr, 0, n, g_lutT_f32, out);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }
@@ -302,7 +313,7 @@ int launch_features_sliding(const int32_t *frame, int w, int h, int16_t *out, cu
   if (rc) return rc;
   const int64_t n = (int64_t)(w - 7) * (h - 7);
   ProfScope prof("features_sliding", st);
-  features_i16_kernel<4><<<grid_for((n + 1) / 2, 3), 192, 0, st>>>(frame, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out, w,
+  features_i16_kernel<4><<<grid_for((n + FEAT_NP - 1) / FEAT_NP, 3), 192, 0, st>>>(frame, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out, w,
                                                                              w - 7);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
@@ -313,7 +324,7 @@ int launch_features_pal(const uint8_t *pal_idx, const int32_t *tile_pal, const i
   if (n <= 0) return TM_OK;
   int rc = features_init(st);
   if (rc) return rc;
-  features_i16_kernel<1><<<grid_for((n + 1) / 2, 3), 192, 0, st>>>(nullptr, pal_idx, 0, tile_pal, palettes, pal_size, n,
+  features_i16_kernel<1><<<grid_for((n + FEAT_NP - 1) / FEAT_NP, 3), 192, 0, st>>>(nullptr, pal_idx, 0, tile_pal, palettes, pal_size, n,
                                                                              g_lutT_f32, out);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
@@ -325,7 +336,7 @@ int launch_features_allpairs(const uint8_t *pal_idx, int64_t n_tiles, const int3
   if (n_pairs <= 0) return TM_OK;
   int rc = features_init(st);
   if (rc) return rc;
-  features_i16_kernel<2><<<grid_for((n_pairs + 1) / 2, 3), 192, 0, st>>>(nullptr, pal_idx, n_pal, nullptr, palettes, pal_size,
+  features_i16_kernel<2><<<grid_for((n_pairs + FEAT_NP - 1) / FEAT_NP, 3), 192, 0, st>>>(nullptr, pal_idx, n_pal, nullptr, palettes, pal_size,
                                                                                    n_pairs, g_lutT_f32, out);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
