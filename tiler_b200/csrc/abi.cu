@@ -766,6 +766,16 @@ extern "C" int tm_matcher_dict_features(tm_matcher *m, int16_t *out) {
 }
 
 // ------------------------------------------------------------------ motion search + Reconstruct
+// The window scan runs on the tensor cores (motion_tc.cu); TM_MOTION_SCALAR=1 selects the CUDA-core kernel (motion.cu)
+// for A/B comparisons.  Both are bit-exact against the oracle.
+static int motion_search_dev(const int16_t *d_cur, int tw, int th, const int16_t *d_dcts, int radius, int32_t *d_px, int32_t *d_py,
+                             uint32_t *d_err, void *ws, size_t wsb, cudaStream_t st) {
+  static int scalar = -1;
+  if (scalar < 0) scalar = getenv("TM_MOTION_SCALAR") && atoi(getenv("TM_MOTION_SCALAR")) ? 1 : 0;
+  if (scalar) return launch_motion_search(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, st);
+  return launch_motion_search_tc(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, ws, wsb, num_sms(), st);
+}
+
 extern "C" int tm_sliding_features(const int32_t *frame, int w, int h, int16_t *out) {
   RC(require_gpu());
   if (!frame || !out || w < 8 || h < 8) return fail(TM_ERR_ARG, "tm_sliding_features: bad argument");
@@ -790,7 +800,9 @@ extern "C" int tm_motion_search(const int16_t *cur_feat, int tw, int th, const i
   const int16_t *d_dcts = s.in(dcts, (size_t)(tw * 8 - 7) * (th * 8 - 7) * 192);
   int32_t *d_px = s.out(pred_x, nt), *d_py = s.out(pred_y, nt);
   uint32_t *d_err = s.out(err, nt);
-  if (s.err == TM_OK) s.err = launch_motion_search(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, s.st);
+  const size_t wsb = motion_tc_ws_bytes(tw, th);
+  void *ws = s.temp(wsb);
+  if (s.err == TM_OK) s.err = motion_search_dev(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, ws, wsb, s.st);
   RC(s.finish());
   return TM_OK;
 }
@@ -812,8 +824,10 @@ extern "C" int tm_predict_motion_frame(const int32_t *prev_frame, const int32_t 
   int16_t *d_cur = (int16_t *)s.temp(nt * 384);
   int16_t *d_dcts = (int16_t *)s.temp((size_t)(w - 7) * (h - 7) * 384);
   if (s.err == TM_OK) s.err = launch_features_rgb_mirrored(d_tiles, d_flags, (int64_t)nt, d_cur, s.st);
+  const size_t wsb = motion_tc_ws_bytes(tw, th);
+  void *ws = s.temp(wsb);
   if (s.err == TM_OK) s.err = launch_features_sliding(d_prev, w, h, d_dcts, s.st);
-  if (s.err == TM_OK) s.err = launch_motion_search(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, s.st);
+  if (s.err == TM_OK) s.err = motion_search_dev(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, ws, wsb, s.st);
   RC(s.finish());
   return TM_OK;
 }
@@ -848,6 +862,8 @@ extern "C" int tm_reconstruct_sequence(tm_matcher *m, const int32_t *canon_tiles
   uint32_t *k_err = (uint32_t *)s.temp(n_all * 4);
   int32_t *mx = (int32_t *)s.temp(nt * 4), *my = (int32_t *)s.temp(nt * 4);
   uint32_t *me = (uint32_t *)s.temp(nt * 4);
+  const size_t wsb = motion ? motion_tc_ws_bytes(tw, th) : 0;
+  void *ws = motion ? s.temp(wsb) : nullptr;
   // the k-NN + re-rank candidates do not depend on the reconstructed frames: one batched pass over the whole sequence
   if (s.err == TM_OK) s.err = launch_features_rgb(d_tiles, (int64_t)n_all, d_ft, s.st);
   if (s.err == TM_OK) s.err = match_feat_dev(m, d_ft, (int64_t)n_all, k, k_tile, k_pal, k_err, s);
@@ -858,7 +874,7 @@ extern "C" int tm_reconstruct_sequence(tm_matcher *m, const int32_t *canon_tiles
     const bool mo = motion && f > 0;
     if (mo) {
       s.err = launch_features_sliding(back, w, h, d_dcts, s.st);
-      if (s.err == TM_OK) s.err = launch_motion_search(d_cur + nt * 192 * f, tw, th, d_dcts, radius, mx, my, me, s.st);
+      if (s.err == TM_OK) s.err = motion_search_dev(d_cur + nt * 192 * f, tw, th, d_dcts, radius, mx, my, me, ws, wsb, s.st);
     }
     const size_t o = nt * f;
     if (s.err == TM_OK)

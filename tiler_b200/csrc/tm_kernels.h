@@ -52,6 +52,10 @@ int launch_features_sliding(const int32_t *frame, int w, int h, int16_t *out, cu
 // motion search of every tile of a frame against the sliding features of the previous frame buffer
 int launch_motion_search(const int16_t *cur_feat, int tw, int th, const int16_t *dcts, int radius_setting, int32_t *pred_x,
                          int32_t *pred_y, uint32_t *err, cudaStream_t st);
+// the same search on the tensor cores (motion_tc.cu): ws of motion_tc_ws_bytes(tw, th) bytes
+size_t motion_tc_ws_bytes(int tw, int th);
+int launch_motion_search_tc(const int16_t *cur_feat, int tw, int th, const int16_t *dcts, int radius_setting, int32_t *pred_x,
+                            int32_t *pred_y, uint32_t *err, void *ws, size_t ws_bytes, int num_ctas, cudaStream_t st);
 // TFrame.Reconstruct's decision + frame-buffer draw for one frame; motion arrays null on the first frame of a sequence
 int launch_reconstruct_decide(const uint8_t *flags, int tw, int th, const int32_t *mp_x, const int32_t *mp_y, const uint32_t *mp_err,
                               const int32_t *knn_tile, const int32_t *knn_pal, const uint32_t *knn_err, const uint8_t *dict_idx,

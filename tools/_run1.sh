@@ -1,3 +1,2 @@
-for v in np2 np3; do echo "$v: $(TM_LIB_PATH=$PWD/gpurun_variants/libtm_$v.so python tools/feat_timing.py 2>&1 | tail -1)"; done
-echo "np4: $(python tools/feat_timing.py 2>&1 | tail -1)"
-bash tools/run_gpu_tests.sh features sliding > gpurun_out/run1.log 2>&1; cat gpurun_out/summary.txt
+timeout 300 bash tools/run_gpu_tests.sh motion reconstruct encode > gpurun_out/run1.log 2>&1; cat gpurun_out/summary.txt; tail -15 gpurun_out/test_motion.log | head -30
+timeout 300 python tools/encode_clip.py > gpurun_out/encode_720p.log 2>&1; tail -1 gpurun_out/encode_720p.log | cut -c1-1100
