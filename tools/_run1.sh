@@ -1,2 +1,3 @@
-timeout 300 bash tools/run_gpu_tests.sh motion reconstruct encode > gpurun_out/run1.log 2>&1; cat gpurun_out/summary.txt; tail -15 gpurun_out/test_motion.log | head -30
-timeout 300 python tools/encode_clip.py > gpurun_out/encode_720p.log 2>&1; tail -1 gpurun_out/encode_720p.log | cut -c1-1100
+bash tools/run_gpu_tests.sh knn > gpurun_out/run1.log 2>&1; tail -1 gpurun_out/summary.txt
+python tools/knn_timing.py 65536 432000 2>&1 | tail -1 | cut -c1-400
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:knn_i8_topk -s 1 -c 1 python tools/knn_probe.py 65536 432000 64 2>&1 | grep -E "dram__|gpu__time" 
