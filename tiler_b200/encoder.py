@@ -25,6 +25,16 @@ def euclidean_to_psnr(err):
     return (10.0 * np.log10(255.0 * 255.0 / m)).astype(np.float32)
 
 
+def _reindex_order(tiles_rgb, use_count):
+    """Order of ReindexTiles(True) (tilingencoder.pas:4626-4696, CompareTileUseCountRev :582-599): use count descending, then
+    CompareDWord on the 64 pixels (unsigned dwords, first difference decides).  One memcmp sort on big-endian bytes followed
+    by a stable sort on the use count, instead of a 65-key lexsort."""
+    be = np.ascontiguousarray(np.asarray(tiles_rgb).astype(">u4")).view(np.uint8).reshape(len(tiles_rgb), 256)
+    o1 = np.argsort(be.view(np.dtype((np.void, 256))).reshape(-1), kind="stable")
+    o2 = np.argsort(-np.asarray(use_count)[o1].astype(np.int64), kind="stable")
+    return o1[o2]
+
+
 def golden_ratio_search(func, min_x, max_x, objective_y, eps_x=1e-6, eps_y=0.5):
     """GoldenRatioSearch (utils.pas:1044-1072).  Returns (result x, last evaluated x): the encoder state after the search
     is the one left by the LAST evaluation, not by the returned abscissa."""
@@ -122,55 +132,72 @@ class TilingEncoder:
         order (use count descending, then RGB pixels as unsigned dwords ascending)."""
         shape = tuple(canon_tiles.shape[:2])
         flat = canon_tiles.reshape(-1, 64)
+        n_all = int(flat.shape[0])
         cls, n_cls = api.tile_classes(flat)
         eff = np.asarray(psnr, dtype=np.float32).copy()
         for f in seq_start_frames:
             eff[f] = eff[f] / np.float32(10.0)
         eff = eff.reshape(-1)
-        if api._is_dev(cls):   # segmented minimum over 3.4 M tiles: a scatter-reduce on the device instead of np.minimum.at
-            cls_min_t = torch.full((n_cls,), float("inf"), dtype=torch.float32, device=cls.device)
-            cls_min_t.scatter_reduce_(0, cls.long(), torch.from_numpy(eff).to(cls.device), reduce="amin")
-            sorted_min = np.sort(cls_min_t.cpu().numpy())
-            cls = cls.cpu().numpy()
-        else:
-            cls = np.asarray(cls)
-            order0 = np.argsort(cls, kind="stable")
-            starts = np.flatnonzero(np.r_[True, np.diff(cls[order0]) != 0])
-            sorted_min = np.sort(np.minimum.reduceat(eff[order0], starts))
-        target = min(int(tile_count), int(flat.shape[0]))
+        target = min(int(tile_count), n_all)
+        fl = canon_flags.reshape(-1)
+        if api._is_dev(cls):
+            # per-class bookkeeping over millions of tiles as device scatter / sort / bincount (torch = memory plumbing);
+            # only the <= tile_count chosen representatives come back to the host for the final ReindexTiles ordering
+            dev = cls.device
+            cl = cls.long()
+            eff_t = torch.from_numpy(eff).to(dev)
+            cls_min = torch.full((n_cls,), float("inf"), dtype=torch.float32, device=dev)
+            cls_min.scatter_reduce_(0, cl, eff_t, reduce="amin")
+            sorted_min = torch.sort(cls_min).values.cpu().numpy()
+            x_res, x_last = golden_ratio_search(lambda x: float(np.searchsorted(sorted_min, np.float32(x), side="right")), 0.0,
+                                                float(C_PSNR_MAX), float(target))
+            x = np.float32(x_last if x_last is not None else x_res)
+            unpred = ~(eff_t > float(x))                                   # IsPredicted := PSNR > x
+            ucl = cl[unpred]
+            use_t = torch.bincount(ucl, minlength=n_cls)
+            rep_t = torch.full((n_cls,), n_all, dtype=torch.int64, device=dev)
+            rep_t.scatter_reduce_(0, ucl, torch.nonzero(unpred).reshape(-1), reduce="amin")   # first unpredicted member
+            chosen_t = torch.nonzero(use_t > 0).reshape(-1)
+            rep_sel = rep_t[chosen_t]
+            rep_tiles_host = flat[rep_sel].cpu().numpy()
+            use_sel = use_t[chosen_t].cpu().numpy()
+            order = _reindex_order(rep_tiles_host, use_sel)               # ReindexTiles(True): (use count desc, CompareDWord asc)
+            order_t = torch.from_numpy(order).to(dev)
+            chosen_t, rep_sel = chosen_t[order_t], rep_sel[order_t]
+            new_of_cls = torch.full((n_cls,), -1, dtype=torch.int32, device=dev)
+            new_of_cls[chosen_t] = torch.arange(chosen_t.numel(), dtype=torch.int32, device=dev)
+            tile_idx = torch.where(unpred, new_of_cls[cl], torch.full_like(cls, -1)).cpu().numpy().astype(np.int32).reshape(shape)
+            self.tiles, self.tile_flags = flat[rep_sel].contiguous(), fl[rep_sel].contiguous()
+            self.use_count = use_sel[order].astype(np.int32)
+            self.reduce_threshold = float(x)
+            return tile_idx
+        cls = np.asarray(cls)
+        order0 = np.argsort(cls, kind="stable")
+        starts = np.flatnonzero(np.r_[True, np.diff(cls[order0]) != 0])
+        sorted_min = np.sort(np.minimum.reduceat(eff[order0], starts))
         x_res, x_last = golden_ratio_search(lambda x: float(np.searchsorted(sorted_min, np.float32(x), side="right")), 0.0,
                                             float(C_PSNR_MAX), float(target))
         x = np.float32(x_last if x_last is not None else x_res)
         unpred = ~(eff > x)                                   # IsPredicted := PSNR > x
-        idx_all = np.arange(flat.shape[0])
+        idx_all = np.arange(n_all)
         use = np.bincount(cls[unpred], minlength=n_cls)
         # representative = first unpredicted member of the class
         ui = idx_all[unpred]
         uc = cls[unpred]
         o2 = np.argsort(uc, kind="stable")                    # ui is ascending, the sort is stable: first of each run = smallest index
         first = np.flatnonzero(np.r_[True, np.diff(uc[o2]) != 0])
-        rep = np.full(n_cls, flat.shape[0], dtype=np.int64)
+        rep = np.full(n_cls, n_all, dtype=np.int64)
         rep[uc[o2][first]] = ui[o2][first]
         chosen = np.nonzero(use > 0)[0]
         rep_idx = rep[chosen]
-        if api._is_dev(flat):
-            rep_t = torch.as_tensor(rep_idx, device=flat.device)
-            rep_tiles_host = flat[rep_t].cpu().numpy()
-        else:
-            rep_tiles_host = flat[rep_idx]
+        rep_tiles_host = flat[rep_idx]
         # ReindexTiles(True): (use count desc, CompareDWord on the 64 pixels asc)
-        keys = [rep_tiles_host[:, c].astype(np.uint32) for c in range(63, -1, -1)] + [-use[chosen].astype(np.int64)]
-        order = np.lexsort(keys)
+        order = _reindex_order(rep_tiles_host, use[chosen])
         chosen, rep_idx = chosen[order], rep_idx[order]
         new_of_cls = np.full(n_cls, -1, dtype=np.int32)
         new_of_cls[chosen] = np.arange(len(chosen), dtype=np.int32)
         tile_idx = np.where(unpred, new_of_cls[cls], -1).astype(np.int32).reshape(shape)
-        fl = canon_flags.reshape(-1)
-        if api._is_dev(flat):
-            rep_t = torch.as_tensor(rep_idx, device=flat.device)
-            self.tiles, self.tile_flags = flat[rep_t].contiguous(), fl[rep_t].contiguous()
-        else:
-            self.tiles, self.tile_flags = np.ascontiguousarray(flat[rep_idx]), np.ascontiguousarray(fl[rep_idx])
+        self.tiles, self.tile_flags = np.ascontiguousarray(flat[rep_idx]), np.ascontiguousarray(fl[rep_idx])
         self.use_count = use[chosen].astype(np.int32)
         self.reduce_threshold = float(x)
         return tile_idx
@@ -214,6 +241,7 @@ class TilingEncoder:
         self.dither()
         t["dither"] = time.perf_counter() - t0; t0 = time.perf_counter()
         self.prepare_reconstruct()
+        t["prepare_reconstruct"] = time.perf_counter() - t0; t0 = time.perf_counter()
         keys = ("tile_idx", "pal_idx", "pred_x", "pred_y", "is_pred", "err", "psnr")
         mine = tdist.shard_sequences([s1 - s0 + 1 for s0, s1 in sequences], world)
         local, recon_of = {}, {}
