@@ -558,3 +558,24 @@ def test_encode_end_to_end_small_clip(tm, oracle):
     assert tmap["is_pred"][[1, 2, 4, 5]].any()
     used = tmap["tile_idx"][tmap["tile_idx"] >= 0]
     assert used.max() == len(res["tiles"]) - 1 and np.array_equal(np.bincount(used, minlength=len(res["tiles"])), res["use_count"])
+
+
+def test_knn_full_range_int16_wrapping(tm, oracle):
+    """The reference accumulates the distance in a Cardinal: it wraps mod 2^32.  Full-range int16 vectors (norms ~ 7e10) and
+    single extreme rows among small ones must give the oracle's wrapped distances and indices for k = 1, 4 and 64."""
+    rng = np.random.default_rng(77)
+    d_small = synth.random_features(3000, 5)
+    q_small = synth.random_features(300, 6)
+    d_big = rng.integers(-32768, 32768, size=(3000, 192)).astype(np.int16)
+    q_big = rng.integers(-32768, 32768, size=(300, 192)).astype(np.int16)
+    d_small = np.clip(d_small, -1500, 1500).astype(np.int16); q_small = np.clip(q_small, -1500, 1500).astype(np.int16)   # norms < 2^29
+    d_one = d_small.copy(); d_one[1234] = 32767          # one row with norm 192 * 32767^2 > 2^29
+    q_one = q_small.copy(); q_one[7] = -32768
+    for d, q in ((d_big, q_big), (d_one, q_small), (d_small, q_one), (d_small, q_small)):
+        knn = tm.KnnShort(d)
+        for k in (1, 4, 64):
+            idx, dist = knn.search(q, k)
+            oi, od = oracle.knn_short(d, q, k)
+            assert np.array_equal(_u32(dist), od), k
+            assert np.array_equal(idx, oi), k
+        knn.close()

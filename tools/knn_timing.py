@@ -6,8 +6,9 @@ from tiler_b200 import api, synth
 
 n_dict = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 n_q = int(sys.argv[2]) if len(sys.argv) > 2 else 148 * 256 * 4
-d = torch.from_numpy(synth.random_features(n_dict, 1)).cuda()
-q = torch.from_numpy(synth.random_features(n_q, 2)).cuda()
+adv = len(sys.argv) > 3 and sys.argv[3] == 'adv'   # adversarial set: every norm < 2^29 -> the no-wrap epilogue
+d = torch.from_numpy(synth.random_features(n_dict, 1, adversarial=adv)).cuda()
+q = torch.from_numpy(synth.random_features(n_q, 2, adversarial=adv)).cuda()
 knn = api.KnnShort(d)
 res = {}
 for k in (1, 64):
