@@ -1,3 +1,2 @@
-bash tools/run_gpu_tests.sh knn > gpurun_out/run1.log 2>&1; cat gpurun_out/summary.txt
-python tools/knn_timing.py 65536 432000 adv 2>&1 | tail -1 | cut -c1-420
-python tools/knn_timing.py 65536 432000 2>&1 | tail -1 | cut -c1-420
+timeout 600 python tools/dither_stress.py 2>&1 | tail -1
+timeout 900 python tools/encode_clip.py --width 1920 --height 1080 --frames 600 --seq 75 --tiles 65536 --decode 1 2>&1 | tail -1 | cut -c1-1500
