@@ -424,7 +424,7 @@ def test_sliding_features_bit_exact(tm, oracle):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("w,h,radius", [(96, 64, 32), (160, 96, 32), (64, 64, 5)])
+@pytest.mark.parametrize("w,h,radius", [(96, 64, 32), (160, 96, 32), (64, 64, 5), (264, 136, 32), (264, 136, 17), (136, 72, 1)])
 def test_motion_search_bit_exact(tm, oracle, w, h, radius):
     frames = _small_clip(w, h, 2, 12)
     tw, th = w // 8, h // 8
