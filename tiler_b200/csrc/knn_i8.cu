@@ -396,9 +396,12 @@ __device__ __forceinline__ void tk_unit(unsigned long long &waddr, uint32_t tau,
   }
 }
 
+// half_out (optional): some value Th <= T_out with at least kh entries <= Th -- the first probe of the bisection whose count
+// fell in [kh, k), for free; T_out itself when no probe did.
 template <int NE>
 __device__ __forceinline__ int tk_threshold(const uint32_t (&dd)[NE], const uint32_t (&ii)[NE], int n_valid, int k, int slack,
-                                            uint32_t &T_out, uint32_t &TI_out) {
+                                            uint32_t &T_out, uint32_t &TI_out, uint32_t *half_out = nullptr, int kh = 0) {
+  uint32_t th = 0xFFFFFFFFu;
   uint32_t mn = 0xFFFFFFFFu, mx = 0u;
 #pragma unroll
   for (int i = 0; i < NE; ++i) {
@@ -413,10 +416,11 @@ __device__ __forceinline__ int tk_threshold(const uint32_t (&dd)[NE], const uint
 #pragma unroll
     for (int i = 0; i < NE; ++i) c += (dd[i] <= mid);
     c = __reduce_add_sync(0xffffffffu, c);
-    if (c < k) lo = mid + 1;
+    if (c < k) { if (c >= kh && th == 0xFFFFFFFFu) th = mid; lo = mid + 1; }
     else { hi = mid; c_hi = c; }
   }
   T_out = hi;
+  if (half_out) *half_out = min(th, hi);
   TI_out = 0xFFFFFFFFu;
   if (c_hi <= k + slack) return c_hi;
   // ties at the threshold distance: keep the (k - #{d < T}) lowest indices among them (rare)
@@ -440,7 +444,12 @@ __device__ __forceinline__ int tk_threshold(const uint32_t (&dd)[NE], const uint
 
 // Whole warp: cut the n candidates of the strip `buf` back to between k and k + TK_SLACK; returns the new count and
 // the new admission threshold.
-__device__ __forceinline__ int tk_cut(unsigned long long *buf, int n, int k, int slack, int lane, uint32_t &tau_out) {
+// other_half: the partner strip's published half-threshold (0xFFFFFFFF: none yet).  half_out: a value Th with at least
+// ceil(k / 2) entries of THIS strip <= Th.  Two strips of a row cover disjoint columns, so max(Th, other_half) has at
+// least k columns of the row below it and is a valid admission threshold for the whole row -- about the k-th distance over
+// ALL columns seen so far instead of the k-th over this strip's half, which halves the steady-state admission rate.
+__device__ __forceinline__ int tk_cut(unsigned long long *buf, int n, int k, int slack, int lane, uint32_t &tau_out, uint32_t other_half,
+                                      uint32_t &half_out) {
   constexpr int NE = TK_CAP / 32;
   __syncwarp();
   uint32_t dd[NE], ii[NE];
@@ -452,7 +461,11 @@ __device__ __forceinline__ int tk_cut(unsigned long long *buf, int n, int k, int
     ii[i] = (uint32_t)key;
   }
   uint32_t T, TI;
-  const int kept = tk_threshold<NE>(dd, ii, n, k, slack, T, TI);
+  uint32_t Th;
+  const int kept = tk_threshold<NE>(dd, ii, n, k, slack, T, TI, &Th, (k + 1) >> 1);
+  half_out = Th;
+  const uint32_t T_row = max(Th, other_half);
+  if (T_row < T) { T = T_row; TI = 0xFFFFFFFFu; }   // the row-wide threshold is tighter: keep every entry <= it
   __syncwarp();   // every lane has its entries in registers before the strip is rewritten
   const uint32_t lt_mask = (1u << lane) - 1u;
   int outp = 0;
@@ -479,7 +492,8 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
   constexpr int NST = STAGES_K1;
   uint8_t *sB = smem;
   int32_t *s_cnt = reinterpret_cast<int32_t *>(sB + NST * B_TILE);   // [256] candidates per thread at the end of a query block
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_cnt + 256);
+  uint32_t *s_thalf = reinterpret_cast<uint32_t *>(s_cnt + 256);      // [2][128] half-thresholds published by the strips of a row
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_thalf + 256);
   uint64_t *full = bars, *empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + 1, *t_full = a_empty + 1,
            *t_empty = t_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
@@ -488,6 +502,7 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
   const int n_tiles = (n_dict + BN - 1) / BN;
   const int n_qblocks = (n_q + BM - 1) / BM;
 
+  if (threadIdx.x < 256) s_thalf[threadIdx.x] = 0xFFFFFFFFu;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_full, 4);
@@ -586,6 +601,8 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
       uint32_t tau = (dbg & 1) ? 0u : 0xFFFFFFFEu;
    // distances of 0xFFFFFFFF (masked columns) are never admitted
       unsigned long long waddr = (unsigned long long)(uintptr_t)mybuf;   // next free slot of this thread's strip
+      uint32_t my_half = 0xFFFFFFFFu;                                     // this strip's published half-threshold
+      volatile uint32_t *oth_half = s_thalf + (h ^ 1) * 128 + row;        // the partner strip's (same row, other column half)
       int jt = 0;
       TKT(0)
       for (int j = 0; j < n_tiles; ++j, ++it) {
@@ -623,6 +640,8 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         TKT(4)
         if (!(dbg & 8)) tk_unit(waddr, tau, nq, col0 + 16, n_dict - col0 - 16, ndB, ppB, xxB, loB);
         TKT(5)
+        // the partner strip may have published a half-threshold since: max(mine, its) bounds the row's k-th distance
+        if (!(dbg & 16)) tau = min(tau, max(my_half, *oth_half));
         // the next check is a tile (HN admissions at most) away
         const uint32_t wlo = (uint32_t)waddr;
         uint32_t fullm = __ballot_sync(0xffffffffu, wlo - base_lo > (uint32_t)((TK_CAP - HN) * 8));
@@ -630,15 +649,20 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
           const int L = __ffs(fullm) - 1;
           fullm &= fullm - 1;
           const int nL = (int)((__shfl_sync(0xffffffffu, wlo, L) - __shfl_sync(0xffffffffu, base_lo, L)) >> 3);
-          uint32_t T;
-          const int kept = tk_cut(wbuf + (size_t)L * TK_CAP, nL, k, slack, lane, T);
-          if (lane == L) { waddr = (unsigned long long)(uintptr_t)(mybuf + kept); tau = T; }
+          uint32_t T, Th;
+          const uint32_t other = (dbg & 16) ? 0xFFFFFFFFu : *(volatile uint32_t *)(s_thalf + (h ^ 1) * 128 + q * 32 + L);
+          const int kept = tk_cut(wbuf + (size_t)L * TK_CAP, nL, k, slack, lane, T, other, Th);
+          if (lane == L) {
+            waddr = (unsigned long long)(uintptr_t)(mybuf + kept); tau = T; my_half = Th;
+            *(volatile uint32_t *)(s_thalf + h * 128 + row) = Th;
+          }
         }
         TKT(6)
       }
       // ---- results of this query block: merge the two column halves of every row
       s_cnt[warp * 32 + lane] = (int)(((uint32_t)waddr - base_lo) >> 3);
       asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      s_thalf[h * 128 + row] = 0xFFFFFFFFu;   // every scan of this block is over; the barrier below publishes the reset
       {
         constexpr int NE = 2 * TK_CAP / 32;
         const uint32_t lt_mask = (1u << lane) - 1u;
@@ -773,7 +797,7 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
   if (rc != TM_OK) return rc;
   constexpr int K1_NH = TM_K1_NH;   // column splits per tile in the k = 1 / k = 4 kernels (2: 8 epilogue warps, 4: 16)
   constexpr int SMEM_K1 = STAGES_K1 * B_TILE + BM * 8 * 4 * (K1_NH - 1) + 256 + 1024;
-  constexpr int SMEM_TK = STAGES_K1 * B_TILE + 256 * 4 + 512 + 1024;
+  constexpr int SMEM_TK = STAGES_K1 * B_TILE + 256 * 4 + 256 * 4 + 512 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(knn_i8_k1_kernel<1, K1_NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;

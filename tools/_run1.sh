@@ -1,3 +1,3 @@
-bash tools/run_gpu_tests.sh > gpurun_out/run_all.log 2>&1; cat gpurun_out/summary.txt
-TM_MOTION_SCALAR=1 timeout 600 python -m pytest tests/test_gpu_core.py -m gpu -q -x -k "motion or reconstruct" 2>&1 | tail -1
-python __graft_entry__.py smoke 2>&1 | tail -1
+bash tools/run_gpu_tests.sh knn matcher kmeans > gpurun_out/run1.log 2>&1; cat gpurun_out/summary.txt
+python tools/knn_timing.py 65536 432000 2>&1 | tail -1 | cut -c1-420
+TM_TK_DBG=16 python tools/knn_timing.py 65536 432000 2>&1 | tail -1 | cut -c1-420
