@@ -264,11 +264,11 @@ class TilingEncoder:
         tm_out = dict(tm)
         tm_out["tile_idx"] = tile_map
         t["reindex"] = time.perf_counter() - t0; t0 = time.perf_counter()
-        data = b""
-        if rank == 0:
-            data = gtm_io.write_gtm(out_path, tm_out, final_tiles, use_count, pal, tw, th, sequences, fps=fps,
-                                    settings_text=f"tiler_b200 PaletteSize={self.palette_size} PaletteCount={self.palette_count}",
-                                    emit_skip_blocks=emit_skip_blocks)
+        # every rank serialises and LZMA-compresses the chunks of its own keyframe sequences; the chunks are all-gathered
+        data = gtm_io.write_gtm(out_path if rank == 0 else None, tm_out, final_tiles, use_count, pal, tw, th, sequences, fps=fps,
+                                settings_text=f"tiler_b200 PaletteSize={self.palette_size} PaletteCount={self.palette_count}",
+                                emit_skip_blocks=emit_skip_blocks, only=(set(mine[rank]) if world > 1 else None),
+                                exchange=((lambda d: tdist.gather_tilemaps(d, mine)) if world > 1 else None))
         t["save"] = time.perf_counter() - t0
         return {"gtm": data, "tilemap": tm_out, "recon": recon, "tiles": final_tiles, "use_count": use_count, "palettes": pal,
                 "recon_sequences": sorted(recon_of), "timings": t, "mean_tile_psnr": float(tm["psnr"].mean()), "dictionary_before_reindex": int(didx.shape[0])}

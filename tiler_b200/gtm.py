@@ -100,10 +100,12 @@ def _cmd(code, data):
 
 
 def write_gtm(path_or_none, tm, tiles_idx, use_count, palettes, tw, th, sequences, fps=24.0, settings_text="",
-              emit_skip_blocks=True):
+              emit_skip_blocks=True, only=None, exchange=None):
     """tm: dict of per-frame arrays [n_frames, th*tw] (tile_idx, pal_idx, pred_x, pred_y, is_pred, mirror) with tile_idx
     already re-indexed; tiles_idx / use_count: the final dictionary; palettes [n_pal, pal_size] int32; sequences: list of
-    (start_frame, end_frame) inclusive.  Returns the file bytes (and writes them when a path is given)."""
+    (start_frame, end_frame) inclusive.  Returns the file bytes (and writes them when a path is given).
+    Multi-process use: `only` = the sequence indices whose chunks THIS process serialises and compresses, `exchange` = a
+    callable that all-gathers {sequence index: (chunk bytes, keyframe info)} dictionaries across the processes."""
     n_frames = int(tm["tile_idx"].shape[0])
     nt = tw * th
     L = lib()
@@ -145,10 +147,13 @@ def write_gtm(path_or_none, tm, tiles_idx, use_count, palettes, tw, th, sequence
         return comp, (ki, f0, len(raw), len(comp), int(round(1000.0 * f0 / fps)))
 
     from concurrent.futures import ThreadPoolExecutor
-    with ThreadPoolExecutor(max_workers=min(8, max(1, len(sequences)))) as pool:
-        done = list(pool.map(one_chunk, list(enumerate(sequences))))
-    chunks = [d[0] for d in done]
-    kf_info = [d[1] for d in done]
+    jobs = [(ki, sq) for ki, sq in enumerate(sequences) if only is None or ki in only]
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as pool:
+        done = dict(zip([j[0] for j in jobs], pool.map(one_chunk, jobs)))
+    if exchange is not None:
+        done = exchange(done)
+    chunks = [done[ki][0] for ki in range(len(sequences))]
+    kf_info = [done[ki][1] for ki in range(len(sequences))]
     # ---- header (TGTMHeader, TGTMKeyFrameInfo: tilingencoder.pas:30-51, 5338-5370, 5470-5476)
     whole_header = 40 + 28 * len(sequences)
     total = sum(len(c) for c in chunks)
