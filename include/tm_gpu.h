@@ -195,6 +195,12 @@ int tm_predict_motion_frame(const int32_t *prev_frame, const int32_t *canon_tile
 int tm_reconstruct_sequence(tm_matcher *m, const int32_t *canon_tiles, const uint8_t *flags, int n_frames, int tw, int th, int radius,
                             int k, int32_t *tile_idx, int32_t *pal_idx, int32_t *pred_x, int32_t *pred_y, uint8_t *is_pred,
                             uint32_t *err, float *psnr, int32_t *recon);
+/* one frame of the same (for hosts that keep their own frame loop): back = previous reconstructed frame buffer [th*8][tw*8]
+   or NULL on the first frame of a keyframe sequence; front = this frame's reconstruction (written) */
+int tm_reconstruct_frame(tm_matcher *m, const int32_t *canon_tiles, const uint8_t *flags, int tw, int th, int radius, int k,
+                         const int32_t *back, int32_t *front, int32_t *tile_idx, int32_t *pal_idx, int32_t *pred_x, int32_t *pred_y,
+                         uint8_t *is_pred, uint32_t *err, float *psnr);
+
 /* ---------------------------------------------------------------- batched: Reduce (tilingencoder.pas:4014-4103, 4720-4781)
    Exact equivalence classes of n RGB tiles [n][64] (MakeTilesUnique on RGB pixels): class_id[n] in [0, *n_classes),
    equal ids <=> all 64 pixels equal.  The numbering is arbitrary (hash order); the host orders the chosen dictionary

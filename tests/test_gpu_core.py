@@ -490,6 +490,22 @@ def test_reconstruct_sequence_bit_exact(tm, oracle, extended):
     m.close()
 
 
+def test_reconstruct_frame_by_frame_equals_sequence(tm, oracle):
+    """tm_reconstruct_frame chained by the host (the Pascal host's own frame loop) = tm_reconstruct_sequence."""
+    w, h, n_frames = 96, 64, 4
+    frames = _small_clip(w, h, n_frames, 16)
+    canon, flags, didx, dpal, pal = _build_small_dictionary(tm, oracle, frames, 160, 4, 16, 7)
+    m = tm.Matcher(didx, dpal, pal, extended=True)
+    seq = m.reconstruct_sequence(canon, flags, 12, 8, radius=32)
+    back = None
+    for f in range(n_frames):
+        r = m.reconstruct_frame(canon[f], flags[f], 12, 8, back=back, radius=32)
+        for key in ("is_pred", "pred_x", "pred_y", "tile_idx", "pal_idx", "err", "recon"):
+            assert np.array_equal(r[key], seq[key][f]), (f, key)
+        back = r["recon"]
+    m.close()
+
+
 def test_reconstruct_sequence_device_tensors(tm, oracle):
     import torch
     w, h, n_frames = 64, 64, 3

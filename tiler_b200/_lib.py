@@ -64,6 +64,7 @@ SIGNATURES = {
     "tm_motion_search": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
     "tm_predict_motion_frame": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
     "tm_reconstruct_sequence": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tm_reconstruct_frame": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tm_mse_rgb": (C.c_int, [_vp, _vp, _i64, C.POINTER(_dbl)]),
     "tm_tile_classes": (C.c_int, [_vp, _i64, _vp, C.POINTER(_i32)]),
     # drop-in exports (extern.pas:178-223)

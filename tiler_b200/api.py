@@ -382,6 +382,24 @@ class Matcher:
                                                  p_isp, p_err, p_psnr, p_recon))
         return {"tile_idx": tile, "pal_idx": pal, "pred_x": px, "pred_y": py, "is_pred": isp, "err": err, "psnr": psnr, "recon": recon}
 
+    def reconstruct_frame(self, canon_tiles, flags, tw, th, back=None, radius=32, k=None):
+        """One frame of TFrame.Reconstruct (tilingencoder.pas:1430-1679): back = previous reconstructed frame [th*8, tw*8] or
+        None on the first frame of a keyframe sequence.  -> dict like reconstruct_sequence, recon = this frame [th*8, tw*8]."""
+        c = _Call(canon_tiles, flags) if back is None else _Call(canon_tiles, flags, back)
+        nt = tw * th
+        tile, p_tile = c.out((nt,), np.int32)
+        pal, p_pal = c.out((nt,), np.int32)
+        px, p_px = c.out((nt,), np.int32)
+        py, p_py = c.out((nt,), np.int32)
+        isp, p_isp = c.out((nt,), np.uint8)
+        err, p_err = c.out((nt,), np.uint32)
+        psnr, p_psnr = c.out((nt,), np.float32)
+        front, p_front = c.out((th * 8, tw * 8), np.int32)
+        check(_lib.lib().tm_reconstruct_frame(self._h, c.inp(canon_tiles, np.int32), c.inp(flags, np.uint8), int(tw), int(th), int(radius),
+                                              int(k or (self.K_EPU if self.extended else 1)), c.inp(back, np.int32), p_front, p_tile, p_pal,
+                                              p_px, p_py, p_isp, p_err, p_psnr))
+        return {"tile_idx": tile, "pal_idx": pal, "pred_x": px, "pred_y": py, "is_pred": isp, "err": err, "psnr": psnr, "recon": front}
+
     def dict_features(self):
         out = np.empty((self.n_dict, DCT), dtype=np.int16)
         check(_lib.lib().tm_matcher_dict_features(self._h, C.c_void_p(out.ctypes.data)))

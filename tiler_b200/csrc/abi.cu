@@ -886,6 +886,52 @@ extern "C" int tm_reconstruct_sequence(tm_matcher *m, const int32_t *canon_tiles
   return TM_OK;
 }
 
+// One frame of TFrame.Reconstruct for hosts that keep their own frame loop: back = previous reconstructed frame buffer
+// (NULL on the first frame of a keyframe sequence: no motion search), front = this frame's reconstruction (written).
+extern "C" int tm_reconstruct_frame(tm_matcher *m, const int32_t *canon_tiles, const uint8_t *flags, int tw, int th, int radius, int k,
+                                    const int32_t *back, int32_t *front, int32_t *tile_idx, int32_t *pal_idx, int32_t *pred_x,
+                                    int32_t *pred_y, uint8_t *is_pred, uint32_t *err, float *psnr) {
+  RC(require_gpu());
+  if (!m || !canon_tiles || !flags || tw < 1 || th < 1 || radius < 0 || radius > 128 || k < 1 || k > 64 || !front || !tile_idx || !pal_idx ||
+      !pred_x || !pred_y || !is_pred || !err)
+    return fail(TM_ERR_ARG, "tm_reconstruct_frame: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const size_t nt = (size_t)tw * th;
+  const int w = tw * 8, h = th * 8;
+  const size_t fpx = (size_t)w * h;
+  const bool motion = back != nullptr && radius - 1 >= 0;
+  const int32_t *d_tiles = s.in(canon_tiles, nt * 64);
+  const uint8_t *d_flags = s.in(flags, nt);
+  const int32_t *d_back = motion ? s.in(back, fpx) : nullptr;
+  int32_t *d_front = s.out(front, fpx);
+  int32_t *d_tile = s.out(tile_idx, nt), *d_pal = s.out(pal_idx, nt), *d_px = s.out(pred_x, nt), *d_py = s.out(pred_y, nt);
+  uint8_t *d_isp = s.out(is_pred, nt);
+  uint32_t *d_err = s.out(err, nt);
+  float *d_psnr = psnr ? s.out(psnr, nt) : nullptr;
+  int16_t *d_ft = (int16_t *)s.temp(nt * 384);
+  int32_t *k_tile = (int32_t *)s.temp(nt * 4), *k_pal = (int32_t *)s.temp(nt * 4);
+  uint32_t *k_err = (uint32_t *)s.temp(nt * 4);
+  int32_t *mx = nullptr, *my = nullptr; uint32_t *me = nullptr;
+  if (s.err == TM_OK) s.err = launch_features_rgb(d_tiles, (int64_t)nt, d_ft, s.st);
+  if (s.err == TM_OK) s.err = match_feat_dev(m, d_ft, (int64_t)nt, k, k_tile, k_pal, k_err, s);
+  if (motion && s.err == TM_OK) {
+    int16_t *d_cur = (int16_t *)s.temp(nt * 384);
+    int16_t *d_dcts = (int16_t *)s.temp((size_t)(w - 7) * (h - 7) * 384);
+    const size_t wsb = motion_tc_ws_bytes(tw, th);
+    void *ws = s.temp(wsb);
+    mx = (int32_t *)s.temp(nt * 4); my = (int32_t *)s.temp(nt * 4); me = (uint32_t *)s.temp(nt * 4);
+    if (s.err == TM_OK) s.err = launch_features_rgb_mirrored(d_tiles, d_flags, (int64_t)nt, d_cur, s.st);
+    if (s.err == TM_OK) s.err = launch_features_sliding(d_back, w, h, d_dcts, s.st);
+    if (s.err == TM_OK) s.err = motion_search_dev(d_cur, tw, th, d_dcts, radius, mx, my, me, ws, wsb, s.st);
+  }
+  if (s.err == TM_OK)
+    s.err = launch_reconstruct_decide(d_flags, tw, th, mx, my, me, k_tile, k_pal, k_err, m->dict_idx, m->palettes, m->pal_size, d_back, d_front,
+                                      d_tile, d_pal, d_px, d_py, d_isp, d_err, d_psnr, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
 /* mean squared error over the three colour channels of two packed-RGB buffers */
 extern "C" int tm_mse_rgb(const int32_t *a, const int32_t *b, int64_t n, double *mse) {
   RC(require_gpu());
