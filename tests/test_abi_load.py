@@ -28,6 +28,17 @@ def test_library_exports_every_declared_symbol():
     assert sorted(_lib.SIGNATURES) == declared
 
 
+def test_gtm_host_library_exports_its_header():
+    import re as _re
+    from tiler_b200 import gtm
+    src = open(os.path.join(ROOT, "include", "tm_gtm.h")).read()
+    src = _re.sub(r"/\*.*?\*/", "", src, flags=_re.S)
+    names = sorted(set(_re.findall(r"\b(tmh_[a-z0-9_]+)\s*\(", src)))
+    assert len(names) == 7
+    for name in names:
+        assert hasattr(gtm.lib(), name), name
+
+
 def test_drop_in_names_match_extern_pas():
     # the symbol names the FreePascal host binds (extern.pas:178-223)
     from tiler_b200 import _lib

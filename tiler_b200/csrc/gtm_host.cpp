@@ -6,6 +6,7 @@
 //
 // Plain C++ on the CPU, built into libtm_gtm.so.  It is NOT part of the GPU product path (libtm_gpu.so): in the
 // reference these jobs stay in the FreePascal host (bitstream writer) and in the player.
+#include "../../include/tm_gtm.h"
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
