@@ -440,6 +440,18 @@ def test_motion_search_bit_exact(tm, oracle, w, h, radius):
     assert np.all(_u32(ge0) == 0) and np.all(gx0 == 0) and np.all(gy0 == 0)
 
 
+def test_motion_search_persistent_ctas(tm, oracle, monkeypatch):
+    """Frames with more 8x16 tile blocks than CTAs (1080p has 255): every CTA walks several blocks.  Forced here with 2 CTAs."""
+    monkeypatch.setenv("TM_MOTION_CTAS", "2")
+    w, h = 264, 136                                   # 33 x 17 tiles -> 3 x 3 tile blocks, 4-5 per CTA
+    frames = _small_clip(w, h, 2, 19)
+    cur = oracle.features_from_rgb(synth.frame_to_tiles(frames[1]))
+    dcts = oracle.sliding_features(frames[0])
+    gx, gy, ge = tm.motion_search(cur, w // 8, h // 8, dcts, 32)
+    ox, oy, oe = oracle.motion_search(cur, w // 8, h // 8, dcts, 32)
+    assert np.array_equal(_u32(ge), oe) and np.array_equal(gx, ox) and np.array_equal(gy, oy)
+
+
 def test_predict_motion_frame_uses_natural_orientation(tm, oracle):
     frames = _small_clip(96, 64, 2, 13)
     tw, th = 12, 8

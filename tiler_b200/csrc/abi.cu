@@ -773,7 +773,9 @@ static int motion_search_dev(const int16_t *d_cur, int tw, int th, const int16_t
   static int scalar = -1;
   if (scalar < 0) scalar = getenv("TM_MOTION_SCALAR") && atoi(getenv("TM_MOTION_SCALAR")) ? 1 : 0;
   if (scalar) return launch_motion_search(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, st);
-  return launch_motion_search_tc(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, ws, wsb, num_sms(), st);
+  int ctas = num_sms();
+  if (const char *e = getenv("TM_MOTION_CTAS")) { const int v = atoi(e); if (v > 0 && v < ctas) ctas = v; }   // tests: several tile blocks per CTA
+  return launch_motion_search_tc(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, ws, wsb, ctas, st);
 }
 
 extern "C" int tm_sliding_features(const int32_t *frame, int w, int h, int16_t *out) {
