@@ -30,6 +30,9 @@ constexpr int kNumFullDistances = 1 << (kEndPosModelIndex >> 1);   // 128
 constexpr int kNumAlignBits = 4;
 constexpr int kMatchMinLen = 2;
 constexpr int kMatchMaxLen = 273;
+#ifndef TMH_LZMA_DEPTH
+#define TMH_LZMA_DEPTH 16   // hash-chain candidates examined per position (48: 2 % smaller streams, 1.6x slower)
+#endif
 typedef uint16_t Prob;
 
 struct LenProbs {
@@ -200,7 +203,7 @@ struct Encoder {
       }
       if (pos + 4 <= n) {
         int64_t c = head[h4(pos)];
-        int depth = 48;
+        int depth = TMH_LZMA_DEPTH;
         uint32_t mlen = bestLen >= 3 ? bestLen : 3;   // a normal match must beat the best repeat (and be >= 4)
         while (c >= 0 && depth-- > 0) {
           const size_t d = pos - (size_t)c;
