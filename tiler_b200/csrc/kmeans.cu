@@ -175,38 +175,49 @@ __global__ void kmeans_finish_kernel(const double *__restrict__ sums, const int6
 }
 
 // k-means++ seeding for f64 rows, same draw sequence as the oracle's tmo_kmeanspp_init (xorshift64*, D^2 sampling by the
-// first prefix sum exceeding u).  One block; thread t owns a contiguous slice of the points.
-__global__ void __launch_bounds__(256)
-kmeanspp_f64_kernel(const double *__restrict__ x, int64_t n, int dim, int k, unsigned long long seed, double *__restrict__ d2,
-                    double *__restrict__ cent) {
+// first prefix sum exceeding u).  Per centroid: a grid-wide kernel refreshes every point's squared distance to the last
+// centroid (one thread per point, the oracle's sequential summation order over the dimensions), then ONE block draws the
+// next centroid: 256 threads sum contiguous slices of d2 in index order, thread 0 adds the 256 partials in order, draws u
+// and walks the owning slice.  (The first version did the distances in that single block as well: 110 ms for 83 000 x 192
+// points and 16 centroids, half of PreparePalettes.)
+__global__ void __launch_bounds__(128)
+kmpp_dist_kernel(const double *__restrict__ x, int64_t n, int dim, const double *__restrict__ last, int first, double *__restrict__ d2) {
   extern __shared__ double s_last[];  // [dim]
+  for (int j = threadIdx.x; j < dim; j += 128) s_last[j] = last[j];
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  if (i >= n) return;
+  const double *xi = x + i * dim;
+  double sum = 0.0;
+  for (int j = 0; j < dim; ++j) { const double df = __dsub_rn(__ldg(xi + j), s_last[j]); sum = __dadd_rn(sum, __dmul_rn(df, df)); }
+  if (first || sum < d2[i]) d2[i] = sum;
+}
+
+// state[0] = xorshift state.  c == 0: draw the first centroid uniformly; else D^2-sample centroid c from d2.
+__global__ void __launch_bounds__(256)
+kmpp_pick_kernel(const double *__restrict__ x, int64_t n, int dim, int c, unsigned long long seed, const double *__restrict__ d2,
+                 unsigned long long *__restrict__ state, double *__restrict__ cent) {
   __shared__ double s_part[256];
   __shared__ long long s_pick;
   const int t = threadIdx.x;
   const int64_t per = (n + 255) / 256, a = min((int64_t)t * per, n), b = min(a + per, n);
-  unsigned long long st = seed ? seed : 0x9E3779B97F4A7C15ULL;
-  if (t == 0) s_pick = (long long)(xorshift64s(st) % (unsigned long long)n);
-  for (int64_t i = a; i < b; ++i) d2[i] = INFINITY;
-  for (int c = 0; c < k; ++c) {
-    __syncthreads();
-    const int64_t pick = s_pick;
-    for (int j = t; j < dim; j += 256) { const double v = x[pick * dim + j]; s_last[j] = v; cent[(int64_t)c * dim + j] = v; }
-    __syncthreads();
-    if (c == k - 1) break;
-    double part = 0.0;
-    for (int64_t i = a; i < b; ++i) {
-      double s = 0.0;
-      for (int j = 0; j < dim; ++j) { const double df = __dsub_rn(x[i * dim + j], s_last[j]); s = __dadd_rn(s, __dmul_rn(df, df)); }
-      double cur = d2[i];
-      if (s < cur) { cur = s; d2[i] = s; }
-      part = __dadd_rn(part, cur);
+  if (c == 0) {
+    if (t == 0) {
+      unsigned long long st = seed ? seed : 0x9E3779B97F4A7C15ULL;
+      s_pick = (long long)(xorshift64s(st) % (unsigned long long)n);
+      state[0] = st;
     }
+  } else {
+    double part = 0.0;
+    for (int64_t i = a; i < b; ++i) part = __dadd_rn(part, d2[i]);
     s_part[t] = part;
     __syncthreads();
     if (t == 0) {
+      unsigned long long st = state[0];
       double total = 0.0;
       for (int i = 0; i < 256; ++i) total = __dadd_rn(total, s_part[i]);
       const double u = (double)(xorshift64s(st) >> 11) * (1.0 / 9007199254740992.0) * total;
+      state[0] = st;
       double acc = 0.0;
       int owner = 255;
       for (int i = 0; i < 256; ++i) {
@@ -222,6 +233,9 @@ kmeanspp_f64_kernel(const double *__restrict__ x, int64_t n, int dim, int k, uns
       s_pick = pk;
     }
   }
+  __syncthreads();
+  const int64_t pick = s_pick;
+  for (int j = t; j < dim; j += 256) cent[(int64_t)c * dim + j] = x[pick * dim + j];
 }
 
 static inline size_t km_al(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -502,8 +516,15 @@ int launch_kmeans_assign_amb(const int16_t *x, const int32_t *amb_list, int n_am
 int launch_kmeanspp_f64(const double *x, int64_t n, int dim, int k, unsigned long long seed, double *d2_ws, double *cent,
                         cudaStream_t st) {
   if (n <= 0 || k < 1 || dim < 1 || dim > 4096) return TM_ERR_ARG;
-  kmeanspp_f64_kernel<<<1, 256, (size_t)dim * sizeof(double), st>>>(x, n, dim, k, seed, d2_ws, cent);
-  note_launch();
+  unsigned long long *state = nullptr;
+  if (cudaMallocAsync(&state, 8, st) != cudaSuccess) return TM_ERR_NOMEM;
+  kmpp_pick_kernel<<<1, 256, 0, st>>>(x, n, dim, 0, seed, d2_ws, state, cent);
+  for (int c = 1; c < k; ++c) {
+    kmpp_dist_kernel<<<(unsigned)((n + 127) / 128), 128, (size_t)dim * sizeof(double), st>>>(x, n, dim, cent + (int64_t)(c - 1) * dim, c == 1, d2_ws);
+    kmpp_pick_kernel<<<1, 256, 0, st>>>(x, n, dim, c, seed, d2_ws, state, cent);
+  }
+  cudaFreeAsync(state, st);
+  note_launch(2 * k - 1);
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }
 
