@@ -771,12 +771,13 @@ int run_palette_quantise(const int32_t *rgb, const int32_t *tile_pal, int64_t n_
   std::vector<int32_t> h_kcount(n_pal);
   int it = 0;
 #define CK(x) do { if ((x) != cudaSuccess) { rc = TM_ERR_CUDA; goto done; } } while (0)
-  CK(cudaMalloc(&keys, n * 8)); CK(cudaMalloc(&keys2, n * 8)); CK(cudaMalloc(&counts, (size_t)n_pal * 8));
-  CK(cudaMalloc(&px, n * 4)); CK(cudaMalloc(&kcount, (size_t)n_pal * 4)); CK(cudaMalloc(&changed, 4));
-  CK(cudaMalloc(&off, (size_t)(n_pal + 1) * 8)); CK(cudaMalloc(&cent, (size_t)n_pal * k * 3 * 8));
-  CK(cudaMalloc(&labels, n * 2)); CK(cudaMalloc(&acc, (size_t)n_pal * k * sizeof(RgbAcc))); CK(cudaMalloc(&d2, n * 4));
+  // stream-ordered scratch: the pool keeps it between calls (plain cudaMalloc / cudaFree cost 0.6 s per call here)
+  CK(cudaMallocAsync(&keys, n * 8, st)); CK(cudaMallocAsync(&keys2, n * 8, st)); CK(cudaMallocAsync(&counts, (size_t)n_pal * 8, st));
+  CK(cudaMallocAsync(&px, n * 4, st)); CK(cudaMallocAsync(&kcount, (size_t)n_pal * 4, st)); CK(cudaMallocAsync(&changed, 4, st));
+  CK(cudaMallocAsync(&off, (size_t)(n_pal + 1) * 8, st)); CK(cudaMallocAsync(&cent, (size_t)n_pal * k * 3 * 8, st));
+  CK(cudaMallocAsync(&labels, n * 2, st)); CK(cudaMallocAsync(&acc, (size_t)n_pal * k * sizeof(RgbAcc), st)); CK(cudaMallocAsync(&d2, n * 4, st));
   cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, keys, keys2, (int)n, 0, bits, st);
-  CK(cudaMalloc(&tmp, tmp_bytes));
+  CK(cudaMallocAsync(&tmp, tmp_bytes, st));
   note_launch(6);
   pixel_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rgb, tile_pal, n_tiles, keys);
   cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, keys, keys2, (int)n, 0, bits, st);
@@ -826,8 +827,9 @@ int run_palette_quantise(const int32_t *rgb, const int32_t *tile_pal, int64_t n_
   if (iters_out) *iters_out = it;
 done:
 #undef CK
-  cudaFree(keys); cudaFree(keys2); cudaFree(counts); cudaFree(px); cudaFree(kcount); cudaFree(changed); cudaFree(off);
-  cudaFree(cent); cudaFree(labels); cudaFree(acc); cudaFree(d2); cudaFree(tmp);
+  for (void *ptr : {(void *)keys, (void *)keys2, (void *)counts, (void *)px, (void *)kcount, (void *)changed, (void *)off, (void *)cent,
+                    (void *)labels, (void *)acc, (void *)d2, tmp})
+    if (ptr) cudaFreeAsync(ptr, st);
   return rc;
 }
 
