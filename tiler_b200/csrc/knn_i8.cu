@@ -454,7 +454,8 @@ __device__ __forceinline__ void tk_tile32(unsigned long long &waddr, uint32_t ta
 // dynamically indexed load and admits it.  The warp-uniform version above walks 16 "does any lane admit pair e" branches
 // per tile; with two warps per scheduler nothing hides a branch bubble, and those 16 branches cost more than the
 // admissions themselves.  Here a lane that admits nothing (most lanes, most tiles) skips everything, and the loop runs
-// max-over-lanes(popcount) ~ 2 times.
+// max-over-lanes(popcount) ~ 2 times.  Measured: 28.5 vs 29.7 ms on random features, 30.0 vs 29.05 ms on the bench's image
+// features (admissions come in runs there, so one lane iterates while 31 wait): kept as an experiment (TM_TK_DBG=32).
 __device__ __forceinline__ void tk_tile32s(unsigned long long &waddr, uint32_t tau, uint32_t nq, int col, const uint32_t (&ndA)[16],
                                            uint32_t (&ppA)[16], const uint32_t (&xxA)[16], const uint32_t (&loA)[16],
                                            const uint32_t (&ndB)[16], uint32_t (&ppB)[16], const uint32_t (&xxB)[16],
@@ -580,77 +581,7 @@ __device__ __forceinline__ int tk_cut(unsigned long long *buf, int n, int k, int
   return outp;
 }
 
-// ---- asynchronous cuts (ASYNC = true): the epilogue warps never stop to cut a strip.  A thread's candidates live in a
-// KEPT region (the survivors of the last cut, <= k + slack) and two ADMISSION buffers; when the buffer in use is nearly
-// full the thread posts a request (strip, buffer, count) to a shared-memory queue and carries on in the other buffer
-// under its old threshold (a stale threshold only admits more, never less).  Five cutter warps serve the queue: load
-// kept + buffer, loose selection, write the survivors back to the kept region, publish the new threshold.  With two
-// TMEM stages a warp that stops for ~2 800 cycles holds up the MMA and with it the other seven; here only a strip whose
-// PREVIOUS request is still in flight can block its warp, and then the warp works the queue itself until it is served
-// (the burst at the start of a query block, when all 256 strips fill at once).
-constexpr int TA_KCAP = 96;                       // kept region: k + TK_SLACK <= 80 entries
-constexpr int TA_ACAP = 160;                      // one admission buffer
-constexpr int TA_STRIP = TA_KCAP + 2 * TA_ACAP;   // 416 entries = 3 328 B per (query row, column half)
-constexpr int TA_THREADS = 512;                   // 8 epilogue warps, TMA warp, 2 MMA issuers, 5 cutter warps
-struct TaShared {
-  uint32_t *tau, *busy, *kcnt, *req, *q /* head, tail, done */, *thalf;
-};
-__device__ __forceinline__ uint32_t lds_v(const uint32_t *p) { return *reinterpret_cast<const volatile uint32_t *>(p); }
-__device__ __forceinline__ void sts_v(uint32_t *p, uint32_t v) { *reinterpret_cast<volatile uint32_t *>(p) = v; }
-
-// Whole warp: take one pending request off the queue and execute it; false when there was none to take.
-__device__ __forceinline__ bool ta_serve(const TaShared &S, unsigned long long *cta_ws, int k, int slack, int lane) {
-  uint32_t req = 0;
-  if (lane == 0) {
-    const uint32_t h = lds_v(S.q), t = lds_v(S.q + 1);
-    if (h != t && atomicCAS(S.q, h, h + 1) == h) {
-      uint32_t *slot = S.req + (h & 255u);
-      while (!((req = lds_v(slot)) & 0x80000000u)) { }
-      sts_v(slot, 0u);
-    }
-  }
-  req = __shfl_sync(0xffffffffu, req, 0);
-  if (req == 0) return false;
-  __threadfence_block();   // the requester's admissions are visible
-  const int strip = (int)(req & 255u), b = (int)((req >> 8) & 1u), na = (int)((req >> 16) & 0xFFu);
-  unsigned long long *K = cta_ws + (size_t)strip * TA_STRIP, *A = K + TA_KCAP + b * TA_ACAP;
-  const int nk = (int)lds_v(S.kcnt + strip);
-  constexpr int NK = TA_KCAP / 32, NA = TA_ACAP / 32, NE = NK + NA;
-  uint32_t dd[NE], ii[NE];
-#pragma unroll
-  for (int i = 0; i < NE; ++i) {
-    const int p = (i < NK ? i : i - NK) * 32 + lane;
-    const unsigned long long key = i < NK ? (p < nk ? ldg_key(K + p) : ~0ull) : (p < na ? ldg_key(A + p) : ~0ull);
-    dd[i] = (uint32_t)(key >> 32);
-    ii[i] = (uint32_t)key;
-  }
-  uint32_t T, TI, Th;
-  tk_threshold<NE>(dd, ii, nk + na, k, slack, T, TI, &Th, (k + 1) >> 1);
-  const uint32_t T_row = max(Th, lds_v(S.thalf + (strip ^ 128)));   // see tk_cut: the partner strip's half-threshold
-  if (T_row < T) { T = T_row; TI = 0xFFFFFFFFu; }
-  __syncwarp();
-  const uint32_t lt_mask = (1u << lane) - 1u;
-  int outp = 0;
-#pragma unroll
-  for (int i = 0; i < NE; ++i) {
-    const bool keep = (dd[i] < T) || (dd[i] == T && ii[i] <= TI && dd[i] != 0xFFFFFFFFu);
-    const uint32_t km = __ballot_sync(0xffffffffu, keep);
-    if (keep) stg_key(K + outp + __popc(km & lt_mask), ((unsigned long long)dd[i] << 32) | ii[i]);
-    outp += __popc(km);
-  }
-  __syncwarp();
-  if (lane == 0) {
-    sts_v(S.kcnt + strip, (uint32_t)outp);
-    sts_v(S.thalf + strip, Th);
-    sts_v(S.tau + strip, T);
-    __threadfence_block();
-    sts_v(S.busy + strip, 0u);
-  }
-  return true;
-}
-
-template <bool ASYNC>
-__global__ void __launch_bounds__(ASYNC ? TA_THREADS : TK_THREADS, 1)
+__global__ void __launch_bounds__(TK_THREADS, 1)
 knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUtensorMap tmap_d,
                    const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict, int k,
                    int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist, int tile_stride,
@@ -662,25 +593,16 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
   uint8_t *s_dist = sB + NST * B_TILE;                                // [8 warps][8 chunks][32 lanes][16 B] staged distances
   int32_t *s_cnt = reinterpret_cast<int32_t *>(s_dist + TK_STAGE_B);  // [256] candidates per thread at the end of a query block
   uint32_t *s_thalf = reinterpret_cast<uint32_t *>(s_cnt + 256);      // [2][128] half-thresholds published by the strips of a row
-  uint32_t *s_async = s_thalf + 256;   // ASYNC only: tau, busy, kcnt, buf, req [256] each + queue words
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_async + (ASYNC ? 5 * 256 + 4 : 0));
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_thalf + 256);
   uint64_t *full = bars, *empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + 1, *t_full = a_empty + 1,
            *t_empty = t_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
-  uint32_t *s_buf = s_async + 3 * 256;
-  const TaShared S = {s_async, s_async + 256, s_async + 2 * 256, s_async + 4 * 256, s_async + 5 * 256, s_thalf};
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (n_dict + BN - 1) / BN;
   const int n_qblocks = (n_q + BM - 1) / BM;
 
   if (threadIdx.x < 256) s_thalf[threadIdx.x] = 0xFFFFFFFFu;
-  if constexpr (ASYNC) {
-    if (threadIdx.x < 256) {
-      S.tau[threadIdx.x] = 0xFFFFFFFEu; S.busy[threadIdx.x] = 0u; S.kcnt[threadIdx.x] = 0u; S.req[threadIdx.x] = 0u;
-    }
-    if (threadIdx.x < 4) S.q[threadIdx.x] = 0u;
-  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_full, 4);
@@ -696,9 +618,6 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
   if (tmem_base != 0) __trap();   // the MMA issue code addresses TMEM with immediates
 
-  if (warp >= 8) {
-  // 512 threads leave 128 registers each: the two epilogue warpgroups take 192, the other two keep 64
-  if constexpr (ASYNC) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;\n");
   if (warp == 8) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -716,7 +635,7 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         }
       }
     }
-  } else if (warp == 9 || warp == 10) {
+  } else if (warp >= 9) {
     // ===================== two MMA issuer warps (even / odd tiles) =====================
     const uint32_t my_parity = (uint32_t)(warp - 9);
     const uint64_t descB0 = umma_desc_sw128(smem_u32(sB));
@@ -744,192 +663,6 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
       tc_commit_elect(a_empty);
     }
     TKT_PRINT("mma [a_full, full, t_empty, issue]", (int)(it / 2))
-  } else if (warp >= 11) {
-    // ===================== cutter warps (ASYNC only) =====================
-    if constexpr (ASYNC) {
-      unsigned long long *cta_ws = ws + (size_t)blockIdx.x * 256 * TA_STRIP;
-#ifdef TM_TK_TIMING
-      long long busy = 0, served = 0; const long long t_begin = clock64_volatile();
-#endif
-      for (;;) {
-#ifdef TM_TK_TIMING
-        const long long t0 = clock64_volatile();
-        if (ta_serve(S, cta_ws, k, slack, lane)) { busy += clock64_volatile() - t0; ++served; continue; }
-#else
-        if (ta_serve(S, cta_ws, k, slack, lane)) continue;
-#endif
-        if (lds_v(S.q + 2) != 0u) break;   // set after the last query block's cuts were all awaited: the queue is empty
-        __nanosleep(64);
-      }
-#ifdef TM_TK_TIMING
-      if (blockIdx.x == 1 && lane == 0) printf("cutter warp %d: served %lld, busy %lld of %lld cycles (%lld per cut)\n", warp, served, busy, clock64_volatile() - t_begin, busy / (served ? served : 1));
-#endif
-    }
-  }
-  } else if constexpr (ASYNC) {
-    // ===================== epilogue with asynchronous cuts: thread = (query row, column half) =====================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 192;\n");
-    const int q = warp & 3, h = warp >> 2;
-    const int row = q * 32 + lane;
-    const int tid = (int)threadIdx.x;   // strip number: h * 128 + row
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    constexpr int HN = BN / 2;
-    const uint32_t s_stage = smem_u32(s_dist) + (uint32_t)(warp * 4096 + lane * 16);
-    unsigned long long *cta_ws = ws + (size_t)blockIdx.x * 256 * TA_STRIP;
-    unsigned long long *my_a = cta_ws + (size_t)tid * TA_STRIP + TA_KCAP;   // this thread's two admission buffers
-    uint32_t it = 0, w = 0;
-#ifdef TM_TK_TIMING
-    long long a_stall = 0, a_loops = 0, a_served = 0, a_posts = 0, a_adm = 0; const long long a_begin = clock64_volatile();
-#endif
-    for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
-      const int64_t qi = (int64_t)qb * BM + row;
-      const bool valid = qi < n_q;
-      const uint32_t nq = valid ? __ldg(qnorm + qi) : 0u;
-      if (h == 0) {   // warps 0-3 also store the query rows into TMEM
-        mbar_wait(a_empty, (w & 1) ^ 1);
-        tc_fence_after();
-        const uint4 *src = reinterpret_cast<const uint4 *>(q_limbs + (valid ? qi : 0) * ROWB);
-#pragma unroll
-        for (int c = 0; c < 6; ++c) {
-          uint32_t r[16];
-#pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            const uint4 t4 = valid ? __ldg(src + c * 4 + v) : make_uint4(0, 0, 0, 0);
-            r[4 * v] = t4.x; r[4 * v + 1] = t4.y; r[4 * v + 2] = t4.z; r[4 * v + 3] = t4.w;
-          }
-          tmem_st16(t_lane + A_COL + c * 16, r);
-        }
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a_full);
-      }
-      uint32_t tau = (dbg & 1) ? 0u : 0xFFFFFFFEu;   // distances of 0xFFFFFFFF (masked columns) are never admitted
-      uint32_t buf = 0;
-      unsigned long long waddr = (unsigned long long)(uintptr_t)my_a;   // next free slot of the admission buffer in use
-      uint32_t abase_lo = (uint32_t)waddr;
-      int jt = 0;
-      for (int j = 0; j < n_tiles; ++j, ++it) {
-        const uint32_t ts = it & 1;
-        const int col0 = jt * BN + h * HN;
-        jt += tile_stride;
-        if (jt >= n_tiles) jt -= n_tiles;
-        uint32_t ndA[16], ndB[16];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(dnorm + col0) + v);
-          ndA[4 * v] = t4.x; ndA[4 * v + 1] = t4.y; ndA[4 * v + 2] = t4.z; ndA[4 * v + 3] = t4.w;
-          const uint4 u4 = __ldg(reinterpret_cast<const uint4 *>(dnorm + col0 + 16) + v);
-          ndB[4 * v] = u4.x; ndB[4 * v + 1] = u4.y; ndB[4 * v + 2] = u4.z; ndB[4 * v + 3] = u4.w;
-        }
-        mbar_wait(&t_full[ts], (it >> 1) & 1);
-        tc_fence_after();
-        const uint32_t t_acc = t_lane + ts * ACC_COLS + h * HN;
-        uint32_t ppA[16], xxA[16], loA[16], ppB[16], xxB[16], loB[16];
-        tmem_ld16(t_acc, ppA);
-        tmem_ld16(t_acc + BN, xxA);
-        tmem_ld16(t_acc + 2 * BN, loA);
-        tmem_ld16(t_acc + 16, ppB);
-        tmem_ld16(t_acc + BN + 16, xxB);
-        tmem_ld16(t_acc + 2 * BN + 16, loB);
-        tmem_ld_wait();
-        tc_fence_before();          // the whole tile is in registers: hand the stage back to the tensor pipe
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[ts]);
-        if (!(dbg & 8)) {
-          if (col0 + HN <= n_dict) {
-            if (dbg & 32) tk_tile32(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB);
-            else tk_tile32s(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB, s_stage);
-          } else {   // ragged last dictionary tile
-            tk_unit(waddr, tau, nq, col0, n_dict - col0, ndA, ppA, xxA, loA);
-            tk_unit(waddr, tau, nq, col0 + 16, n_dict - col0 - 16, ndB, ppB, xxB, loB);
-          }
-        }
-        // thresholds published by the cutters: this strip's own, and the row-wide bound from the two half-thresholds
-        tau = min(tau, lds_v(S.tau + tid));
-        if (!(dbg & 16)) tau = min(tau, max(lds_v(s_thalf + tid), lds_v(s_thalf + (tid ^ 128))));
-        const uint32_t cnt = ((uint32_t)waddr - abase_lo) >> 3;
-        const bool fullb = cnt > (uint32_t)(TA_ACAP - HN);   // the next tile could overflow the buffer
-        if (__any_sync(0xffffffffu, fullb)) {
-#ifdef TM_TK_TIMING
-          const long long t0 = clock64_volatile();
-          while (__any_sync(0xffffffffu, fullb && lds_v(S.busy + tid) != 0u)) { ++a_loops; if (ta_serve(S, cta_ws, k, slack, lane)) ++a_served; }
-          a_stall += clock64_volatile() - t0;
-          if (fullb) { ++a_posts; a_adm += cnt; }
-#else
-          while (__any_sync(0xffffffffu, fullb && lds_v(S.busy + tid) != 0u)) ta_serve(S, cta_ws, k, slack, lane);
-#endif
-          if (fullb) {
-            __threadfence_block();
-            sts_v(S.busy + tid, 1u);
-            const uint32_t slot = atomicAdd(S.q + 1, 1u) & 255u;
-            sts_v(S.req + slot, 0x80000000u | (uint32_t)tid | (buf << 8) | (cnt << 16));
-            buf ^= 1u;
-            waddr = (unsigned long long)(uintptr_t)(my_a + buf * TA_ACAP);
-            abase_lo = (uint32_t)waddr;
-          }
-        }
-      }
-      // ---- results of this query block: every cut has landed, then merge the two column halves of every row
-#ifdef TM_TK_TIMING
-      a_adm += ((uint32_t)waddr - abase_lo) >> 3;
-#endif
-      while (__any_sync(0xffffffffu, lds_v(S.busy + tid) != 0u)) ta_serve(S, cta_ws, k, slack, lane);
-      s_cnt[tid] = (int)(((uint32_t)waddr - abase_lo) >> 3);
-      s_buf[tid] = buf;
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
-      s_thalf[tid] = 0xFFFFFFFFu;   // every scan and cut of this block is over; the barrier below publishes the resets
-      S.tau[tid] = 0xFFFFFFFEu;
-      {
-        constexpr int NK = TA_KCAP / 32, NA = TA_ACAP / 32, NE = 2 * (NK + NA);
-        const uint32_t lt_mask = (1u << lane) - 1u;
-        for (int L = 16 * h; L < 16 * h + 16; ++L) {   // warp (q, h) merges rows [16 h, 16 h + 16) of quarter q
-          const int64_t qL = (int64_t)qb * BM + q * 32 + L;
-          if (qL >= n_q) break;
-          uint32_t dd[NE], ii[NE];
-          int n_all = 0;
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int st = hh * 128 + q * 32 + L;
-            const int nk = (int)lds_v(S.kcnt + st), na = s_cnt[st];
-            const unsigned long long *K = cta_ws + (size_t)st * TA_STRIP, *A = K + TA_KCAP + s_buf[st] * TA_ACAP;
-            n_all += nk + na;
-#pragma unroll
-            for (int i = 0; i < NK + NA; ++i) {
-              const int p = (i < NK ? i : i - NK) * 32 + lane;
-              const unsigned long long key = i < NK ? (p < nk ? ldg_key(K + p) : ~0ull) : (p < na ? ldg_key(A + p) : ~0ull);
-              dd[hh * (NK + NA) + i] = (uint32_t)(key >> 32);
-              ii[hh * (NK + NA) + i] = (uint32_t)key;
-            }
-          }
-          uint32_t T = 0xFFFFFFFEu, TI = 0xFFFFFFFFu;
-          if (n_all > k) tk_threshold<NE>(dd, ii, n_all, k, 0, T, TI);
-          int outp = 0;
-#pragma unroll
-          for (int i = 0; i < NE; ++i) {
-            const bool keep = (dd[i] < T) || (dd[i] == T && ii[i] <= TI && dd[i] != 0xFFFFFFFFu);
-            const uint32_t km = __ballot_sync(0xffffffffu, keep);
-            if (keep) {
-              const int pos = outp + __popc(km & lt_mask);
-              out_idx[qL * k + pos] = (int32_t)ii[i];
-              out_dist[qL * k + pos] = dd[i];
-            }
-            outp += __popc(km);
-          }
-          for (int pos = outp + lane; pos < k; pos += 32) {   // fewer than k dictionary rows: empty slots are (-1, 0xFFFFFFFF)
-            out_idx[qL * k + pos] = -1;
-            out_dist[qL * k + pos] = 0xFFFFFFFFu;
-          }
-        }
-      }
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");   // the merges have read every strip
-      S.kcnt[tid] = 0u;
-    }
-    asm volatile("bar.sync 1, 256;\n" ::: "memory");
-#ifdef TM_TK_TIMING
-    if (blockIdx.x == 1 && lane == 0) printf("epi warp %d: tiles %u, total %lld cycles, stalled %lld in %lld loops (%lld cuts served), lane 0: %lld posts, %lld admissions\n", warp, it, clock64_volatile() - a_begin, a_stall, a_loops, a_served, a_posts, a_adm);
-#endif
-    if (threadIdx.x == 0) sts_v(S.q + 2, 1u);   // cutters may leave
   } else {
     // ===================== epilogue: thread = (query row, column half) =====================
     const int q = warp & 3, h = warp >> 2;
@@ -1006,8 +739,10 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         TKT(3)
         if (!(dbg & 8)) {
           if (col0 + HN <= n_dict) {
-            if (dbg & 32) tk_tile32(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB);
-            else tk_tile32s(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB, s_stage);
+            // dbg & 32: per-lane admission loop over staged distances -- 4 % faster on uncorrelated (random) features, 3 %
+            // slower on image features, where a row admits runs of neighbouring dictionary tiles and one lane loops alone
+            if (dbg & 32) tk_tile32s(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB, s_stage);
+            else tk_tile32(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB);
           } else {   // ragged last dictionary tile
             tk_unit(waddr, tau, nq, col0, n_dict - col0, ndA, ppA, xxA, loA);
             tk_unit(waddr, tau, nq, col0 + 16, n_dict - col0 - 16, ndB, ppB, xxB, loB);
@@ -1174,13 +909,11 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
   constexpr int K1_NH = TM_K1_NH;   // column splits per tile in the k = 1 / k = 4 kernels (2: 8 epilogue warps, 4: 16)
   constexpr int SMEM_K1 = STAGES_K1 * B_TILE + BM * 8 * 4 * (K1_NH - 1) + 256 + 1024;
   constexpr int SMEM_TK = STAGES_TK * B_TILE + TK_STAGE_B + 256 * 4 + 256 * 4 + 512 + 1024;
-  constexpr int SMEM_TA = SMEM_TK + (5 * 256 + 4) * 4;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(knn_i8_k1_kernel<1, K1_NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
     if (cudaFuncSetAttribute(knn_i8_k1_kernel<4, K1_NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
-    if (cudaFuncSetAttribute(knn_i8_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK) != cudaSuccess) return TM_ERR_CUDA;
-    if (cudaFuncSetAttribute(knn_i8_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TA) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaFuncSetAttribute(knn_i8_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK) != cudaSuccess) return TM_ERR_CUDA;
     attr_set = true;
   }
   {
@@ -1195,35 +928,24 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
     while (gcd(tile_stride, n_tiles_h) != 1) ++tile_stride;
     const int n_qblocks = (n_q + BM - 1) / BM;
     const int grid = n_qblocks < num_ctas ? n_qblocks : num_ctas;
-    static int kdbg = -1;   // TM_TK_DBG bits: 1 admit nothing (top-k), 2 no dictionary loads, 4 no MMAs, 8 no epilogue arithmetic
+    static int kdbg = -1;   // TM_TK_DBG bits: 1 admit nothing (top-k), 2 no dictionary loads, 4 no MMAs, 8 no epilogue arithmetic, 16 no threshold sharing, 32 staged admission
     if (kdbg < 0) kdbg = getenv("TM_TK_DBG") ? atoi(getenv("TM_TK_DBG")) : 0;
     if (k == 1) knn_i8_k1_kernel<1, K1_NH><<<grid, k1_threads(K1_NH), SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride, kdbg);
     else if (k == 4) knn_i8_k1_kernel<4, K1_NH><<<grid, k1_threads(K1_NH), SMEM_K1, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, out_idx, out_dist, tile_stride, kdbg);
     else {
-      // candidate strips: stream-ordered scratch (the pool keeps it cached between calls).  The kernels bump only the low
-      // word of their write pointers, so no strip may straddle a 4 GB boundary: 2 KB strips are 2 KB aligned; the 3 328-byte
-      // strips of the asynchronous kernel start a whole number of strips below the boundary when the range crosses one.
-      static int slack = -1, dbg = 0, async = 0;   // TM_TK_SLACK / TM_TK_DBG: tuning and timing experiments (dbg = 1 admits nothing)
+      // candidate strips: stream-ordered scratch (the pool keeps it cached between calls); 2 KB alignment keeps every
+      // strip inside one 4 GB window, so the kernel bumps only the low word of its write pointer
+      static_assert((TK_CAP * 8) % 2048 == 0, "a strip must not straddle a 4 GB boundary");
+      void *raw = nullptr;
+      const size_t strips = (size_t)grid * 256 * TK_CAP * 8;
+      if (cudaMallocAsync(&raw, strips + 2048, st) != cudaSuccess) return TM_ERR_NOMEM;
+      unsigned long long *strip_ws = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(raw) + 2047) & ~uintptr_t(2047));
+      static int slack = -1, dbg = 0;   // TM_TK_SLACK / TM_TK_DBG: tuning and timing experiments (dbg = 1 admits nothing)
       if (slack < 0) {
         slack = getenv("TM_TK_SLACK") ? atoi(getenv("TM_TK_SLACK")) : TK_SLACK;
         dbg = getenv("TM_TK_DBG") ? atoi(getenv("TM_TK_DBG")) : 0;
-        async = getenv("TM_TK_ASYNC") ? atoi(getenv("TM_TK_ASYNC")) : 0;
       }
-      void *raw = nullptr;
-      if (async) {
-        const size_t strip_b = (size_t)TA_STRIP * 8, total = (size_t)grid * 256 * strip_b;
-        if (cudaMallocAsync(&raw, total + strip_b, st) != cudaSuccess) return TM_ERR_NOMEM;
-        uintptr_t lo = reinterpret_cast<uintptr_t>(raw);
-        if ((lo >> 32) != ((lo + total + strip_b - 1) >> 32)) lo += ((((lo >> 32) + 1) << 32) - lo) % strip_b;
-        const int sl = slack < TA_KCAP - k ? slack : TA_KCAP - k;
-        knn_i8_topk_kernel<true><<<grid, TA_THREADS, SMEM_TA, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride,
-                                                                   reinterpret_cast<unsigned long long *>(lo), sl, dbg);
-      } else {
-        const size_t strips = (size_t)grid * 256 * TK_CAP * 8;
-        if (cudaMallocAsync(&raw, strips + 2048, st) != cudaSuccess) return TM_ERR_NOMEM;
-        unsigned long long *strip_ws = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(raw) + 2047) & ~uintptr_t(2047));
-        knn_i8_topk_kernel<false><<<grid, TK_THREADS, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride, strip_ws, slack, dbg);
-      }
+      knn_i8_topk_kernel<<<grid, TK_THREADS, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride, strip_ws, slack, dbg);
       cudaFreeAsync(raw, st);
     }
   }
