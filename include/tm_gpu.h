@@ -166,7 +166,9 @@ int tm_matcher_create(const uint8_t *dict_idx, const int32_t *dict_pal, int64_t 
                       int n_pal, int extended, tm_matcher **out);
 int tm_matcher_destroy(tm_matcher *m);
 /* DoXY for tiles with no usable motion prediction (first frame of a keyframe sequence, or mpErr above the dead band):
-   source tiles as RGB [n_q][64] (already canonicalised) -> TTileMapItem fields TileIdx / PalIdx and the error. */
+   source tiles as RGB [n_q][64] (already canonicalised) -> TTileMapItem fields TileIdx / PalIdx and the error.
+   A host batch of 8 or more k-NN waves (SMs x 128 tiles) is uploaded in four pieces (a short first one) on a second stream while the pieces
+   already resident are matched; pinned host memory makes that overlap real, pageable memory still works. */
 int tm_match_tiles_rgb(tm_matcher *m, const int32_t *rgb, int64_t n_q, int k, int32_t *tile_idx, int32_t *pal_idx, uint32_t *err);
 /* same from precomputed features [n_q][192] */
 int tm_match_tiles_feat(tm_matcher *m, const int16_t *feat, int64_t n_q, int k, int32_t *tile_idx, int32_t *pal_idx, uint32_t *err);

@@ -295,6 +295,27 @@ def test_matcher_small_dictionary(tm, oracle):
     m.close()
 
 
+def test_matcher_host_batch_pipelined_upload(tm, oracle):
+    """tm_match_tiles_rgb with a large HOST batch uploads it in pieces on a second stream while earlier pieces are matched
+    (csrc/abi.cu); the result must equal the one-piece device-resident call, and the oracle on a sample of rows."""
+    import torch
+    tiles, pal, tp, idx = _dictionary(oracle, 300, 4, 16, 75)
+    n = 8 * 148 * 128 + 1234                       # above the threshold, ragged last piece
+    q = rand_tiles(4096, 76)
+    q = np.ascontiguousarray(np.tile(q, (n // 4096 + 1, 1))[:n])
+    q[:, 0] ^= (np.arange(n, dtype=np.int64) % 251).astype(q.dtype)   # rows differ between the pieces
+    m = tm.Matcher(idx, tp, pal, extended=True)
+    th, ph, eh = m.match_rgb(q, 16)                                   # host buffers: pipelined upload
+    td, pd_, ed = m.match_rgb(torch.from_numpy(q).cuda(), 16)         # device-resident: one piece
+    assert np.array_equal(th, td.cpu().numpy()) and np.array_equal(ph, pd_.cpu().numpy())
+    assert np.array_equal(_u32(eh), _u32(ed.cpu().numpy()))
+    rows = np.r_[0:64, n // 4 - 32:n // 4 + 32, n - 64:n]
+    dict_feat = oracle.features_from_pal(idx, tp, pal)
+    ot, op, oe = oracle.match_tiles(oracle.features_from_rgb(q[rows]), dict_feat, idx, tp, pal, k=16, extended=True)
+    assert np.array_equal(th[rows], ot) and np.array_equal(ph[rows], op) and np.array_equal(_u32(eh)[rows], oe)
+    m.close()
+
+
 # ---------------------------------------------------------------- drop-in symbols
 def test_dropin_ann_short(tm, oracle):
     d = synth.random_features(500, 80)

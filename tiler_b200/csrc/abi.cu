@@ -746,10 +746,45 @@ extern "C" int tm_match_tiles_rgb(tm_matcher *m, const int32_t *rgb, int64_t n_q
     return fail(TM_ERR_ARG, "tm_match_tiles_rgb: bad argument");
   std::lock_guard<std::recursive_mutex> lk(g_mu);
   Stage s(t_stream);
-  const int32_t *d_rgb = s.in(rgb, (size_t)n_q * 64);
   int32_t *d_tile = s.out(tile_idx, (size_t)n_q), *d_pal = s.out(pal_idx, (size_t)n_q);
   uint32_t *d_err = s.out(err, (size_t)n_q);
   int16_t *d_feat = (int16_t *)s.temp((size_t)n_q * 384);
+  // A large batch of HOST tiles is uploaded in four pieces on a second stream while the pieces already on the device are
+  // matched: only the first piece (two k-NN waves, 10 MB of the 110 MB of a 720p sequence) stays exposed.  Pieces are
+  // whole waves of k-NN query blocks (SMs x 128 rows) so the split costs the search no tail.
+  const int64_t wave = (int64_t)num_sms() * knn_rows_per_cta();
+  if (!is_device_ptr(rgb) && n_q >= 8 * wave) {
+    static cudaStream_t cs = nullptr;
+    static cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (!cs) {
+      CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      for (auto &e : ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    int32_t *d_rgb = (int32_t *)s.temp((size_t)n_q * 256);
+    s.any_host = true;
+    const int64_t first = 2 * wave, piece = ((n_q - first + 2) / 3 + wave - 1) / wave * wave;
+    int64_t cut[5] = {0, first, first + piece, first + 2 * piece, n_q};
+    for (int i = 2; i < 4; ++i) if (cut[i] > n_q) cut[i] = n_q;
+    if (s.err == TM_OK) {
+      CU(cudaEventRecord(ev[4], s.st));   // the scratch (stream-ordered allocation on s.st) exists
+      CU(cudaStreamWaitEvent(cs, ev[4], 0));
+      for (int i = 0; i < 4; ++i) {
+        const int64_t off = cut[i], n = cut[i + 1] - off;
+        if (n > 0) CU(cudaMemcpyAsync(d_rgb + off * 64, rgb + off * 64, (size_t)n * 256, cudaMemcpyHostToDevice, cs));
+        CU(cudaEventRecord(ev[i], cs));
+      }
+      for (int i = 0; i < 4 && s.err == TM_OK; ++i) {
+        const int64_t off = cut[i], n = cut[i + 1] - off;
+        if (n <= 0) continue;
+        CU(cudaStreamWaitEvent(s.st, ev[i], 0));
+        s.err = launch_features_rgb(d_rgb + off * 64, n, d_feat + off * 192, s.st);
+        if (s.err == TM_OK) s.err = match_feat_dev(m, d_feat + off * 192, n, k, d_tile + off, d_pal + off, d_err + off, s);
+      }
+    }
+    RC(s.finish());
+    return TM_OK;
+  }
+  const int32_t *d_rgb = s.in(rgb, (size_t)n_q * 64);
   if (s.err == TM_OK) s.err = launch_features_rgb(d_rgb, n_q, d_feat, s.st);
   if (s.err == TM_OK) s.err = match_feat_dev(m, d_feat, n_q, k, d_tile, d_pal, d_err, s);
   RC(s.finish());
