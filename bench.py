@@ -273,11 +273,11 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": "knn_i8_topk_kernel", "achieved": achieved_tflops,
                      "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tflops / pk["bf16_tflops_sustained"],
-                     "traffic": 6.1367e9 * (TILES_PER_STEP / 432000.0), "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
-                     "ncu --set full capture of this kernel in this bench (profiles/r01_knn_topk_bench_raw.csv): 1.155 GB + 4.982 GB per "
+                     "traffic": 5.98e9 * (flops_per_launch / (432000.0 * N_DICT * 384)), "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
+                     "ncu --set full capture of this kernel in this bench (profiles/r01_knn_topk_bench_raw.csv): 1.545 GB + 4.435 GB per "
                      "launch; algorithmic bytes per launch = 166 MB query limbs + 25 MB dictionary + 221 MB top-64 results.  The excess is "
                      "the per-row candidate strips (78 MB workspace, ~1000 admissions of 8 B per query row) being written back from L2; "
-                     "6.1 GB in 28.2 ms is 3.3 % of HBM bandwidth, the kernel is bound by its epilogue (DESIGN.md 4.1)",
+                     "6.0 GB in 29.4 ms is 3 % of HBM bandwidth, the kernel is bound by its epilogue (DESIGN.md 4.1)",
                      "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                      "algorithmic_flops_per_launch": flops_per_launch, "launches_per_step": knn_n / args.steps, "kernel_ms_per_launch": knn_launch_ms,
                      "note": "384 flop per 192-d distance evaluation; the exact int8-limb scheme issues 4 int8 MMAs (= 2 "
