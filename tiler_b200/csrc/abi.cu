@@ -754,12 +754,17 @@ extern "C" int tm_match_tiles_rgb(tm_matcher *m, const int32_t *rgb, int64_t n_q
   // whole waves of k-NN query blocks (SMs x 128 rows) so the split costs the search no tail.
   const int64_t wave = (int64_t)num_sms() * knn_rows_per_cta();
   if (!is_device_ptr(rgb) && n_q >= 8 * wave) {
-    static cudaStream_t cs = nullptr;
-    static cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-    if (!cs) {
-      CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-      for (auto &e : ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    static cudaStream_t cs_dev[64] = {};        // copy stream and events of each device (one process may drive several)
+    static cudaEvent_t ev_dev[64][5] = {};
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(TM_ERR_ARG, "tm_match_tiles_rgb: device ordinal out of range");
+    if (!cs_dev[dev]) {
+      CU(cudaStreamCreateWithFlags(&cs_dev[dev], cudaStreamNonBlocking));
+      for (auto &e : ev_dev[dev]) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    cudaStream_t cs = cs_dev[dev];
+    cudaEvent_t *ev = ev_dev[dev];
     int32_t *d_rgb = (int32_t *)s.temp((size_t)n_q * 256);
     s.any_host = true;
     const int64_t first = 2 * wave, piece = ((n_q - first + 2) / 3 + wave - 1) / wave * wave;
