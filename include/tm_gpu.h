@@ -151,6 +151,13 @@ int tm_kmeans_partial_step(const double *x, int64_t n, int dim, int k, const dou
                            double *partial_sums, int64_t *partial_counts, int64_t *changed, double *inertia);
 int tm_kmeans_finish_step(const double *sums, const int64_t *counts, int k, int dim, int nan_empty, double *centroids);
 
+/* the BICO stand-in in one call (bico_create / insert_line x n / get_results, tilingencoder.pas:4149-4172): <= k weighted
+   summary points of the n weighted rows x[n][dim] (weight = UseCount).  n <= k: the rows themselves.  Else unweighted
+   k-means++ seeding from `seed`, at most max_iter weighted Lloyd updates (bico_get_results uses 8), empty clusters dropped.
+   centroids[k][dim] / weights[k] are HOST arrays (weights may be NULL); *count = number of summary points. */
+int tm_coreset_weighted(const double *x, const double *w, int64_t n, int dim, int64_t k, int max_iter, uint64_t seed,
+                        double *centroids, double *weights, int64_t *count);
+
 /* ---------------------------------------------------------------- batched: palette colour quantisation (:4434-4564) */
 /* all palettes at once: rgb tiles [n_tiles][64], tile_pal[n_tiles] in [0, n_pal) -> palettes[n_pal][pal_size]
    (k-means on the palette's pixels sorted by (G,R,B), centroids rounded, sorted by (V,S,H), padded with the null colour).

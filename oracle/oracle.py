@@ -257,6 +257,19 @@ def kmeanspp_init(x, k, seed):
     return cent
 
 
+def coreset_weighted(x, w, k, seed, max_iter=8):
+    """tmo_coreset_weighted: the BICO stand-in.  -> (centroids [m, dim], weights [m])."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    cent = np.empty((int(k), x.shape[1]), dtype=np.float64)
+    wts = np.empty(int(k), dtype=np.float64)
+    f = lib().tmo_coreset_weighted
+    f.restype = C.c_int64
+    m = f(_p(x, C.c_double), _p(w, C.c_double), C.c_int64(x.shape[0]), int(x.shape[1]), C.c_int64(k), int(max_iter),
+          C.c_uint64(seed), _p(cent, C.c_double), _p(wts, C.c_double))
+    return cent[:m].copy(), wts[:m].copy()
+
+
 def quantize_palette(pixels, pal_size, init=None, seed=1):
     px = np.ascontiguousarray(pixels, dtype=np.int32).reshape(-1)
     out = np.empty(pal_size, dtype=np.int32)

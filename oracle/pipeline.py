@@ -1,0 +1,226 @@
+"""CPU restatement of the encoder's HOST-SIDE steps between the compute stages, written from the reference alone.
+
+TEST INFRASTRUCTURE ONLY (like everything under oracle/): imported by tests/ to check tiler_b200.encoder; it imports
+nothing from tiler_b200.  Plain Python / numpy loops and sorts that follow the Pascal statement by statement -- small
+clips only.  Every function cites the reference lines it follows.
+"""
+import math
+
+import numpy as np
+
+from . import oracle as O
+
+C_INV_PHI = 2.0 / (1.0 + math.sqrt(5.0))                                   # cInvPhi (utils.pas:42-43)
+C_PSNR_MAX = 10.0 * math.log(255.0 * 255.0 / 0.5) / math.log(10.0)          # cPsnrMaxValue (utils.pas:111)
+C_PSYV_EPSILON = 1e-6                                                      # cPsyVEpsilon
+
+
+def quicksort(items, compare):
+    """extern.pas:370-418: the repo's own QuickSort (middle pivot, Hoare partition, the pivot INDEX follows swaps), in
+    place on a Python list.  Not stable: ties land where this exact procedure puts them."""
+    def qs(first, last):
+        if last <= first:
+            return
+        while True:
+            i, j, p = first, last, (first + last) >> 1
+            while True:
+                while compare(items[i], items[p]) < 0:
+                    i += 1
+                while compare(items[j], items[p]) > 0:
+                    j -= 1
+                if i <= j:
+                    items[i], items[j] = items[j], items[i]
+                    if p == i:
+                        p = j
+                    elif p == j:
+                        p = i
+                    i += 1
+                    j -= 1
+                if i > j:
+                    break
+            if first < j:
+                qs(first, j)
+            first = i
+            if i >= last:
+                break
+    qs(0, len(items) - 1)
+    return items
+
+
+def golden_ratio_search(func, min_x, max_x, objective_y, eps_x, eps_y):
+    """GoldenRatioSearch (utils.pas:1044-1072), recursion unrolled.  The encoder's state after the search is whatever the
+    LAST call of func left behind; the returned abscissa is not re-evaluated (:1048-1052 returns MinX without calling)."""
+    while True:
+        if abs(min_x - max_x) <= eps_x:                       # SameValue(MinX, MaxX, EpsilonX)
+            return min_x
+        t = (1.0 - C_INV_PHI) if min_x < max_x else C_INV_PHI
+        x = min_x + (max_x - min_x) * t                       # lerp
+        y = func(x)
+        if abs(y - objective_y) <= eps_y:                     # CompareValue(y, ObjectiveY, EpsilonY) = 0
+            return x
+        if y < objective_y:
+            min_x = x
+        else:
+            max_x = x
+
+
+def pad_frames(frames):
+    """Tilemap size rounds up to whole tiles (:1776) and the screen IS the tilemap (ReframeUI, :2631-2638); pixels beyond
+    the image stay 0 (AllocMem'd tiles, :1310)."""
+    n, h, w = frames.shape
+    th, tw = (h - 1) // 8 + 1, (w - 1) // 8 + 1
+    out = np.zeros((n, th * 8, tw * 8), dtype=np.int32)
+    out[:, :h, :w] = frames
+    return out, tw, th
+
+
+def load(frames):
+    """TFrame.LoadFromImage + AsyncLoadFromImage (:1289-1411): frame -> 8x8 tiles -> mirror canonicalisation."""
+    frames, tw, th = pad_frames(np.asarray(frames, dtype=np.int32))
+    n = frames.shape[0]
+    nt = tw * th
+    tiles = frames.reshape(n, th, 8, tw, 8).transpose(0, 1, 3, 2, 4).reshape(n, nt, 64)
+    canon = np.empty_like(tiles)
+    flags = np.zeros((n, nt), np.uint8)
+    for f in range(n):
+        for t in range(nt):
+            hm, vm = O.mirror_heuristics(tiles[f, t])
+            px = tiles[f, t].reshape(8, 8)
+            if hm:
+                px = px[:, ::-1]
+            if vm:
+                px = px[::-1, :]
+            canon[f, t] = px.reshape(64)
+            flags[f, t] = int(hm) | (int(vm) << 1)
+    return frames, canon, flags, tw, th
+
+
+def predict_motion(frames, canon, flags, tw, th, radius):
+    """TTilingEncoder.PredictMotion (:1964-1991): frame f against the previous SOURCE frame; frame 0 against frame 1 (the
+    loop starts at -Min(1, High) so the buffer first holds frame 1); a one-frame clip against the zeroed buffer."""
+    n = frames.shape[0]
+    psnr = np.empty((n, tw * th), np.float32)
+    for f in range(n):
+        prev = frames[f - 1] if f > 0 else (frames[1] if n > 1 else np.zeros_like(frames[0]))
+        cur = O.features_from_rgb_mirrored(canon[f], flags[f])
+        _, _, e = O.motion_search(cur, tw, th, O.sliding_features(prev), radius)
+        psnr[f] = [O.euclidean_to_psnr(int(v)) for v in e]
+    return psnr
+
+
+def reduce(canon, flags, psnr, seq_starts, tile_count):
+    """TTilingEncoder.Reduce (:1908-1926): SolveTileCount = GoldenRatioSearch over STCGREval (:4014-4046), which marks a
+    tile predicted when PSNR > x (PSNR / 10.0 > x on the first frame of its keyframe sequence: Single promoted to Double,
+    compared with the Double x), transfers the unpredicted tiles (:4048-4103) and merges exact duplicates
+    (MakeTilesUnique(True), :4720-4781); then ReindexTiles(True) (:4626-4696).
+    -> dictionary tiles, their mirror flags, use counts, tilemap TileIdx [n, nt] (-1 = predicted), threshold."""
+    n, nt = canon.shape[:2]
+    flat = canon.reshape(-1, 64)
+    fl = flags.reshape(-1)
+    p64 = psnr.astype(np.float64)
+    starts = set(int(s) for s in seq_starts)
+    eff = np.stack([p64[f] / 10.0 if f in starts else p64[f] for f in range(n)]).reshape(-1)
+    keys = [flat[i].astype(np.uint32).tobytes() for i in range(len(flat))]
+    state = {}
+
+    def stcgr_eval(x):
+        pred = eff > x
+        groups = {}                                            # MakeTilesUnique: identical RGB pixels -> one tile
+        for i in np.flatnonzero(~pred):
+            groups.setdefault(keys[i], []).append(int(i))
+        state["pred"], state["groups"], state["x"] = pred, groups, x
+        return float(len(groups))                              # GetTileCount(True)
+
+    target = min(int(tile_count), len(flat))
+    golden_ratio_search(stcgr_eval, 0.0, C_PSNR_MAX, float(target), C_PSYV_EPSILON, 0.5)
+    groups = state["groups"]
+    # ReindexTiles(True): CompareTileUseCountRev (:582-599) = use count descending, then CompareDWord over the 64 pixels
+    # (unsigned dwords, first difference decides).  Keys are unique after MakeTilesUnique, so any sort gives this order.
+    items = [(-len(m), tuple(flat[m[0]].astype(np.uint32).tolist()), m) for m in groups.values()]
+    items.sort(key=lambda it: (it[0], it[1]))
+    tile_idx = np.full(n * nt, -1, np.int32)
+    rep = []
+    for new, (_, _, members) in enumerate(items):
+        tile_idx[members] = new
+        rep.append(members[0])      # which duplicate survives is unspecified in the reference (non-stable sort): first in frame order here
+    rep = np.asarray(rep, dtype=np.int64)
+    use = np.asarray([-it[0] for it in items], dtype=np.int32)
+    return flat[rep].copy(), fl[rep].copy(), use, tile_idx.reshape(n, nt), state["x"]
+
+
+def palettize(dict_tiles, use_count, palette_count, seed, dithering_mode=O.PVS_WEIGHTED_SPE_DCT, coreset_iters=8):
+    """DoPalettization (:4105-4245): LAB features (ComputeTilePsyVisFeatures, DitheringMode) -> coreset of 8 x PaletteCount
+    points, tiles inserted with weight UseCount (:4149-4173; BICO itself is unpinned: oracle.coreset_weighted defines the
+    stand-in) -> nearest coreset point per tile (ANN, eps 0, :4183-4188) -> k-means of the coreset points, UNWEIGHTED
+    (yakmo, :4198-4207; k-means++ draw order unpinned: our seeded generator) -> identity mapping when the coreset has
+    <= PaletteCount points (:4214-4219), no k-means when PaletteCount = 1 (:4209-4212) -> palettes re-indexed by
+    descending tile count with the repo's QuickSort (:4221-4244).  -> PalIdx_Initial per tile."""
+    feats = np.stack([O.tile_features_f64(t, dithering_mode, True) for t in dict_tiles])
+    n_core_req = palette_count << 3
+    core, _ = O.coreset_weighted(feats, np.asarray(use_count, dtype=np.float64), n_core_req, seed, coreset_iters)
+    ann, _ = O.knn_double(core, feats)
+    if len(core) > palette_count:
+        if palette_count > 1:
+            yk, _, _, _ = O.kmeans_lloyd(core, O.kmeanspp_init(core, palette_count, seed), max_iter=300)
+        else:
+            yk = np.zeros(len(core), np.int32)
+    else:
+        yk = np.arange(len(core), dtype=np.int32)
+    pals = [[0, p] for p in range(palette_count)]              # [UseCount, PalIdx_Initial]
+    for a in ann:
+        pals[int(yk[a])][0] += 1
+    quicksort(pals, lambda a, b: (b[0] > a[0]) - (b[0] < a[0]))   # ComparePaletteUseCount (utils.pas:750-753)
+    lut = np.empty(palette_count, np.int32)
+    for new, (_, old) in enumerate(pals):
+        lut[old] = new
+    return lut[yk[ann]].astype(np.int32)
+
+
+def quantize(dict_tiles, tile_pal, palette_count, palette_size, seed):
+    """DoQuantization / QuantizeUsingYakmo per palette (:4434-4564)."""
+    return np.stack([O.quantize_palette(dict_tiles[tile_pal == p].reshape(-1), palette_size, seed=seed)[0]
+                     for p in range(palette_count)])
+
+
+def reindex(dict_idx, tile_idx):
+    """TTilingEncoder.Reindex (:1993-2038): MakeTilesUnique(False) merges dictionary tiles with identical palette indices
+    into the first of the sorted run, use counts are recounted from every tilemap item with TileIdx >= 0, then
+    ReindexTiles(False): drop unused tiles, order by (use count descending, CompareByte on the 64 indices), remap."""
+    dict_idx = np.asarray(dict_idx, dtype=np.uint8).reshape(-1, 64)
+    tmap = np.asarray(tile_idx, dtype=np.int64)
+    first_of = {}
+    merge = np.arange(len(dict_idx))
+    for i in range(len(dict_idx)):
+        k = dict_idx[i].tobytes()
+        merge[i] = first_of.setdefault(k, i)
+    use = np.zeros(len(dict_idx), np.int64)
+    flat = tmap.reshape(-1)
+    merged = np.where(flat >= 0, merge[np.maximum(flat, 0)], -1)
+    for t in merged[merged >= 0]:
+        use[t] += 1
+    keep = [i for i in range(len(dict_idx)) if use[i] > 0]
+    keep.sort(key=lambda i: (-int(use[i]), dict_idx[i].tobytes()))
+    new_of = np.full(len(dict_idx), -1, np.int64)
+    for new, i in enumerate(keep):
+        new_of[i] = new
+    out = np.where(merged >= 0, new_of[np.maximum(merged, 0)], -1).astype(np.int32).reshape(tmap.shape)
+    return dict_idx[keep].copy(), use[keep].astype(np.int32), out
+
+
+def encode(frames, seqs, tile_count, palette_count, palette_size, seed, radius=32, use_tk=True, y2_mixed=4, extended=True):
+    """TTilingEncoder.Run (:5529-5554) up to, but not including, the stream writer: Load -> PredictMotion -> Reduce ->
+    PreparePalettes (without OptimizePalettes) -> Dither -> Reconstruct -> Reindex."""
+    frames_p, canon, flags, tw, th = load(frames)
+    psnr = predict_motion(frames_p, canon, flags, tw, th, radius)
+    dtiles, dflags, use, _, x = reduce(canon, flags, psnr, [s for s, _ in seqs], tile_count)
+    tpal = palettize(dtiles, use, palette_count, seed)
+    pal = quantize(dtiles, tpal, palette_count, palette_size, seed)
+    didx = O.dither(dtiles, dflags, tpal, pal, use_tk=use_tk, y2_mixed_colors=y2_mixed)
+    dfeat = O.features_from_pal(didx, tpal, pal)
+    parts = [O.reconstruct_sequence(canon[s0:s1 + 1], flags[s0:s1 + 1], tw, th, dfeat, didx, tpal, pal, radius=radius, extended=extended)
+             for s0, s1 in seqs]
+    tm = {k: np.concatenate([p[k] for p in parts]) for k in ("tile_idx", "pal_idx", "pred_x", "pred_y", "is_pred", "recon", "err")}
+    ftiles, fuse, fmap = reindex(didx, tm["tile_idx"])
+    return {"tiles": ftiles, "use_count": fuse, "tile_idx": fmap, "pal_idx": tm["pal_idx"], "pred_x": tm["pred_x"], "pred_y": tm["pred_y"],
+            "is_pred": tm["is_pred"], "recon": tm["recon"], "err": tm["err"], "palettes": pal, "mirror": flags, "tile_pal": tpal,
+            "dict_tiles_rgb": dtiles, "threshold": x, "psnr": psnr, "tw": tw, "th": th}

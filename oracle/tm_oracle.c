@@ -718,6 +718,76 @@ int tmo_kmeans_lloyd(const double *x, int64_t n, int dim, int k, int max_iter, d
   return it;
 }
 
+/* Weighted Lloyd with bounded effort: the stand-in for BICO.dll's streaming coreset (bico_create / insert_line /
+   get_results, extern.pas:218-223; call site tilingencoder.pas:4149-4172).  BICO's source and projections are absent
+   (parity unpinned), so the coreset is DEFINED here and the GPU library reproduces it bit for bit: n <= k -> every point
+   is its own summary; else unweighted k-means++ seeding (tmo_kmeanspp_init), at most max_iter weighted updates
+   (centroid = sum w x / sum w, same blocked summation order as tmo_kmeans_lloyd, product rounded before the add), empty
+   clusters dropped.  Returns the number of summary points; weights_out = summed weights. */
+int64_t tmo_coreset_weighted(const double *x, const double *w, int64_t n, int dim, int64_t k, int max_iter, uint64_t seed,
+                             double *cent_out, double *weights_out) {
+  if (n <= k) {
+    memcpy(cent_out, x, sizeof(double) * (size_t)n * dim);
+    if (weights_out) memcpy(weights_out, w, sizeof(double) * (size_t)n);
+    return n;
+  }
+  double *cent = (double *)malloc(sizeof(double) * (size_t)k * dim);
+  double *sums = (double *)calloc((size_t)k * dim, sizeof(double)), *blk = (double *)calloc((size_t)k * dim, sizeof(double));
+  double *ws = (double *)calloc((size_t)k, sizeof(double)), *bw = (double *)calloc((size_t)k, sizeof(double));
+  int64_t *cnt = (int64_t *)calloc((size_t)k, sizeof(int64_t));
+  int32_t *labels = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+  tmo_kmeanspp_init(x, n, dim, (int)k, seed, cent);
+  for (int64_t i = 0; i < n; ++i) labels[i] = -1;
+  int it = 0;
+  for (;;) {
+    int64_t changed = 0;
+#pragma omp parallel for schedule(static) reduction(+:changed)
+    for (int64_t i = 0; i < n; ++i) {
+      double best = INFINITY; int32_t bi = labels[i] >= 0 ? labels[i] : 0;
+      for (int64_t c = 0; c < k; ++c) {
+        double s = 0.0;
+        const double *cv = cent + c * dim, *xv = x + i * dim;
+        for (int j = 0; j < dim; ++j) { double d = xv[j] - cv[j]; s += d * d; }
+        if (s < best) { best = s; bi = (int32_t)c; }
+      }
+      if (bi != labels[i]) { labels[i] = bi; ++changed; }
+    }
+    if (changed == 0 || it >= max_iter) break;
+    ++it;
+    memset(sums, 0, sizeof(double) * (size_t)k * dim); memset(blk, 0, sizeof(double) * (size_t)k * dim);
+    memset(ws, 0, sizeof(double) * (size_t)k); memset(bw, 0, sizeof(double) * (size_t)k);
+    memset(cnt, 0, sizeof(int64_t) * (size_t)k);
+    for (int64_t i = 0; i < n; ++i) {
+      const int32_t c = labels[i];
+      double *bv = blk + (int64_t)c * dim; const double *xv = x + i * dim;
+      for (int j = 0; j < dim; ++j) { const double p = w[i] * xv[j]; bv[j] += p; }
+      bw[c] += w[i];
+      if (++cnt[c] % TMO_KM_BLOCK == 0) {
+        double *sv = sums + (int64_t)c * dim;
+        for (int j = 0; j < dim; ++j) { sv[j] += bv[j]; bv[j] = 0.0; }
+        ws[c] += bw[c]; bw[c] = 0.0;
+      }
+    }
+    for (int64_t c = 0; c < k; ++c) {
+      if (cnt[c] % TMO_KM_BLOCK != 0) {
+        double *sv = sums + c * dim, *bv = blk + c * dim;
+        for (int j = 0; j < dim; ++j) sv[j] += bv[j];
+        ws[c] += bw[c];
+      }
+      if (cnt[c] > 0) for (int j = 0; j < dim; ++j) cent[c * dim + j] = sums[c * dim + j] / ws[c];
+    }
+  }
+  int64_t m = 0;
+  for (int64_t c = 0; c < k; ++c) {
+    if (!(it > 0 ? ws[c] > 0.0 : 1)) continue;
+    memcpy(cent_out + m * dim, cent + c * dim, sizeof(double) * (size_t)dim);
+    if (weights_out) weights_out[m] = it > 0 ? ws[c] : 0.0;
+    ++m;
+  }
+  free(cent); free(sums); free(blk); free(ws); free(bw); free(cnt); free(labels);
+  return m;
+}
+
 /* ------------------------------------------------------------------ palette colour quantisation */
 
 typedef struct { int r, g, b; uint8_t h, s, v; int order; } cm_item;

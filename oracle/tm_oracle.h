@@ -113,6 +113,10 @@ int tmo_kmeans_lloyd(const double *x, int64_t n, int dim, int k, int max_iter, d
 /* deterministic k-means++ seeding with an explicit xorshift RNG (OUR definition; yakmo's draw order is unpinned) */
 void tmo_kmeanspp_init(const double *x, int64_t n, int dim, int k, uint64_t seed, double *centroids);
 
+/* ---- coreset: the BICO.dll stand-in (extern.pas:218-223; tilingencoder.pas:4149-4172), defined by this restatement ---- */
+int64_t tmo_coreset_weighted(const double *x, const double *w, int64_t n, int dim, int64_t k, int max_iter, uint64_t seed,
+                             double *cent_out, double *weights_out);
+
 /* ---- palette colour quantisation (tilingencoder.pas:4434-4564) ---- */
 /* pixels: n packed 0x00BBGGRR; init centroids explicit (k rows x 3, may be NULL -> kmeans++ with seed);
    writes pal_size entries (sorted V,S,H; padded with null colour); returns colour count */

@@ -1,0 +1,229 @@
+"""GPU parity at the BASELINE.json config sizes and on the reference's REAL data (round-2 additions).
+
+Every comparison is CUDA output (through the C ABI) against the CPU oracle (oracle/), never against another kernel:
+  * configs[1] shape: 65 536-tile dictionary x 16 palettes, a 512-row sample of a 432 000-tile batch through oracle.match_tiles
+  * configs[2] slice: one tensor-core assignment against 262 144 centroids, 2 000 points against an exact f64 scan
+  * configs[4] shape: 32 palettes x 256 colours, 2 048 (tile, palette) pairs, both ditherers
+  * configs[0]: 320x180x24 end to end (the 180 rows zero-padded to 184 inside encode()) against oracle/pipeline.py
+  * the dithered tiles and palettes of docs/demo/city_cif.gtm and football_cif.gtm (tests/golden/demo_tiles.npz)
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import rand_tiles, ROOT
+from tiler_b200 import synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _u32(a):
+    return np.asarray(a).view(np.uint32) if np.asarray(a).dtype == np.int32 else np.asarray(a)
+
+
+# ------------------------------------------------------------------ configs[1]: 65 536 x 16 x 16, k = 64, extended re-rank
+def test_config_b_match_sample_against_oracle(tm, oracle):
+    from tiler_b200.encoder import TilingEncoder
+    clip = synth.make_clip(1280, 720, 6, cut_every=0, seed=synth.SEED + 5)
+    tiles = synth.clip_to_tiles(clip).reshape(-1, 64)                          # 86 400 source tiles
+    enc = TilingEncoder(palette_size=16, palette_count=16)
+    canon, flags = enc.load_tiles(tiles[None])
+    enc.reduce_sample(canon, flags, 65536)
+    enc.prepare_palettes()
+    enc.dither()
+    enc.prepare_reconstruct()
+    didx, dpal, pal = np.asarray(enc.tile_idx), np.asarray(enc.tile_pal), np.asarray(enc.palettes)
+    assert didx.shape == (65536, 64) and pal.shape == (16, 16)
+    dict_feat = oracle.features_from_pal(didx, dpal, pal)
+    assert np.array_equal(enc.matcher.dict_features(), dict_feat)              # PrepareReconstruct at full dictionary size
+    # a full keyframe-sequence batch (432 000 tiles = 5 frames repeated): every k-NN wave shape of the bench step
+    batch = np.ascontiguousarray(np.tile(canon.reshape(-1, 64), (5, 1)))
+    assert batch.shape[0] == 432000
+    ti, pi, er = enc.matcher.match_rgb(batch, 64)
+    sel = np.linspace(0, batch.shape[0] - 1, 512).astype(np.int64)
+    qf = oracle.features_from_rgb(batch[sel])
+    ot, op, oe = oracle.match_tiles(qf, dict_feat, didx, dpal, pal, k=64, extended=True)
+    assert np.array_equal(_u32(er)[sel], oe)
+    assert np.array_equal(ti[sel], ot) and np.array_equal(pi[sel], op)
+    # the raw 64-NN of the same rows: same distance multiset, same index set wherever the 64th distance is not tied
+    knn = tm.KnnShort(dict_feat)
+    gi, gd = knn.search(qf, 64)
+    oi, od = oracle.knn_short(dict_feat, qf, 64)
+    assert np.array_equal(_u32(gd), od) and np.array_equal(gi, oi)
+    knn.close()
+    enc.finish_reconstruct()
+
+
+# ------------------------------------------------------------------ configs[2] slice: K = 262 144 centroids
+def test_config_c_assignment_slice_against_exact_f64(tm, oracle):
+    rng = np.random.default_rng(2024)
+    K, n = 262144, 148 * 128 * 2
+    centres = synth.random_features(K, 11, adversarial=True).astype(np.float64)
+    centres += rng.uniform(-0.5, 0.5, size=centres.shape)                      # f64 centroids, not on the int16 lattice
+    pick = rng.integers(0, K, size=n)
+    x = np.clip(np.rint(centres[pick] + rng.normal(0, 25, size=(n, 192))), -32768, 32767).astype(np.int16)
+    labels = np.full(n, -1, np.int32)
+    labels, sums, counts, changed, inertia = tm.kmeans_partial_step_i16(x, centres, labels)
+    sel = rng.choice(n, size=2000, replace=False)
+    oi, od = oracle.knn_double(centres, x[sel].astype(np.float64))
+    assert np.array_equal(np.asarray(labels)[sel], oi)                          # exact f64 decision, first minimum
+    assert changed == n and int(np.asarray(counts).sum()) == n
+    # per-cluster partial sums of the shard: every point lands in its label's row
+    want = np.zeros((K, 192)); np.add.at(want, np.asarray(labels), x.astype(np.float64))
+    assert np.array_equal(np.asarray(sums), want)                               # integer-valued sums: exact in any order
+
+
+# ------------------------------------------------------------------ configs[4] shape: 32 palettes x 256 colours
+@pytest.mark.parametrize("use_tk", [True, False])
+def test_config_e_dither_256_colours_against_oracle(tm, oracle, use_tk):
+    frame = synth.pack_rgb(synth.make_clip(512, 256, 1, cut_every=0, seed=77))[0]
+    tiles = synth.frame_to_tiles(frame)                                        # 2 048 tiles of a generator frame
+    canon, flags = tm.mirror_canonicalise(tiles)
+    bands = (np.arange(len(tiles)) * 32 // len(tiles)).astype(np.int32)        # 32 spatial bands -> 32 palettes
+    pal, _ = tm.palquant_kmeans(canon, bands, 32, 256, seed=7)
+    for p in range(0, 32, 5):
+        want, _ = oracle.quantize_palette(canon[bands == p].reshape(-1), 256, seed=7)
+        assert np.array_equal(np.asarray(pal)[p], want)
+    rng = np.random.default_rng(9)
+    pair_tile = rng.integers(0, len(tiles), size=2048).astype(np.int32)
+    pair_pal = rng.integers(0, 32, size=2048).astype(np.int32)
+    got = tm.dither(canon, flags, pair_pal, pal, use_thomas_knoll=use_tk, y2_mixed_colors=4, pair_tile=pair_tile)
+    want = oracle.dither(canon, flags, pair_pal, np.asarray(pal), use_tk=use_tk, y2_mixed_colors=4, pair_tile=pair_tile)
+    assert np.array_equal(got, want)
+
+
+# ------------------------------------------------------------------ configs[0]: 320x180x24, one keyframe sequence, end to end
+def test_config_a_encode_320x180_against_oracle_pipeline(tm, oracle):
+    """The whole encode against oracle/pipeline.py (which imports nothing from the product).  Stated tolerance: decoded-frame
+    PSNR within 0.05 dB (north star); the stages are deterministic and bit-exact, so the comparison is equality of the
+    dictionary, palettes, tilemap and reconstructed frames, and of the frames the stream decodes to."""
+    from oracle import pipeline as P
+    from tiler_b200 import gtm
+    from tiler_b200.encoder import TilingEncoder, psnr_rgb
+    w, h, n = 320, 180, 24
+    frames = synth.pack_rgb(synth.make_clip(w, h, n, cut_every=0, seed=synth.SEED))
+    seqs = [(0, n - 1)]
+    n_pal, pal_size, tile_count = 64, 16, 4000
+    enc = TilingEncoder(palette_size=pal_size, palette_count=n_pal, seed=0x42381337)
+    res = enc.encode(frames, seqs, tile_count=tile_count, radius=32)
+    ref = P.encode(frames, seqs, tile_count, n_pal, pal_size, 0x42381337, radius=32)
+    assert (ref["tw"], ref["th"]) == (40, 23)                                   # (h - 1) div 8 + 1 (:1776)
+    assert enc.reduce_threshold == ref["threshold"]
+    assert np.array_equal(res["palettes"], ref["palettes"])
+    assert np.array_equal(res["tiles"], ref["tiles"]) and np.array_equal(res["use_count"], ref["use_count"])
+    tmap = res["tilemap"]
+    for key in ("tile_idx", "pal_idx", "pred_x", "pred_y", "is_pred"):
+        assert np.array_equal(np.asarray(tmap[key]).reshape(n, -1), np.asarray(ref[key]).reshape(n, -1)), key
+    assert np.array_equal(res["recon"], ref["recon"])
+    decoded, hdr = gtm.decode_gtm(res["gtm"])
+    assert (hdr["width"], hdr["height"], hdr["frame_count"]) == (320, 184, n)
+    assert np.array_equal(decoded, ref["recon"])
+    src = np.zeros((n, 184, 320), np.int32); src[:, :180] = frames
+    assert abs(psnr_rgb(decoded, src) - psnr_rgb(ref["recon"], src)) <= 0.05
+
+
+# ------------------------------------------------------------------ the reference's real dithered tiles and palettes
+@pytest.mark.parametrize("name", ["city_cif", "football_cif"])
+def test_demo_stream_tiles_features_knn_and_matcher(tm, oracle, name):
+    z = np.load(os.path.join(GOLD, "demo_tiles.npz"))
+    didx, dpal, pal = z[name + "_tiles"], z[name + "_tile_pal"], z[name + "_palettes"]
+    n = len(didx)
+    dict_feat = oracle.features_from_pal(didx, dpal, pal)
+    assert np.array_equal(tm.features_from_pal(didx, dpal, pal), dict_feat)     # all 20 000 real tiles, bit-exact
+    # queries: the RGB rendering of every 9th tile under ANOTHER palette of the same stream (what the extended re-rank sees)
+    rng = np.random.default_rng(4)
+    qsel = np.arange(0, n, 9)
+    qpal = rng.integers(0, len(pal), size=len(qsel))
+    q_rgb = pal[qpal[:, None], didx[qsel]].astype(np.int32)
+    qf = oracle.features_from_rgb(q_rgb)
+    assert np.array_equal(tm.features_from_rgb(q_rgb), qf)
+    knn = tm.KnnShort(dict_feat)
+    for k in (1, 64):
+        gi, gd = knn.search(qf[:700], k)
+        oi, od = oracle.knn_short(dict_feat, qf[:700], k)
+        assert np.array_equal(_u32(gd), od), k
+        ties = (od[:, -1:] == od).sum(1) > 1 if k > 1 else np.zeros(len(od), bool)
+        assert np.array_equal(gi[~ties], oi[~ties]) and np.array_equal(gi, oi), k   # identical tie order as well ((distance, index))
+    knn.close()
+    m = tm.Matcher(didx, dpal, pal, extended=True)
+    ti, pi, er = m.match_rgb(q_rgb[:700], 64)
+    ot, op, oe = oracle.match_tiles(qf[:700], dict_feat, didx, dpal, pal, k=64, extended=True)
+    assert np.array_equal(_u32(er), oe) and np.array_equal(ti, ot) and np.array_equal(pi, op)
+    m.close()
+    # re-dithering the rendered real tiles against their own real palette (Thomas Knoll and Yliluoma)
+    flags = np.zeros(256, np.uint8)
+    rgb_own = pal[dpal[:256, None], didx[:256]].astype(np.int32)
+    for use_tk in (True, False):
+        assert np.array_equal(tm.dither(rgb_own, flags, dpal[:256], pal, use_thomas_knoll=use_tk),
+                              oracle.dither(rgb_own, flags, dpal[:256], pal, use_tk=use_tk))
+
+
+# ------------------------------------------------------------------ DoPalettization chain and its coreset stand-in
+def test_palettization_chain_against_oracle(tm, oracle):
+    from oracle import pipeline as P
+    from tiler_b200.encoder import TilingEncoder
+    tiles = rand_tiles(3000, 31)
+    use = np.random.default_rng(2).integers(1, 40, size=3000).astype(np.int32)
+    feats = np.stack([oracle.tile_features_f64(t, oracle.PVS_WEIGHTED_SPE_DCT, True) for t in tiles])
+    got_c, got_w = tm.coreset_weighted(feats, use.astype(np.float64), 96, seed=0x42381337)
+    ref_c, ref_w = oracle.coreset_weighted(feats, use.astype(np.float64), 96, seed=0x42381337)
+    assert np.array_equal(got_c, ref_c) and np.array_equal(got_w, ref_w)       # the BICO stand-in, bit for bit
+    # drop-in BICO symbols: the same summary through bico_create / insert_line / get_results
+    b = tm.Bico(192, 3000, 96, 32, 96, 0x42381337)
+    for row, wt in zip(feats, use):
+        b.insert_line(row, float(wt))
+    bc, bw = b.get_results()
+    b.destroy()
+    assert np.array_equal(bc, ref_c) and np.array_equal(bw, ref_w)
+    for n_pal in (12, 1):
+        enc = TilingEncoder(palette_size=16, palette_count=n_pal, seed=0x42381337)
+        enc.tiles, enc.tile_flags, enc.use_count = tiles, np.zeros(3000, np.uint8), use
+        enc.prepare_palettes()
+        # the GPU features are within 1e-5 relative of the oracle's (libm pow), so the chain is compared from the oracle's own
+        # features only where no decision sits inside that tolerance: labels must agree on >= 99.9 % of the tiles
+        want = P.palettize(tiles, use, n_pal, 0x42381337)
+        agree = (np.asarray(enc.tile_pal) == want).mean()
+        assert agree >= 0.999, agree
+    # coreset smaller than the palette count: identity mapping (:4214-4219)
+    enc = TilingEncoder(palette_size=16, palette_count=64, seed=1)
+    enc.tiles, enc.tile_flags, enc.use_count = tiles[:40], np.zeros(40, np.uint8), use[:40]
+    enc.prepare_palettes()
+    assert enc.coreset_size == 40 and len(np.unique(np.asarray(enc.tile_pal))) == 40
+
+
+# ------------------------------------------------------------------ the CUDA-core motion kernel (QuickTest prune), bit-exact too
+def test_motion_scalar_kernel_in_subprocess():
+    """abi.cu reads TM_MOTION_SCALAR once per process: run the motion / Reconstruct parity tests again in a child process with
+    the CUDA-core kernel (motion_search_kernel: QuickTestEuclideanDCTPtr prune, utils.pas:755-759) selected."""
+    env = dict(os.environ, TM_MOTION_SCALAR="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_core.py"), "-m", "gpu", "-q", "-x", "-k",
+                        "motion_search_bit_exact or reconstruct_sequence_bit_exact or predict_motion_frame"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+
+
+# ------------------------------------------------------------------ one process driving two devices (per-device state)
+def test_two_devices_in_one_process(tm, oracle):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process (gpurun --gpus 2)")
+    d = synth.random_features(3000, 1)
+    q = synth.random_features(500, 2)
+    oi, od = oracle.knn_short(d, q, 64)
+    tiles = rand_tiles(64, 3)
+    want_f = oracle.features_from_rgb(tiles)
+    for dev in (0, 1, 0):
+        dd, qq = torch.from_numpy(d).to(f"cuda:{dev}"), torch.from_numpy(q).to(f"cuda:{dev}")
+        knn = tm.KnnShort(dd)
+        gi, gd = knn.search(qq, 64)
+        assert np.array_equal(gi.cpu().numpy(), oi) and np.array_equal(_u32(gd.cpu().numpy()), od)
+        knn.close()
+        f = tm.features_from_rgb(torch.from_numpy(tiles).to(f"cuda:{dev}"))
+        assert np.array_equal(f.cpu().numpy(), want_f)
+        f64 = tm.features_f64(torch.from_numpy(tiles).to(f"cuda:{dev}"))
+        assert f64.device.index == dev

@@ -50,6 +50,7 @@ SIGNATURES = {
     "tm_kmeans_partial_step_i16": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_dbl)]),
     "tm_kmeans_partial_step": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_dbl)]),
     "tm_kmeans_finish_step": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
+    "tm_coreset_weighted": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _i32, _u64, _vp, _vp, C.POINTER(_i64)]),
     "tm_palquant_kmeans": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _u64, _vp, C.POINTER(_i32)]),
     "tm_dl3quant_batch": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),
     "tm_dl1quant_batch": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp]),

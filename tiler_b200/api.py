@@ -224,6 +224,20 @@ def kmeans_fit(x, k, init=None, seed=1, max_iter=300, nan_empty=False):
     return labels, cent, inertia.value, iters.value
 
 
+def coreset_weighted(x, w, k, seed, max_iter=8):
+    """The BICO stand-in (bico_create / insert_line / get_results, tilingencoder.pas:4149-4172) in one call: <= k weighted
+    summary points of the weighted rows x [n, dim].  -> (centroids [m, dim], weights [m]) as numpy arrays (the host sizes
+    its next step from m, :4168)."""
+    c = _Call(x, w)
+    n, dim = x.shape
+    cent = np.empty((int(k), int(dim)), dtype=np.float64)
+    wts = np.empty(int(k), dtype=np.float64)
+    m = C.c_int64()
+    check(_lib.lib().tm_coreset_weighted(c.inp(x, np.float64), c.inp(w, np.float64), n, int(dim), int(k), int(max_iter), C.c_uint64(seed),
+                                         C.c_void_p(cent.ctypes.data), C.c_void_p(wts.ctypes.data), C.byref(m)))
+    return cent[:m.value].copy(), wts[:m.value].copy()
+
+
 def kmeans_fit_i16(x, k, init, max_iter=300, nan_empty=False):
     """Lloyd on int16 feature rows [n,192]: tensor-core candidate search + exact f64 decision (tm_kmeans_fit_i16).
     -> labels, centroids (f64), inertia, iterations, number of points that needed the exact f64 fallback."""

@@ -54,25 +54,27 @@ static int fail(int code, const char *what) {
 #define CU(x) do { if ((x) != cudaSuccess) return fail(TM_ERR_CUDA, #x); } while (0)
 #define RC(x) do { int _rc = (x); if (_rc != TM_OK) return fail(_rc, #x); } while (0)
 
-static int g_gpu_ok = -1;
+// The current device of the calling thread is checked (and its memory pool configured) once PER DEVICE: a process may drive
+// several (tm_set_device, or the caller's own cudaSetDevice between calls).
+static int g_gpu_ok[TM_MAX_DEVICES + 1];   // 0 unknown, 1 usable, -1 not an sm_100 device; [TM_MAX_DEVICES] = "no device at all"
 static int require_gpu() {
-  if (g_gpu_ok < 0) {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { cudaGetLastError(); g_gpu_ok = 0; }
-    else {
-      int dev = 0; cudaGetDevice(&dev);
-      cudaDeviceProp p;
-      g_gpu_ok = (cudaGetDeviceProperties(&p, dev) == cudaSuccess && p.major == 10) ? 1 : 0;
-      if (g_gpu_ok) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-          unsigned long long thr = ~0ull;
-          cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
+  int n = 0;
+  int &none = g_gpu_ok[TM_MAX_DEVICES];
+  if (none == 0) none = (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) ? -1 : 1;
+  if (none < 0) { cudaGetLastError(); return fail(TM_ERR_NOGPU, "no sm_100 (B200) device: libtm_gpu has no CPU fallback"); }
+  const int dev = cur_device();
+  if (g_gpu_ok[dev] == 0) {
+    cudaDeviceProp p;
+    g_gpu_ok[dev] = (cudaGetDeviceProperties(&p, dev) == cudaSuccess && p.major == 10) ? 1 : -1;
+    if (g_gpu_ok[dev] > 0) {
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
       }
     }
   }
-  if (!g_gpu_ok) return fail(TM_ERR_NOGPU, "no sm_100 (B200) device: libtm_gpu has no CPU fallback");
+  if (g_gpu_ok[dev] < 0) return fail(TM_ERR_NOGPU, "no sm_100 (B200) device: libtm_gpu has no CPU fallback");
   return TM_OK;
 }
 
@@ -132,9 +134,10 @@ struct Stage {
 };
 
 static int num_sms() {
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
-  return sms;
+  static int sms[TM_MAX_DEVICES] = {};
+  const int dev = cur_device();
+  if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+  return sms[dev];
 }
 
 // ------------------------------------------------------------------ handles
@@ -173,7 +176,7 @@ extern "C" int tm_device_count(void) {
   for (int i = 0; i < n; ++i) { cudaDeviceProp p; if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok; }
   return ok;
 }
-extern "C" int tm_set_device(int device) { CU(cudaSetDevice(device)); g_gpu_ok = -1; return TM_OK; }
+extern "C" int tm_set_device(int device) { CU(cudaSetDevice(device)); return TM_OK; }
 extern "C" int tm_set_stream(void *s) { t_stream = (cudaStream_t)s; return TM_OK; }
 extern "C" const char *tm_last_error(void) { return t_err.c_str(); }
 extern "C" int64_t tm_kernel_launches(void) { return (int64_t)g_launches.load(); }
@@ -771,20 +774,27 @@ extern "C" int tm_match_tiles_rgb(tm_matcher *m, const int32_t *rgb, int64_t n_q
     int64_t cut[5] = {0, first, first + piece, first + 2 * piece, n_q};
     for (int i = 2; i < 4; ++i) if (cut[i] > n_q) cut[i] = n_q;
     if (s.err == TM_OK) {
-      CU(cudaEventRecord(ev[4], s.st));   // the scratch (stream-ordered allocation on s.st) exists
-      CU(cudaStreamWaitEvent(cs, ev[4], 0));
-      for (int i = 0; i < 4; ++i) {
+      // Copy i + 1 is queued AFTER the kernels of piece i are launched: with pageable input the host blocks inside
+      // cudaMemcpyAsync while it stages the bytes, and this order lets the resident piece be matched meanwhile.  No early
+      // return below: every exit first drains the copy stream, so neither the scratch (freed on s.st) nor the caller's host
+      // buffer is still in use by a copy when the call returns.
+      auto ok = [&](cudaError_t e) { if (e != cudaSuccess && s.err == TM_OK) s.err = TM_ERR_CUDA; return e == cudaSuccess; };
+      auto queue_copy = [&](int i) {
         const int64_t off = cut[i], n = cut[i + 1] - off;
-        if (n > 0) CU(cudaMemcpyAsync(d_rgb + off * 64, rgb + off * 64, (size_t)n * 256, cudaMemcpyHostToDevice, cs));
-        CU(cudaEventRecord(ev[i], cs));
-      }
+        if (n > 0) ok(cudaMemcpyAsync(d_rgb + off * 64, rgb + off * 64, (size_t)n * 256, cudaMemcpyHostToDevice, cs));
+        ok(cudaEventRecord(ev[i], cs));
+      };
+      ok(cudaEventRecord(ev[4], s.st));   // the scratch (stream-ordered allocation on s.st) exists
+      ok(cudaStreamWaitEvent(cs, ev[4], 0));
+      if (s.err == TM_OK) queue_copy(0);
       for (int i = 0; i < 4 && s.err == TM_OK; ++i) {
         const int64_t off = cut[i], n = cut[i + 1] - off;
-        if (n <= 0) continue;
-        CU(cudaStreamWaitEvent(s.st, ev[i], 0));
-        s.err = launch_features_rgb(d_rgb + off * 64, n, d_feat + off * 192, s.st);
-        if (s.err == TM_OK) s.err = match_feat_dev(m, d_feat + off * 192, n, k, d_tile + off, d_pal + off, d_err + off, s);
+        ok(cudaStreamWaitEvent(s.st, ev[i], 0));
+        if (n > 0 && s.err == TM_OK) s.err = launch_features_rgb(d_rgb + off * 64, n, d_feat + off * 192, s.st);
+        if (n > 0 && s.err == TM_OK) s.err = match_feat_dev(m, d_feat + off * 192, n, k, d_tile + off, d_pal + off, d_err + off, s);
+        if (i + 1 < 4 && s.err == TM_OK) queue_copy(i + 1);
       }
+      if (s.err != TM_OK) cudaStreamSynchronize(cs);
     }
     RC(s.finish());
     return TM_OK;
@@ -1108,33 +1118,48 @@ extern "C" void bico_insert_line(tm_bico *b, const double *row, double weight) {
   b->rows.insert(b->rows.end(), row, row + b->dim);
   b->weights.push_back(weight);
 }
-extern "C" int64_t bico_get_results(tm_bico *b, double *centroids, double *weights) {
-  if (!b || !centroids) return 0;
-  const int64_t n = (int64_t)b->weights.size();
-  const int dim = (int)b->dim;
-  if (n == 0) return 0;
-  if (n <= b->coreset) {   // every point is its own summary
-    memcpy(centroids, b->rows.data(), (size_t)n * dim * sizeof(double));
-    if (weights) memcpy(weights, b->weights.data(), (size_t)n * sizeof(double));
-    return n;
-  }
-  if (require_gpu() != TM_OK) return 0;
-  const int k = (int)b->coreset;
+// The BICO stand-in as one batched call: <= k weighted summary points of n weighted rows (host or device arrays in; the
+// summary always comes back to HOST arrays: the host reads the count to size its next step, tilingencoder.pas:4168).
+// n <= k: identity.  Else unweighted k-means++ seeding, at most max_iter weighted Lloyd updates, empty clusters dropped
+// (oracle/tm_oracle.c: tmo_coreset_weighted defines the result bit for bit).
+extern "C" int tm_coreset_weighted(const double *x, const double *w, int64_t n, int dim, int64_t k, int max_iter, uint64_t seed,
+                                   double *centroids, double *weights, int64_t *count) {
+  RC(require_gpu());
+  if (!x || !w || !centroids || !count || n < 1 || n > 0x7fffffff || dim < 1 || dim > 1024 || k < 1 || k > 0x7fffffff || max_iter < 1 ||
+      is_device_ptr(centroids) || is_device_ptr(weights))
+    return fail(TM_ERR_ARG, "tm_coreset_weighted: bad argument (centroids / weights are host arrays)");
   std::lock_guard<std::recursive_mutex> lk(g_mu);
   Stage s(t_stream);
-  const double *d_x = s.in(b->rows.data(), (size_t)n * dim), *d_w = s.in(b->weights.data(), (size_t)n);
+  if (n <= k) {   // every point is its own summary
+    CU(cudaMemcpyAsync(centroids, x, (size_t)n * dim * 8, cudaMemcpyDefault, s.st));
+    if (weights) CU(cudaMemcpyAsync(weights, w, (size_t)n * 8, cudaMemcpyDefault, s.st));
+    CU(cudaStreamSynchronize(s.st));
+    *count = n;
+    return TM_OK;
+  }
+  const double *d_x = s.in(x, (size_t)n * dim), *d_w = s.in(w, (size_t)n);
   int32_t *d_labels = (int32_t *)s.temp((size_t)n * 4);
   std::vector<double> h_cent((size_t)k * dim), h_ws((size_t)k);
   double *d_cent = s.out(h_cent.data(), (size_t)k * dim), *d_ws = s.out(h_ws.data(), (size_t)k);
-  // weighted Lloyd (bounded effort: a coreset is a summary, not a converged clustering)
-  if (s.err == TM_OK) s.err = kmeans_fit_dev(d_x, d_w, n, dim, k, 8, nullptr, b->seed, 0, d_labels, d_cent, d_ws, nullptr, nullptr, s);
-  if (s.finish(true) != TM_OK) { fail(TM_ERR_CUDA, "bico_get_results"); return 0; }
+  if (s.err == TM_OK) s.err = kmeans_fit_dev(d_x, d_w, n, dim, (int)k, max_iter, nullptr, seed, 0, d_labels, d_cent, d_ws, nullptr, nullptr, s);
+  RC(s.finish(true));
   int64_t m = 0;
-  for (int c = 0; c < k; ++c) {
+  for (int64_t c = 0; c < k; ++c) {
     if (!(h_ws[c] > 0.0)) continue;   // drop empty clusters: the host accepts any count <= coresetsize (:4168)
     memcpy(centroids + (size_t)m * dim, &h_cent[(size_t)c * dim], (size_t)dim * sizeof(double));
     if (weights) weights[m] = h_ws[c];
     ++m;
   }
+  *count = m;
+  return TM_OK;
+}
+
+extern "C" int64_t bico_get_results(tm_bico *b, double *centroids, double *weights) {
+  if (!b || !centroids) return 0;
+  const int64_t n = (int64_t)b->weights.size();
+  if (n == 0) return 0;
+  int64_t m = 0;
+  // bounded effort (8 weighted Lloyd updates): a coreset is a summary, not a converged clustering
+  if (tm_coreset_weighted(b->rows.data(), b->weights.data(), n, (int)b->dim, b->coreset, 8, b->seed, centroids, weights, &m) != TM_OK) return 0;
   return m;
 }

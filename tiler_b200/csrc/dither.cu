@@ -204,17 +204,20 @@ dither_kernel(const int32_t *__restrict__ rgb, const uint8_t *__restrict__ mirro
   out_idx[pair * 64 + px] = result;
 }
 
-static Plan *g_plans = nullptr;
-static int g_plans_cap = 0;
+static Plan *g_plans_dev[TM_MAX_DEVICES] = {};   // mixing plans of the palettes, per device
+static int g_plans_cap_dev[TM_MAX_DEVICES] = {};
 
 int launch_dither(const int32_t *rgb, const uint8_t *mirror_flags, const int32_t *pair_tile, const int32_t *pair_pal,
                   int64_t n_pairs, const int32_t *palettes, int pal_size, int n_pal, int use_tk, int y2_mixed, uint8_t *out_idx,
                   cudaStream_t st) {
   if (n_pairs <= 0) return TM_OK;
   if (pal_size < 1 || pal_size > MAXP || n_pal < 1 || y2_mixed < 1 || y2_mixed > 16) return TM_ERR_ARG;
+  Plan *&g_plans = g_plans_dev[cur_device()];
+  int &g_plans_cap = g_plans_cap_dev[cur_device()];
   if (n_pal > g_plans_cap) {
     if (g_plans) cudaFree(g_plans);
     g_plans = nullptr;
+    g_plans_cap = 0;
     if (cudaMalloc(&g_plans, sizeof(Plan) * (size_t)n_pal) != cudaSuccess) return TM_ERR_NOMEM;
     g_plans_cap = n_pal;
   }
@@ -222,11 +225,10 @@ int launch_dither(const int32_t *rgb, const uint8_t *mirror_flags, const int32_t
   note_launch(2);
   const size_t smem = (size_t)2 * pal_size * sizeof(int4) + (size_t)pal_size * 128;
   const unsigned grid = (unsigned)((n_pairs + 1) / 2);
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[TM_MAX_DEVICES] = {};
+  if (first_use_on_device(attr)) {
     cudaFuncSetAttribute(dither_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MAXP * 16 + MAXP * 128);
     cudaFuncSetAttribute(dither_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * MAXP * 16 + MAXP * 128);
-    attr = true;
   }
   if (use_tk)
     dither_kernel<true><<<grid, 128, smem, st>>>(rgb, mirror_flags, pair_tile, pair_pal, n_pairs, g_plans, y2_mixed, out_idx);

@@ -48,8 +48,10 @@ __constant__ double c_weights[192] = {
 
 // DCT bases built on the host exactly as InitLuts does (tilingencoder.pas:1703-1714): [special][v][u][y][x].
 // Device copies are transposed to [special][pixel][coefficient].
-static float *g_lutT_f32 = nullptr;   // [2][64][64]
-static double *g_lutT_f64 = nullptr;  // [2][64][64]
+static float *g_lutT_f32_dev[TM_MAX_DEVICES] = {};   // [2][64][64] per device
+static double *g_lutT_f64_dev[TM_MAX_DEVICES] = {};  // [2][64][64] per device
+#define g_lutT_f32 (g_lutT_f32_dev[cur_device()])
+#define g_lutT_f64 (g_lutT_f64_dev[cur_device()])
 
 int features_init(cudaStream_t st) {
   if (g_lutT_f32) return TM_OK;
@@ -348,11 +350,10 @@ int launch_features_f64(const int32_t *rgb, int64_t n, int mode, int use_lab, do
   int rc = features_init(st);
   if (rc) return rc;
   const int special = (mode == 3 || mode == 4), weighted = (mode == 1 || mode == 4);
-  static bool attr = false;
-  if (!attr) {
+  static bool attr[TM_MAX_DEVICES] = {};
+  if (first_use_on_device(attr)) {
     if (cudaFuncSetAttribute(features_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * (int)sizeof(double)) != cudaSuccess)
       return TM_ERR_CUDA;
-    attr = true;
   }
   features_f64_kernel<<<grid_for(n, 2), 192, 4096 * sizeof(double), st>>>(rgb, n, weighted, use_lab, g_lutT_f64 + special * 4096, out);
   note_launch();

@@ -74,6 +74,9 @@ constexpr int KMAX = 64;         // largest k
 #ifndef TM_K1_NH
 #define TM_K1_NH 2
 #endif
+#ifndef TM_STAG
+#define TM_STAG 0
+#endif
 
 // ------------------------------------------------------------------ k = 1 kernel: 8 epilogue warps
 // Same pipeline as above, but every TMEM lane quarter is drained by TWO warps (w and w + 4 may both address quarter
@@ -97,7 +100,8 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
   uint64_t *bars = reinterpret_cast<uint64_t *>(s_merge + BM * KS * (NH - 1));
   uint64_t *full = bars, *empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + 1, *t_full = a_empty + 1,
            *t_empty = t_full + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+  uint64_t *stag = t_empty + 2;   // [4 quarters][NH splits][2 stages]: warp h of a quarter has its TMEM reads in flight
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(stag + 4 * NH * 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (n_dict + BN - 1) / BN;
@@ -108,6 +112,7 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
     mbar_init(a_full, 4);
     mbar_init(a_empty, 2);
     for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], NEW); }
+    for (int g = 0; g < 4 * NH * 2; ++g) mbar_init(&stag[g], 1);
     fence_barrier_init();
   }
   if (warp == NEW + 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -213,6 +218,12 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
           nd[4 * v] = t4.x + nq; nd[4 * v + 1] = t4.y + nq; nd[4 * v + 2] = t4.z + nq; nd[4 * v + 3] = t4.w + nq;
         }
         mbar_wait(&t_full[ts], (it >> 1) & 1);
+#if TM_STAG
+        // The warps of a lane quarter take turns on the quarter's TMEM read port: warp h starts its reads only when warp
+        // h - 1 has its own in flight (TM_STAG = 1) or complete (2).  Left alone the warps run in lock-step -- all read,
+        // then all compute -- and the read port idles while the ALUs work and vice versa.
+        if (h > 0) mbar_wait(&stag[((q * NH + h - 1) << 1) | ts], (it >> 1) & 1);
+#endif
         tc_fence_after();
         const uint32_t t_acc = t_lane + ts * ACC_COLS + h * HN;
         // one burst: all three accumulators of this thread's 32 columns, then the stage goes straight back to the tensor
@@ -224,7 +235,13 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
           tmem_ld16(t_acc + BN + c * 16, reinterpret_cast<uint32_t(&)[16]>(xx[c * 16]));
           tmem_ld16(t_acc + 2 * BN + c * 16, reinterpret_cast<uint32_t(&)[16]>(lo[c * 16]));
         }
+#if TM_STAG == 1
+        if (h < NH - 1 && lane == 0) mbar_arrive(&stag[((q * NH + h) << 1) | ts]);
+#endif
         tmem_ld_wait();
+#if TM_STAG == 2
+        if (h < NH - 1 && lane == 0) mbar_arrive(&stag[((q * NH + h) << 1) | ts]);
+#endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[ts]);
@@ -326,9 +343,13 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
 #endif
 constexpr int TK_CAP = TM_TK_CAP;  // candidate slots per (query row, column half)
 constexpr int TK_SLACK = 16;     // a loose cut keeps between k and k + TK_SLACK candidates
+constexpr int TK_CUT_FIRST = 4, TK_CUT_RATIO = 4;   // scheduled row-wide cuts after 4, 16, 64, 256, ... dictionary tiles
 constexpr int TK_THREADS = 352;  // 8 epilogue warps + TMA warp + 2 MMA issuer warps
-constexpr int STAGES_TK = 7;     // dictionary ring depth of the top-k kernels (one stage less than k = 1: 32 KB stage the distances)
-constexpr int TK_STAGE_B = 256 * 32 * 4;   // staged distances: 32 per epilogue thread
+constexpr int STAGES_TK = 8;     // dictionary ring depth of the top-k kernel
+// Ring of dictionary-norm slots (64 norms = 256 bytes per tile, copied by the TMA producer next to the tile).  A slot is read
+// by the epilogue right after the TMEM read of its tile and rewritten STAGES_TK + 3 tiles later at the earliest (the
+// producer runs at most STAGES_TK tiles ahead of MMA completion, the MMAs at most 2 tiles ahead of the TMEM reads).
+constexpr int TK_NRING = STAGES_TK + 4;
 
 __device__ __forceinline__ unsigned long long ldg_key(const unsigned long long *p) {
   unsigned long long v;
@@ -449,43 +470,6 @@ __device__ __forceinline__ void tk_tile32(unsigned long long &waddr, uint32_t ta
   }
 }
 
-// tk_tile32 with the admissions driven by each lane's OWN pair mask.  The 32 distances of a thread are parked in shared
-// memory (8 conflict-free 16-byte stores), then a lane loops over the set bits of its mask, reads the pair back with a
-// dynamically indexed load and admits it.  The warp-uniform version above walks 16 "does any lane admit pair e" branches
-// per tile; with two warps per scheduler nothing hides a branch bubble, and those 16 branches cost more than the
-// admissions themselves.  Here a lane that admits nothing (most lanes, most tiles) skips everything, and the loop runs
-// max-over-lanes(popcount) ~ 2 times.  Measured: 28.5 vs 29.7 ms on random features, 30.0 vs 29.05 ms on the bench's image
-// features (admissions come in runs there, so one lane iterates while 31 wait): kept as an experiment (TM_TK_DBG=32).
-__device__ __forceinline__ void tk_tile32s(unsigned long long &waddr, uint32_t tau, uint32_t nq, int col, const uint32_t (&ndA)[16],
-                                           uint32_t (&ppA)[16], const uint32_t (&xxA)[16], const uint32_t (&loA)[16],
-                                           const uint32_t (&ndB)[16], uint32_t (&ppB)[16], const uint32_t (&xxB)[16],
-                                           const uint32_t (&loB)[16], uint32_t s_stage /* this warp's 4 KB + lane * 16 */) {
-#pragma unroll
-  for (int e = 0; e < 16; ++e) ppA[e] = tk_dist(ndA[e] + nq, ppA[e], xxA[e], loA[e]);
-#pragma unroll
-  for (int e = 0; e < 16; ++e) ppB[e] = tk_dist(ndB[e] + nq, ppB[e], xxB[e], loB[e]);
-  uint32_t m = 0;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) m |= (min(ppA[2 * e], ppA[2 * e + 1]) <= tau) ? (1u << e) : 0u;
-#pragma unroll
-  for (int e = 0; e < 8; ++e) m |= (min(ppB[2 * e], ppB[2 * e + 1]) <= tau) ? (0x100u << e) : 0u;
-  if (m != 0) {
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(s_stage + c * 512), "r"(ppA[4 * c]), "r"(ppA[4 * c + 1]), "r"(ppA[4 * c + 2]), "r"(ppA[4 * c + 3]) : "memory");
-      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(s_stage + (4 + c) * 512), "r"(ppB[4 * c]), "r"(ppB[4 * c + 1]), "r"(ppB[4 * c + 2]), "r"(ppB[4 * c + 3]) : "memory");
-    }
-    do {
-      const int e = __ffs(m) - 1;   // pair e = columns col + 2 e, col + 2 e + 1: 16-byte chunk e / 2, half e & 1
-      m &= m - 1;
-      uint32_t d0, d1;
-      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(d0), "=r"(d1) : "r"(s_stage + (e >> 1) * 512 + (e & 1) * 8) : "memory");
-      tk_admit(waddr, (uint32_t)(col + 2 * e), d0, tau);
-      tk_admit(waddr, (uint32_t)(col + 2 * e + 1), d1, tau);
-    } while (m != 0);
-  }
-}
-
 // half_out (optional): some value Th <= T_out with at least kh entries <= Th -- the first probe of the bisection whose count
 // fell in [kh, k), for free; T_out itself when no probe did.
 template <int NE>
@@ -581,22 +565,70 @@ __device__ __forceinline__ int tk_cut(unsigned long long *buf, int n, int k, int
   return outp;
 }
 
+// Whole warp: ROW-WIDE cut of the two strips of one query row (b0: column half 0, b1: column half 1; n0 / n1 entries).
+// Finds T leaving between k and k + slack entries of the UNION at or below it (a valid admission threshold for every later
+// column of the row, and ~sqrt(2) tighter in rank than what either strip could certify alone), compacts each strip in
+// place and returns the new counts.  With fewer than k entries in the union nothing can be dropped.
+// Scheduled cuts call this for every row of the CTA at the same dictionary tile, so no warp waits for another warp's cut,
+// and two rows are in flight per call site (the loads of the second row overlap the selection of the first).
+__device__ __forceinline__ void tk_row_load(const unsigned long long *b0, const unsigned long long *b1, int n0, int n1, int lane,
+                                            uint32_t (&dd)[2 * (TK_CAP / 32)], uint32_t (&ii)[2 * (TK_CAP / 32)]) {
+  constexpr int NE = TK_CAP / 32;
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    const int p = i * 32 + lane;
+    const unsigned long long k0 = p < n0 ? ldg_key(b0 + p) : ~0ull, k1 = p < n1 ? ldg_key(b1 + p) : ~0ull;
+    dd[i] = (uint32_t)(k0 >> 32); ii[i] = (uint32_t)k0;
+    dd[NE + i] = (uint32_t)(k1 >> 32); ii[NE + i] = (uint32_t)k1;
+  }
+}
+__device__ __forceinline__ uint32_t tk_row_cut(unsigned long long *b0, unsigned long long *b1, int n0, int n1, int k, int slack, int lane,
+                                               const uint32_t (&dd)[2 * (TK_CAP / 32)], const uint32_t (&ii)[2 * (TK_CAP / 32)], int &c0,
+                                               int &c1) {
+  constexpr int NE = TK_CAP / 32;
+  c0 = n0; c1 = n1;
+  if (n0 + n1 <= k) return 0xFFFFFFFEu;
+  uint32_t T, TI;
+  tk_threshold<2 * NE>(dd, ii, n0 + n1, k, slack, T, TI);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  int o0 = 0, o1 = 0;
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    const bool keep = (dd[i] < T) || (dd[i] == T && ii[i] <= TI && dd[i] != 0xFFFFFFFFu);
+    const uint32_t km = __ballot_sync(0xffffffffu, keep);
+    if (keep) stg_key(b0 + o0 + __popc(km & lt_mask), ((unsigned long long)dd[i] << 32) | ii[i]);
+    o0 += __popc(km);
+  }
+#pragma unroll
+  for (int i = 0; i < NE; ++i) {
+    const bool keep = (dd[NE + i] < T) || (dd[NE + i] == T && ii[NE + i] <= TI && dd[NE + i] != 0xFFFFFFFFu);
+    const uint32_t km = __ballot_sync(0xffffffffu, keep);
+    if (keep) stg_key(b1 + o1 + __popc(km & lt_mask), ((unsigned long long)dd[NE + i] << 32) | ii[NE + i]);
+    o1 += __popc(km);
+  }
+  c0 = o0; c1 = o1;
+  return T;
+}
+
 __global__ void __launch_bounds__(TK_THREADS, 1)
 knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUtensorMap tmap_d,
                    const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict, int k,
                    int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist, int tile_stride,
-                   unsigned long long *ws /* [gridDim.x][256][TK_CAP], 2 KB aligned */, int slack, int dbg) {
+                   unsigned long long *ws /* [gridDim.x][256][TK_CAP], 2 KB aligned */, int slack, int dbg, int cut_first,
+                   int cut_ratio /* scheduled row-wide cuts after cut_first, cut_first * cut_ratio, ... tiles; 0 = none */) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int NST = STAGES_TK;
   uint8_t *sB = smem;
-  uint8_t *s_dist = sB + NST * B_TILE;                                // [8 warps][8 chunks][32 lanes][16 B] staged distances
-  int32_t *s_cnt = reinterpret_cast<int32_t *>(s_dist + TK_STAGE_B);  // [256] candidates per thread at the end of a query block
+  int32_t *s_cnt = reinterpret_cast<int32_t *>(sB + NST * B_TILE);    // [256] candidates per thread (row-wide cuts, end of a query block)
   uint32_t *s_thalf = reinterpret_cast<uint32_t *>(s_cnt + 256);      // [2][128] half-thresholds published by the strips of a row
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_thalf + 256);
+  uint32_t *s_tau = s_thalf + 256;                                    // [128] row-wide threshold left by a scheduled cut
+  uint32_t *s_nd = s_tau + 128;                                       // [TK_NRING][64] dictionary norms of the tiles in flight
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_nd + TK_NRING * BN);
   uint64_t *full = bars, *empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + 1, *t_full = a_empty + 1,
            *t_empty = t_full + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
+  uint64_t *stag = t_empty + 2;   // [4 quarters][2 stages]: the first warp of a quarter has its TMEM reads in flight
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(stag + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (n_dict + BN - 1) / BN;
@@ -608,6 +640,7 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
     mbar_init(a_full, 4);
     mbar_init(a_empty, 2);
     for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], 8); }
+    for (int g = 0; g < 8; ++g) mbar_init(&stag[g], 1);
     fence_barrier_init();
   }
   if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -628,8 +661,9 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
           const uint32_t s = it % NST, r = it / NST;
           mbar_wait(&empty[s], (r & 1) ^ 1);
           if (dbg & 2) { mbar_arrive(&full[s]); jt += tile_stride; if (jt >= n_tiles) jt -= n_tiles; continue; }   // timing experiment: no dictionary traffic
-          mbar_expect_tx(&full[s], B_TILE);
+          mbar_expect_tx(&full[s], B_TILE + BN * 4);
           for (int c = 0; c < 3; ++c) tma_load_2d(sB + s * B_TILE + c * CHUNK_B, &tmap_d, &full[s], c * 128, jt * BN);
+          bulk_load_1d(s_nd + (it % TK_NRING) * BN, dnorm + (size_t)jt * BN, BN * 4, &full[s]);   // norms are padded to whole tiles
           jt += tile_stride;
           if (jt >= n_tiles) jt -= n_tiles;
         }
@@ -669,7 +703,6 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
     const int row = q * 32 + lane;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     constexpr int HN = BN / 2;   // 32 columns per thread and tile
-    const uint32_t s_stage = smem_u32(s_dist) + (uint32_t)(warp * 4096 + lane * 16);
     unsigned long long *cta_ws = ws + (size_t)blockIdx.x * 256 * TK_CAP;
     unsigned long long *wbuf = cta_ws + (size_t)(warp * 32) * TK_CAP;   // this warp's 32 strips
     unsigned long long *mybuf = wbuf + (size_t)lane * TK_CAP;
@@ -703,25 +736,19 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
    // distances of 0xFFFFFFFF (masked columns) are never admitted
       unsigned long long waddr = (unsigned long long)(uintptr_t)mybuf;   // next free slot of this thread's strip
       uint32_t my_half = 0xFFFFFFFFu;                                     // this strip's published half-threshold
-      volatile uint32_t *oth_half = s_thalf + (h ^ 1) * 128 + row;        // the partner strip's (same row, other column half)
       int jt = 0;
+      int next_cut = cut_first > 0 ? cut_first : 0x7fffffff;
       TKT(0)
       for (int j = 0; j < n_tiles; ++j, ++it) {
         const uint32_t ts = it & 1;
         const int col0 = jt * BN + h * HN;
         jt += tile_stride;
         if (jt >= n_tiles) jt -= n_tiles;
-        // dictionary norms of this tile half: independent of the MMA, so fetched before waiting for it
-        uint32_t ndA[16], ndB[16];
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(dnorm + col0) + v);
-          ndA[4 * v] = t4.x; ndA[4 * v + 1] = t4.y; ndA[4 * v + 2] = t4.z; ndA[4 * v + 3] = t4.w;
-          const uint4 u4 = __ldg(reinterpret_cast<const uint4 *>(dnorm + col0 + 16) + v);
-          ndB[4 * v] = u4.x; ndB[4 * v + 1] = u4.y; ndB[4 * v + 2] = u4.z; ndB[4 * v + 3] = u4.w;
-        }
         TKT(1)
         mbar_wait(&t_full[ts], (it >> 1) & 1);
+#if TM_STAG
+        if (h > 0) mbar_wait(&stag[(q << 1) | ts], (it >> 1) & 1);   // see knn_i8_k1_kernel: the quarter's two warps take turns on the read port
+#endif
         tc_fence_after();
         TKT(2)
         const uint32_t t_acc = t_lane + ts * ACC_COLS + h * HN;
@@ -732,17 +759,31 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         tmem_ld16(t_acc + 16, ppB);
         tmem_ld16(t_acc + BN + 16, xxB);
         tmem_ld16(t_acc + 2 * BN + 16, loB);
+#if TM_STAG == 1
+        if (h == 0 && lane == 0) mbar_arrive(&stag[(q << 1) | ts]);
+#endif
+        // dictionary norms of this tile half from the ring the TMA producer fills (broadcast reads; they overlap the TMEM reads)
+        uint32_t ndA[16], ndB[16];
+        {
+          const uint4 *nsrc = reinterpret_cast<const uint4 *>(s_nd + (it % TK_NRING) * BN + h * HN);
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            const uint4 t4 = nsrc[v], u4 = nsrc[4 + v];
+            ndA[4 * v] = t4.x; ndA[4 * v + 1] = t4.y; ndA[4 * v + 2] = t4.z; ndA[4 * v + 3] = t4.w;
+            ndB[4 * v] = u4.x; ndB[4 * v + 1] = u4.y; ndB[4 * v + 2] = u4.z; ndB[4 * v + 3] = u4.w;
+          }
+        }
         tmem_ld_wait();
+#if TM_STAG == 2
+        if (h == 0 && lane == 0) mbar_arrive(&stag[(q << 1) | ts]);
+#endif
         tc_fence_before();          // the whole tile is in registers: hand the stage back to the tensor pipe
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[ts]);
         TKT(3)
         if (!(dbg & 8)) {
           if (col0 + HN <= n_dict) {
-            // dbg & 32: per-lane admission loop over staged distances -- 4 % faster on uncorrelated (random) features, 3 %
-            // slower on image features, where a row admits runs of neighbouring dictionary tiles and one lane loops alone
-            if (dbg & 32) tk_tile32s(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB, s_stage);
-            else tk_tile32(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB);
+            tk_tile32(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB);
           } else {   // ragged last dictionary tile
             tk_unit(waddr, tau, nq, col0, n_dict - col0, ndA, ppA, xxA, loA);
             tk_unit(waddr, tau, nq, col0 + 16, n_dict - col0 - 16, ndB, ppB, xxB, loB);
@@ -750,8 +791,6 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         }
         TKT(4)
         TKT(5)
-        // the partner strip may have published a half-threshold since: max(mine, its) bounds the row's k-th distance
-        if (!(dbg & 16)) tau = min(tau, max(my_half, *oth_half));
         // the next check is a tile (HN admissions at most) away
         const uint32_t wlo = (uint32_t)waddr;
         uint32_t fullm = __ballot_sync(0xffffffffu, wlo - base_lo > (uint32_t)((TK_CAP - HN) * 8));
@@ -766,6 +805,30 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
             waddr = (unsigned long long)(uintptr_t)(mybuf + kept); tau = T; my_half = Th;
             *(volatile uint32_t *)(s_thalf + h * 128 + row) = Th;
           }
+        }
+        // ---- scheduled ROW-WIDE cut: every warp of the CTA cuts all its rows after the same dictionary tile
+        if (j + 1 == next_cut) {
+          next_cut = (cut_ratio > 1 && (long long)next_cut * cut_ratio < n_tiles) ? next_cut * cut_ratio : 0x7fffffff;
+          s_cnt[warp * 32 + lane] = (int)(((uint32_t)waddr - base_lo) >> 3);
+          asm volatile("bar.sync %0, 64;\n" ::"r"(2 + q) : "memory");   // the two warps of this lane quarter: strips and counts visible
+          // warp (q, h) cuts rows [16 h, 16 h + 16) of the quarter, two at a time
+          for (int rr = 16 * h; rr < 16 * h + 16; rr += 2) {
+            const int r0 = q * 32 + rr, r1 = r0 + 1;
+            unsigned long long *a0 = cta_ws + (size_t)r0 * TK_CAP, *a1 = cta_ws + (size_t)(128 + r0) * TK_CAP;
+            unsigned long long *c0p = cta_ws + (size_t)r1 * TK_CAP, *c1p = cta_ws + (size_t)(128 + r1) * TK_CAP;
+            const int na0 = s_cnt[r0], na1 = s_cnt[128 + r0], nc0 = s_cnt[r1], nc1 = s_cnt[128 + r1];
+            uint32_t ddA[2 * (TK_CAP / 32)], iiA[2 * (TK_CAP / 32)], ddC[2 * (TK_CAP / 32)], iiC[2 * (TK_CAP / 32)];
+            tk_row_load(a0, a1, na0, na1, lane, ddA, iiA);
+            tk_row_load(c0p, c1p, nc0, nc1, lane, ddC, iiC);
+            int k0, k1;
+            const uint32_t TA = tk_row_cut(a0, a1, na0, na1, k, slack, lane, ddA, iiA, k0, k1);
+            if (lane == 0) { s_cnt[r0] = k0; s_cnt[128 + r0] = k1; s_tau[r0] = TA; }
+            const uint32_t TC = tk_row_cut(c0p, c1p, nc0, nc1, k, slack, lane, ddC, iiC, k0, k1);
+            if (lane == 0) { s_cnt[r1] = k0; s_cnt[128 + r1] = k1; s_tau[r1] = TC; }
+          }
+          asm volatile("bar.sync %0, 64;\n" ::"r"(2 + q) : "memory");
+          waddr = (unsigned long long)(uintptr_t)(mybuf + s_cnt[warp * 32 + lane]);
+          tau = min(tau, s_tau[row]);
         }
         TKT(6)
       }
@@ -907,14 +970,13 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
   int rc = make_tmap_rows_u8(&td, d_limbs, (uint64_t)n_dict, ROWB, BN);
   if (rc != TM_OK) return rc;
   constexpr int K1_NH = TM_K1_NH;   // column splits per tile in the k = 1 / k = 4 kernels (2: 8 epilogue warps, 4: 16)
-  constexpr int SMEM_K1 = STAGES_K1 * B_TILE + BM * 8 * 4 * (K1_NH - 1) + 256 + 1024;
-  constexpr int SMEM_TK = STAGES_TK * B_TILE + TK_STAGE_B + 256 * 4 + 256 * 4 + 512 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  constexpr int SMEM_K1 = STAGES_K1 * B_TILE + BM * 8 * 4 * (K1_NH - 1) + 768 + 1024;
+  constexpr int SMEM_TK = STAGES_TK * B_TILE + 256 * 4 + 256 * 4 + 128 * 4 + TK_NRING * BN * 4 + 768 + 1024;
+  static bool attr_set[TM_MAX_DEVICES] = {};
+  if (first_use_on_device(attr_set)) {
     if (cudaFuncSetAttribute(knn_i8_k1_kernel<1, K1_NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
     if (cudaFuncSetAttribute(knn_i8_k1_kernel<4, K1_NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
     if (cudaFuncSetAttribute(knn_i8_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK) != cudaSuccess) return TM_ERR_CUDA;
-    attr_set = true;
   }
   {
     ProfScope prof(k == 1 ? "knn_k1" : (k == 4 ? "knn_k4" : "knn_topk"), st);
@@ -940,12 +1002,14 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
       const size_t strips = (size_t)grid * 256 * TK_CAP * 8;
       if (cudaMallocAsync(&raw, strips + 2048, st) != cudaSuccess) return TM_ERR_NOMEM;
       unsigned long long *strip_ws = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(raw) + 2047) & ~uintptr_t(2047));
-      static int slack = -1, dbg = 0;   // TM_TK_SLACK / TM_TK_DBG: tuning and timing experiments (dbg = 1 admits nothing)
+      static int slack = -1, dbg = 0, cut_first = TK_CUT_FIRST, cut_ratio = TK_CUT_RATIO;   // TM_TK_SLACK / TM_TK_DBG / TM_TK_CUTS="first,ratio": tuning and timing experiments
       if (slack < 0) {
         slack = getenv("TM_TK_SLACK") ? atoi(getenv("TM_TK_SLACK")) : TK_SLACK;
         dbg = getenv("TM_TK_DBG") ? atoi(getenv("TM_TK_DBG")) : 0;
+        if (const char *e = getenv("TM_TK_CUTS")) { if (sscanf(e, "%d,%d", &cut_first, &cut_ratio) != 2) { cut_first = TK_CUT_FIRST; cut_ratio = TK_CUT_RATIO; } }
       }
-      knn_i8_topk_kernel<<<grid, TK_THREADS, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride, strip_ws, slack, dbg);
+      knn_i8_topk_kernel<<<grid, TK_THREADS, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride, strip_ws, slack, dbg,
+                                                            cut_first, cut_ratio);
       cudaFreeAsync(raw, st);
     }
   }

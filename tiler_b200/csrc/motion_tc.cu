@@ -310,10 +310,9 @@ int launch_motion_search_tc(const int16_t *cur_feat, int tw, int th, const int16
   rc = make_tmap_rows_u8(&tc, c_limbs, (uint64_t)npad, ROWB, BN);
   if (rc != TM_OK) return rc;
   constexpr int SMEM = NST * B_TILE + BM * 8 + 256 + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[TM_MAX_DEVICES] = {};
+  if (first_use_on_device(attr_set)) {
     if (cudaFuncSetAttribute(motion_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return TM_ERR_CUDA;
-    attr_set = true;
   }
   const int n_blocks = ((tw + BTW - 1) / BTW) * ((th + BTH - 1) / BTH);
   const int grid = n_blocks < num_ctas ? n_blocks : num_ctas;

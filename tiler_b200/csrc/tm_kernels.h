@@ -67,6 +67,22 @@ int launch_sq_err_rgb(const int32_t *a, const int32_t *b, int64_t n, unsigned lo
 int launch_mirror_canonicalise(int32_t *rgb, int64_t n, uint8_t *flags, cudaStream_t st);
 int features_init(cudaStream_t st);
 
+// Per-device state: function attributes (dynamic shared memory opt-in), lookup tables and scratch belong to ONE device, and a
+// process may drive several (tm_set_device / torch.cuda.set_device before a call).  Callers hold the library lock.
+constexpr int TM_MAX_DEVICES = 64;
+inline int cur_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return (d >= 0 && d < TM_MAX_DEVICES) ? d : 0;
+}
+// true exactly once per device for the flag array of one call site
+inline bool first_use_on_device(bool (&done)[TM_MAX_DEVICES]) {
+  const int d = cur_device();
+  if (done[d]) return false;
+  done[d] = true;
+  return true;
+}
+
 // ---- dither.cu
 int launch_dither(const int32_t *rgb, const uint8_t *mirror_flags, const int32_t *pair_tile, const int32_t *pair_pal,
                   int64_t n_pairs, const int32_t *palettes, int pal_size, int n_pal, int use_tk, int y2_mixed, uint8_t *out_idx,

@@ -5,8 +5,7 @@ batched calls into libtm_gpu.so instead of the per-tile DLL calls of the referen
 `encode()` chains every step of TTilingEncoder.Run (Load -> PredictMotion -> Reduce -> PreparePalettes -> Dither ->
 Reconstruct -> Reindex -> Save, tilingencoder.pas:5530-5552) on a clip already in memory; the heavy steps are library
 calls, the bookkeeping between them (threshold search over per-class PSNRs, dictionary ordering, stream writing) is
-host code as it is in the reference.  Not here: video decoding (FFmpeg), keyframe detection (sequences are an input)
-and OptimizePalettes (it only permutes colour order).  `reduce_sample()` is the old stand-in that samples dictionary
+host code as it is in the reference.  Not here: video decoding (FFmpeg) and keyframe detection (sequences are an input).  `reduce_sample()` is the old stand-in that samples dictionary
 tiles without the motion pass; bench.py's match-stage step still uses it.
 """
 import numpy as np
@@ -33,6 +32,35 @@ def _reindex_order(tiles_rgb, use_count):
     o1 = np.argsort(be.view(np.dtype((np.void, 256))).reshape(-1), kind="stable")
     o2 = np.argsort(-np.asarray(use_count)[o1].astype(np.int64), kind="stable")
     return o1[o2]
+
+
+def _quicksort_desc(counts):
+    """Permutation QuickSort(..., ComparePaletteUseCount) leaves (extern.pas:370-418, utils.pas:750-753): descending by
+    count; equal counts land where the reference's middle-pivot Hoare partition (pivot index tracked through swaps) puts
+    them, so the procedure is replayed rather than replaced by a stable sort."""
+    key = [int(c) for c in counts]
+    idx = list(range(len(key)))
+    stack = [(0, len(key) - 1)]
+    while stack:
+        first, last = stack.pop()
+        while last > first:
+            i, j, p = first, last, (first + last) >> 1
+            while True:
+                while key[idx[i]] > key[idx[p]]:
+                    i += 1
+                while key[idx[j]] < key[idx[p]]:
+                    j -= 1
+                if i <= j:
+                    idx[i], idx[j] = idx[j], idx[i]
+                    p = j if p == i else (i if p == j else p)
+                    i += 1
+                    j -= 1
+                if i > j:
+                    break
+            if first < j:
+                stack.append((first, j))   # disjoint sub-ranges: the order in which they are sorted does not matter
+            first = i
+    return np.asarray(idx, dtype=np.int64)
 
 
 def golden_ratio_search(func, min_x, max_x, objective_y, eps_x=1e-6, eps_y=0.5):
@@ -134,9 +162,10 @@ class TilingEncoder:
         flat = canon_tiles.reshape(-1, 64)
         n_all = int(flat.shape[0])
         cls, n_cls = api.tile_classes(flat)
-        eff = np.asarray(psnr, dtype=np.float32).copy()
+        # STCGREval (:4028-4031) promotes the Single PSNR to Double, divides by 10.0 in double and compares with the Double x
+        eff = np.asarray(psnr, dtype=np.float32).astype(np.float64)
         for f in seq_start_frames:
-            eff[f] = eff[f] / np.float32(10.0)
+            eff[f] = eff[f] / 10.0
         eff = eff.reshape(-1)
         target = min(int(tile_count), n_all)
         fl = canon_flags.reshape(-1)
@@ -146,12 +175,12 @@ class TilingEncoder:
             dev = cls.device
             cl = cls.long()
             eff_t = torch.from_numpy(eff).to(dev)
-            cls_min = torch.full((n_cls,), float("inf"), dtype=torch.float32, device=dev)
+            cls_min = torch.full((n_cls,), float("inf"), dtype=torch.float64, device=dev)
             cls_min.scatter_reduce_(0, cl, eff_t, reduce="amin")
             sorted_min = torch.sort(cls_min).values.cpu().numpy()
-            x_res, x_last = golden_ratio_search(lambda x: float(np.searchsorted(sorted_min, np.float32(x), side="right")), 0.0,
+            x_res, x_last = golden_ratio_search(lambda x: float(np.searchsorted(sorted_min, x, side="right")), 0.0,
                                                 float(C_PSNR_MAX), float(target))
-            x = np.float32(x_last if x_last is not None else x_res)
+            x = float(x_last if x_last is not None else x_res)
             unpred = ~(eff_t > float(x))                                   # IsPredicted := PSNR > x
             ucl = cl[unpred]
             use_t = torch.bincount(ucl, minlength=n_cls)
@@ -175,9 +204,9 @@ class TilingEncoder:
         order0 = np.argsort(cls, kind="stable")
         starts = np.flatnonzero(np.r_[True, np.diff(cls[order0]) != 0])
         sorted_min = np.sort(np.minimum.reduceat(eff[order0], starts))
-        x_res, x_last = golden_ratio_search(lambda x: float(np.searchsorted(sorted_min, np.float32(x), side="right")), 0.0,
+        x_res, x_last = golden_ratio_search(lambda x: float(np.searchsorted(sorted_min, x, side="right")), 0.0,
                                             float(C_PSNR_MAX), float(target))
-        x = np.float32(x_last if x_last is not None else x_res)
+        x = float(x_last if x_last is not None else x_res)
         unpred = ~(eff > x)                                   # IsPredicted := PSNR > x
         idx_all = np.arange(n_all)
         use = np.bincount(cls[unpred], minlength=n_cls)
@@ -214,11 +243,19 @@ class TilingEncoder:
         from . import dist as tdist
         rank, world = tdist.world_info() if sharded else (0, 1)
         n, H, W = (int(v) for v in frames_packed.shape)
-        assert H % 8 == 0 and W % 8 == 0
-        tw, th = W // 8, H // 8
+        # the tilemap rounds up to whole tiles and the screen IS the tilemap (:1776, ReframeUI :2631-2638); pixels beyond the
+        # image stay 0 (AllocMem'd frame tiles, :1310): configs[0] is 320x180 -> 40x23 tiles, a 320x184 screen
+        tw, th = (W - 1) // 8 + 1, (H - 1) // 8 + 1
         nt = tw * th
         t = {}
         t0 = time.perf_counter()
+        if (H, W) != (th * 8, tw * 8):
+            if api._is_dev(frames_packed):
+                padded = torch.zeros((n, th * 8, tw * 8), dtype=frames_packed.dtype, device=frames_packed.device)
+            else:
+                padded = np.zeros((n, th * 8, tw * 8), dtype=np.int32)
+            padded[:, :H, :W] = frames_packed
+            frames_packed, H, W = padded, th * 8, tw * 8
         if self.device is not None:   # frames -> tiles is a pure layout change: done on the device (torch = memory plumbing)
             fr_dev = frames_packed if api._is_dev(frames_packed) else torch.from_numpy(np.ascontiguousarray(frames_packed)).to(self.device)
             tiles = fr_dev.view(n, th, 8, tw, 8).permute(0, 1, 3, 2, 4).contiguous().view(n, nt, 64)
@@ -239,6 +276,8 @@ class TilingEncoder:
         self.prepare_palettes()
         t["prepare_palettes"] = time.perf_counter() - t0; t0 = time.perf_counter()
         self.dither()
+        if self.device is not None:
+            api.synchronize()          # the call only enqueues on device tensors: bill the stage its own time
         t["dither"] = time.perf_counter() - t0; t0 = time.perf_counter()
         self.prepare_reconstruct()
         t["prepare_reconstruct"] = time.perf_counter() - t0; t0 = time.perf_counter()
@@ -289,22 +328,39 @@ class TilingEncoder:
 
     # --- PreparePalettes (tilingencoder.pas:1843-1871)
     def prepare_palettes(self):
-        # DoPalettization (:4105-4245): LAB "special weighted DCT" features -> palette label per tile.  The CPU-era
-        # BICO coreset + ANN + yakmo chain is replaced by Lloyd on the full tile set (k-means++ seeding).
+        """DoPalettization (:4105-4245) as the reference chains it, each DLL stage one batched library call:
+        LAB "special weighted DCT" features -> coreset of 8 x PaletteCount points, tiles weighted by UseCount (:4149-4173;
+        BICO's streaming CF-tree is replaced by the library's weighted-Lloyd summary, tm_coreset_weighted) -> nearest
+        coreset point of every tile (ANN, :4183-4188) -> UNWEIGHTED k-means of the coreset points into PaletteCount
+        clusters (yakmo, :4198-4207) -> identity when the coreset has <= PaletteCount points (:4214-4219), no k-means when
+        PaletteCount = 1 (:4209-4212) -> palettes re-indexed by descending tile count (:4221-4244).  Then DoQuantization for
+        every palette in one call (:4534-4564).  OptimizePalettes (:4265-4432) is optimize_palettes()."""
+        P = self.palette_count
         feats = api.features_f64(self.tiles, self.dithering_mode, use_lab=True)
-        if self.palette_count > 1:
-            labels, _, _, _ = api.kmeans_fit(feats, self.palette_count, init=None, seed=self.seed, max_iter=300)
+        n = int(feats.shape[0])
+        use = self.use_count if self.use_count is not None else np.ones(n, dtype=np.int32)
+        core, _ = api.coreset_weighted(feats, self._to(np.asarray(use, dtype=np.float64)), P << 3, self.seed)
+        core_d = self._to(core)
+        ann, _ = api.knn_double(core_d, feats)
+        ann = ann.cpu().numpy() if api._is_dev(ann) else np.asarray(ann)
+        if len(core) > P:
+            if P > 1:
+                yk, _, _, _ = api.kmeans_fit(core_d, P, init=None, seed=self.seed, max_iter=300)
+                yk = yk.cpu().numpy() if api._is_dev(yk) else np.asarray(yk)
+            else:
+                yk = np.zeros(len(core), dtype=np.int32)
         else:
-            labels = np.zeros(feats.shape[0], dtype=np.int32)
-        lab = labels.cpu().numpy() if api._is_dev(labels) else np.asarray(labels)
-        # palettes re-indexed by descending use count (:4229-4234)
-        counts = np.bincount(lab, minlength=self.palette_count)
-        order = np.argsort(-counts, kind="stable")
-        lut = np.empty(self.palette_count, dtype=np.int32)
-        lut[order] = np.arange(self.palette_count, dtype=np.int32)
+            yk = np.arange(len(core), dtype=np.int32)
+        lab = yk[ann]
+        # palettes re-indexed by descending use count with the repo's own non-stable QuickSort (:4229-4234, extern.pas:370)
+        counts = np.bincount(lab, minlength=P)
+        order = _quicksort_desc(counts)
+        lut = np.empty(P, dtype=np.int32)
+        lut[order] = np.arange(P, dtype=np.int32)
         self.tile_pal = self._to(lut[lab].astype(np.int32))
+        self.coreset_size = int(len(core))
         # DoQuantization per palette (:4534-4564), all palettes in one call
-        self.palettes, _ = api.palquant_kmeans(self.tiles, self.tile_pal, self.palette_count, self.palette_size, seed=self.seed)
+        self.palettes, _ = api.palquant_kmeans(self.tiles, self.tile_pal, P, self.palette_size, seed=self.seed)
         return self.palettes
 
     # --- Dither (tilingencoder.pas:1873-1907)
