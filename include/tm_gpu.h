@@ -53,6 +53,12 @@ int tm_synchronize(void);
 /* per-kernel CUDA-event timing on the launching stream (names: "knn_k1", "knn_topk", "rerank", "features_rgb") */
 int tm_profile_enable(int on);
 int tm_profile_read(const char *name, double *total_ms, int64_t *count);
+/* Feature arithmetic of the SLIDING-WINDOW features (DoDCTs, tilingencoder.pas:1437-1462; tm_sliding_features,
+   tm_predict_motion_frame, tm_reconstruct_*): 0 (default) = bit-exact, DCTInner_asm's summation order (utils.pas:874-1035);
+   1 = fast: separable row/column DCT in f64, within 1 LSB of mode 0 on < 1e-3 of the coefficients (measured ~5e-6).  Tile
+   features (tm_features_from_*) are always bit-exact.  Process-wide. */
+int tm_set_feature_mode(int mode);
+int tm_get_feature_mode(void);
 
 /* ---------------------------------------------------------------- drop-in: ANN_short.dll (extern.pas:182-185) */
 typedef struct tm_knn_short tm_knn_short;

@@ -107,7 +107,8 @@ def test_config_a_encode_320x180_against_oracle_pipeline(tm, oracle):
     w, h, n = 320, 180, 24
     frames = synth.pack_rgb(synth.make_clip(w, h, n, cut_every=0, seed=synth.SEED))
     seqs = [(0, n - 1)]
-    n_pal, pal_size, tile_count = 64, 16, 4000
+    # LoadDefaultSettings (:3817-3845): PaletteSize 16, PaletteCount 1024, QualityBasedTileCount 7.0 -> 7 * EqualQualityTileCount(22080) = 15008
+    n_pal, pal_size, tile_count = 1024, 16, 15008
     enc = TilingEncoder(palette_size=pal_size, palette_count=n_pal, seed=0x42381337)
     res = enc.encode(frames, seqs, tile_count=tile_count, radius=32)
     ref = P.encode(frames, seqs, tile_count, n_pal, pal_size, 0x42381337, radius=32)
@@ -227,3 +228,41 @@ def test_two_devices_in_one_process(tm, oracle):
         assert np.array_equal(f.cpu().numpy(), want_f)
         f64 = tm.features_f64(torch.from_numpy(tiles).to(f"cuda:{dev}"))
         assert f64.device.index == dev
+
+
+# ------------------------------------------------------------------ fast (separable f64) sliding-window features
+@pytest.mark.parametrize("w,h", [(96, 64), (100, 52), (320, 184), (15, 8)])
+def test_sliding_features_fast_mode_within_contract(tm, oracle, w, h):
+    """tm_set_feature_mode(1): <= 1 LSB per coefficient and <= 1e-3 of the coefficients differing from the bit-exact features
+    (SURVEY "Parity contract"); the bit-exact mode is restored afterwards and still equals the oracle."""
+    frame = synth.pack_rgb(synth.make_clip(max(w, 16), max(h, 16), 1, cut_every=0, seed=w * 1000 + h, n_sprites=3))[0][:h, :w]
+    frame = np.ascontiguousarray(frame)
+    want = oracle.sliding_features(frame)
+    prev = tm.set_feature_mode(tm.FEATURES_FAST)
+    try:
+        got = tm.sliding_features(frame)
+    finally:
+        tm.set_feature_mode(prev)
+    d = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    assert d.max() <= 1
+    assert (d != 0).mean() <= 1e-3, (d != 0).mean()
+    assert np.array_equal(tm.sliding_features(frame), want)
+
+
+def test_fast_features_encode_psnr_within_tolerance(tm, oracle):
+    """End to end with the fast sliding-window features: decoded-frame PSNR within 0.05 dB of the bit-exact encode; tile indices
+    that differ are counted (they sit inside the distance tolerance of +-1 LSB features)."""
+    from tiler_b200 import gtm
+    from tiler_b200.encoder import TilingEncoder, psnr_rgb
+    w, h, n = 160, 96, 8
+    frames = synth.pack_rgb(synth.make_clip(w, h, n, cut_every=4, seed=77, n_sprites=5))
+    seqs = [(0, 3), (4, 7)]
+    exact = TilingEncoder(palette_size=16, palette_count=4, seed=3).encode(frames, seqs, tile_count=400)
+    fast = TilingEncoder(palette_size=16, palette_count=4, seed=3, feature_mode="fast").encode(frames, seqs, tile_count=400)
+    assert tm.set_feature_mode(tm.FEATURES_EXACT) == tm.FEATURES_EXACT          # encode() restored the process-wide mode
+    pe = psnr_rgb(gtm.decode_gtm(exact["gtm"])[0], frames)
+    pf = psnr_rgb(gtm.decode_gtm(fast["gtm"])[0], frames)
+    assert abs(pe - pf) <= 0.05, (pe, pf)
+    differing = (np.asarray(exact["tilemap"]["is_pred"]) != np.asarray(fast["tilemap"]["is_pred"])).mean()
+    print(f"fast features: PSNR {pf:.4f} dB vs {pe:.4f} dB, {differing:.2%} of the tilemap items change their predicted flag")
+    assert differing <= 0.02

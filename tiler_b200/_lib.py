@@ -33,6 +33,8 @@ SIGNATURES = {
     "tm_last_error": (C.c_char_p, []),
     "tm_kernel_launches": (C.c_int64, []),
     "tm_synchronize": (C.c_int, []),
+    "tm_set_feature_mode": (C.c_int, [_i32]),
+    "tm_get_feature_mode": (C.c_int, []),
     "tm_profile_enable": (C.c_int, [_i32]),
     "tm_profile_read": (C.c_int, [C.c_char_p, C.POINTER(_dbl), C.POINTER(_i64)]),
     "tm_features_from_rgb": (C.c_int, [_vp, _i64, _vp]),

@@ -99,6 +99,17 @@ def synchronize():
     check(_lib.lib().tm_synchronize())
 
 
+FEATURES_EXACT, FEATURES_FAST = 0, 1
+
+
+def set_feature_mode(mode):
+    """Arithmetic of the sliding-window features (DoDCTs): FEATURES_EXACT = DCTInner_asm's summation order, bit-exact (default);
+    FEATURES_FAST = separable f64 DCT, <= 1 LSB away on < 1e-3 of the coefficients.  Returns the previous mode."""
+    prev = int(_lib.lib().tm_get_feature_mode())
+    check(_lib.lib().tm_set_feature_mode(int(mode)))
+    return prev
+
+
 # ------------------------------------------------------------------ features (tilingencoder.pas:3049-3182)
 def features_from_rgb(rgb):
     """ConvertToCpnPixels + ComputeCpnPixelsPsyVisFeatures(pvsWeightedDCT): RGB tiles [n,64] int32 -> int16 [n,192]."""

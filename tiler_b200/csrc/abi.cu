@@ -206,6 +206,13 @@ extern "C" int tm_profile_read(const char *name, double *total_ms, int64_t *coun
   return TM_OK;
 }
 extern "C" int tm_synchronize(void) { CU(cudaStreamSynchronize(t_stream)); return TM_OK; }
+extern "C" int tm_set_feature_mode(int mode) {
+  if (mode != 0 && mode != 1) return fail(TM_ERR_ARG, "tm_set_feature_mode: 0 (bit-exact) or 1 (fast)");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  set_feature_mode(mode);
+  return TM_OK;
+}
+extern "C" int tm_get_feature_mode(void) { return get_feature_mode(); }
 
 // ------------------------------------------------------------------ features
 extern "C" int tm_features_from_rgb(const int32_t *rgb, int64_t n, int16_t *out) {

@@ -281,6 +281,137 @@ __global__ void __launch_bounds__(128) mirror_kernel(int32_t *__restrict__ rgb, 
       for (int i = 0; i < 8; ++i) { const int32_t a = p[j * 8 + i]; p[j * 8 + i] = p[(7 - j) * 8 + i]; p[(7 - j) * 8 + i] = a; }
 }
 
+// ------------------------------------------------------------------ sliding-window features, FAST mode (separable, f64)
+// DoDCTs (tilingencoder.pas:1437-1462) asks for the weighted DCT of the 8x8 window at EVERY pixel offset of a frame buffer.
+// The bit-exact kernel above spends 64 f32 products, their pair adds and 32 f32->f64 conversions per coefficient to reproduce
+// DCTInner_asm's summation order, and nothing is shared between overlapping windows.  The 2-D basis is separable
+// (lut[v][u][y][x] = cos((x+1/2) u pi/8) cos((y+1/2) v pi/8) ratio[v][u], tilingencoder.pas:1709), so in exact arithmetic
+//   row pass   R[y][ox][u]      = sum_x P[y][ox+x] cos((x+1/2) u pi/8)        -- shared by the 8 windows that contain the row segment
+//   column pass F[oy][ox][v][u] = sum_j R[oy+j][ox][u] cos((j+1/2) v pi/8)
+// is 72 multiply-adds per coefficient column instead of 512.  Everything runs in f64 (B200 keeps a 1:2 FP64 rate), which is
+// MORE accurate than the reference's f32 products; the result differs from the reference only where the reference's own f32
+// rounding noise (~3e-4 absolute) straddles a .5 rounding boundary: <= 1 LSB, ~5e-6 of the coefficients on the synthetic clip
+// (contract: <= 1 LSB, <= 1e-3 of the coefficients; SURVEY "Parity contract").  Selected with tm_set_feature_mode(1); the
+// bit-exact kernel stays the default.
+//
+// Thread = (plane, ox, u): it marches down the rows of its window column with the last 8 row-pass values in a register ring
+// (the loop is unrolled over the 8 ring phases, so the ring is statically indexed and the column-pass cosines are constant-bank
+// operands), and emits the 8 coefficients (v = 0..7) of window (y - 7, ox) at every row y.  A block = 8 window columns x 3
+// planes x 8 u; its 8 x 192 coefficients per row leave through shared memory as one contiguous 3 KB store.
+__constant__ double c_cos8[8][8];      // [k][i] = cos((i + 1/2) k pi / 8)
+__constant__ double c_scale[192];      // [cpn][v][u] = (double)cDCTUVRatio[v][u] * cDCTWeights[cpn][v][u]
+constexpr int SF_OXB = 8;              // window columns per block
+constexpr int SF_SEG = 64;             // window rows per block
+constexpr int SF_CH = 16;              // frame rows converted per chunk
+
+template <int PH>
+__device__ __forceinline__ double sf_col(const double (&ring)[8], int v) {
+  double f = 0.0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) f = fma(ring[r], c_cos8[v][(r - PH - 1) & 7], f);   // ring[r] holds window row (r - PH - 1) mod 8
+  return f;
+}
+
+template <int PH>
+__device__ __forceinline__ void sf_step(const double *__restrict__ prow /* plane row, this thread's first pixel */, const double (&cu)[8],
+                                        const double (&sc)[8], const int (&dst)[8], double (&ring)[8], bool emit, int16_t *__restrict__ o) {
+  double r = 0.0;
+#pragma unroll
+  for (int x = 0; x < 8; ++x) r = fma(prow[x], cu[x], r);
+  ring[PH] = r;
+  if (emit) {
+#pragma unroll
+    for (int v = 0; v < 8; ++v) o[dst[v]] = (int16_t)__double2int_rn(__dmul_rn(sf_col<PH>(ring, v), sc[v]));
+  }
+}
+
+__global__ void __launch_bounds__(192, 2)
+features_sliding_fast_kernel(const int32_t *__restrict__ frame, int fw, int fh, int16_t *__restrict__ out) {
+  __shared__ double s_pl[3][SF_CH][SF_OXB + 8];          // converted planes of the current row chunk (15 of 16 columns used)
+  __shared__ __align__(16) int16_t s_out[2][SF_OXB][192];
+  const int t = threadIdx.x;
+  const int u = t & 7, oxl = (t >> 3) & 7, cpn = t >> 6;
+  const int pw = fw - 7, ph_rows = fh - 7;
+  const int ox0 = blockIdx.x * SF_OXB;
+  const int oy0 = blockIdx.y * SF_SEG;
+  const int oy1 = min(oy0 + SF_SEG, ph_rows);              // window rows [oy0, oy1)
+  const int y_end = oy1 + 7;                               // frame rows [oy0, y_end)
+  double cu[8], sc[8], ring[8];
+  int dst[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    cu[i] = c_cos8[u][i];
+    sc[i] = c_scale[cpn * 64 + i * 8 + u];
+    dst[i] = cpn * 64 + c_snake[i * 8 + u];
+    ring[i] = 0.0;
+  }
+  int buf = 0;
+  bool pending = false;
+  int pend_oy = 0;
+  auto flush = [&](int b, int oy) {   // 8 windows x 384 bytes, contiguous in the output: thread t moves 16 bytes
+    const int wdw = t / 24;
+    if (ox0 + wdw < pw)
+      reinterpret_cast<uint4 *>(out + ((int64_t)oy * pw + ox0) * 192)[t] = reinterpret_cast<const uint4 *>(&s_out[b][0][0])[t];
+  };
+  for (int yc = oy0; yc < y_end; yc += SF_CH) {
+    __syncthreads();   // the previous chunk's planes are no longer read
+    // convert the chunk: RGBToYUV (utils.pas:478-490), double evaluation, single storage (what ConvertToCpnPixels leaves)
+    for (int i = t; i < SF_CH * (SF_OXB + 7); i += 192) {
+      const int yl = i / (SF_OXB + 7), xl = i - yl * (SF_OXB + 7);
+      const int y = yc + yl, x = ox0 + xl;
+      float py = 0.f, pu = 0.f, pv = 0.f;
+      if (y < fh && x < fw) {
+        const int32_t col = __ldg(frame + (int64_t)y * fw + x);
+        rgb_to_yuv(col & 255, (col >> 8) & 255, (col >> 16) & 255, py, pu, pv);
+      }
+      s_pl[0][yl][xl] = (double)py; s_pl[1][yl][xl] = (double)pu; s_pl[2][yl][xl] = (double)pv;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int g = 0; g < SF_CH; g += 8) {
+#define SF_ROW(PH)                                                                                                        \
+      {                                                                                                                   \
+        const int y = yc + g + PH;                                                                                        \
+        if (y < y_end) {                                                                                                  \
+          const bool emit = y - oy0 >= 7;                                                                                 \
+          if (pending) flush(buf ^ 1, pend_oy);                                                                           \
+          sf_step<PH>(&s_pl[cpn][g + PH][oxl], cu, sc, dst, ring, emit, &s_out[buf][oxl][0]);                             \
+          __syncthreads();                                                                                                \
+          pending = emit; pend_oy = y - 7;                                                                                \
+          if (emit) buf ^= 1;                                                                                             \
+        }                                                                                                                 \
+      }
+      SF_ROW(0) SF_ROW(1) SF_ROW(2) SF_ROW(3) SF_ROW(4) SF_ROW(5) SF_ROW(6) SF_ROW(7)
+#undef SF_ROW
+    }
+  }
+  if (pending) flush(buf ^ 1, pend_oy);
+}
+
+static int features_fast_init(cudaStream_t st) {
+  static bool done[TM_MAX_DEVICES] = {};
+  if (!first_use_on_device(done)) return TM_OK;
+  double hc[8][8], hs[192];
+  const double PI = 3.14159265358979323846;
+  for (int k = 0; k < 8; ++k)
+    for (int i = 0; i < 8; ++i) hc[k][i] = cos((i + 0.5) * k * PI / 8.0);
+  for (int c = 0; c < 3; ++c)
+    for (int v = 0; v < 8; ++v)
+      for (int u = 0; u < 8; ++u) {
+        const float rf = (v == 0 && u == 0) ? 0.5f : ((v == 0 || u == 0) ? (float)sqrt(0.5) : 1.0f);   // cDCTUVRatio (utils.pas:100-109)
+        double w;
+        if (cudaMemcpyFromSymbol(&w, c_weights, 8, (size_t)(c * 64 + v * 8 + u) * 8) != cudaSuccess) return TM_ERR_CUDA;
+        hs[c * 64 + v * 8 + u] = (double)rf * w;
+      }
+  if (cudaMemcpyToSymbolAsync(c_cos8, hc, sizeof(hc), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return TM_ERR_CUDA;
+  if (cudaMemcpyToSymbolAsync(c_scale, hs, sizeof(hs), 0, cudaMemcpyHostToDevice, st) != cudaSuccess) return TM_ERR_CUDA;
+  return cudaStreamSynchronize(st) == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+static int g_feature_mode = 0;   // 0: bit-exact (DCTInner_asm order), 1: fast separable f64 for the sliding-window features
+void set_feature_mode(int mode) { g_feature_mode = mode ? 1 : 0; }
+int get_feature_mode() { return g_feature_mode; }
+
 static int grid_for(int64_t n, int per_sm) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -315,6 +446,14 @@ int launch_features_sliding(const int32_t *frame, int w, int h, int16_t *out, cu
   if (rc) return rc;
   const int64_t n = (int64_t)(w - 7) * (h - 7);
   ProfScope prof("features_sliding", st);
+  if (g_feature_mode == 1) {
+    rc = features_fast_init(st);
+    if (rc) return rc;
+    const dim3 grid((unsigned)((w - 7 + SF_OXB - 1) / SF_OXB), (unsigned)((h - 7 + SF_SEG - 1) / SF_SEG));
+    features_sliding_fast_kernel<<<grid, 192, 0, st>>>(frame, w, h, out);
+    note_launch();
+    return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+  }
   features_i16_kernel<4><<<grid_for((n + FEAT_NP - 1) / FEAT_NP, 3), 192, 0, st>>>(frame, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out, w,
                                                                              w - 7);
   note_launch();

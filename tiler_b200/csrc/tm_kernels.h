@@ -66,6 +66,8 @@ int launch_reconstruct_decide(const uint8_t *flags, int tw, int th, const int32_
 int launch_sq_err_rgb(const int32_t *a, const int32_t *b, int64_t n, unsigned long long *acc, cudaStream_t st);
 int launch_mirror_canonicalise(int32_t *rgb, int64_t n, uint8_t *flags, cudaStream_t st);
 int features_init(cudaStream_t st);
+void set_feature_mode(int mode);   // 0 bit-exact, 1 fast (sliding-window features only)
+int get_feature_mode();
 
 // Per-device state: function attributes (dynamic shared memory opt-in), lookup tables and scratch belong to ONE device, and a
 // process may drive several (tm_set_device / torch.cuda.set_device before a call).  Callers hold the library lock.

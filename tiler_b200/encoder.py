@@ -92,7 +92,7 @@ class TilingEncoder:
 
     def __init__(self, palette_size=16, palette_count=16, dithering_mode=api.PVS_WEIGHTED_SPE_DCT,
                  dithering_use_thomas_knoll=True, dithering_yliluoma2_mixed_colors=4,
-                 frame_tiling_extended_palette_usage=True, seed=0x42381337, device=None):
+                 frame_tiling_extended_palette_usage=True, seed=0x42381337, device=None, feature_mode="exact"):
         self.palette_size = int(np.clip(palette_size, 2, 256))      # reference clamps to 2..64 (:2965); 256 = stress shape
         self.palette_count = int(np.clip(palette_count, 1, 65536))
         self.dithering_mode = dithering_mode
@@ -101,6 +101,9 @@ class TilingEncoder:
         self.extended = bool(frame_tiling_extended_palette_usage)
         self.seed = seed
         self.device = device  # None: host arrays through the ABI; a torch device: everything stays in HBM
+        # "exact": every feature in DCTInner_asm's summation order (bit-exact); "fast": the sliding-window features of the motion
+        # searches (DoDCTs) through the separable f64 kernel (<= 1 LSB on < 1e-3 of the coefficients, PSNR within 0.05 dB)
+        self.feature_mode = api.FEATURES_FAST if feature_mode == "fast" else api.FEATURES_EXACT
         self.tiles = None       # dictionary tiles, RGB [n,64] (canonical orientation)
         self.tile_flags = None  # their initial mirrors
         self.tile_pal = None    # PalIdx_Initial
@@ -239,6 +242,13 @@ class TilingEncoder:
         PredictMotion is sharded by frame and Reconstruct by keyframe sequence (no data-path collective, the
         per-tile PSNRs and the tilemaps are gathered on the host); Reduce, palettes and dithering are deterministic and run
         replicated; rank 0 writes the stream.  The bytes equal the single-GPU encode's."""
+        prev_mode = api.set_feature_mode(self.feature_mode)
+        try:
+            return self._encode(frames_packed, sequences, tile_count, radius, fps, out_path, emit_skip_blocks, sharded)
+        finally:
+            api.set_feature_mode(prev_mode)
+
+    def _encode(self, frames_packed, sequences, tile_count, radius, fps, out_path, emit_skip_blocks, sharded):
         import time
         from . import dist as tdist
         rank, world = tdist.world_info() if sharded else (0, 1)
