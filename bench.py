@@ -140,6 +140,58 @@ def encode_leg(dev, frames, world=1, feature_mode="fast"):
             "note": "wall clock incl. host bookkeeping, LZMA and the H2D/D2H copies; reconstruction PSNR vs the source clip"}
 
 
+def kmeans_c_leg(dev, rank, world, iters=5):
+    """BASELINE.json configs[2]: the dictionary-k-means Lloyd loop in isolation -- 4 194 304 dithered-tile vectors (192-d int16)
+    -> 262 144 centroids, points sharded contiguously over the ranks, centroids replicated, one NCCL all-reduce of the
+    [K,192] f64 sums (403 MB) + [K] counts per iteration (tiler_b200/dist.py).  Synthetic data per SURVEY 8d: mixture of K
+    Gaussians (centres from the adversarial feature distribution, sigma 25), generated on the device; the initial centroids
+    are K points of the same mixture drawn from a seed every rank shares.  `iters` Lloyd iterations, each phase timed with
+    CUDA events on the launching stream, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from tiler_b200 import dist as tdist, synth
+    N, K = 4194304, 262144
+    lo, hi = tdist.shard_rows(N, rank, world)
+    centres = torch.from_numpy(synth.random_features(K, 11, adversarial=True)).to(dev)
+    g = torch.Generator(device=dev); g.manual_seed(777)                       # shared: identical initial centroids everywhere
+    pick0 = torch.randint(0, K, (K,), generator=g, device=dev)
+    init = (centres[pick0].float() + 25.0 * torch.randn((K, 192), generator=g, device=dev)).round().clamp(-32768, 32767).double()
+    n_loc = hi - lo
+    x = torch.empty((n_loc, 192), dtype=torch.int16, device=dev)
+    blk = 1 << 19                                                             # the data set is the same at every N: block b has its own seed
+    for a in range(lo, hi, blk):
+        b = min(hi, a + blk)
+        g.manual_seed(5000 + a // blk)
+        pick = torch.randint(0, K, (blk,), generator=g, device=dev)
+        pts = (centres[pick].float() + 25.0 * torch.randn((blk, 192), generator=g, device=dev)).round().clamp(-32768, 32767).to(torch.int16)
+        x[a - lo:b - lo] = pts[a % blk:a % blk + (b - a)] if (a % blk or b - a != blk) else pts
+    del centres
+    tdist.kmeans_fit_i16_sharded(x, init, max_iter=1, check_every=1 << 30)      # warm-up: kernels loaded, pools grown, NCCL rings up
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    tm = {}
+    t0 = time.perf_counter()
+    labels, cent, inertia, it = tdist.kmeans_fit_i16_sharded(x, init, max_iter=iters, check_every=1 << 30, timings=tm)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    n_it = len(tm["assign_ms"])
+    per = torch.tensor([sum(tm["assign_ms"]) / n_it, sum(tm["allreduce_ms"]) / n_it, sum(tm["update_ms"][:-1]) / max(n_it - 1, 1), wall],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(per, op=dist.ReduceOp.MAX)
+    a_ms, r_ms, u_ms, wall = (float(v) for v in per)
+    ar_bytes = K * 192 * 8 + (K + 2) * 8
+    return {"workload": "configs[2]: 4194304 x 192 int16 -> 262144 centroids, points sharded, centroids replicated", "n_gpus": world,
+            "iterations": n_it, "points_per_rank": int(n_loc), "assign_ms": a_ms, "allreduce_ms": r_ms, "update_ms": u_ms,
+            "iteration_ms": a_ms + r_ms + u_ms, "wall_s": wall,
+            "assign_evals_per_s": N * K / (a_ms * 1e-3), "assign_tflops_algorithmic": N * K * 384 / (a_ms * 1e-3) / 1e12,
+            "allreduce_bytes": ar_bytes, "allreduce_busbw_GBps": (2.0 * (world - 1) / world) * ar_bytes / (r_ms * 1e-3) / 1e9 if world > 1 else None,
+            "inertia": inertia, "centroid_checksum": float(cent.sum().item()),
+            "note": "assign = exact 4-NN on tensor cores (knn_i8_k1_kernel<4>) + exact f64 decision + per-cluster partial sums; "
+                    "allreduce = ncclAllReduce(sum) of f64 sums and int64 counts; update = centroid division; max over ranks"}
+
+
 def build_dictionary(enc, canon_tiles, canon_flags, stages):
     """Reduce stand-in + PreparePalettes + Dither + PrepareReconstruct, each timed (setup, not the metric)."""
     import torch
@@ -228,7 +280,7 @@ def run_ours(args):
 
     # ---- end to end through the C ABI with host buffers ----
     host_np = [host_tiles[s].numpy() for s in range(n_seq_local)]
-    m.match_rgb(host_np[0], K_EPU)
+    spot = m.match_rgb(host_np[0], K_EPU)      # also kept for the untimed oracle spot-check of the cpu_baseline leg
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
@@ -250,6 +302,13 @@ def run_ours(args):
         encode_res = encode_leg(dev, clip_frames, world, "fast")
         encode_exact = encode_leg(dev, clip_frames, world, "exact")
         encode_res["psnr_delta_vs_exact_db"] = encode_res["psnr_rgb_db"] - encode_exact["psnr_rgb_db"]
+    kmeans_res = None
+    if not args.no_kmeans:
+        if clip_frames is None:
+            m.close()
+            del dev_tiles
+        torch.cuda.empty_cache()
+        kmeans_res = kmeans_c_leg(dev, rank, world)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -260,6 +319,9 @@ def run_ours(args):
     # the timed region over their summed CUDA-event durations
     flops_per_launch = evals_per_step * 384 * args.steps / max(knn_n, 1)
     achieved_tflops = flops_per_launch / (knn_launch_ms * 1e-3) / 1e12
+    traffic_bytes, traffic_file = traffic_from_capture()
+    if traffic_bytes is not None:
+        traffic_bytes *= flops_per_launch / (432000.0 * N_DICT * 384)   # per launch of THIS run (the capture is of a whole-step launch)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -277,11 +339,9 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "roofline": {"bound": "tensor", "kernel": "knn_i8_topk_kernel", "achieved": achieved_tflops,
                      "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tflops / pk["bf16_tflops_sustained"],
-                     "traffic": 5.98e9 * (flops_per_launch / (432000.0 * N_DICT * 384)), "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
-                     "ncu --set full capture of this kernel in this bench (profiles/r01_knn_topk_bench_raw.csv): 1.545 GB + 4.435 GB per "
-                     "launch; algorithmic bytes per launch = 166 MB query limbs + 25 MB dictionary + 221 MB top-64 results.  The excess is "
-                     "the per-row candidate strips (78 MB workspace, ~1000 admissions of 8 B per query row) being written back from L2; "
-                     "6.0 GB in 29.4 ms is 3 % of HBM bandwidth, the kernel is bound by its epilogue (DESIGN.md 4.1)",
+                     "traffic": traffic_bytes, "traffic_source": (f"dram__bytes_read.sum + dram__bytes_write.sum of one launch, read from "
+                     f"profiles/{traffic_file} (ncu --set full capture of this bench command)" if traffic_file else None),
+                     "algorithmic_bytes_per_launch": TILES_PER_STEP * 384 + N_DICT * 384 + TILES_PER_STEP * K_EPU * 8,
                      "peak_source": pk["source"] + ", sustained bf16 figure (kernel timed inside a long step)",
                      "algorithmic_flops_per_launch": flops_per_launch, "launches_per_step": knn_n / args.steps, "kernel_ms_per_launch": knn_launch_ms,
                      "note": "384 flop per 192-d distance evaluation; the exact int8-limb scheme issues 4 int8 MMAs (= 2 "
@@ -290,18 +350,49 @@ def run_ours(args):
         "stages": stages,
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_sample(enc, host_np[0])
+        line["cpu_baseline"], line["oracle_spot_check"] = cpu_baseline_sample(enc, host_np[0], spot)
     if encode_res is not None:
         line["encode"] = encode_res
         line["encode_exact"] = encode_exact
+    if kmeans_res is not None:
+        line["kmeans_c"] = kmeans_res
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline_sample(enc, canon_tiles_host, n_sample=24576):
+def traffic_from_capture():
+    """dram__bytes_read.sum + dram__bytes_write.sum of knn_i8_topk_kernel from the newest committed `ncu --set full` capture of
+    this bench (profiles/rNN_knn_topk_bench_raw.csv, written by tools/ncu_summary.py).  -> (bytes per launch, file name)."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_knn_topk_bench_raw.csv")))
+    if not files:
+        return None, None
+    rd = wr = None
+    with open(files[-1], newline="") as fh:
+        rows = [r for r in csv.reader(fh) if r]
+    # `ncu --page raw --csv`: a row of metric names, a row of units, then one row per captured launch
+    hdr = next((i for i, r in enumerate(rows) if "dram__bytes_read.sum" in r), None)
+    if hdr is not None and hdr + 2 < len(rows):
+        names, units, vals = rows[hdr], rows[hdr + 1], rows[hdr + 2]
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            c = names.index(name)
+            v = float(vals[c].replace(",", "")) * mult.get(units[c], 1.0)
+            if name.endswith("read.sum"):
+                rd = v
+            else:
+                wr = v
+    if rd is None or wr is None:
+        return None, os.path.basename(files[-1])
+    return rd + wr, os.path.basename(files[-1])
+
+
+def cpu_baseline_sample(enc, canon_tiles_host, gpu_result, n_sample=24576):
     """The oracle (CPU restatement of the reference's per-tile path: features, brute-force 64-NN with the SSE distance,
-    extended-palette re-rank), OpenMP over tiles like MTProcs, on a bounded sample of the step's tiles."""
+    extended-palette re-rank), OpenMP over tiles like MTProcs, on a bounded sample of the step's tiles.  The same sample is the
+    untimed SPOT-CHECK of what the bench times: the GPU's (TileIdx, PalIdx, err) of these rows must equal the oracle's."""
     from oracle import oracle as O
     O.set_num_threads(os.cpu_count() or 1)
     pal = enc.palettes.cpu().numpy()
@@ -312,11 +403,18 @@ def cpu_baseline_sample(enc, canon_tiles_host, n_sample=24576):
     q = np.ascontiguousarray(canon_tiles_host[sel])
     t0 = time.perf_counter()
     qf = O.features_from_rgb(q)
-    O.match_tiles(qf, dict_feat, didx, dpal, pal, k=K_EPU, extended=True)
+    ot, op, oe = O.match_tiles(qf, dict_feat, didx, dpal, pal, k=K_EPU, extended=True)
     dt = time.perf_counter() - t0
-    return {"value": n_sample * N_DICT / dt, "unit": UNIT, "cores": O.num_threads(), "kind": "port",
+    gt, gp, ge = (np.asarray(a)[sel] for a in gpu_result)
+    bad = int((gt != ot).sum() + (gp != op).sum() + (ge.view(np.uint32) != oe).sum())
+    check = {"rows": int(n_sample), "mismatches": bad, "ok": bad == 0,
+             "what": "TileIdx / PalIdx / err of the sampled rows of one timed batch, GPU (C ABI, host buffers) vs oracle.match_tiles"}
+    if bad:
+        raise SystemExit(f"bench: GPU match differs from the oracle on {bad} values of the {n_sample}-row spot-check")
+    return {"value": n_sample * N_DICT / dt, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "same_algorithm": False,
+            "algorithm": "brute-force 64-NN (the reference's ANN_short.dll is a kd-tree, binary only; in 192-d it degenerates towards a linear scan)",
             "sample": f"{n_sample} of the step's {TILES_PER_STEP} tiles (features + brute-force 64-NN + extended-palette re-rank), "
-                      f"{dt:.1f} s on {O.num_threads()} threads"}
+                      f"{dt:.1f} s on {O.num_threads()} threads"}, check
 
 
 def run_reference(args):
@@ -362,7 +460,7 @@ def run_reference(args):
         "frames_per_sec": (n_sample / TILES_PER_FRAME) / dt,
         "config": {"workload": "configs[1] (bounded sample per step): 65536-tile dictionary, 16 palettes x 16 colours, k=64, "
                                "extended palette re-rank", "tiles_per_step": n_sample, "dictionary_tiles": N_DICT},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": O.num_threads(), "kind": "port", "same_algorithm": False, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -376,6 +474,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=6144)
     ap.add_argument("--no-encode", action="store_true", help="skip the whole-clip encode leg (N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kmeans", action="store_true", help="skip the configs[2] k-means leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

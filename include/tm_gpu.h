@@ -112,6 +112,8 @@ int tm_dl1quant_batch(const uint8_t *rgb888, const int64_t *img_off, int n_img, 
 /* ---------------------------------------------------------------- batched: features (tilingencoder.pas:3049-3182) */
 /* RGB tiles [n][64] -> int16 features [n][192] (ConvertToCpnPixels + ComputeCpnPixelsPsyVisFeatures, pvsWeightedDCT, YUV) */
 int tm_features_from_rgb(const int32_t *rgb, int64_t n, int16_t *out);
+/* RGB tiles read through mirror flags (ConvertToCpnPixels with AHMirror / AVMirror, :3049-3101): bit 0 H, bit 1 V */
+int tm_features_from_rgb_mirrored(const int32_t *rgb, const uint8_t *flags, int64_t n, int16_t *out);
 /* palette-index tiles [n][64] + tile_pal[n] + palettes[n_pal][pal_size] -> features (PrepareReconstruct.DoPsyV, :4570-4583) */
 int tm_features_from_pal(const uint8_t *pal_idx, const int32_t *tile_pal, const int32_t *palettes, int pal_size, int n_pal,
                          int64_t n, int16_t *out);
@@ -151,6 +153,17 @@ int tm_kmeans_fit_i16(const int16_t *x, int64_t n, int k, int max_iter, const do
                       double *centroids, double *inertia, int *iters, int64_t *ambiguous);
 int tm_kmeans_partial_step_i16(const int16_t *x, int64_t n, int k, const double *centroids, int32_t *labels, double *partial_sums,
                                int64_t *partial_counts, int64_t *changed, double *inertia);
+/* Persistent shard state for the sharded Lloyd loop (config C: 4 194 304 x 192 -> 262 144 centroids on 1/2/4/8 GPUs): the
+   shard's points are split into limb rows once.  x [n][192] host (copied) or device (must outlive the handle).
+   tm_kmeans_i16_step: one assignment of the shard against the replicated centroids[k][192] + the per-cluster partial sums
+   [k][192] and counts [k] the caller all-reduces (NCCL) before tm_kmeans_finish_step.  With device arrays nothing is copied
+   to the host: stats (int64[2], optional) accumulates {labels changed, points that needed the exact f64 scan}, inertia
+   (optional) receives the shard's sum of squared distances. */
+typedef struct tm_kmeans_i16 tm_kmeans_i16;
+int tm_kmeans_i16_create(const int16_t *x, int64_t n, int k, tm_kmeans_i16 **out);
+int tm_kmeans_i16_destroy(tm_kmeans_i16 *h);
+int tm_kmeans_i16_step(tm_kmeans_i16 *h, const double *centroids, int32_t *labels, double *partial_sums, int64_t *partial_counts,
+                       int64_t *stats, double *inertia);
 /* one Lloyd step for a SHARD of the points (multi-GPU): assignment against replicated centroids, then per-cluster
    partial sums [k][dim] and counts [k] that the caller all-reduces (NCCL) before tm_kmeans_finish_step. */
 int tm_kmeans_partial_step(const double *x, int64_t n, int dim, int k, const double *centroids, int32_t *labels,
@@ -183,6 +196,12 @@ int tm_matcher_destroy(tm_matcher *m);
    A host batch of 8 or more k-NN waves (SMs x 128 tiles) is uploaded in four pieces (a short first one) on a second stream while the pieces
    already resident are matched; pinned host memory makes that overlap real, pageable memory still works. */
 int tm_match_tiles_rgb(tm_matcher *m, const int32_t *rgb, int64_t n_q, int k, int32_t *tile_idx, int32_t *pal_idx, uint32_t *err);
+/* mirror-variant search (north star "including H/V-mirror ... variants", BASELINE configs[4]; a superset of the reference, which
+   matches the canonical orientation only): every source tile is also tried H-, V- and HV-mirrored (features of the mirrored
+   tile in exact reference arithmetic); first strict minimum of the error over variant 0..3.  variant[i] bit 0 / bit 1 = the
+   extra H / V mirror of the winning match: the tilemap's mirror bits are the tile's canonical flags XOR variant. */
+int tm_match_tiles_rgb_mirrors(tm_matcher *m, const int32_t *rgb, int64_t n_q, int k, int32_t *tile_idx, int32_t *pal_idx, uint32_t *err,
+                               uint8_t *variant);
 /* same from precomputed features [n_q][192] */
 int tm_match_tiles_feat(tm_matcher *m, const int16_t *feat, int64_t n_q, int k, int32_t *tile_idx, int32_t *pal_idx, uint32_t *err);
 /* the dictionary's own features (device pointer, [n_dict][192]) for inspection/tests */
@@ -221,6 +240,19 @@ int tm_reconstruct_frame(tm_matcher *m, const int32_t *canon_tiles, const uint8_
    equal ids <=> all 64 pixels equal.  The numbering is arbitrary (hash order); the host orders the chosen dictionary
    (ReindexTiles, :4626-4696). */
 int tm_tile_classes(const int32_t *rgb, int64_t n, int32_t *class_id, int32_t *n_classes);
+
+/* The tile-count search over the duplicate classes (STCGREval + GoldenRatioSearch, tilingencoder.pas:4014-4046, utils.pas:1044-1072).
+   eff_psnr[n] = the tile's motion PSNR as a double (divided by 10.0 on the first frame of its keyframe sequence, :4028-4031).
+   tm_reduce_class_min: per class the smallest eff_psnr of its members, all classes sorted ascending -> the number of distinct
+   unpredicted tiles for a threshold x is the count of values <= x, so the host's golden-ratio search needs no pass over the tiles.
+   tm_reduce_apply: for the chosen x, unpredicted[i] = !(eff_psnr[i] > x); use_count[c] = unpredicted members of class c (the
+   dictionary tile's UseCount after MakeTilesUnique), first_member[c] = smallest unpredicted tile index of the class (n if none).
+   tm_reduce_remap: TMI.TileIdx = new_of_class[class] for unpredicted tiles, -1 otherwise (TransferTiles + ReindexTiles remap). */
+int tm_reduce_class_min(const int32_t *class_id, const double *eff_psnr, int64_t n, int64_t n_classes, double *sorted_min);
+int tm_reduce_apply(const int32_t *class_id, const double *eff_psnr, int64_t n, int64_t n_classes, double x, int32_t *use_count,
+                    int32_t *first_member, uint8_t *unpredicted);
+int tm_reduce_remap(const int32_t *class_id, const uint8_t *unpredicted, const int32_t *new_of_class, int64_t n, int64_t n_classes,
+                    int32_t *tile_idx);
 
 /* mean squared error over the three colour channels of two packed-RGB buffers of n pixels */
 int tm_mse_rgb(const int32_t *a, const int32_t *b, int64_t n, double *mse);

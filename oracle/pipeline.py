@@ -207,6 +207,38 @@ def reindex(dict_idx, tile_idx):
     return dict_idx[keep].copy(), use[keep].astype(np.int32), out
 
 
+def merge_tiles(dict_tiles, use_count, clusters, best, tile_idx):
+    """InitMergeTiles / MergeTiles / FinishMergeTiles (:4783-4840) followed by ReindexTiles(True) (:4626-4696), statement by
+    statement: clusters[i] = cluster of tile i, best[c] = the tile cluster c keeps."""
+    n = len(dict_tiles)
+    use = [int(u) for u in use_count]
+    active = [True] * n
+    merge_index = [-1] * n                                                    # InitMergeTiles
+    members = {}
+    for i, c in enumerate(clusters):
+        members.setdefault(int(c), []).append(i)
+    for c, idxs in members.items():                                           # MergeTiles(idxs, len, best[c], nil, nil)
+        b = int(best[c])
+        for t in idxs:
+            if t == b:
+                continue
+            use[b] += use[t]
+            active[t] = False
+            use[t] = 0
+            merge_index[t] = b
+    tmap = np.asarray(tile_idx, dtype=np.int64).copy()
+    flat = tmap.reshape(-1)
+    for i in range(len(flat)):                                                # FinishMergeTiles
+        t = flat[i]
+        if t >= 0 and merge_index[t] >= 0:
+            flat[i] = merge_index[t]
+    keep = [i for i in range(n) if active[i] and use[i] > 0]                  # ReindexTiles(True)
+    keep.sort(key=lambda i: (-use[i], tuple(np.asarray(dict_tiles[i]).astype(np.uint32).tolist())))
+    new_of = {old: new for new, old in enumerate(keep)}
+    out = np.array([new_of[t] if t >= 0 else -1 for t in flat], dtype=np.int32).reshape(tmap.shape)
+    return np.asarray(dict_tiles)[keep].copy(), np.array([use[i] for i in keep], dtype=np.int32), out
+
+
 def encode(frames, seqs, tile_count, palette_count, palette_size, seed, radius=32, use_tk=True, y2_mixed=4, extended=True):
     """TTilingEncoder.Run (:5529-5554) up to, but not including, the stream writer: Load -> PredictMotion -> Reduce ->
     PreparePalettes (without OptimizePalettes) -> Dither -> Reconstruct -> Reindex."""

@@ -266,3 +266,84 @@ def test_fast_features_encode_psnr_within_tolerance(tm, oracle):
     differing = (np.asarray(exact["tilemap"]["is_pred"]) != np.asarray(fast["tilemap"]["is_pred"])).mean()
     print(f"fast features: PSNR {pf:.4f} dB vs {pe:.4f} dB, {differing:.2%} of the tilemap items change their predicted flag")
     assert differing <= 0.02
+
+
+# ------------------------------------------------------------------ persistent shard handle of the sharded Lloyd loop
+def test_kmeans_i16_shard_handle_equals_single_call_fit(tm, oracle):
+    """tiler_b200.dist.kmeans_fit_i16_sharded (limb rows split once, stopping test read every 4 iterations, nothing copied to the
+    host per step) against tm_kmeans_fit_i16 and the oracle's f64 Lloyd from the same initial centroids."""
+    import torch
+    from tiler_b200 import dist as tdist
+    x = synth.random_features(6000, 9, adversarial=True)
+    init = x[:96].astype(np.float64)
+    ol, oc, oin, oit = oracle.kmeans_lloyd(x.astype(np.float64), init, max_iter=300)
+    gl, gc, gin, git, _ = tm.kmeans_fit_i16(x, 96, init, max_iter=300)
+    assert np.array_equal(gl, ol) and np.array_equal(gc, oc)
+    xs, ini = torch.from_numpy(x).cuda(), torch.from_numpy(init).cuda()
+    for every in (1, 4):
+        tms = {}
+        sl, sc, sin, sit = tdist.kmeans_fit_i16_sharded(xs, ini, max_iter=300, check_every=every, timings=tms)
+        assert np.array_equal(sl.cpu().numpy(), ol) and np.array_equal(sc.cpu().numpy(), oc)
+        assert abs(sin - oin) <= 1e-9 * oin and oit <= sit < oit + every
+        assert len(tms["assign_ms"]) == sit + 1
+
+
+# ------------------------------------------------------------------ MergeTiles hook: a k-means-built dictionary (north star stage 3)
+def test_cluster_dictionary_through_merge_tiles_hook(tm, oracle):
+    from oracle import pipeline as P
+    from tiler_b200.encoder import TilingEncoder
+    frames = synth.pack_rgb(synth.make_clip(128, 96, 4, cut_every=0, seed=19, n_sprites=4))
+    _, canon, flags, tw, th = P.load(frames)
+    psnr = P.predict_motion(P.pad_frames(frames)[0], canon, flags, tw, th, 32)
+    enc = TilingEncoder(palette_size=16, palette_count=2)
+    tmap = enc.reduce(canon, flags, psnr, [0], 300)
+    d_tiles, d_use = np.asarray(enc.tiles).copy(), np.asarray(enc.use_count).copy()
+    n, k = len(d_tiles), 60
+    new_map = enc.cluster_dictionary(k, tmap)
+    # the same clustering restated with the oracle: f64 Lloyd from the k most used tiles, nearest member kept, MergeTiles
+    feats = oracle.features_from_rgb(d_tiles).astype(np.float64)
+    lab, cen, _, _ = oracle.kmeans_lloyd(feats, feats[:k].copy(), max_iter=300)
+    d = ((feats - cen[lab]) ** 2).sum(1)
+    best = np.array([min(np.flatnonzero(lab == c), key=lambda i: (d[i], i)) if (lab == c).any() else -1 for c in range(k)])
+    r_tiles, r_use, r_map = P.merge_tiles(d_tiles, d_use, lab, best, tmap)
+    assert len(r_tiles) <= k and r_use.sum() == d_use.sum()
+    assert np.array_equal(np.asarray(enc.tiles), r_tiles) and np.array_equal(enc.use_count, r_use) and np.array_equal(new_map, r_map)
+    # the clustered dictionary still encodes: palettes, dithering and the matcher accept it
+    enc.prepare_palettes(); enc.dither(); enc.prepare_reconstruct()
+    ti, pi, er = enc.reconstruct(canon[0])
+    assert ti.min() >= 0 and ti.max() < len(r_tiles)
+    enc.finish_reconstruct()
+
+
+# ------------------------------------------------------------------ mirror-variant search (north star / configs[4])
+@pytest.mark.parametrize("extended", [True, False])
+def test_mirror_variant_search_against_oracle(tm, oracle, extended):
+    rng = np.random.default_rng(61)
+    tiles = rand_tiles(900, 71)
+    canon, flags = tm.mirror_canonicalise(tiles)
+    pal = np.stack([oracle.quantize_palette(canon[p::4].reshape(-1), 16, seed=3)[0] for p in range(4)])
+    dpal = (np.arange(600) % 4).astype(np.int32)
+    didx = oracle.dither(canon[:600], flags[:600], dpal, pal)
+    # queries: dictionary source tiles deliberately stored in a NON-canonical orientation, plus unrelated tiles
+    q = canon[300:900].copy().reshape(-1, 8, 8)
+    flip = rng.integers(0, 4, size=len(q))
+    for i, v in enumerate(flip):
+        if v & 1: q[i] = q[i][:, ::-1]
+        if v & 2: q[i] = q[i][::-1, :]
+    q = np.ascontiguousarray(q.reshape(-1, 64))
+    m = tm.Matcher(didx, dpal, pal, extended=extended)
+    ti, pi, er, var = m.match_rgb_mirrors(q)
+    m.close()
+    dict_feat = oracle.features_from_pal(didx, dpal, pal)
+    res = []
+    for v in range(4):
+        qf = oracle.features_from_rgb_mirrored(q, np.full(len(q), v, np.uint8))
+        assert np.array_equal(tm.features_from_rgb_mirrored(q, np.full(len(q), v, np.uint8)), qf)
+        res.append(oracle.match_tiles(qf, dict_feat, didx, dpal, pal, k=64, extended=extended))
+    e4 = np.stack([r[2] for r in res]).astype(np.int64)
+    bv = e4.argmin(0)                                             # first minimum: the canonical orientation keeps ties
+    rows = np.arange(len(q))
+    assert np.array_equal(var, bv)
+    assert np.array_equal(_u32(er), e4[bv, rows].astype(np.uint32))
+    assert np.array_equal(ti, np.stack([r[0] for r in res])[bv, rows]) and np.array_equal(pi, np.stack([r[1] for r in res])[bv, rows])
+    assert (var[:300][flip[:300] != 0] != 0).mean() > 0.5            # re-flipped dictionary tiles are found through a mirror variant

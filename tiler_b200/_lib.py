@@ -50,6 +50,9 @@ SIGNATURES = {
     "tm_kmeans_fit": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _u64, _i32, _vp, _vp, C.POINTER(_dbl), C.POINTER(_i32)]),
     "tm_kmeans_fit_i16": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _vp, C.POINTER(_dbl), C.POINTER(_i32), C.POINTER(_i64)]),
     "tm_kmeans_partial_step_i16": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_dbl)]),
+    "tm_kmeans_i16_create": (C.c_int, [_vp, _i64, _i32, C.POINTER(_vp)]),
+    "tm_kmeans_i16_destroy": (C.c_int, [_vp]),
+    "tm_kmeans_i16_step": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tm_kmeans_partial_step": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _vp, _vp, _vp, C.POINTER(_i64), C.POINTER(_dbl)]),
     "tm_kmeans_finish_step": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "tm_coreset_weighted": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _i32, _u64, _vp, _vp, C.POINTER(_i64)]),
@@ -62,6 +65,8 @@ SIGNATURES = {
     "tm_matcher_destroy": (C.c_int, [_vp]),
     "tm_match_tiles_rgb": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "tm_match_tiles_feat": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "tm_match_tiles_rgb_mirrors": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "tm_features_from_rgb_mirrored": (C.c_int, [_vp, _vp, _i64, _vp]),
     "tm_matcher_dict_features": (C.c_int, [_vp, _vp]),
     "tm_sliding_features": (C.c_int, [_vp, _i32, _i32, _vp]),
     "tm_motion_search": (C.c_int, [_vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp]),
@@ -70,6 +75,9 @@ SIGNATURES = {
     "tm_reconstruct_frame": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tm_mse_rgb": (C.c_int, [_vp, _vp, _i64, C.POINTER(_dbl)]),
     "tm_tile_classes": (C.c_int, [_vp, _i64, _vp, C.POINTER(_i32)]),
+    "tm_reduce_class_min": (C.c_int, [_vp, _vp, _i64, _i64, _vp]),
+    "tm_reduce_apply": (C.c_int, [_vp, _vp, _i64, _i64, _dbl, _vp, _vp, _vp]),
+    "tm_reduce_remap": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     # drop-in exports (extern.pas:178-223)
     "ann_kdtree_short_create": (_vp, [_vp, _i32, _i32, _i32, _i32]),
     "ann_kdtree_short_destroy": (None, [_vp]),

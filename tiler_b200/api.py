@@ -120,6 +120,15 @@ def features_from_rgb(rgb):
     return out
 
 
+def features_from_rgb_mirrored(rgb, flags):
+    """Features of stored tiles read through mirror flags (bit 0 H, bit 1 V): ConvertToCpnPixels with AHMirror / AVMirror."""
+    c = _Call(rgb, flags)
+    n = _n_rows(rgb, 64)
+    out, po = c.out((n, DCT), np.int16)
+    check(_lib.lib().tm_features_from_rgb_mirrored(c.inp(rgb, np.int32), c.inp(flags, np.uint8), n, po))
+    return out
+
+
 def features_from_pal(pal_idx, tile_pal, palettes):
     """PrepareReconstruct.DoPsyV (tilingencoder.pas:4570-4583): indexed tiles + their palettes -> int16 [n,192]."""
     c = _Call(pal_idx, tile_pal, palettes)
@@ -282,6 +291,48 @@ def kmeans_partial_step_i16(x, centroids, labels):
     return lab, sums, counts, changed.value, inertia.value
 
 
+class KmeansI16Shard:
+    """tm_kmeans_i16_create / _step / _destroy: one rank's shard of the sharded Lloyd loop.  The points are split into limb
+    rows once; step() takes and returns device tensors (or numpy arrays) and copies nothing to the host."""
+
+    def __init__(self, x, k):
+        c = _Call(x)
+        self._x = c.inp(x, np.int16)          # keeps the rows alive: the handle references device rows in place
+        self._keep = c.keep
+        self.n, self.k, self.dev = _n_rows(x, DCT), int(k), c.dev
+        self.device = c.device if c.dev else None
+        h = C.c_void_p()
+        check(_lib.lib().tm_kmeans_i16_create(self._x, self.n, self.k, C.byref(h)))
+        self._h = h
+
+    def step(self, centroids, labels, sums=None, counts=None, stats=None, inertia=None):
+        """labels updated in place; -> (sums [k,192] f64, counts [k] int64).  stats: int64[2] accumulator tensor (changed,
+        exact-scan points), inertia: f64[1] tensor, both optional."""
+        c = _Call(centroids, labels)
+        if sums is None:
+            sums, _ = c.out((self.k, DCT), np.float64)
+        if counts is None:
+            counts, _ = c.out((self.k,), np.int64)
+
+        def ptr(a):
+            if a is None:
+                return None
+            return C.c_void_p(a.data_ptr()) if _is_dev(a) else C.c_void_p(a.ctypes.data)
+        check(_lib.lib().tm_kmeans_i16_step(self._h, c.inp(centroids, np.float64), ptr(labels), ptr(sums), ptr(counts), ptr(stats), ptr(inertia)))
+        return sums, counts
+
+    def close(self):
+        if self._h:
+            _lib.lib().tm_kmeans_i16_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def kmeans_partial_step(x, centroids, labels):
     """One Lloyd step on a shard: assignment + per-cluster partial sums/counts (to be all-reduced across GPUs)."""
     c = _Call(x, centroids, labels)
@@ -383,6 +434,19 @@ class Matcher:
         """Source tiles as RGB [n,64] -> (TileIdx, PalIdx, err) per tile."""
         return self._run(_lib.lib().tm_match_tiles_rgb, rgb, 64, np.int32, k or (self.K_EPU if self.extended else 1))
 
+    def match_rgb_mirrors(self, rgb, k=None):
+        """Mirror-variant search (tm_match_tiles_rgb_mirrors). -> (tile_idx, pal_idx, err, variant); variant bit 0 / 1 = extra
+        H / V mirror of the winning match."""
+        c = _Call(rgb)
+        n = _n_rows(rgb, 64)
+        kk = int(k) if k else (self.K_EPU if self.extended else 1)
+        tile, pt = c.out((n,), np.int32)
+        pal, pp = c.out((n,), np.int32)
+        err, pe = c.out((n,), np.uint32)
+        var, pv = c.out((n,), np.uint8)
+        check(_lib.lib().tm_match_tiles_rgb_mirrors(self._h, c.inp(rgb, np.int32), n, kk, pt, pp, pe, pv))
+        return tile, pal, err, var
+
     def match_feat(self, feat, k=None):
         return self._run(_lib.lib().tm_match_tiles_feat, feat, DCT, np.int16, k or (self.K_EPU if self.extended else 1))
 
@@ -483,6 +547,36 @@ def tile_classes(rgb):
     cnt = C.c_int()
     check(_lib.lib().tm_tile_classes(c.inp(rgb, np.int32), n, pc, C.byref(cnt)))
     return cls, cnt.value
+
+
+def reduce_class_min(class_id, eff_psnr, n_classes):
+    """Per duplicate class the smallest effective PSNR of its members, sorted ascending (STCGREval's count for any threshold)."""
+    c = _Call(class_id, eff_psnr)
+    n = int(np.prod(class_id.shape))
+    out, po = c.out((int(n_classes),), np.float64)
+    check(_lib.lib().tm_reduce_class_min(c.inp(class_id, np.int32), c.inp(eff_psnr, np.float64), n, int(n_classes), po))
+    return out
+
+
+def reduce_apply(class_id, eff_psnr, n_classes, x):
+    """IsPredicted := PSNR > x for every tile -> (use_count [n_classes], first unpredicted member [n_classes], unpredicted [n])."""
+    c = _Call(class_id, eff_psnr)
+    n = int(np.prod(class_id.shape))
+    use, pu = c.out((int(n_classes),), np.int32)
+    rep, pr = c.out((int(n_classes),), np.int32)
+    unp, pn = c.out((n,), np.uint8)
+    check(_lib.lib().tm_reduce_apply(c.inp(class_id, np.int32), c.inp(eff_psnr, np.float64), n, int(n_classes), float(x), pu, pr, pn))
+    return use, rep, unp
+
+
+def reduce_remap(class_id, unpredicted, new_of_class):
+    """Tilemap TileIdx after TransferTiles + ReindexTiles: new_of_class[class] where unpredicted, else -1."""
+    c = _Call(class_id, unpredicted, new_of_class)
+    n = int(np.prod(class_id.shape))
+    out, po = c.out((n,), np.int32)
+    check(_lib.lib().tm_reduce_remap(c.inp(class_id, np.int32), c.inp(unpredicted, np.uint8), c.inp(new_of_class, np.int32), n,
+                                     int(np.prod(new_of_class.shape)), po))
+    return out
 
 
 def mse_rgb(a, b):

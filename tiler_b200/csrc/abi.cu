@@ -530,6 +530,79 @@ extern "C" int tm_kmeans_fit_i16(const int16_t *x, int64_t n, int k, int max_ite
   return TM_OK;
 }
 
+// ---- persistent shard state for the multi-GPU Lloyd loop: the points are split into limb rows ONCE, every step only
+// re-rounds the centroids, and nothing of a step's result comes back to the host (the one 8-byte read inside the step is
+// the count of uncertified points, which decides whether the second-level search is launched at all).
+struct tm_kmeans_i16 {
+  int64_t n = 0; int k = 0;
+  int16_t *x_own = nullptr;     // device copy of host points (null when the caller's rows already live on the device)
+  KmI16 w{};
+  void *ws = nullptr; size_t ws_bytes = 0;
+  double *part = nullptr;       // 1024 block partials of the inertia sum
+};
+
+extern "C" int tm_kmeans_i16_destroy(tm_kmeans_i16 *h) {
+  if (!h) return TM_OK;
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  cudaFree(h->x_own); cudaFree(h->w.x_limbs); cudaFree(h->w.x_norm); cudaFree(h->w.rc); cudaFree(h->w.c_limbs); cudaFree(h->w.c_norm);
+  cudaFree(h->w.cand); cudaFree(h->w.cdist); cudaFree(h->w.amb_list); cudaFree(h->w.counters); cudaFree(h->w.dist); cudaFree(h->ws);
+  cudaFree(h->part);
+  delete h;
+  return TM_OK;
+}
+
+extern "C" int tm_kmeans_i16_create(const int16_t *x, int64_t n, int k, tm_kmeans_i16 **out) {
+  RC(require_gpu());
+  if (!x || !out || n < 1 || n > 0x7fffffff || k < 1) return fail(TM_ERR_ARG, "tm_kmeans_i16_create: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  cudaStream_t st = t_stream;
+  tm_kmeans_i16 *h = new tm_kmeans_i16();
+  h->n = n; h->k = k;
+  KmI16 &w = h->w;
+  const int64_t kpad = (k + 63) / 64 * 64;
+  h->ws_bytes = kmeans_update_ws_bytes(n, k);
+  bool ok = true;
+  auto alloc = [&](void **p, size_t bytes) { if (ok && cudaMalloc(p, bytes ? bytes : 16) != cudaSuccess) ok = false; };
+  if (!is_device_ptr(x)) {
+    alloc((void **)&h->x_own, (size_t)n * 384);
+    if (ok && cudaMemcpyAsync(h->x_own, x, (size_t)n * 384, cudaMemcpyHostToDevice, st) != cudaSuccess) ok = false;
+  }
+  w.x = h->x_own ? h->x_own : x; w.n = n; w.k = k;
+  alloc((void **)&w.x_limbs, (size_t)n * 384); alloc((void **)&w.x_norm, (size_t)n * 4);
+  alloc((void **)&w.rc, (size_t)k * 384); alloc((void **)&w.c_limbs, (size_t)k * 384); alloc((void **)&w.c_norm, (size_t)kpad * 4);
+  alloc((void **)&w.cand, (size_t)n * KMEANS_KC * 4); alloc((void **)&w.cdist, (size_t)n * KMEANS_KC * 4);
+  alloc((void **)&w.amb_list, (size_t)n * 4); alloc((void **)&w.counters, 8); alloc((void **)&w.dist, (size_t)n * 8);
+  alloc(&h->ws, h->ws_bytes); alloc((void **)&h->part, 1024 * 8);
+  int rc = ok ? TM_OK : TM_ERR_NOMEM;
+  if (rc == TM_OK && cudaMemsetAsync(w.c_norm, 0, (size_t)kpad * 4, st) != cudaSuccess) rc = TM_ERR_CUDA;
+  if (rc == TM_OK) rc = launch_limb_split(w.x, n, w.x_limbs, w.x_norm, st);
+  if (rc == TM_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = TM_ERR_CUDA;
+  if (rc != TM_OK) { tm_kmeans_i16_destroy(h); return fail(rc, "tm_kmeans_i16_create"); }
+  *out = h;
+  return TM_OK;
+}
+
+extern "C" int tm_kmeans_i16_step(tm_kmeans_i16 *h, const double *centroids, int32_t *labels, double *partial_sums, int64_t *partial_counts,
+                                  int64_t *stats, double *inertia) {
+  RC(require_gpu());
+  if (!h || !centroids || !labels || !partial_sums || !partial_counts) return fail(TM_ERR_ARG, "tm_kmeans_i16_step: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const double *d_cent = s.in(centroids, (size_t)h->k * 192);
+  int32_t *d_labels = s.inout(labels, (size_t)h->n);
+  double *d_sums = s.out(partial_sums, (size_t)h->k * 192);
+  int64_t *d_counts = s.out(partial_counts, (size_t)h->k);
+  int64_t *d_stats = stats ? s.inout(stats, 2) : nullptr;
+  double *d_inertia = inertia ? s.out(inertia, 1) : nullptr;
+  int ch = 0, n_bf = 0;
+  if (s.err == TM_OK) s.err = km_i16_assign(h->w, d_cent, d_labels, &ch, &n_bf, s);
+  if (s.err == TM_OK) s.err = launch_kmeans_update_i16(h->w.x, h->n, d_labels, h->k, d_sums, d_counts, h->ws, h->ws_bytes, 0, 0, s.st);
+  if (s.err == TM_OK && d_stats) s.err = launch_kmeans_stats_add(d_stats, h->w.counters, n_bf, s.st);
+  if (s.err == TM_OK && d_inertia) s.err = launch_sum_f64(h->w.dist, h->n, h->part, d_inertia, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
 // multi-GPU building block: one assignment over this rank's shard + per-cluster partial sums/counts
 extern "C" int tm_kmeans_partial_step_i16(const int16_t *x, int64_t n, int k, const double *centroids, int32_t *labels,
                                           double *partial_sums, int64_t *partial_counts, int64_t *changed, double *inertia) {
@@ -813,6 +886,47 @@ extern "C" int tm_match_tiles_rgb(tm_matcher *m, const int32_t *rgb, int64_t n_q
   return TM_OK;
 }
 
+extern "C" int tm_features_from_rgb_mirrored(const int32_t *rgb, const uint8_t *flags, int64_t n, int16_t *out) {
+  RC(require_gpu());
+  if (n < 0 || (n > 0 && (!rgb || !flags || !out))) return fail(TM_ERR_ARG, "tm_features_from_rgb_mirrored: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int32_t *d_rgb = s.in(rgb, (size_t)n * 64);
+  const uint8_t *d_fl = s.in(flags, (size_t)n);
+  int16_t *d_out = s.out(out, (size_t)n * 192);
+  if (s.err == TM_OK) s.err = launch_features_rgb_mirrored(d_rgb, d_fl, n, d_out, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+// DoXY's k-NN branch with the 4 mirror variants of every source tile (a superset of the reference: variant 0 is its result)
+extern "C" int tm_match_tiles_rgb_mirrors(tm_matcher *m, const int32_t *rgb, int64_t n_q, int k, int32_t *tile_idx, int32_t *pal_idx, uint32_t *err,
+                                          uint8_t *variant) {
+  RC(require_gpu());
+  if (!m || n_q < 0 || n_q * 4 > 0x7fffffff || k < 1 || k > 64 || (n_q > 0 && (!rgb || !tile_idx || !pal_idx || !err || !variant)))
+    return fail(TM_ERR_ARG, "tm_match_tiles_rgb_mirrors: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int32_t *d_rgb = s.in(rgb, (size_t)n_q * 64);
+  int32_t *d_tile = s.out(tile_idx, (size_t)n_q), *d_pal = s.out(pal_idx, (size_t)n_q);
+  uint32_t *d_err = s.out(err, (size_t)n_q);
+  uint8_t *d_var = s.out(variant, (size_t)n_q);
+  if (n_q > 0) {
+    int16_t *d_feat = (int16_t *)s.temp((size_t)n_q * 4 * 384);
+    uint8_t *d_fl = (uint8_t *)s.temp((size_t)n_q);
+    int32_t *t4 = (int32_t *)s.temp((size_t)n_q * 16), *p4 = (int32_t *)s.temp((size_t)n_q * 16);
+    uint32_t *e4 = (uint32_t *)s.temp((size_t)n_q * 16);
+    for (int v = 0; v < 4 && s.err == TM_OK; ++v) {   // features of the tile as mirrored by v (bit 0 H, bit 1 V), exact reference arithmetic
+      if (cudaMemsetAsync(d_fl, v, (size_t)n_q, s.st) != cudaSuccess) { s.err = TM_ERR_CUDA; break; }
+      s.err = launch_features_rgb_mirrored(d_rgb, d_fl, n_q, d_feat + (size_t)v * n_q * 192, s.st);
+    }
+    if (s.err == TM_OK) s.err = match_feat_dev(m, d_feat, n_q * 4, k, t4, p4, e4, s);   // one batched search over all variants
+    if (s.err == TM_OK) s.err = launch_mirror_combine(t4, p4, e4, n_q, d_tile, d_pal, d_err, d_var, s.st);
+  }
+  RC(s.finish());
+  return TM_OK;
+}
+
 extern "C" int tm_matcher_dict_features(tm_matcher *m, int16_t *out) {
   RC(require_gpu());
   if (!m || !out) return fail(TM_ERR_ARG, "tm_matcher_dict_features: bad argument");
@@ -1024,6 +1138,54 @@ extern "C" int tm_tile_classes(const int32_t *rgb, int64_t n, int32_t *class_id,
   if (s.err == TM_OK && cudaMemcpyAsync(&host_cnt, d_cnt, 4, cudaMemcpyDeviceToHost, s.st) != cudaSuccess) s.err = TM_ERR_CUDA;
   RC(s.finish(true));
   *n_classes = host_cnt;
+  return TM_OK;
+}
+
+// ---- the tile-count search's bookkeeping over the duplicate classes (STCGREval / TransferTiles, :4014-4103)
+extern "C" int tm_reduce_class_min(const int32_t *class_id, const double *eff_psnr, int64_t n, int64_t n_classes, double *sorted_min) {
+  RC(require_gpu());
+  if (!class_id || !eff_psnr || !sorted_min || n < 1 || n > 0x7fffffff || n_classes < 1 || n_classes > n)
+    return fail(TM_ERR_ARG, "tm_reduce_class_min: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int32_t *d_cls = s.in(class_id, (size_t)n);
+  const double *d_eff = s.in(eff_psnr, (size_t)n);
+  double *d_out = s.out(sorted_min, (size_t)n_classes);
+  const size_t wsb = class_min_ws_bytes(n_classes);
+  void *ws = s.temp(wsb);
+  if (s.err == TM_OK) s.err = run_class_min_sorted(d_cls, d_eff, n, n_classes, d_out, ws, wsb, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+extern "C" int tm_reduce_apply(const int32_t *class_id, const double *eff_psnr, int64_t n, int64_t n_classes, double x, int32_t *use_count,
+                               int32_t *first_member, uint8_t *unpredicted) {
+  RC(require_gpu());
+  if (!class_id || !eff_psnr || !use_count || !first_member || !unpredicted || n < 1 || n > 0x7fffffff || n_classes < 1)
+    return fail(TM_ERR_ARG, "tm_reduce_apply: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int32_t *d_cls = s.in(class_id, (size_t)n);
+  const double *d_eff = s.in(eff_psnr, (size_t)n);
+  int32_t *d_use = s.out(use_count, (size_t)n_classes), *d_rep = s.out(first_member, (size_t)n_classes);
+  uint8_t *d_un = s.out(unpredicted, (size_t)n);
+  if (s.err == TM_OK) s.err = run_reduce_apply(d_cls, d_eff, n, n_classes, x, d_use, d_rep, d_un, s.st);
+  RC(s.finish());
+  return TM_OK;
+}
+
+extern "C" int tm_reduce_remap(const int32_t *class_id, const uint8_t *unpredicted, const int32_t *new_of_class, int64_t n, int64_t n_classes,
+                               int32_t *tile_idx) {
+  RC(require_gpu());
+  if (!class_id || !unpredicted || !new_of_class || !tile_idx || n < 1 || n_classes < 1) return fail(TM_ERR_ARG, "tm_reduce_remap: bad argument");
+  std::lock_guard<std::recursive_mutex> lk(g_mu);
+  Stage s(t_stream);
+  const int32_t *d_cls = s.in(class_id, (size_t)n);
+  const uint8_t *d_un = s.in(unpredicted, (size_t)n);
+  const int32_t *d_new = s.in(new_of_class, (size_t)n_classes);
+  int32_t *d_out = s.out(tile_idx, (size_t)n);
+  if (s.err == TM_OK) s.err = run_reduce_remap(d_cls, d_un, d_new, n, d_out, s.st);
+  RC(s.finish());
   return TM_OK;
 }
 

@@ -241,6 +241,41 @@ kmpp_pick_kernel(const double *__restrict__ x, int64_t n, int dim, int c, unsign
 static inline size_t km_al(size_t v) { return (v + 255) & ~(size_t)255; }
 // member blocks of large clusters: each has > KM_BLOCK members, so there are at most 2n / KM_BLOCK of them
 static inline int64_t km_max_blocks(int64_t n) { return 2 * (n / KM_BLOCK) + 1; }
+// stats[0] += labels changed in this step (device counter), stats[1] += points that needed the exact f64 scan
+__global__ void kmeans_stats_add_kernel(long long *__restrict__ stats, const int32_t *__restrict__ counters, long long n_bf) {
+  stats[0] += (long long)counters[0];
+  stats[1] += n_bf;
+}
+int launch_kmeans_stats_add(int64_t *stats, const int32_t *counters, int64_t n_bf, cudaStream_t st) {
+  kmeans_stats_add_kernel<<<1, 1, 0, st>>>(reinterpret_cast<long long *>(stats), counters, (long long)n_bf);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+// out[0] = sum of v[0..n) (reporting scalar: block partials in index order, then one thread adds the partials in order)
+__global__ void __launch_bounds__(256) sum_f64_partial_kernel(const double *__restrict__ v, int64_t n, double *__restrict__ part) {
+  __shared__ double s[256];
+  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
+  double a = 0.0;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) a += v[i];
+  s[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o]; __syncthreads(); }
+  if (threadIdx.x == 0) part[blockIdx.x] = s[0];
+}
+__global__ void sum_f64_final_kernel(const double *__restrict__ part, int nb, double *__restrict__ out) {
+  double a = 0.0;
+  for (int i = 0; i < nb; ++i) a += part[i];
+  out[0] = a;
+}
+int launch_sum_f64(const double *v, int64_t n, double *part /* >= 1024 doubles */, double *out, cudaStream_t st) {
+  const int nb = (int)(n < 1024 * 256 ? (n + 255) / 256 : 1024);
+  sum_f64_partial_kernel<<<nb > 0 ? nb : 1, 256, 0, st>>>(v, n, part);
+  sum_f64_final_kernel<<<1, 1, 0, st>>>(part, nb > 0 ? nb : 1, out);
+  note_launch(2);
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
 size_t kmeans_update_ws_bytes(int64_t n, int k, int dim) {
   size_t sort_tmp = 0, scan_tmp = 0;
   cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (const int32_t *)nullptr, (int32_t *)nullptr, (const int32_t *)nullptr,

@@ -157,6 +157,36 @@ int launch_match_plain(const int32_t *knn_idx, const uint32_t *knn_dist, int64_t
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }
 
+// Mirror-variant search (north star: "including H/V-mirror ... variants"; BASELINE configs[4]): the match of a source tile is
+// tried in its stored orientation and H-, V-, HV-mirrored; variant v's result arrays are [v][n].  The FIRST strict minimum of
+// the error over v = 0..3 wins, so the canonical orientation keeps ties (the reference never searches mirrors: v = 0 is its
+// result, tilingencoder.pas:1393-1411, 1625-1637).
+__global__ void __launch_bounds__(256) mirror_combine_kernel(const int32_t *__restrict__ t4, const int32_t *__restrict__ p4,
+                                                             const uint32_t *__restrict__ e4, int64_t n, int32_t *__restrict__ out_tile,
+                                                             int32_t *__restrict__ out_pal, uint32_t *__restrict__ out_err,
+                                                             uint8_t *__restrict__ out_variant) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int bv = 0;
+  uint32_t be = e4[i];
+#pragma unroll
+  for (int v = 1; v < 4; ++v) {
+    const uint32_t e = e4[(int64_t)v * n + i];
+    if (e < be) { be = e; bv = v; }
+  }
+  out_tile[i] = t4[(int64_t)bv * n + i];
+  out_pal[i] = p4[(int64_t)bv * n + i];
+  out_err[i] = be;
+  out_variant[i] = (uint8_t)bv;
+}
+int launch_mirror_combine(const int32_t *t4, const int32_t *p4, const uint32_t *e4, int64_t n, int32_t *out_tile, int32_t *out_pal,
+                          uint32_t *out_err, uint8_t *out_variant, cudaStream_t st) {
+  if (n <= 0) return TM_OK;
+  mirror_combine_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t4, p4, e4, n, out_tile, out_pal, out_err, out_variant);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
 int launch_distance_pairs(const int16_t *a, const int16_t *b, int64_t n, uint32_t *out, cudaStream_t st) {
   if (n <= 0) return TM_OK;
   distance_pairs_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(a, b, n, out);

@@ -111,4 +111,96 @@ int run_tile_classes(const int32_t *rgb, int64_t n, int32_t *class_id, int32_t *
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }
 
+// ------------------------------------------------------------------ tile-count search bookkeeping (STCGREval, :4014-4046)
+// Per duplicate class the SMALLEST effective PSNR of its members decides from which threshold x on the class contributes a
+// dictionary tile (a tile is unpredicted when not PSNR > x), so the count of distinct unpredicted tiles for any x is a binary
+// search in the sorted class minima: the golden-ratio search (utils.pas:1044-1072) then needs no further pass over the tiles.
+// All three kernels are one pass over n tiles with atomics on per-class slots: HBM-bound (12-16 bytes per tile).
+__device__ __forceinline__ unsigned long long f64_order_key(double v) {   // monotone map double -> uint64 (negative values included)
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+__device__ __forceinline__ double f64_from_order_key(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFULL) : ~k;
+  return __longlong_as_double((long long)b);
+}
+__global__ void __launch_bounds__(256) fill_u64_kernel(unsigned long long *__restrict__ p, int64_t n, unsigned long long v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void __launch_bounds__(256) class_min_kernel(const int32_t *__restrict__ cls, const double *__restrict__ eff, int64_t n,
+                                                        unsigned long long *__restrict__ key) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) atomicMin(key + cls[i], f64_order_key(eff[i]));
+}
+__global__ void __launch_bounds__(256) keys_to_f64_kernel(const unsigned long long *__restrict__ key, int64_t n, double *__restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = f64_from_order_key(key[i]);
+}
+size_t class_min_ws_bytes(int64_t n_cls) {
+  size_t sort_tmp = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)n_cls);
+  return ((sort_tmp + 255) & ~(size_t)255) + (size_t)n_cls * 16 + 256;
+}
+// sorted_min[n_cls]: the classes' minimum effective PSNR, ascending
+int run_class_min_sorted(const int32_t *cls, const double *eff, int64_t n, int64_t n_cls, double *sorted_min, void *ws, size_t ws_bytes,
+                         cudaStream_t st) {
+  if (n <= 0 || n_cls <= 0 || n_cls > 0x7fffffff || ws_bytes < class_min_ws_bytes(n_cls)) return TM_ERR_ARG;
+  size_t sort_tmp = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, sort_tmp, (const unsigned long long *)nullptr, (unsigned long long *)nullptr, (int)n_cls);
+  uint8_t *p = (uint8_t *)ws;
+  void *d_tmp = p; p += (sort_tmp + 255) & ~(size_t)255;
+  unsigned long long *ka = (unsigned long long *)p; p += (size_t)n_cls * 8;
+  unsigned long long *kb = (unsigned long long *)p;
+  ProfScope prof("reduce_class_min", st);
+  fill_u64_kernel<<<(unsigned)((n_cls + 255) / 256), 256, 0, st>>>(ka, n_cls, ~0ull);
+  class_min_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cls, eff, n, ka);
+  if (cub::DeviceRadixSort::SortKeys(d_tmp, sort_tmp, ka, kb, (int)n_cls, 0, 64, st) != cudaSuccess) return TM_ERR_CUDA;
+  keys_to_f64_kernel<<<(unsigned)((n_cls + 255) / 256), 256, 0, st>>>(kb, n_cls, sorted_min);
+  note_launch(4);
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+// IsPredicted := PSNR > x (:4028-4031); per class: number of unpredicted members (the dictionary tile's UseCount after
+// MakeTilesUnique, :4783-4815) and the first unpredicted member in frame order (the representative that is transferred)
+__global__ void __launch_bounds__(256) reduce_apply_kernel(const int32_t *__restrict__ cls, const double *__restrict__ eff, int64_t n, double x,
+                                                           int32_t *__restrict__ use, int32_t *__restrict__ rep, uint8_t *__restrict__ unpred) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const bool u = !(eff[i] > x);
+  unpred[i] = u ? 1 : 0;
+  if (u) {
+    const int32_t c = cls[i];
+    atomicAdd(use + c, 1);
+    atomicMin(rep + c, (int32_t)i);
+  }
+}
+__global__ void __launch_bounds__(256) fill_i32_kernel(int32_t *__restrict__ p, int64_t n, int32_t v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+int run_reduce_apply(const int32_t *cls, const double *eff, int64_t n, int64_t n_cls, double x, int32_t *use, int32_t *rep, uint8_t *unpred,
+                     cudaStream_t st) {
+  if (n <= 0 || n > 0x7fffffff || n_cls <= 0) return TM_ERR_ARG;
+  ProfScope prof("reduce_apply", st);
+  fill_i32_kernel<<<(unsigned)((n_cls + 255) / 256), 256, 0, st>>>(use, n_cls, 0);
+  fill_i32_kernel<<<(unsigned)((n_cls + 255) / 256), 256, 0, st>>>(rep, n_cls, (int32_t)n);
+  reduce_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cls, eff, n, x, use, rep, unpred);
+  note_launch(3);
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+// TMI.TileIdx := new index of the tile's class when unpredicted, -1 otherwise (TransferTiles + ReindexTiles' remap, :4066-4090, :4682-4693)
+__global__ void __launch_bounds__(256) reduce_remap_kernel(const int32_t *__restrict__ cls, const uint8_t *__restrict__ unpred,
+                                                           const int32_t *__restrict__ new_of_cls, int64_t n, int32_t *__restrict__ tile_idx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) tile_idx[i] = unpred[i] ? new_of_cls[cls[i]] : -1;
+}
+int run_reduce_remap(const int32_t *cls, const uint8_t *unpred, const int32_t *new_of_cls, int64_t n, int32_t *tile_idx, cudaStream_t st) {
+  if (n <= 0) return TM_ERR_ARG;
+  reduce_remap_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(cls, unpred, new_of_cls, n, tile_idx);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
 }  // namespace tmg

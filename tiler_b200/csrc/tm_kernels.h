@@ -99,6 +99,9 @@ int launch_match_rerank(const int16_t *q_feat, int64_t n_q, const int32_t *knn_i
 int launch_knn_f64(const double *dict, int64_t n_dict, int dim, const double *q, int64_t n_q, int32_t *idx, double *dist,
                    cudaStream_t st);
 
+int launch_mirror_combine(const int32_t *t4, const int32_t *p4, const uint32_t *e4, int64_t n, int32_t *out_tile, int32_t *out_pal,
+                          uint32_t *out_err, uint8_t *out_variant, cudaStream_t st);
+
 // ---- kmeans.cu
 int launch_kmeans_assign_f64(const double *x, int64_t n, int dim, const double *cent, int k, int32_t *labels, double *dist,
                              int32_t *changed, cudaStream_t st);
@@ -126,12 +129,21 @@ int launch_kmeans_finish(const double *sums, const int64_t *counts, int k, int d
 int launch_match_plain(const int32_t *knn_idx, const uint32_t *knn_dist, int64_t n_q, const int32_t *dict_pal, int64_t n_dict,
                        int32_t *out_tile, int32_t *out_pal, uint32_t *out_err, cudaStream_t st);
 size_t kmeans_update_ws_bytes(int64_t n, int k, int dim = 192);
+int launch_kmeans_stats_add(int64_t *stats, const int32_t *counters, int64_t n_bf, cudaStream_t st);
+int launch_sum_f64(const double *v, int64_t n, double *part, double *out, cudaStream_t st);
 int run_palette_quantise(const int32_t *rgb, const int32_t *tile_pal, int64_t n_tiles, int n_pal, int pal_size, const double *init,
                          unsigned long long seed, int max_iter, int32_t *palettes_out, int32_t *iters_out, cudaStream_t st);
 
 // ---- reduce.cu: exact equivalence classes of 256-byte tiles (MakeTilesUnique on RGB pixels)
 size_t tile_classes_ws_bytes(int64_t n);
 int run_tile_classes(const int32_t *rgb, int64_t n, int32_t *class_id, int32_t *n_classes_dev, void *ws, size_t ws_bytes, cudaStream_t st);
+
+size_t class_min_ws_bytes(int64_t n_cls);
+int run_class_min_sorted(const int32_t *cls, const double *eff, int64_t n, int64_t n_cls, double *sorted_min, void *ws, size_t ws_bytes,
+                         cudaStream_t st);
+int run_reduce_apply(const int32_t *cls, const double *eff, int64_t n, int64_t n_cls, double x, int32_t *use, int32_t *rep, uint8_t *unpred,
+                     cudaStream_t st);
+int run_reduce_remap(const int32_t *cls, const uint8_t *unpred, const int32_t *new_of_cls, int64_t n, int32_t *tile_idx, cudaStream_t st);
 
 // ---- dlquant.cu
 int run_dl3quant(const uint8_t *rgb, const int64_t *img_off, int n_img, int64_t max_pixels, int quant_to, int bpc, uint8_t *pal_out,

@@ -65,21 +65,52 @@ def kmeans_fit_sharded(x_shard, init, max_iter=300, nan_empty=False):
     return labels, cent, inertia, it
 
 
-def kmeans_fit_i16_sharded(x_shard, init, max_iter=300, nan_empty=False):
-    """Same as kmeans_fit_sharded for int16 tile vectors: the assignment of every shard runs on the tensor cores
-    (tm_kmeans_partial_step_i16), the [k,192] sums and [k] counts are all-reduced, centroids stay replicated."""
+def kmeans_fit_i16_sharded(x_shard, init, max_iter=300, nan_empty=False, check_every=4, timings=None):
+    """Same as kmeans_fit_sharded for int16 tile vectors (config C).  The shard's points are split into limb rows once
+    (api.KmeansI16Shard); every iteration is: assignment on the tensor cores + per-cluster partial sums (one library call, no
+    host copy) -> all-reduce of the [k,192] f64 sums and of [k] counts + 2 counters (NCCL over NVLink) -> centroid update.
+    The stopping test (no label changed on any rank) reads the all-reduced counter on the host only every `check_every`
+    iterations: converged iterations in between change nothing, so the result equals the every-iteration test's.
+    timings (optional dict): per-iteration device times in ms of the three phases, from CUDA events."""
     from . import api
+    dev = x_shard.device
+    k = int(init.shape[0])
     cent = init.clone()
-    labels = torch.full((x_shard.shape[0],), -1, dtype=torch.int32, device=x_shard.device)
+    labels = torch.full((x_shard.shape[0],), -1, dtype=torch.int32, device=dev)
+    shard = api.KmeansI16Shard(x_shard, k)
+    sums = torch.empty((k, 192), dtype=torch.float64, device=dev)
+    meta = torch.zeros(k + 2, dtype=torch.int64, device=dev)        # [counts (k) | labels changed | exact-scan points]
+    multi = dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    ev = []
     it = 0
+    inertia = torch.zeros(1, dtype=torch.float64, device=dev)
     while True:
-        labels, sums, counts, changed, inertia = api.kmeans_partial_step_i16(x_shard, cent, labels)
-        sums, counts, changed, inertia = allreduce_partials(sums, counts, changed, inertia)
-        if changed == 0 or it >= max_iter:
-            break
+        meta[k:].zero_()
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timings is not None else None
+        if e: e[0].record()
+        shard.step(cent, labels, sums=sums, counts=meta[:k], stats=meta[k:], inertia=inertia)
+        if e: e[1].record()
+        if multi:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+            dist.all_reduce(meta, op=dist.ReduceOp.SUM)
+        if e: e[2].record()
+        last = it >= max_iter
+        if last or it % check_every == 0:
+            if int(meta[k].item()) == 0 or last:       # the only host read of the loop
+                if e: e[3].record(); ev.append(e)
+                break
         it += 1
-        cent = api.kmeans_finish_step(sums, counts, cent, nan_empty=nan_empty)
-    return labels, cent, inertia, it
+        cent = api.kmeans_finish_step(sums, meta[:k], cent, nan_empty=nan_empty)
+        if e: e[3].record(); ev.append(e)
+    if multi:
+        dist.all_reduce(inertia, op=dist.ReduceOp.SUM)
+    shard.close()
+    if timings is not None:
+        torch.cuda.synchronize()
+        timings["assign_ms"] = [a[0].elapsed_time(a[1]) for a in ev]
+        timings["allreduce_ms"] = [a[1].elapsed_time(a[2]) for a in ev]
+        timings["update_ms"] = [a[2].elapsed_time(a[3]) for a in ev]
+    return labels, cent, float(inertia.item()), it
 
 
 def gather_tilemaps(local, world_shards):

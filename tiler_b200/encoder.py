@@ -172,66 +172,35 @@ class TilingEncoder:
         eff = eff.reshape(-1)
         target = min(int(tile_count), n_all)
         fl = canon_flags.reshape(-1)
-        if api._is_dev(cls):
-            # per-class bookkeeping over millions of tiles as device scatter / sort / bincount (torch = memory plumbing);
-            # only the <= tile_count chosen representatives come back to the host for the final ReindexTiles ordering
-            dev = cls.device
-            cl = cls.long()
-            eff_t = torch.from_numpy(eff).to(dev)
-            cls_min = torch.full((n_cls,), float("inf"), dtype=torch.float64, device=dev)
-            cls_min.scatter_reduce_(0, cl, eff_t, reduce="amin")
-            sorted_min = torch.sort(cls_min).values.cpu().numpy()
-            x_res, x_last = golden_ratio_search(lambda x: float(np.searchsorted(sorted_min, x, side="right")), 0.0,
-                                                float(C_PSNR_MAX), float(target))
-            x = float(x_last if x_last is not None else x_res)
-            unpred = ~(eff_t > float(x))                                   # IsPredicted := PSNR > x
-            ucl = cl[unpred]
-            use_t = torch.bincount(ucl, minlength=n_cls)
-            rep_t = torch.full((n_cls,), n_all, dtype=torch.int64, device=dev)
-            rep_t.scatter_reduce_(0, ucl, torch.nonzero(unpred).reshape(-1), reduce="amin")   # first unpredicted member
-            chosen_t = torch.nonzero(use_t > 0).reshape(-1)
-            rep_sel = rep_t[chosen_t]
-            rep_tiles_host = flat[rep_sel].cpu().numpy()
-            use_sel = use_t[chosen_t].cpu().numpy()
-            order = _reindex_order(rep_tiles_host, use_sel)               # ReindexTiles(True): (use count desc, CompareDWord asc)
-            order_t = torch.from_numpy(order).to(dev)
-            chosen_t, rep_sel = chosen_t[order_t], rep_sel[order_t]
-            new_of_cls = torch.full((n_cls,), -1, dtype=torch.int32, device=dev)
-            new_of_cls[chosen_t] = torch.arange(chosen_t.numel(), dtype=torch.int32, device=dev)
-            tile_idx = torch.where(unpred, new_of_cls[cl], torch.full_like(cls, -1)).cpu().numpy().astype(np.int32).reshape(shape)
-            self.tiles, self.tile_flags = flat[rep_sel].contiguous(), fl[rep_sel].contiguous()
-            self.use_count = use_sel[order].astype(np.int32)
-            self.reduce_threshold = float(x)
-            return tile_idx
-        cls = np.asarray(cls)
-        order0 = np.argsort(cls, kind="stable")
-        starts = np.flatnonzero(np.r_[True, np.diff(cls[order0]) != 0])
-        sorted_min = np.sort(np.minimum.reduceat(eff[order0], starts))
+        # per-class bookkeeping over millions of tiles runs in the library (csrc/reduce.cu); only per-class arrays and the
+        # <= tile_count chosen representatives come back to the host for the final ReindexTiles ordering
+        to_host = lambda a: a.cpu().numpy() if api._is_dev(a) else np.asarray(a)
+        eff_d = self._to(eff)
+        sorted_min = to_host(api.reduce_class_min(cls, eff_d, n_cls))
         x_res, x_last = golden_ratio_search(lambda x: float(np.searchsorted(sorted_min, x, side="right")), 0.0,
                                             float(C_PSNR_MAX), float(target))
         x = float(x_last if x_last is not None else x_res)
-        unpred = ~(eff > x)                                   # IsPredicted := PSNR > x
-        idx_all = np.arange(n_all)
-        use = np.bincount(cls[unpred], minlength=n_cls)
-        # representative = first unpredicted member of the class
-        ui = idx_all[unpred]
-        uc = cls[unpred]
-        o2 = np.argsort(uc, kind="stable")                    # ui is ascending, the sort is stable: first of each run = smallest index
-        first = np.flatnonzero(np.r_[True, np.diff(uc[o2]) != 0])
-        rep = np.full(n_cls, n_all, dtype=np.int64)
-        rep[uc[o2][first]] = ui[o2][first]
+        use_d, rep_d, unpred_d = api.reduce_apply(cls, eff_d, n_cls, x)       # IsPredicted := PSNR > x
+        use, rep = to_host(use_d), to_host(rep_d)
         chosen = np.nonzero(use > 0)[0]
-        rep_idx = rep[chosen]
-        rep_tiles_host = flat[rep_idx]
-        # ReindexTiles(True): (use count desc, CompareDWord on the 64 pixels asc)
-        order = _reindex_order(rep_tiles_host, use[chosen])
+        rep_idx = rep[chosen].astype(np.int64)
+        if api._is_dev(flat):
+            rep_t = torch.from_numpy(rep_idx).to(flat.device)
+            rep_tiles_host = flat[rep_t].cpu().numpy()
+        else:
+            rep_tiles_host = flat[rep_idx]
+        order = _reindex_order(rep_tiles_host, use[chosen])                  # ReindexTiles(True): (use count desc, CompareDWord asc)
         chosen, rep_idx = chosen[order], rep_idx[order]
         new_of_cls = np.full(n_cls, -1, dtype=np.int32)
         new_of_cls[chosen] = np.arange(len(chosen), dtype=np.int32)
-        tile_idx = np.where(unpred, new_of_cls[cls], -1).astype(np.int32).reshape(shape)
-        self.tiles, self.tile_flags = np.ascontiguousarray(flat[rep_idx]), np.ascontiguousarray(fl[rep_idx])
+        tile_idx = to_host(api.reduce_remap(cls, unpred_d, self._to(new_of_cls))).reshape(shape)
+        if api._is_dev(flat):
+            rep_t = torch.from_numpy(rep_idx).to(flat.device)
+            self.tiles, self.tile_flags = flat[rep_t].contiguous(), fl[rep_t].contiguous()
+        else:
+            self.tiles, self.tile_flags = np.ascontiguousarray(flat[rep_idx]), np.ascontiguousarray(fl[rep_idx])
         self.use_count = use[chosen].astype(np.int32)
-        self.reduce_threshold = float(x)
+        self.reduce_threshold = x
         return tile_idx
 
     # --- whole pipeline (TTilingEncoder.Run, tilingencoder.pas:5530-5552)
@@ -321,6 +290,57 @@ class TilingEncoder:
         t["save"] = time.perf_counter() - t0
         return {"gtm": data, "tilemap": tm_out, "recon": recon, "tiles": final_tiles, "use_count": use_count, "palettes": pal,
                 "recon_sequences": sorted(recon_of), "timings": t, "mean_tile_psnr": float(tm["psnr"].mean()), "dictionary_before_reindex": int(didx.shape[0])}
+
+    # --- MergeTiles hook (tilingencoder.pas:4783-4840): where a clustering-built dictionary plugs in
+    def merge_tiles(self, clusters, best, tile_idx):
+        """InitMergeTiles + one MergeTiles(indices, n, BestIdx, nil, nil) per cluster + FinishMergeTiles + ReindexTiles(True):
+        every tile of a cluster other than `best[c]` hands its UseCount to the best tile, goes inactive and leaves a MergeIndex;
+        tilemap items follow the MergeIndex; the surviving tiles are re-ordered (use count descending, RGB pixels ascending).
+        clusters[i] = cluster of dictionary tile i, best[c] = index of the tile cluster c keeps.  -> remapped tilemap TileIdx."""
+        clusters = np.asarray(clusters.cpu() if api._is_dev(clusters) else clusters).astype(np.int64)
+        best = np.asarray(best).astype(np.int64)
+        tmap = np.asarray(tile_idx).astype(np.int64)
+        n = len(clusters)
+        use = np.asarray(self.use_count).astype(np.int64)
+        merge_index = np.full(n, -1, dtype=np.int64)                          # InitMergeTiles (:4817-4823)
+        tgt = best[clusters]
+        moved = tgt != np.arange(n)
+        merge_index[moved] = tgt[moved]                                       # MergeTiles (:4800-4813)
+        new_use = np.bincount(tgt, weights=use, minlength=n).astype(np.int64)
+        new_use[moved] = 0
+        flat = tmap.reshape(-1)
+        mi = np.where(flat >= 0, merge_index[np.maximum(flat, 0)], -1)        # FinishMergeTiles (:4825-4840)
+        flat = np.where(mi >= 0, mi, flat)
+        keep = np.nonzero(new_use > 0)[0]                                     # ReindexTiles(True) (:4626-4696)
+        tiles_h = self.tiles.cpu().numpy() if api._is_dev(self.tiles) else np.asarray(self.tiles)
+        fl_h = self.tile_flags.cpu().numpy() if api._is_dev(self.tile_flags) else np.asarray(self.tile_flags)
+        order = keep[_reindex_order(tiles_h[keep], new_use[keep])]
+        new_of = np.full(n, -1, dtype=np.int64)
+        new_of[order] = np.arange(len(order))
+        out = np.where(flat >= 0, new_of[np.maximum(flat, 0)], -1).astype(np.int32).reshape(tmap.shape)
+        self.tiles, self.tile_flags = self._to(np.ascontiguousarray(tiles_h[order])), self._to(np.ascontiguousarray(fl_h[order]))
+        self.use_count = new_use[order].astype(np.int32)
+        return out
+
+    def cluster_dictionary(self, k, tile_idx, max_iter=300):
+        """The north star's stage 3: k-means of the dictionary tiles' 192-d feature vectors (tensor-core assignment,
+        tm_kmeans_fit_i16) into k clusters, each keeping its member nearest to the centroid (ties: lowest index), merged
+        through the MergeTiles hook.  Initial centroids = the k most used tiles (the dictionary is ordered by use count).
+        -> remapped tilemap TileIdx; self.tiles / use_count shrink to <= k tiles."""
+        feats = api.features_from_rgb(self.tiles)
+        f_h = feats.cpu().numpy() if api._is_dev(feats) else np.asarray(feats)
+        n = f_h.shape[0]
+        k = int(min(k, n))
+        init = f_h[:k].astype(np.float64)
+        labels, cent, _, _, _ = api.kmeans_fit_i16(feats, k, self._to(init), max_iter=max_iter)
+        lab = labels.cpu().numpy() if api._is_dev(labels) else np.asarray(labels)
+        cen = cent.cpu().numpy() if api._is_dev(cent) else np.asarray(cent)
+        d = ((f_h.astype(np.float64) - cen[lab]) ** 2).sum(1)
+        order = np.lexsort((np.arange(n), d, lab))                            # per cluster: smallest distance, then lowest index
+        first = np.r_[True, lab[order][1:] != lab[order][:-1]]
+        best = np.full(k, -1, dtype=np.int64)
+        best[lab[order][first]] = order[first]
+        return self.merge_tiles(lab, best, tile_idx)
 
     # --- Reduce stand-in used by bench.py's match-stage step: samples dictionary tiles, no motion pass
     def reduce_sample(self, canon_tiles, canon_flags, tile_count):
