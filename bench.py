@@ -258,11 +258,16 @@ def run_ours(args):
     sampler.start()
     launches0 = api.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_range = bool(os.environ.get("TM_CUDA_PROFILER_RANGE"))   # `ncu --profile-from-start off`: only the timed steps are captured
+    if prof_range:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
         res = m.match_rgb(dev_tiles[(args.warmup + i) % n_seq_local], K_EPU)
     e1.record()
     barrier()
+    if prof_range:
+        torch.cuda.profiler.stop()
     sampler.stop_flag.set()
     launches = api.kernel_launches() - launches0
     ms_total = e0.elapsed_time(e1)

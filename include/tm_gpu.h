@@ -70,6 +70,10 @@ void ann_kdtree_short_destroy(tm_knn_short *h);
 int ann_kdtree_short_search(tm_knn_short *h, const int16_t *q, uint32_t eps, uint32_t *err);
 /* k nearest, ascending (distance, index); slots beyond the dataset size get idx -1 / err 0xFFFFFFFF */
 void ann_kdtree_short_search_multi(tm_knn_short *h, int *idxs, uint32_t *errs, int k, const int16_t *q, uint32_t eps);
+/* The per-query searches above (and ann_kdtree_search) are thread-safe and MICRO-BATCHED: concurrent callers on one handle
+   (the host's MTProcs pool threads, tilingencoder.pas:1547, 1563, 4128) are combined into one kernel launch per batch -- a
+   leader takes every request queued while the previous batch was on the GPU.  queries / batches served so far: */
+int tm_rendezvous_stats(tm_knn_short *h, int64_t *queries, int64_t *batches);
 
 /* ---------------------------------------------------------------- drop-in: ANN.dll (extern.pas:178-180) */
 typedef struct tm_knn_double tm_knn_double;

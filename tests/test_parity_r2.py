@@ -347,3 +347,36 @@ def test_mirror_variant_search_against_oracle(tm, oracle, extended):
     assert np.array_equal(_u32(er), e4[bv, rows].astype(np.uint32))
     assert np.array_equal(ti, np.stack([r[0] for r in res])[bv, rows]) and np.array_equal(pi, np.stack([r[1] for r in res])[bv, rows])
     assert (var[:300][flip[:300] != 0] != 0).mean() > 0.5            # re-flipped dictionary tiles are found through a mirror variant
+
+
+# ------------------------------------------------------------------ drop-in per-query searches from many host threads
+def test_dropin_search_micro_batching_from_threads(tm, oracle):
+    """ann_kdtree_short_search / _search_multi and ann_kdtree_search called like the host's MTProcs workers do (one query per
+    call, many threads): results equal the oracle's and the calls are combined into far fewer launches than queries."""
+    from concurrent.futures import ThreadPoolExecutor
+    d = synth.random_features(5000, 21)
+    q = synth.random_features(640, 22)
+    oi1, od1 = oracle.knn_short(d, q, 1)
+    oi64, od64 = oracle.knn_short(d, q, 64)
+    t = tm.AnnKdTreeShort(d)
+
+    def work(i):
+        idx, err = t.search(q[i])
+        mi, me = t.search_multi(q[i], 64)
+        return idx, err, mi, me
+    with ThreadPoolExecutor(max_workers=32) as pool:
+        res = list(pool.map(work, range(len(q))))
+    assert [r[0] for r in res] == list(oi1[:, 0]) and [r[1] for r in res] == list(od1[:, 0])
+    assert all(np.array_equal(r[2], oi64[i]) and np.array_equal(r[3], od64[i]) for i, r in enumerate(res))
+    nq, nb = t.rendezvous_stats()
+    print(f"rendezvous: {nq} queries in {nb} batched launches ({nq / nb:.1f} per launch)")
+    assert nq == 2 * len(q) and nb < nq
+    t.destroy()
+    pts = np.random.default_rng(5).normal(size=(300, 24))
+    qs = np.random.default_rng(6).normal(size=(200, 24))
+    wi, wd = oracle.knn_double(pts, qs)
+    a = tm.AnnKdTree(pts)
+    with ThreadPoolExecutor(max_workers=16) as pool:
+        got = list(pool.map(lambda i: a.search(qs[i]), range(len(qs))))
+    a.destroy()
+    assert [g[0] for g in got] == list(wi) and np.allclose([g[1] for g in got], wd, rtol=1e-12)

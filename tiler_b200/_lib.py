@@ -83,6 +83,7 @@ SIGNATURES = {
     "ann_kdtree_short_destroy": (None, [_vp]),
     "ann_kdtree_short_search": (C.c_int, [_vp, _vp, C.c_uint32, C.POINTER(C.c_uint32)]),
     "ann_kdtree_short_search_multi": (None, [_vp, _vp, _vp, _i32, _vp, C.c_uint32]),
+    "tm_rendezvous_stats": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "ann_kdtree_create": (_vp, [_vp, _i32, _i32, _i32, _i32]),
     "ann_kdtree_destroy": (None, [_vp]),
     "ann_kdtree_search": (C.c_int, [_vp, _vp, _dbl, C.POINTER(_dbl)]),

@@ -613,6 +613,12 @@ class AnnKdTreeShort:
                                                  C.c_void_p(q.ctypes.data), 0)
         return idxs, errs
 
+    def rendezvous_stats(self):
+        """(queries answered, batched launches) of the per-query searches on this handle."""
+        q, b = C.c_int64(), C.c_int64()
+        check(_lib.lib().tm_rendezvous_stats(self._h, C.byref(q), C.byref(b)))
+        return q.value, b.value
+
     def destroy(self):
         if self._h:
             _lib.lib().ann_kdtree_short_destroy(self._h)

@@ -7,6 +7,7 @@
 
 #include <cuda_runtime.h>
 #include <mutex>
+#include <condition_variable>
 #include <string>
 #include <vector>
 #include <cstring>
@@ -141,14 +142,50 @@ static int num_sms() {
 }
 
 // ------------------------------------------------------------------ handles
+// Micro-batching rendezvous of the per-query drop-in searches.  The host calls ann_kdtree_*_search once per 8x8
+// tile from MaxThreadCount pool threads (tilingencoder.pas:1547, 1563, 4128); one kernel launch per query cannot feed a GPU.
+// Requests queue on the handle; the first thread that finds no batch in flight becomes the leader, takes EVERYTHING queued
+// (its own request included), runs one batched search and wakes the others.  While a batch is on the GPU the next requests
+// accumulate, so T concurrent callers settle at ~T queries per launch without any timed wait, and a single caller pays nothing.
+struct KnnReq { const void *q; int k; int32_t *idx; void *dist; bool done; };
+struct Rendezvous {
+  std::mutex mu;
+  std::condition_variable cv;
+  std::vector<KnnReq *> pending;
+  bool leader = false;
+  long long batches = 0, queries = 0;   // statistics (tm_rendezvous_stats)
+  template <class Exec> void submit(KnnReq &r, Exec exec) {
+    std::unique_lock<std::mutex> lk(mu);
+    pending.push_back(&r);
+    while (!r.done) {
+      if (!leader) {
+        leader = true;
+        std::vector<KnnReq *> batch;
+        batch.swap(pending);
+        lk.unlock();
+        exec(batch);
+        lk.lock();
+        for (KnnReq *b : batch) b->done = true;
+        ++batches; queries += (long long)batch.size();
+        leader = false;
+        cv.notify_all();
+      } else {
+        cv.wait(lk);
+      }
+    }
+  }
+};
 struct tm_knn_short {
   int64_t n = 0;
   uint8_t *limbs = nullptr;    // [n][384]
   uint32_t *norms = nullptr;   // [ceil64(n)]
+  uint32_t *norm_max = nullptr;   // largest exact squared norm of the rows (device scalar, saturated)
+  Rendezvous rv;
 };
 struct tm_knn_double {
   int64_t n = 0; int dim = 0;
   double *pts = nullptr;
+  Rendezvous rv;
 };
 struct tm_yakmo {
   uint32_t k = 0; int max_iter = 300; uint64_t seed = 0;
@@ -284,13 +321,15 @@ static int knn_short_create_dev(const int16_t *d_feat, int64_t n, cudaStream_t s
   tm_knn_short *h = new tm_knn_short();
   h->n = n;
   const int64_t npad = (n + 63) / 64 * 64;
-  if (cudaMalloc(&h->limbs, (size_t)(n > 0 ? n : 1) * 384) != cudaSuccess || cudaMalloc(&h->norms, (size_t)(npad > 0 ? npad : 64) * 4) != cudaSuccess) {
-    cudaFree(h->limbs); delete h;
+  if (cudaMalloc(&h->limbs, (size_t)(n > 0 ? n : 1) * 384) != cudaSuccess || cudaMalloc(&h->norms, (size_t)(npad > 0 ? npad : 64) * 4) != cudaSuccess ||
+      cudaMalloc(&h->norm_max, 4) != cudaSuccess) {
+    cudaFree(h->limbs); cudaFree(h->norms); delete h;
     return TM_ERR_NOMEM;
   }
   cudaMemsetAsync(h->norms, 0, (size_t)(npad > 0 ? npad : 64) * 4, st);
-  int rc = launch_limb_split(d_feat, n, h->limbs, h->norms, st);
-  if (rc != TM_OK) { cudaFree(h->limbs); cudaFree(h->norms); delete h; return rc; }
+  cudaMemsetAsync(h->norm_max, 0, 4, st);
+  int rc = launch_limb_split(d_feat, n, h->limbs, h->norms, st, h->norm_max);
+  if (rc != TM_OK) { cudaFree(h->limbs); cudaFree(h->norms); cudaFree(h->norm_max); delete h; return rc; }
   *out = h;
   return TM_OK;
 }
@@ -309,7 +348,7 @@ extern "C" int tm_knn_short_create(const int16_t *feat, int64_t n, tm_knn_short 
 extern "C" int tm_knn_short_destroy(tm_knn_short *h) {
   if (!h) return TM_OK;
   std::lock_guard<std::recursive_mutex> lk(g_mu);
-  cudaFree(h->limbs); cudaFree(h->norms);
+  cudaFree(h->limbs); cudaFree(h->norms); cudaFree(h->norm_max);
   delete h;
   return TM_OK;
 }
@@ -320,10 +359,13 @@ static int knn_short_batch_dev(tm_knn_short *h, const int16_t *d_q, int64_t n_q,
   if (n_q == 0) return TM_OK;
   uint8_t *q_limbs = (uint8_t *)s.temp((size_t)n_q * 384);
   uint32_t *q_norm = (uint32_t *)s.temp((size_t)n_q * 4);
+  uint32_t *q_nmax = (uint32_t *)s.temp(4);
   if (s.err) return s.err;
-  int rc = launch_limb_split(d_q, n_q, q_limbs, q_norm, s.st);
+  if (cudaMemsetAsync(q_nmax, 0, 4, s.st) != cudaSuccess) return TM_ERR_CUDA;
+  int rc = launch_limb_split(d_q, n_q, q_limbs, q_norm, s.st, q_nmax);
   if (rc) return rc;
-  return launch_knn_i8(q_limbs, q_norm, (int)n_q, h->limbs, h->norms, (int)h->n, k, d_idx, d_dist, nullptr, num_sms(), sorted, s.st);
+  return launch_knn_i8(q_limbs, q_norm, (int)n_q, h->limbs, h->norms, (int)h->n, k, d_idx, d_dist, nullptr, num_sms(), sorted, s.st, q_nmax,
+                       h->norm_max);
 }
 
 extern "C" int tm_knn_short_batch(tm_knn_short *h, const int16_t *q, int64_t n_q, int k, int32_t *idx, uint32_t *dist, int sorted) {
@@ -1200,18 +1242,57 @@ extern "C" tm_knn_short *ann_kdtree_short_create(int16_t **rows, int n, int dim,
   return h;
 }
 extern "C" void ann_kdtree_short_destroy(tm_knn_short *h) { tm_knn_short_destroy(h); }
+// one batched search for every request queued on the handle (requests of one batch may ask for different k: grouped)
+static void knn_short_exec(tm_knn_short *h, std::vector<KnnReq *> &batch) {
+  std::vector<bool> taken(batch.size(), false);
+  for (size_t a = 0; a < batch.size(); ++a) {
+    if (taken[a]) continue;
+    const int k = batch[a]->k;
+    std::vector<size_t> grp;
+    for (size_t b = a; b < batch.size(); ++b)
+      if (!taken[b] && batch[b]->k == k) { grp.push_back(b); taken[b] = true; }
+    const size_t m = grp.size();
+    std::vector<int16_t> qbuf(m * 192);
+    std::vector<int32_t> ibuf(m * k);
+    std::vector<uint32_t> dbuf(m * k);
+    for (size_t i = 0; i < m; ++i) memcpy(&qbuf[i * 192], batch[grp[i]]->q, 192 * sizeof(int16_t));
+    const bool ok = k >= 1 && k <= 64 && tm_knn_short_batch(h, qbuf.data(), (int64_t)m, k, ibuf.data(), dbuf.data(), 1) == TM_OK;
+    for (size_t i = 0; i < m; ++i) {
+      KnnReq *r = batch[grp[i]];
+      for (int j = 0; j < k; ++j) {   // out-of-range = "no result" for the host (:1549, :1566)
+        r->idx[j] = ok ? ibuf[i * k + j] : -1;
+        if (r->dist) ((uint32_t *)r->dist)[j] = ok ? dbuf[i * k + j] : 0xFFFFFFFFu;
+      }
+    }
+  }
+}
 extern "C" int ann_kdtree_short_search(tm_knn_short *h, const int16_t *q, uint32_t eps, uint32_t *err) {
   (void)eps;
   int32_t idx = -1; uint32_t d = 0xFFFFFFFFu;
-  if (tm_knn_short_batch(h, q, 1, 1, &idx, &d, 1) != TM_OK) idx = -1;
+  if (h && q) {
+    KnnReq r{q, 1, &idx, &d, false};
+    h->rv.submit(r, [h](std::vector<KnnReq *> &b) { knn_short_exec(h, b); });
+  }
   if (err) *err = d;
   return idx;
 }
 extern "C" void ann_kdtree_short_search_multi(tm_knn_short *h, int *idxs, uint32_t *errs, int k, const int16_t *q, uint32_t eps) {
   (void)eps;
   if (k < 1 || !idxs || !errs) return;
-  if (k > 64 || tm_knn_short_batch(h, q, 1, k, idxs, errs, 1) != TM_OK)
-    for (int i = 0; i < k; ++i) { idxs[i] = -1; errs[i] = 0xFFFFFFFFu; }   // out-of-range = "no result" for the host (:1566)
+  if (!h || !q || k > 64) {
+    for (int i = 0; i < k; ++i) { idxs[i] = -1; errs[i] = 0xFFFFFFFFu; }
+    return;
+  }
+  KnnReq r{q, k, idxs, errs, false};
+  h->rv.submit(r, [h](std::vector<KnnReq *> &b) { knn_short_exec(h, b); });
+}
+/* queries answered / batched launches so far on this handle (tests, tuning) */
+extern "C" int tm_rendezvous_stats(tm_knn_short *h, int64_t *queries, int64_t *batches) {
+  if (!h) return fail(TM_ERR_ARG, "tm_rendezvous_stats: bad argument");
+  std::lock_guard<std::mutex> lk(h->rv.mu);
+  if (queries) *queries = h->rv.queries;
+  if (batches) *batches = h->rv.batches;
+  return TM_OK;
 }
 
 extern "C" tm_knn_double *ann_kdtree_create(double **rows, int n, int dim, int bucket, int split) {
@@ -1236,7 +1317,17 @@ extern "C" void ann_kdtree_destroy(tm_knn_double *h) {
 extern "C" int ann_kdtree_search(tm_knn_double *h, const double *q, double eps, double *err) {
   (void)eps;
   int32_t idx = -1; double d = INFINITY;
-  if (!h || tm_knn_double_batch(h->pts, h->n, h->dim, q, 1, &idx, &d) != TM_OK) idx = -1;
+  if (h && q) {
+    KnnReq r{q, 1, &idx, &d, false};
+    h->rv.submit(r, [h](std::vector<KnnReq *> &batch) {   // DoANN (:4128) calls this once per dictionary tile from the pool threads
+      const size_t m = batch.size(), dim = (size_t)h->dim;
+      std::vector<double> qbuf(m * dim), dbuf(m);
+      std::vector<int32_t> ibuf(m);
+      for (size_t i = 0; i < m; ++i) memcpy(&qbuf[i * dim], batch[i]->q, dim * sizeof(double));
+      const bool ok = tm_knn_double_batch(h->pts, h->n, h->dim, qbuf.data(), (int64_t)m, ibuf.data(), dbuf.data()) == TM_OK;
+      for (size_t i = 0; i < m; ++i) { batch[i]->idx[0] = ok ? ibuf[i] : -1; *(double *)batch[i]->dist = ok ? dbuf[i] : INFINITY; }
+    });
+  }
   if (err) *err = d;
   return idx;
 }

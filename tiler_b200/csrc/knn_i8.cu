@@ -36,8 +36,8 @@ constexpr int A_COL = 2 * ACC_COLS;  // query rows live in TMEM columns [384, 48
 // ------------------------------------------------------------------ limb split + norms
 // in: [n][192] int16 -> limbs [n][384] (hi bytes then lo bytes), norms[n] = sum v^2 mod 2^32
 __global__ void __launch_bounds__(192) limb_split_kernel(const int16_t *__restrict__ in, int64_t n, uint8_t *__restrict__ limbs,
-                                                        uint32_t *__restrict__ norms) {
-  __shared__ uint32_t s_norm[8];
+                                                        uint32_t *__restrict__ norms, uint32_t *__restrict__ norm_max) {
+  __shared__ unsigned long long s_norm[8];   // exact (64-bit) squared norms: 192 * 32768^2 > 2^32
   const int r = threadIdx.x / 24, seg = threadIdx.x % 24;
   const int64_t row = (int64_t)blockIdx.x * 8 + r;
   if (threadIdx.x < 8) s_norm[threadIdx.x] = 0;
@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(192) limb_split_kernel(const int16_t *__restri
   if (row < n) {
     const uint4 v = __ldg(reinterpret_cast<const uint4 *>(in + row * 192) + seg);
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-    uint32_t hi[2], lo[2], acc = 0;
+    uint32_t hi[2], lo[2];
+    unsigned long long acc = 0;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const uint32_t a = w[2 * i], b = w[2 * i + 1];
@@ -55,7 +56,7 @@ __global__ void __launch_bounds__(192) limb_split_kernel(const int16_t *__restri
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int32_t e0 = (int16_t)(w[2 * i + h] & 0xffff), e1 = (int16_t)(w[2 * i + h] >> 16);
-        acc += (uint32_t)(e0 * e0) + (uint32_t)(e1 * e1);
+        acc += (unsigned long long)(uint32_t)(e0 * e0) + (unsigned long long)(uint32_t)(e1 * e1);
       }
     }
     uint8_t *dst = limbs + row * ROWB + seg * 8;
@@ -66,7 +67,12 @@ __global__ void __launch_bounds__(192) limb_split_kernel(const int16_t *__restri
   __syncthreads();
   if (threadIdx.x < 8) {
     const int64_t rr = (int64_t)blockIdx.x * 8 + threadIdx.x;
-    if (rr < n) norms[rr] = s_norm[threadIdx.x];
+    if (rr < n) {
+      norms[rr] = (uint32_t)s_norm[threadIdx.x];   // mod 2^32, like the reference's Cardinal arithmetic
+      // largest exact squared norm of the set (saturated): the top-k epilogue may compare with signed arithmetic only when
+      // every distance provably stays below 2^31, i.e. every norm below 2^29
+      if (norm_max) atomicMax(norm_max, (s_norm[threadIdx.x] >> 32) ? 0xFFFFFFFFu : (uint32_t)s_norm[threadIdx.x]);
+    }
   }
 }
 
@@ -470,6 +476,57 @@ __device__ __forceinline__ void tk_tile32(unsigned long long &waddr, uint32_t ta
   }
 }
 
+// ---- no-wrap variant of tk_tile32 (every squared norm of the queries and of the dictionary is below 2^29, so every distance
+// is below 2^31: true for any real feature set, |coefficient| <= 13 212).  The per-thread constant kk = |q|^2 - tau - 1 rides
+// in the norm add, so  e = d - tau - 1  comes out of the same four instructions as d did, and "admit" is the SIGN of e: the
+// pair mask is one OR and one funnel shift per column pair (2 instructions) instead of min / compare / select / add (3.3).
+// Admitted entries store d = e + tau + 1.
+__device__ __forceinline__ void tk_admit_nw(unsigned long long &waddr, uint32_t idx, uint32_t e, uint32_t tau1) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, d;\n\t"
+      "setp.lt.s32 p, %2, 0;\n\t"
+      "add.u32 d, %2, %3;\n\t"
+      "@p st.global.v2.u32 [%0], {%1, d};\n\t"
+      "mov.b64 {lo, hi}, %0;\n\t"
+      "@p add.u32 lo, lo, 8;\n\t"
+      "mov.b64 %0, {lo, hi};\n\t}\n"
+      : "+l"(waddr)
+      : "r"(idx), "r"(e), "r"(tau1)
+      : "memory");
+}
+__device__ __forceinline__ void tk_tile32_nw(unsigned long long &waddr, uint32_t tau, uint32_t nq, int col, const uint32_t (&ndA)[16],
+                                             uint32_t (&ppA)[16], const uint32_t (&xxA)[16], const uint32_t (&loA)[16],
+                                             const uint32_t (&ndB)[16], uint32_t (&ppB)[16], const uint32_t (&xxB)[16],
+                                             const uint32_t (&loB)[16]) {
+  const uint32_t kk = nq - tau - 1u, tau1 = tau + 1u;
+#pragma unroll
+  for (int e = 0; e < 16; ++e) ppA[e] = tk_dist(ndA[e] + kk, ppA[e], xxA[e], loA[e]);
+#pragma unroll
+  for (int e = 0; e < 16; ++e) ppB[e] = tk_dist(ndB[e] + kk, ppB[e], xxB[e], loB[e]);
+  uint32_t mine = 0;   // after the 16 shifts: bit 15 - p <-> pair p (p < 8: columns 2p, 2p + 1; p >= 8: columns 16 + 2(p - 8), ...)
+#pragma unroll
+  for (int e = 0; e < 8; ++e) mine = __funnelshift_l(ppA[2 * e] | ppA[2 * e + 1], mine, 1);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) mine = __funnelshift_l(ppB[2 * e] | ppB[2 * e + 1], mine, 1);
+  const uint32_t any = __reduce_or_sync(0xffffffffu, mine);
+  if (any != 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (any & (0x8000u >> e)) {
+        tk_admit_nw(waddr, (uint32_t)(col + 2 * e), ppA[2 * e], tau1);
+        tk_admit_nw(waddr, (uint32_t)(col + 2 * e + 1), ppA[2 * e + 1], tau1);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      if (any & (0x80u >> e)) {
+        tk_admit_nw(waddr, (uint32_t)(col + 16 + 2 * e), ppB[2 * e], tau1);
+        tk_admit_nw(waddr, (uint32_t)(col + 16 + 2 * e + 1), ppB[2 * e + 1], tau1);
+      }
+    }
+  }
+}
+
 // half_out (optional): some value Th <= T_out with at least kh entries <= Th -- the first probe of the bisection whose count
 // fell in [kh, k), for free; T_out itself when no probe did.
 template <int NE>
@@ -615,7 +672,8 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
                    const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict, int k,
                    int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist, int tile_stride,
                    unsigned long long *ws /* [gridDim.x][256][TK_CAP], 2 KB aligned */, int slack, int dbg, int cut_first,
-                   int cut_ratio /* scheduled row-wide cuts after cut_first, cut_first * cut_ratio, ... tiles; 0 = none */) {
+                   int cut_ratio /* scheduled row-wide cuts after cut_first, cut_first * cut_ratio, ... tiles; 0 = none */,
+                   const uint32_t *__restrict__ q_nmax, const uint32_t *__restrict__ d_nmax /* largest squared norms, or null */) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int NST = STAGES_TK;
@@ -707,6 +765,8 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
     unsigned long long *wbuf = cta_ws + (size_t)(warp * 32) * TK_CAP;   // this warp's 32 strips
     unsigned long long *mybuf = wbuf + (size_t)lane * TK_CAP;
     const uint32_t base_lo = (uint32_t)(uintptr_t)mybuf;
+    // signed comparisons are exact when no distance can reach 2^31: every squared norm below 2^29 ((|q| + |t|)^2 < 2^31)
+    const bool nowrap = !(dbg & 64) && q_nmax && d_nmax && __ldg(q_nmax) < (1u << 29) && __ldg(d_nmax) < (1u << 29);
     uint32_t it = 0, w = 0;
     TKT_DECL
     for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
@@ -732,8 +792,8 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full);
       }
-      uint32_t tau = (dbg & 1) ? 0u : 0xFFFFFFFEu;
-   // distances of 0xFFFFFFFF (masked columns) are never admitted
+      // distances of 0xFFFFFFFF (masked columns) are never admitted; without wrap every distance is below 2^31
+      uint32_t tau = (dbg & 1) ? 0u : (nowrap ? 0x7FFFFFFEu : 0xFFFFFFFEu);
       unsigned long long waddr = (unsigned long long)(uintptr_t)mybuf;   // next free slot of this thread's strip
       uint32_t my_half = 0xFFFFFFFFu;                                     // this strip's published half-threshold
       int jt = 0;
@@ -783,7 +843,8 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         TKT(3)
         if (!(dbg & 8)) {
           if (col0 + HN <= n_dict) {
-            tk_tile32(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB);
+            if (nowrap) tk_tile32_nw(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB);
+            else tk_tile32(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB);
           } else {   // ragged last dictionary tile
             tk_unit(waddr, tau, nq, col0, n_dict - col0, ndA, ppA, xxA, loA);
             tk_unit(waddr, tau, nq, col0 + 16, n_dict - col0 - 16, ndB, ppB, xxB, loB);
@@ -953,16 +1014,16 @@ int make_tmap_rows_u8(CUtensorMap *map, const void *base, uint64_t rows, uint32_
 size_t knn_workspace_bytes(int num_ctas) { (void)num_ctas; return 0; }   // top-k state lives in shared memory
 int knn_rows_per_cta() { return BM; }
 
-int launch_limb_split(const int16_t *in, int64_t n, uint8_t *limbs, uint32_t *norms, cudaStream_t st) {
+int launch_limb_split(const int16_t *in, int64_t n, uint8_t *limbs, uint32_t *norms, cudaStream_t st, uint32_t *norm_max) {
   if (n <= 0) return TM_OK;
-  limb_split_kernel<<<(unsigned)((n + 7) / 8), 192, 0, st>>>(in, n, limbs, norms);
+  limb_split_kernel<<<(unsigned)((n + 7) / 8), 192, 0, st>>>(in, n, limbs, norms, norm_max);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }
 
 int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const uint8_t *d_limbs, const uint32_t *d_norm,
                   int n_dict, int k, int32_t *out_idx, uint32_t *out_dist, void *ws, int num_ctas, int sort_rows,
-                  cudaStream_t st) {
+                  cudaStream_t st, const uint32_t *q_norm_max, const uint32_t *d_norm_max) {
   (void)ws;
   if (n_q <= 0) return TM_OK;
   if (k < 1 || k > KMAX || n_dict <= 0) return TM_ERR_ARG;
@@ -1009,7 +1070,7 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
         if (const char *e = getenv("TM_TK_CUTS")) { if (sscanf(e, "%d,%d", &cut_first, &cut_ratio) != 2) { cut_first = TK_CUT_FIRST; cut_ratio = TK_CUT_RATIO; } }
       }
       knn_i8_topk_kernel<<<grid, TK_THREADS, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride, strip_ws, slack, dbg,
-                                                            cut_first, cut_ratio);
+                                                            cut_first, cut_ratio, q_norm_max, d_norm_max);
       cudaFreeAsync(raw, st);
     }
   }

@@ -64,21 +64,35 @@ match_rerank_kernel(const int16_t *__restrict__ q_feat, int64_t n_q, const int32
     n_p += __popc(pm);
     __syncwarp();
   }
-  // lexicographic minimum of (err, tile, pal) == strict-minimum scan in ascending (tile, pal) order
+  // lexicographic minimum of (err, tile, pal) == strict-minimum scan in ascending (tile, pal) order.
+  // Eight lanes share one candidate row: lane g of the group reads 48 contiguous bytes, so a warp-wide load touches four
+  // 384-byte rows in whole 128-byte lines (one lane per row meant 32 different lines per load instruction and made the kernel
+  // wait on L1/L2 wavefronts); the 8 partial sums are folded with three shuffles.  Every lane of a group ends up with the same
+  // running best, so the final warp reduction is unchanged.
   uint32_t best_e = 0xFFFFFFFFu;
   int32_t best_t = 0x7FFFFFFF, best_p = 0x7FFFFFFF;
   const int total = n_t * n_p;
-  for (int e = lane; e < total; e += 32) {
-    const int32_t t = s_tile[w][e / n_p], p = s_pal[w][e % n_p];
-    const uint4 *pf = reinterpret_cast<const uint4 *>(pair_feat + ((size_t)t * n_pal + p) * 192);
+  const int grp = lane >> 3, gl = lane & 7;
+  uint32_t qreg[12];                                   // this lane's 24 query coefficients: words [12 gl, 12 gl + 12)
+#pragma unroll
+  for (int c = 0; c < 12; ++c) qreg[c] = s_q[w][12 * gl + c];
+  for (int e0 = 0; e0 < total; e0 += 4) {
+    const int e = e0 + grp;
+    const bool live = e < total;
+    const int32_t t = live ? s_tile[w][e / n_p] : 0, p = live ? s_pal[w][e % n_p] : 0;
     uint32_t s = 0;
-#pragma unroll 4
-    for (int c = 0; c < 24; ++c) {
-      const uint4 f = __ldg(pf + c);
-      s += sqdiff2(s_q[w][4 * c], f.x) + sqdiff2(s_q[w][4 * c + 1], f.y) + sqdiff2(s_q[w][4 * c + 2], f.z) +
-           sqdiff2(s_q[w][4 * c + 3], f.w);
+    if (live) {
+      const uint4 *pf = reinterpret_cast<const uint4 *>(pair_feat + ((size_t)t * n_pal + p) * 192) + 3 * gl;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const uint4 f = __ldg(pf + c);
+        s += sqdiff2(qreg[4 * c], f.x) + sqdiff2(qreg[4 * c + 1], f.y) + sqdiff2(qreg[4 * c + 2], f.z) + sqdiff2(qreg[4 * c + 3], f.w);
+      }
     }
-    if (s < best_e || (s == best_e && (t < best_t || (t == best_t && p < best_p)))) { best_e = s; best_t = t; best_p = p; }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (live && (s < best_e || (s == best_e && (t < best_t || (t == best_t && p < best_p))))) { best_e = s; best_t = t; best_p = p; }
   }
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {

@@ -14,6 +14,7 @@ ap.add_argument("--frames", type=int, default=240); ap.add_argument("--seq", typ
 ap.add_argument("--tiles", type=int, default=65536); ap.add_argument("--palettes", type=int, default=16)
 ap.add_argument("--palette-size", type=int, default=16); ap.add_argument("--out", default="")
 ap.add_argument("--decode", type=int, default=1)
+ap.add_argument("--feature-mode", default="fast", choices=["fast", "exact"])
 ap.add_argument("--sharded", type=int, default=0, help="run under torchrun: PredictMotion by frame, Reconstruct by sequence")
 a = ap.parse_args()
 t0 = time.perf_counter()
@@ -26,12 +27,14 @@ torch.cuda.set_device(local)
 if a.sharded and world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-enc = TilingEncoder(palette_size=a.palette_size, palette_count=a.palettes, device=torch.device("cuda", local))
-TilingEncoder(palette_size=a.palette_size, palette_count=a.palettes, device=torch.device("cuda", local)).encode(
+enc = TilingEncoder(palette_size=a.palette_size, palette_count=a.palettes, device=torch.device("cuda", local), feature_mode=a.feature_mode)
+TilingEncoder(palette_size=a.palette_size, palette_count=a.palettes, device=torch.device("cuda", local), feature_mode=a.feature_mode).encode(
     np.ascontiguousarray(frames[:2]), [(0, 1)], tile_count=1024, sharded=bool(a.sharded))   # untimed warm-up: kernels, torch ops, memory pool
 torch.cuda.synchronize()
 l0 = api.kernel_launches()
-api.profile_enable(True)
+api.profile_enable(not os.environ.get("TM_CUDA_PROFILER_RANGE"))
+if os.environ.get("TM_CUDA_PROFILER_RANGE"):
+    torch.cuda.profiler.start()
 t0 = time.perf_counter()
 if a.sharded and world > 1:
     dist.barrier()
@@ -42,6 +45,8 @@ if a.sharded and world > 1:
     dist.barrier()
 torch.cuda.synchronize()
 t_enc = time.perf_counter() - t0
+if os.environ.get("TM_CUDA_PROFILER_RANGE"):
+    torch.cuda.profiler.stop()
 if rank != 0:
     if a.sharded and world > 1:
         dist.destroy_process_group()

@@ -1,0 +1,55 @@
+"""One launch of every hot-path kernel at a BASELINE-config shape, device-resident, for `ncu --set full` (profiles/r02_kernels_*).
+Order matters: the colour-quantisation loop (hundreds of launches) comes last so that a launch-count limit cuts it short."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from tiler_b200 import api, synth
+from tiler_b200.encoder import TilingEncoder
+
+dev = torch.device("cuda", 0)
+clip = synth.make_clip(1280, 720, 6, cut_every=0, seed=synth.SEED + 5)
+frames = torch.from_numpy(synth.pack_rgb(clip)).to(dev)
+tiles = torch.from_numpy(synth.clip_to_tiles(clip).reshape(-1, 64)).to(dev)            # 86 400 tiles
+enc = TilingEncoder(palette_size=16, palette_count=16, device=dev)
+canon, flags = enc.load_tiles(tiles[None])
+enc.reduce_sample(canon, flags, 65536)
+enc.prepare_palettes(); enc.dither(); enc.prepare_reconstruct()
+batch = canon.reshape(-1, 64).repeat(5, 1).contiguous()                                 # 432 000 tiles: one keyframe sequence
+torch.cuda.synchronize()
+torch.cuda.profiler.start()                                                             # ncu --profile-from-start off: setup is not captured
+feat = api.features_from_rgb(batch)                                                     # features_i16_kernel<0>
+enc.matcher.match_rgb(batch, 64)                                                        # limb split, k-NN top-64, match_rerank_kernel
+knn = api.KnnShort(enc.matcher.dict_features())
+knn.search(feat, 1, sorted=False)                                                       # knn_i8_k1_kernel<1>
+for mode in (api.FEATURES_FAST, api.FEATURES_EXACT):                                    # sliding-window features, both kernels
+    api.set_feature_mode(mode)
+    d = api.sliding_features(frames[0])
+cur = api.features_from_rgb(torch.from_numpy(synth.frame_to_tiles(synth.pack_rgb(clip)[1])).to(dev))
+api.motion_search(cur, 160, 90, d, 32)                                                  # motion_tc_kernel
+big = canon.reshape(-1, 64).repeat(40, 1).contiguous()                                  # 3 456 000 tiles (configs[1] clip size)
+cls, n_cls = api.tile_classes(big)                                                      # tile_hash_kernel, class_boundary_kernel
+eff = torch.rand(big.shape[0], dtype=torch.float64, device=dev) * 50
+api.reduce_class_min(cls, eff, n_cls); api.reduce_apply(cls, eff, n_cls, 25.0)          # reduce.cu bookkeeping
+# configs[4] slice: 8 100 tiles of a 4K frame x 32 palettes x 256 colours
+f4k = synth.pack_rgb(synth.make_clip(3840, 2160, 1, seed=synth.SEED, n_sprites=40))[0]
+t4k = torch.from_numpy(synth.frame_to_tiles(f4k)).to(dev)
+c4k, fl4k = api.mirror_canonicalise(t4k)
+band = torch.from_numpy(((np.arange(t4k.shape[0]) // 480) * 32 // 270).astype(np.int32)).to(dev)
+pal256 = torch.randint(0, 1 << 24, (32, 256), dtype=torch.int32, device=dev)
+sub = torch.arange(0, t4k.shape[0], 16, dtype=torch.int32, device=dev)
+pt, pp = sub.repeat_interleave(32), torch.arange(32, dtype=torch.int32, device=dev).repeat(sub.numel())
+for tk in (True, False):
+    api.dither(c4k, fl4k, pp, pal256, use_thomas_knoll=tk, y2_mixed_colors=4, pair_tile=pt)    # dither_kernel<true/false>
+imgs = [np.ascontiguousarray(np.stack([(f4k[y0:y0 + 256, :1024] >> s) & 255 for s in (0, 8, 16)], -1).astype(np.uint8)) for y0 in range(0, 2048, 256)]
+api.dlquant_batch(imgs, 16, lookup_bpc=5, which=3)                                      # dl3 kernels
+x64 = api.features_f64(enc.tiles, api.PVS_WEIGHTED_SPE_DCT, use_lab=True)               # features_f64_kernel
+api.kmeans_fit(x64, 128, init=x64[:128].clone(), max_iter=1)                            # kmeans_assign_f64 / update
+xs = torch.from_numpy(synth.random_features(1 << 20, 3, adversarial=True)).to(dev)
+cen = xs[:65536].double()
+sh = api.KmeansI16Shard(xs, 65536)
+lab = torch.full((xs.shape[0],), -1, dtype=torch.int32, device=dev)
+sh.step(cen, lab)                                                                       # knn_i8_k1_kernel<4>, kmeans_rerank_i16, update
+sh.close()
+api.palquant_kmeans(c4k, band, 32, 256, seed=1)                                         # rgb_assign_kernel ... (last)
+torch.cuda.synchronize()
+print("ok")

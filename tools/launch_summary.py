@@ -13,7 +13,10 @@ s = sum(tot.values())
 print(f"{len(rows)} launches, {s:.1f} ms of kernel time (cold-cache, serialised by the profiler)")
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1])[:14]:
     print(f"{v:10.3f} ms {cnt[k]:5d}x {v / s * 100:5.1f}%  {k[:70]}")
-last = max(i for i, r in enumerate(rows) if "features_i16_kernel<0>" in r[ik])
+cands = [i for i, r in enumerate(rows) if "features_i16_kernel<0>" in r[ik]]
+if not cands:
+    sys.exit(0)
+last = max(cands)
 step = rows[last:]
 ss = sum(float(r[iv].replace(",", "")) for r in step) / 1e6
 print("last timed step:")
