@@ -105,10 +105,11 @@ def encode_leg(dev, frames, world=1, feature_mode="fast"):
     import torch.distributed as dist
     enc = TilingEncoder(palette_size=PAL_SIZE, palette_count=N_PAL, device=dev, seed=0x42381337, feature_mode=feature_mode)
     frames = torch.from_numpy(frames).pin_memory().numpy()   # the clip sits in pinned host memory before the clock starts
-    # untimed warm-up on the first keyframe sequence: loads every kernel / torch op of the encode path and grows the
-    # stream-ordered memory pool to the per-sequence working set, as a long-running encoder process would have
+    # untimed warm-up with the same clip shape: loads every kernel / torch op of the encode path and grows torch's caching
+    # allocator and the library's stream-ordered pool to the working set, as a long-running encoder process would have (a first
+    # cudaMalloc of the ~1 GB clip buffers alone varies between 20 and 300 ms)
     TilingEncoder(palette_size=PAL_SIZE, palette_count=N_PAL, device=dev, seed=0x42381337, feature_mode=feature_mode).encode(
-        np.ascontiguousarray(frames[:FRAMES_PER_SEQ]), [(0, FRAMES_PER_SEQ - 1)], tile_count=N_DICT, sharded=False)
+        frames, seqs, tile_count=N_DICT, sharded=world > 1)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()

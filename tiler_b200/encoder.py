@@ -139,6 +139,7 @@ class TilingEncoder:
         py_all = np.empty((n, nt), np.int32)
         psnr, px, py = psnr_all, px_all, py_all
         fr = self._to(frames_packed)
+        pending = []          # device-resident encoder: results stay on the device until the loop is over (one copy, no per-frame sync)
         for f in range(lo, hi):
             if f > 0:
                 prev = fr[f - 1]
@@ -147,10 +148,18 @@ class TilingEncoder:
             else:
                 prev = fr[0] * 0
             x, y, e = api.predict_motion_frame(prev, canon_tiles[f], canon_flags[f], tw, th, radius)
-            e = e.cpu().numpy() if api._is_dev(e) else e
+            if api._is_dev(e):
+                pending.append((x, y, e))
+                continue
             psnr[f] = euclidean_to_psnr(np.asarray(e).view(np.uint32))
-            px[f] = x.cpu().numpy() if api._is_dev(x) else x
-            py[f] = y.cpu().numpy() if api._is_dev(y) else y
+            px[f] = x
+            py[f] = y
+        if pending:
+            xs = torch.stack([p[0] for p in pending]).cpu().numpy()
+            ys = torch.stack([p[1] for p in pending]).cpu().numpy()
+            es = torch.stack([p[2] for p in pending]).cpu().numpy()
+            px[lo:hi], py[lo:hi] = xs, ys
+            psnr[lo:hi] = euclidean_to_psnr(es.view(np.uint32))
         return psnr_all[lo:hi], px_all[lo:hi], py_all[lo:hi]
 
     # --- Reduce (tilingencoder.pas:1908-1926, 4014-4103, 4626-4696, 4720-4781)
