@@ -36,6 +36,12 @@ int tmh_gtm_decoder_dims(tmh_gtm_decoder *d, int *w, int *h, int64_t *frames);
    Returns the number of frames produced by this call, -1 on a malformed stream. */
 int64_t tmh_gtm_decode(tmh_gtm_decoder *d, const uint8_t *s, int64_t n, int32_t *frames_out, int64_t max_frames);
 
+/* TTilingEncoder.OptimizePalettes (tilingencoder.pas:4246-4432) over the reference's Powell minimiser (powell.pas): reorders
+   the colours INSIDE each palette (palettes [n_pal][pal_size] int32 0x00BBGGRR, in place) so that the per-column standard
+   deviation accumulated over all palettes is maximal; host code in the reference too (not behind a DLL).  n_threads <= 0: one
+   per hardware thread.  Returns the number of outer passes, -1 on bad arguments. */
+int tmh_optimize_palettes(int32_t *palettes, int n_pal, int pal_size, int n_threads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -182,6 +182,235 @@ def quantize(dict_tiles, tile_pal, palette_count, palette_size, seed):
                      for p in range(palette_count)])
 
 
+# ------------------------------------------------------------------ OptimizePalettes (tilingencoder.pas:4246-4432) over powell.pas
+def _sign(x):
+    return 1.0 if x > 0 else (-1.0 if x < 0 else 0.0)
+
+
+def _bracket(f, xa, xb):
+    """powell.pas:56-146."""
+    gold, small, grow = (1 + math.sqrt(5)) / 2, 1e-21, 110
+    fa, fb = f(xa), f(xb)
+    if fa < fb:
+        xa, xb, fa, fb = xb, xa, fb, fa
+    xc = xb + gold * (xb - xa)
+    fc = f(xc)
+    it = 0
+    while fc < fb:
+        tmp1 = (xb - xa) * (fb - fc)
+        tmp2 = (xb - xc) * (fb - fa)
+        val = tmp2 - tmp1
+        denom = 2 * small if abs(val) < small else 2 * val
+        w = xb - ((xb - xc) * tmp2 - (xb - xa) * tmp1) / denom
+        wlim = xb + grow * (xc - xb)
+        if it > 1000:
+            raise RuntimeError("bracket: Too many iterations")
+        it += 1
+        fw = 0
+        if (w - xc) * (xb - w) > 0:
+            fw = f(w)
+            if fw < fc:
+                xa, xb, fa, fb = xb, w, fb, fw
+                break
+            elif fw > fb:
+                xc, fc = w, fw
+                break
+            w = xc + gold * (xc - xb)
+            fw = f(w)
+        elif (w - wlim) * (wlim - xc) >= 0:
+            w = wlim
+            fw = f(w)
+        elif (w - wlim) * (xc - w) > 0:
+            fw = f(w)
+            if fw < fc:
+                xb, xc = xc, w
+                w = xc + gold * (xc - xb)
+                fb, fc = fc, fw
+                fw = f(w)
+        else:
+            w = xc + gold * (xc - xb)
+            fw = f(w)
+        xa, xb, xc = xb, xc, w
+        fa, fb, fc = fb, fc, fw
+    if xa > xc:
+        xa, xc = xc, xa
+    return xa, xb, xc
+
+
+def _brent_helper(f, a, x, b, fx, xtol, maxiter):
+    """powell.pas:148-260."""
+    cg = (3 - math.sqrt(5)) / 2
+    if a > b:
+        a, b = b, a
+    w = v = x
+    fw = fv = fx
+    deltax = rat = 0.0
+    it = 0
+    while it < maxiter:
+        xmid = 0.5 * (a + b)
+        if abs(x - xmid) <= 2 * xtol - 0.5 * (b - a):
+            break
+        if abs(deltax) <= xtol:
+            deltax = a - x if x >= xmid else b - x
+            rat = cg * deltax
+        else:
+            tmp1 = (x - w) * (fx - fv)
+            tmp2 = (x - v) * (fx - fw)
+            p = (x - v) * tmp2 - (x - w) * tmp1
+            tmp2 = 2 * (tmp2 - tmp1)
+            if tmp2 > 0:
+                p = -p
+            tmp2 = abs(tmp2)
+            dx_temp = deltax
+            deltax = rat
+            if p > tmp2 * (a - x) and p < tmp2 * (b - x) and abs(p) < abs(0.5 * tmp2 * dx_temp):
+                rat = p / tmp2
+                u = x + rat
+                if u - a < xtol or b - u < xtol:
+                    rat = _sign(xmid - x) * xtol
+            else:
+                deltax = a - x if x >= xmid else b - x
+                rat = cg * deltax
+        u = x + rat if abs(rat) > xtol else x + _sign(rat) * xtol
+        fu = f(u)
+        if fu > fx:
+            if u < x:
+                a = u
+            else:
+                b = u
+            if fu <= fw or w == x:
+                v, w, fv, fw = w, u, fw, fu
+            elif fu <= fv or v == x or v == w:
+                v, fv = u, fu
+        else:
+            if u >= x:
+                a = x
+            else:
+                b = x
+            v, w, x = w, x, u
+            fv, fw, fx = fw, fx, fu
+        it += 1
+    return x, fx
+
+
+def _linesearch_powell(f, p, xi, xtol):
+    """powell.pas:294-324; p and xi are Python lists modified IN PLACE (var parameters)."""
+    n = len(p)
+    sqsos = math.sqrt(sum(v * v for v in xi))
+    atol = 1.0
+    if sqsos != 0:
+        atol = 5 * xtol / sqsos
+    atol = min(0.1, atol)
+    along = lambda t: f([p[i] + t * xi[i] for i in range(n)])
+    a, b, c = _bracket(along, 0.0, 1.0)
+    alpha, fret = _brent_helper(along, a, b, c, along(b), atol, 100)
+    for i in range(n):
+        xi[i] = xi[i] * alpha
+        p[i] = p[i] + xi[i]
+    return fret
+
+
+def powell_minimize(f, x, scale, xtol, ftol, maxiter):
+    """powell.pas:326-385.  Lists are references like FreePascal dynamic arrays: `direc[n - 1] = direc1` shares the array."""
+    n = len(x)
+    direc1 = [0.0] * n
+    tmp = [0.0] * n
+    direc = [[scale if i == j else 0.0 for j in range(n)] for i in range(n)]
+    fval = f(x)
+    x1 = list(x)
+    it = 0
+    while True:
+        fx = fval
+        bigind, delta = 0, 0.0
+        for i in range(n):
+            fx2 = fval
+            fval = _linesearch_powell(f, x, direc[i], xtol)
+            if fx2 - fval > delta:
+                delta, bigind = fx2 - fval, i
+        it += 1
+        if fx - fval <= ftol or it >= maxiter:
+            break
+        for i in range(n):
+            direc1[i] = x[i] - x1[i]
+            tmp[i] = x[i] + direc1[i]
+            x1[i] = x[i]
+        fx2 = f(tmp)
+        if fx > fx2:
+            t = 2 * (fx + fx2 - 2 * fval)
+            temp = fx - fval - delta
+            t = t * temp * temp
+            temp = fx - fx2
+            t = t - delta * temp * temp
+            if t < 0:
+                fval = _linesearch_powell(f, x, direc1, xtol)
+                direc[bigind] = direc[n - 1]
+                direc[n - 1] = direc1
+    return fval
+
+
+def _optimize_one(args):
+    """DoPal (:4320-4392) for one palette of one pass: PowellMinimize over PowellOP (:4264-4305)."""
+    row_a, acc, mean, S = args
+    rgb = lambda c: (c & 255, (c >> 8) & 255, (c >> 16) & 255)
+    last = [None]
+
+    def op(x):
+        perm = [(0, 0)] + [(int(round(x[c - 1] * 1000)), c) for c in range(1, S)]     # (Count, Index); Python round = half to even
+        perm.sort()
+        sd = [0, 0, 0]
+        row = []
+        for c in range(S):
+            col = row_a[perm[c][1]]
+            row.append(col)
+            for k, v in enumerate(rgb(col)):
+                sd[k] += (acc[c][k] + v - mean[k]) ** 2
+        last[0] = row
+        return -((299 * math.sqrt(sd[0] / S) + 587 * math.sqrt(sd[1] / S) + 114 * math.sqrt(sd[2] / S)) / 1000)
+    x = [float(c) for c in range(1, S)]
+    powell_minimize(op, x, 1.0, 1.0, 1.0, 0x7FFFFFFF)
+    f = -op(x)
+    return last[0], f
+
+
+def optimize_palettes(palettes):
+    """TTilingEncoder.OptimizePalettes (:4307-4432) with PowellOP (:4264-4305), statement by statement.  The palettes of a pass
+    are independent (the reference runs them on its thread pool, :4415); large palette sets use worker processes."""
+    pal = [[int(c) & 0xFFFFFFFF for c in row] for row in np.asarray(palettes)]
+    P, S = len(pal), len(pal[0])
+    rgb = lambda c: (c & 255, (c >> 8) & 255, (c >> 16) & 255)
+    mean = [0, 0, 0]
+    for row in pal:
+        for c in row:
+            for k, v in enumerate(rgb(c)):
+                mean[k] += v
+    mean = [m // S for m in mean]
+    pool = None
+    if P >= 64:
+        import multiprocessing as mp
+        import os
+        pool = mp.get_context("fork").Pool(min(os.cpu_count() or 1, 32))
+    prev_fsum = fsum = 0.0
+    iteration = 0
+    try:
+        while True:
+            prev_fsum = max(fsum, prev_fsum)
+            iteration += 1
+            # "accumulate the whole palette except the one that will be permutated" (:4357-4377): column sums over all palettes
+            # minus the palette's own colours (integers: the same values as the reference's loop over the other palettes)
+            tot = [[sum(rgb(pal[p][c])[k] for p in range(P)) for k in range(3)] for c in range(S)]
+            jobs = [(pal[a], [[tot[c][k] - rgb(pal[a][c])[k] for k in range(3)] for c in range(S)], mean, S) for a in range(P)]
+            res = pool.map(_optimize_one, jobs, chunksize=8) if pool else [_optimize_one(j) for j in jobs]
+            pal = [r[0] for r in res]
+            fsum = sum(r[1] for r in res) / P
+            if fsum <= prev_fsum:
+                break
+    finally:
+        if pool:
+            pool.close()
+    out = np.array(pal, dtype=np.uint32).astype(np.int64)
+    return np.where(out >= 1 << 31, out - (1 << 32), out).astype(np.int32), iteration
+
+
 def reindex(dict_idx, tile_idx):
     """TTilingEncoder.Reindex (:1993-2038): MakeTilesUnique(False) merges dictionary tiles with identical palette indices
     into the first of the sorted run, use counts are recounted from every tilemap item with TileIdx >= 0, then
@@ -239,14 +468,17 @@ def merge_tiles(dict_tiles, use_count, clusters, best, tile_idx):
     return np.asarray(dict_tiles)[keep].copy(), np.array([use[i] for i in keep], dtype=np.int32), out
 
 
-def encode(frames, seqs, tile_count, palette_count, palette_size, seed, radius=32, use_tk=True, y2_mixed=4, extended=True):
+def encode(frames, seqs, tile_count, palette_count, palette_size, seed, radius=32, use_tk=True, y2_mixed=4, extended=True,
+           optimize=True):
     """TTilingEncoder.Run (:5529-5554) up to, but not including, the stream writer: Load -> PredictMotion -> Reduce ->
-    PreparePalettes (without OptimizePalettes) -> Dither -> Reconstruct -> Reindex."""
+    PreparePalettes (with OptimizePalettes unless optimize=False) -> Dither -> Reconstruct -> Reindex."""
     frames_p, canon, flags, tw, th = load(frames)
     psnr = predict_motion(frames_p, canon, flags, tw, th, radius)
     dtiles, dflags, use, _, x = reduce(canon, flags, psnr, [s for s, _ in seqs], tile_count)
     tpal = palettize(dtiles, use, palette_count, seed)
     pal = quantize(dtiles, tpal, palette_count, palette_size, seed)
+    if optimize:
+        pal, _ = optimize_palettes(pal)
     didx = O.dither(dtiles, dflags, tpal, pal, use_tk=use_tk, y2_mixed_colors=y2_mixed)
     dfeat = O.features_from_pal(didx, tpal, pal)
     parts = [O.reconstruct_sequence(canon[s0:s1 + 1], flags[s0:s1 + 1], tw, th, dfeat, didx, tpal, pal, radius=radius, extended=extended)

@@ -157,3 +157,20 @@ def test_pipeline_reduce_and_reindex_semantics(oracle):
     assert len(ft) == len(np.unique(didx[np.unique(tmap[tmap >= 0])], axis=0)) and fu.sum() == unpred.sum()
     assert all(np.array_equal(ft[fm[f, t]], didx[tmap[f, t]]) for f in range(3) for t in range(30) if tmap[f, t] >= 0)
     assert (np.diff(fu) <= 0).all()
+
+
+def test_optimize_palettes_host_port_matches_pipeline_port():
+    """OptimizePalettes + the Powell minimiser (tilingencoder.pas:4246-4432, powell.pas) exist twice: C++ host code of the product
+    (libtm_gtm.so) and the Python restatement in oracle/pipeline.py.  The minimiser's path depends on every floating-point detail
+    (and on FreePascal's reference semantics of dynamic arrays), so equal permutations on several shapes pin both to each other."""
+    from oracle import pipeline as P
+    from tiler_b200 import gtm
+    for n_pal, pal_size, n_null in ((1, 16, 0), (2, 2, 0), (3, 8, 2), (16, 16, 1), (5, 64, 7)):
+        pal = rand_palettes(n_pal, pal_size, 100 + n_pal, n_null=n_null)
+        got, it_got = gtm.optimize_palettes(pal, n_threads=3)
+        want, it_want = P.optimize_palettes(pal)
+        assert it_got == it_want and np.array_equal(got, want)
+        assert np.array_equal(np.sort(got, axis=1), np.sort(pal, axis=1))      # a permutation inside each palette, nothing else
+    single, _ = gtm.optimize_palettes(rand_palettes(8, 16, 7), n_threads=1)
+    multi, _ = gtm.optimize_palettes(rand_palettes(8, 16, 7), n_threads=8)
+    assert np.array_equal(single, multi)                                       # palettes of a pass are independent: thread count is free

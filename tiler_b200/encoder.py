@@ -92,7 +92,8 @@ class TilingEncoder:
 
     def __init__(self, palette_size=16, palette_count=16, dithering_mode=api.PVS_WEIGHTED_SPE_DCT,
                  dithering_use_thomas_knoll=True, dithering_yliluoma2_mixed_colors=4,
-                 frame_tiling_extended_palette_usage=True, seed=0x42381337, device=None, feature_mode="exact"):
+                 frame_tiling_extended_palette_usage=True, seed=0x42381337, device=None, feature_mode="exact",
+                 optimize_palettes=True):
         self.palette_size = int(np.clip(palette_size, 2, 256))      # reference clamps to 2..64 (:2965); 256 = stress shape
         self.palette_count = int(np.clip(palette_count, 1, 65536))
         self.dithering_mode = dithering_mode
@@ -104,6 +105,7 @@ class TilingEncoder:
         # "exact": every feature in DCTInner_asm's summation order (bit-exact); "fast": the sliding-window features of the motion
         # searches (DoDCTs) through the separable f64 kernel (<= 1 LSB on < 1e-3 of the coefficients, PSNR within 0.05 dB)
         self.feature_mode = api.FEATURES_FAST if feature_mode == "fast" else api.FEATURES_EXACT
+        self.optimize = bool(optimize_palettes)   # PreparePalettes ends with OptimizePalettes (:1868); False leaves the (V,S,H) order
         self.tiles = None       # dictionary tiles, RGB [n,64] (canonical orientation)
         self.tile_flags = None  # their initial mirrors
         self.tile_pal = None    # PalIdx_Initial
@@ -400,6 +402,16 @@ class TilingEncoder:
         self.coreset_size = int(len(core))
         # DoQuantization per palette (:4534-4564), all palettes in one call
         self.palettes, _ = api.palquant_kmeans(self.tiles, self.tile_pal, P, self.palette_size, seed=self.seed)
+        if self.optimize:
+            self.optimize_palettes()
+        return self.palettes
+
+    def optimize_palettes(self):
+        """OptimizePalettes (:4246-4432): Powell search (powell.pas) over colour permutations inside each palette, repeated over
+        all palettes until the mean objective stops improving.  Host code in the reference (no DLL): libtm_gtm.so, CPU threads."""
+        pal_h = self.palettes.cpu().numpy() if api._is_dev(self.palettes) else np.asarray(self.palettes)
+        new, self.optimize_passes = gtm_io.optimize_palettes(pal_h)
+        self.palettes = self._to(new)
         return self.palettes
 
     # --- Dither (tilingencoder.pas:1873-1907)

@@ -39,6 +39,8 @@ def lib():
         L.tmh_gtm_decoder_dims.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int64)]
         L.tmh_gtm_decode.restype = C.c_int64
         L.tmh_gtm_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]
+        L.tmh_optimize_palettes.restype = C.c_int
+        L.tmh_optimize_palettes.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         _LIB = L
     return _LIB
 
@@ -68,6 +70,16 @@ def lzma_decode(data, offset=0, max_out=None):
         if n < 0:
             raise RuntimeError(f"tmh_lzma_decode failed ({n})")
         return out[:n].tobytes(), used.value
+
+
+# ------------------------------------------------------------------ OptimizePalettes (tilingencoder.pas:4246-4432, powell.pas)
+def optimize_palettes(palettes, n_threads=0):
+    """Reorders the colours inside each palette (host code in the reference too).  -> (new palettes [n_pal, pal_size], passes)."""
+    pal = np.ascontiguousarray(palettes, dtype=np.int32).copy()
+    it = lib().tmh_optimize_palettes(pal.ctypes.data, int(pal.shape[0]), int(pal.shape[1]), int(n_threads))
+    if it < 0:
+        raise ValueError("tmh_optimize_palettes: bad argument")
+    return pal, int(it)
 
 
 # ------------------------------------------------------------------ dictionary bookkeeping (Reindex, tilingencoder.pas:1992-2040)
