@@ -180,7 +180,6 @@ struct tm_knn_short {
   uint8_t *limbs = nullptr;    // [n][384]
   uint32_t *norms = nullptr;   // [ceil64(n)]
   uint32_t *norm_max = nullptr;   // largest exact squared norm of the rows (device scalar, saturated)
-  uint8_t *ext = nullptr;         // [n][128]: dictionary-side constants of the top-k kernel's folded threshold
   Rendezvous rv;
 };
 struct tm_knn_double {
@@ -326,16 +325,14 @@ static int knn_short_create_dev(const int16_t *d_feat, int64_t n, cudaStream_t s
   // dictionaries of the same size over and over, and a raw cudaMalloc / cudaFree of hundreds of MB costs 0.1-0.3 s each time
   if (cudaMallocAsync((void **)&h->limbs, (size_t)(n > 0 ? n : 1) * 384, st) != cudaSuccess ||
       cudaMallocAsync((void **)&h->norms, (size_t)(npad > 0 ? npad : 64) * 4, st) != cudaSuccess ||
-      cudaMallocAsync((void **)&h->norm_max, 4, st) != cudaSuccess ||
-      cudaMallocAsync((void **)&h->ext, (size_t)(n > 0 ? n : 1) * 128, st) != cudaSuccess) {
-    cudaFreeAsync(h->limbs, st); cudaFreeAsync(h->norms, st); cudaFreeAsync(h->norm_max, st); delete h;
+      cudaMallocAsync((void **)&h->norm_max, 4, st) != cudaSuccess) {
+    cudaFreeAsync(h->limbs, st); cudaFreeAsync(h->norms, st); delete h;
     return TM_ERR_NOMEM;
   }
   cudaMemsetAsync(h->norms, 0, (size_t)(npad > 0 ? npad : 64) * 4, st);
   cudaMemsetAsync(h->norm_max, 0, 4, st);
   int rc = launch_limb_split(d_feat, n, h->limbs, h->norms, st, h->norm_max);
-  if (rc == TM_OK) rc = launch_knn_ext(h->norms, n, h->ext, st);
-  if (rc != TM_OK) { cudaFreeAsync(h->limbs, st); cudaFreeAsync(h->norms, st); cudaFreeAsync(h->norm_max, st); cudaFreeAsync(h->ext, st); delete h; return rc; }
+  if (rc != TM_OK) { cudaFreeAsync(h->limbs, st); cudaFreeAsync(h->norms, st); cudaFreeAsync(h->norm_max, st); delete h; return rc; }
   *out = h;
   return TM_OK;
 }
@@ -354,7 +351,7 @@ extern "C" int tm_knn_short_create(const int16_t *feat, int64_t n, tm_knn_short 
 extern "C" int tm_knn_short_destroy(tm_knn_short *h) {
   if (!h) return TM_OK;
   std::lock_guard<std::recursive_mutex> lk(g_mu);
-  cudaFreeAsync(h->limbs, t_stream); cudaFreeAsync(h->norms, t_stream); cudaFreeAsync(h->norm_max, t_stream); cudaFreeAsync(h->ext, t_stream);
+  cudaFreeAsync(h->limbs, t_stream); cudaFreeAsync(h->norms, t_stream); cudaFreeAsync(h->norm_max, t_stream);
   delete h;
   return TM_OK;
 }
@@ -371,7 +368,7 @@ static int knn_short_batch_dev(tm_knn_short *h, const int16_t *d_q, int64_t n_q,
   int rc = launch_limb_split(d_q, n_q, q_limbs, q_norm, s.st, q_nmax);
   if (rc) return rc;
   return launch_knn_i8(q_limbs, q_norm, (int)n_q, h->limbs, h->norms, (int)h->n, k, d_idx, d_dist, nullptr, num_sms(), sorted, s.st, q_nmax,
-                       h->norm_max, h->ext);
+                       h->norm_max);
 }
 
 extern "C" int tm_knn_short_batch(tm_knn_short *h, const int16_t *q, int64_t n_q, int k, int32_t *idx, uint32_t *dist, int sorted) {

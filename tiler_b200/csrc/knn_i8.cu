@@ -351,13 +351,11 @@ constexpr int TK_CAP = TM_TK_CAP;  // candidate slots per (query row, column hal
 constexpr int TK_SLACK = 16;     // a loose cut keeps between k and k + TK_SLACK candidates
 constexpr int TK_CUT_FIRST = 4, TK_CUT_RATIO = 4;   // scheduled row-wide cuts after 4, 16, 64, 256, ... dictionary tiles
 constexpr int TK_THREADS = 352;  // 8 epilogue warps + TMA warp + 2 MMA issuer warps
-constexpr int STAGES_TK = 8;       // dictionary ring depth of the top-k kernel, unsigned path (24 KB stages)
-constexpr int STAGES_TK_FOLD = 6;  // folded path: 32 KB stages (3 limb chunks + the extension chunk)
-constexpr int A_EXT_COL = A_COL + 96;    // query-side extension K-steps live in TMEM columns [480, 504)
+constexpr int STAGES_TK = 8;     // dictionary ring depth of the top-k kernel
 // Ring of dictionary-norm slots (64 norms = 256 bytes per tile, copied by the TMA producer next to the tile).  A slot is read
 // by the epilogue right after the TMEM read of its tile and rewritten STAGES_TK + 3 tiles later at the earliest (the
 // producer runs at most STAGES_TK tiles ahead of MMA completion, the MMAs at most 2 tiles ahead of the TMEM reads).
-constexpr int TK_NRING = STAGES_TK + 4;   // largest ring of the two instantiations (the kernel uses its own stage count + 4)
+constexpr int TK_NRING = STAGES_TK + 4;
 
 __device__ __forceinline__ unsigned long long ldg_key(const unsigned long long *p) {
   unsigned long long v;
@@ -478,77 +476,33 @@ __device__ __forceinline__ void tk_tile32(unsigned long long &waddr, uint32_t ta
   }
 }
 
-// ---- admission threshold folded into the MMA (no-wrap case: every squared norm of the queries and of the dictionary is
-// below 2^29, so every distance is below 2^31 -- true for any real feature set, |coefficient| <= 13 212).
-//   d - tau - 1 = (|q|^2 - tau - 1) + |t|^2 - 2 S,   S = 65536 HH + 256 X + LL.
-// Pick tau_eff in {tau, tau + 1} with |q|^2 - tau_eff - 1 even, R = (|q|^2 - tau_eff - 1) / 2 (a ROW constant), C = |t|^2 >> 1
-// (a COLUMN constant), p = |t|^2 & 1:   d - tau_eff - 1 = 2 (R + C - S) + p,  so  d <= tau_eff  <=>  m := R + C - S < 0.
-// One more K-step per accumulator subtracts R and C inside the tensor core: the query side of the step holds the bytes of R
-// (and constants), the dictionary side constants (and the bytes of C), split over the three accumulators with their weights
-//   HH -= r2 + c2,  X -= r1 + c1,  LL -= r0 + c0      (R = 65536 r2 + 256 r1 + r0,  C = 65536 c2 + 256 c1 + c0).
-// The epilogue then needs TWO multiply-adds per distance (m = -(65536 HH + 256 X + LL)) and no norm at all, and "admit" is
-// the sign of m.  An admitted entry stores d = 2 m + p + tau_eff + 1.  The query side is rewritten (tcgen05.st) when a
-// scheduled cut has lowered tau, at a moment when the tensor pipe is provably idle (see the tile loop).
-__device__ __forceinline__ uint32_t tk_tau_eff(uint32_t nq, uint32_t tau) { return tau + ((nq - tau - 1u) & 1u); }
-// query-side extension words: K-step 0 (s8) = [r2 >> 7, r2 & 127, -128, -1], K-steps 1 / 2 (u8) = [r1 | r0, 2, 1]
-__device__ __forceinline__ void tk_a_ext_words(uint32_t nq, uint32_t tau_eff, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
-  const int32_t R = (int32_t)(nq - tau_eff - 1u) >> 1;
-  const int32_t r2 = R >> 16;
-  w0 = ((uint32_t)(r2 >> 7) & 255u) | (((uint32_t)r2 & 127u) << 8) | (0x80u << 16) | (0xFFu << 24);
-  w1 = (((uint32_t)R >> 8) & 255u) | (2u << 8) | (1u << 16);
-  w2 = ((uint32_t)R & 255u) | (2u << 8) | (1u << 16);
-}
-__device__ __forceinline__ void tk_write_a_ext(uint32_t t_lane, uint32_t nq, uint32_t tau_eff) {
-  uint32_t w0, w1, w2;
-  tk_a_ext_words(nq, tau_eff, w0, w1, w2);
-  uint32_t r[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) r[i] = 0;
-  r[0] = w0; r[8] = w1;
-  tmem_st16(t_lane + A_EXT_COL, r);
-  r[0] = w2; r[8] = 0;
-  tmem_st16(t_lane + A_EXT_COL + 16, r);
-}
-// dictionary-side extension rows: [n][128 bytes]; K-step 0 (s8) = [-128, -1, c2 >> 7, c2 & 127], K-steps 1 / 2 (s8) =
-// [-1, -(c >> 1), -(c & 1)] for c = c1 / c0
-__global__ void __launch_bounds__(256) knn_ext_kernel(const uint32_t *__restrict__ norms, int64_t n, uint32_t *__restrict__ ext) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t C = norms[i] >> 1;
-  const uint32_t c2 = C >> 16, c1 = (C >> 8) & 255u, c0 = C & 255u;
-  uint32_t *row = ext + i * 32;
-#pragma unroll
-  for (int w = 0; w < 32; ++w) row[w] = 0;
-  row[0] = 0x80u | (0xFFu << 8) | (((c2 >> 7) & 255u) << 16) | ((c2 & 127u) << 24);
-  row[8] = 0xFFu | (((0u - (c1 >> 1)) & 255u) << 8) | (((0u - (c1 & 1u)) & 255u) << 16);
-  row[16] = 0xFFu | (((0u - (c0 >> 1)) & 255u) << 8) | (((0u - (c0 & 1u)) & 255u) << 16);
-}
-__device__ __forceinline__ void tk_admit_m(unsigned long long &waddr, uint32_t idx, uint32_t m, uint32_t d) {
+// ---- no-wrap variant of tk_tile32 (every squared norm of the queries and of the dictionary is below 2^29, so every distance
+// is below 2^31: true for any real feature set, |coefficient| <= 13 212).  The per-thread constant kk = |q|^2 - tau - 1 rides
+// in the norm add, so  e = d - tau - 1  comes out of the same four instructions as d did, and "admit" is the SIGN of e: the
+// pair mask is one OR and one funnel shift per column pair (2 instructions) instead of min / compare / select / add (3.3).
+// Admitted entries store d = e + tau + 1.
+__device__ __forceinline__ void tk_admit_nw(unsigned long long &waddr, uint32_t idx, uint32_t e, uint32_t tau1) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b32 lo, hi;\n\t"
+      "{\n\t.reg .pred p;\n\t.reg .b32 lo, hi, d;\n\t"
       "setp.lt.s32 p, %2, 0;\n\t"
-      "@p st.global.v2.u32 [%0], {%1, %3};\n\t"
+      "add.u32 d, %2, %3;\n\t"
+      "@p st.global.v2.u32 [%0], {%1, d};\n\t"
       "mov.b64 {lo, hi}, %0;\n\t"
       "@p add.u32 lo, lo, 8;\n\t"
       "mov.b64 %0, {lo, hi};\n\t}\n"
       : "+l"(waddr)
-      : "r"(idx), "r"(m), "r"(d)
+      : "r"(idx), "r"(e), "r"(tau1)
       : "memory");
 }
-// one tile half (32 columns) of the folded path.  base = tau_eff + 1 of the constants this tile was multiplied with; nd_half =
-// this half's 32 dictionary norms in shared memory (only their parity is read, and only for pairs some lane admits);
-// nvalid < 32 on the ragged last dictionary tile (columns beyond the dictionary never compete).
-__device__ __forceinline__ void tk_tile32_fold(unsigned long long &waddr, uint32_t base, int col, const uint32_t *__restrict__ nd_half, int nvalid,
-                                               uint32_t (&ppA)[16], const uint32_t (&xxA)[16], const uint32_t (&loA)[16],
-                                               uint32_t (&ppB)[16], const uint32_t (&xxB)[16], const uint32_t (&loB)[16]) {
+__device__ __forceinline__ void tk_tile32_nw(unsigned long long &waddr, uint32_t tau, uint32_t nq, int col, const uint32_t (&ndA)[16],
+                                             uint32_t (&ppA)[16], const uint32_t (&xxA)[16], const uint32_t (&loA)[16],
+                                             const uint32_t (&ndB)[16], uint32_t (&ppB)[16], const uint32_t (&xxB)[16],
+                                             const uint32_t (&loB)[16]) {
+  const uint32_t kk = nq - tau - 1u, tau1 = tau + 1u;
 #pragma unroll
-  for (int e = 0; e < 16; ++e) ppA[e] = (ppA[e] * 0xFFFFFF00u - xxA[e]) * 256u - loA[e];
+  for (int e = 0; e < 16; ++e) ppA[e] = tk_dist(ndA[e] + kk, ppA[e], xxA[e], loA[e]);
 #pragma unroll
-  for (int e = 0; e < 16; ++e) ppB[e] = (ppB[e] * 0xFFFFFF00u - xxB[e]) * 256u - loB[e];
-  if (nvalid < 32) {
-#pragma unroll
-    for (int e = 0; e < 16; ++e) { if (e >= nvalid) ppA[e] = 0x7FFFFFFFu; if (16 + e >= nvalid) ppB[e] = 0x7FFFFFFFu; }
-  }
+  for (int e = 0; e < 16; ++e) ppB[e] = tk_dist(ndB[e] + kk, ppB[e], xxB[e], loB[e]);
   uint32_t mine = 0;   // after the 16 shifts: bit 15 - p <-> pair p (p < 8: columns 2p, 2p + 1; p >= 8: columns 16 + 2(p - 8), ...)
 #pragma unroll
   for (int e = 0; e < 8; ++e) mine = __funnelshift_l(ppA[2 * e] | ppA[2 * e + 1], mine, 1);
@@ -559,17 +513,15 @@ __device__ __forceinline__ void tk_tile32_fold(unsigned long long &waddr, uint32
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       if (any & (0x8000u >> e)) {
-        const uint2 pn = *reinterpret_cast<const uint2 *>(nd_half + 2 * e);
-        tk_admit_m(waddr, (uint32_t)(col + 2 * e), ppA[2 * e], 2u * ppA[2 * e] + base + (pn.x & 1u));
-        tk_admit_m(waddr, (uint32_t)(col + 2 * e + 1), ppA[2 * e + 1], 2u * ppA[2 * e + 1] + base + (pn.y & 1u));
+        tk_admit_nw(waddr, (uint32_t)(col + 2 * e), ppA[2 * e], tau1);
+        tk_admit_nw(waddr, (uint32_t)(col + 2 * e + 1), ppA[2 * e + 1], tau1);
       }
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       if (any & (0x80u >> e)) {
-        const uint2 pn = *reinterpret_cast<const uint2 *>(nd_half + 16 + 2 * e);
-        tk_admit_m(waddr, (uint32_t)(col + 16 + 2 * e), ppB[2 * e], 2u * ppB[2 * e] + base + (pn.x & 1u));
-        tk_admit_m(waddr, (uint32_t)(col + 16 + 2 * e + 1), ppB[2 * e + 1], 2u * ppB[2 * e + 1] + base + (pn.y & 1u));
+        tk_admit_nw(waddr, (uint32_t)(col + 16 + 2 * e), ppB[2 * e], tau1);
+        tk_admit_nw(waddr, (uint32_t)(col + 16 + 2 * e + 1), ppB[2 * e + 1], tau1);
       }
     }
   }
@@ -715,34 +667,22 @@ __device__ __forceinline__ uint32_t tk_row_cut(unsigned long long *b0, unsigned 
   return T;
 }
 
-// FOLD = true: the admission threshold is folded into the MMA (27 MMAs per tile, signed two-instruction epilogue); runs only
-// when every squared norm is below 2^29.  FOLD = false: the general unsigned epilogue (distances may wrap mod 2^32 like the
-// reference's Cardinal).  The host launches both; the one whose precondition fails (device-side norm bounds) exits at once,
-// so nothing of the decision comes back to the host.
-template <bool FOLD>
 __global__ void __launch_bounds__(TK_THREADS, 1)
 knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CUtensorMap tmap_d,
-                   const __grid_constant__ CUtensorMap tmap_x /* dictionary-side extension rows [n_dict][128] (knn_ext_kernel) */,
                    const uint32_t *__restrict__ qnorm, const uint32_t *__restrict__ dnorm, int n_q, int n_dict, int k,
                    int32_t *__restrict__ out_idx, uint32_t *__restrict__ out_dist, int tile_stride,
                    unsigned long long *ws /* [gridDim.x][256][TK_CAP], 2 KB aligned */, int slack, int dbg, int cut_first,
                    int cut_ratio /* scheduled row-wide cuts after cut_first, cut_first * cut_ratio, ... tiles; 0 = none */,
                    const uint32_t *__restrict__ q_nmax, const uint32_t *__restrict__ d_nmax /* largest squared norms, or null */) {
-  // signed arithmetic is exact when no distance can reach 2^31: every squared norm below 2^29 ((|q| + |t|)^2 < 2^31)
-  const bool can_fold = !(dbg & 64) && q_nmax && d_nmax && __ldg(q_nmax) < (1u << 29) && __ldg(d_nmax) < (1u << 29);
-  if (can_fold != FOLD) return;   // the other instantiation does this search
-  constexpr bool fold = FOLD;
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int NST = FOLD ? STAGES_TK_FOLD : STAGES_TK;
-  constexpr int TK_B_TILE = FOLD ? 4 * CHUNK_B : B_TILE;   // a folded stage = the 3 limb chunks + the extension chunk
-  constexpr int NRING = NST + 4;                            // see TK_NRING
+  constexpr int NST = STAGES_TK;
   uint8_t *sB = smem;
-  int32_t *s_cnt = reinterpret_cast<int32_t *>(sB + NST * TK_B_TILE); // [256] candidates per thread (row-wide cuts, end of a query block)
+  int32_t *s_cnt = reinterpret_cast<int32_t *>(sB + NST * B_TILE);    // [256] candidates per thread (row-wide cuts, end of a query block)
   uint32_t *s_thalf = reinterpret_cast<uint32_t *>(s_cnt + 256);      // [2][128] half-thresholds published by the strips of a row
   uint32_t *s_tau = s_thalf + 256;                                    // [128] row-wide threshold left by a scheduled cut
   uint32_t *s_nd = s_tau + 128;                                       // [TK_NRING][64] dictionary norms of the tiles in flight
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_nd + TK_NRING * BN);   // sized for the larger ring
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_nd + TK_NRING * BN);
   uint64_t *full = bars, *empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + 1, *t_full = a_empty + 1,
            *t_empty = t_full + 2;
   uint64_t *stag = t_empty + 2;   // [4 quarters][2 stages]: the first warp of a quarter has its TMEM reads in flight
@@ -751,6 +691,7 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (n_dict + BN - 1) / BN;
   const int n_qblocks = (n_q + BM - 1) / BM;
+
   if (threadIdx.x < 256) s_thalf[threadIdx.x] = 0xFFFFFFFFu;
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -761,7 +702,7 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
     fence_barrier_init();
   }
   if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  if (warp == 8 && lane == 0) { tma_prefetch_desc(&tmap_d); tma_prefetch_desc(&tmap_x); }
+  if (warp == 8 && lane == 0) tma_prefetch_desc(&tmap_d);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -778,10 +719,9 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
           const uint32_t s = it % NST, r = it / NST;
           mbar_wait(&empty[s], (r & 1) ^ 1);
           if (dbg & 2) { mbar_arrive(&full[s]); jt += tile_stride; if (jt >= n_tiles) jt -= n_tiles; continue; }   // timing experiment: no dictionary traffic
-          mbar_expect_tx(&full[s], B_TILE + BN * 4 + (fold ? CHUNK_B : 0));
-          for (int c = 0; c < 3; ++c) tma_load_2d(sB + s * TK_B_TILE + c * CHUNK_B, &tmap_d, &full[s], c * 128, jt * BN);
-          if (fold) tma_load_2d(sB + s * TK_B_TILE + 3 * CHUNK_B, &tmap_x, &full[s], 0, jt * BN);
-          bulk_load_1d(s_nd + (it % NRING) * BN, dnorm + (size_t)jt * BN, BN * 4, &full[s]);   // norms are padded to whole tiles
+          mbar_expect_tx(&full[s], B_TILE + BN * 4);
+          for (int c = 0; c < 3; ++c) tma_load_2d(sB + s * B_TILE + c * CHUNK_B, &tmap_d, &full[s], c * 128, jt * BN);
+          bulk_load_1d(s_nd + (it % TK_NRING) * BN, dnorm + (size_t)jt * BN, BN * 4, &full[s]);   // norms are padded to whole tiles
           jt += tile_stride;
           if (jt >= n_tiles) jt -= n_tiles;
         }
@@ -806,11 +746,8 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         mbar_wait(&t_empty[ts], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         TKT(2)
-        const uint64_t dB = descB0 + (uint64_t)((s * TK_B_TILE) >> 4);
-        if (!(dbg & 4)) {
-          if (fold) { if (my_parity == 0) mma_i8_tile27_elect<0>((uint32_t)dB); else mma_i8_tile27_elect<1>((uint32_t)dB); }
-          else { if (my_parity == 0) mma_i8_tile_elect<0>((uint32_t)dB); else mma_i8_tile_elect<1>((uint32_t)dB); }
-        }
+        const uint64_t dB = descB0 + (uint64_t)((s * B_TILE) >> 4);
+        if (!(dbg & 4)) { if (my_parity == 0) mma_i8_tile_elect<0>((uint32_t)dB); else mma_i8_tile_elect<1>((uint32_t)dB); }
         tc_commit_elect(&t_full[ts]);
         tc_commit_elect(&empty[s]);
         TKT(3)
@@ -828,6 +765,8 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
     unsigned long long *wbuf = cta_ws + (size_t)(warp * 32) * TK_CAP;   // this warp's 32 strips
     unsigned long long *mybuf = wbuf + (size_t)lane * TK_CAP;
     const uint32_t base_lo = (uint32_t)(uintptr_t)mybuf;
+    // signed comparisons are exact when no distance can reach 2^31: every squared norm below 2^29 ((|q| + |t|)^2 < 2^31)
+    const bool nowrap = !(dbg & 64) && q_nmax && d_nmax && __ldg(q_nmax) < (1u << 29) && __ldg(d_nmax) < (1u << 29);
     uint32_t it = 0, w = 0;
     TKT_DECL
     for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
@@ -848,18 +787,13 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
           }
           tmem_st16(t_lane + A_COL + c * 16, r);
         }
-        if (fold) tk_write_a_ext(t_lane, nq, tk_tau_eff(nq, (dbg & 1) ? 0u : 0x7FFFFFFEu));
         tmem_st_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a_full);
       }
       // distances of 0xFFFFFFFF (masked columns) are never admitted; without wrap every distance is below 2^31
-      uint32_t tau = (dbg & 1) ? 0u : (fold ? 0x7FFFFFFEu : 0xFFFFFFFEu);
-      // folded path: tau_mma = the tau_eff the tensor core currently subtracts for this row; a lower one becomes effective
-      // two tiles after the query-side constants were rewritten (switch_it)
-      uint32_t tau_mma = tk_tau_eff(nq, tau), tau_mma_new = tau_mma, switch_it = 0xFFFFFFFFu;
-      bool rewrite_due = false;
+      uint32_t tau = (dbg & 1) ? 0u : (nowrap ? 0x7FFFFFFEu : 0xFFFFFFFEu);
       unsigned long long waddr = (unsigned long long)(uintptr_t)mybuf;   // next free slot of this thread's strip
       uint32_t my_half = 0xFFFFFFFFu;                                     // this strip's published half-threshold
       int jt = 0;
@@ -870,7 +804,6 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         const int col0 = jt * BN + h * HN;
         jt += tile_stride;
         if (jt >= n_tiles) jt -= n_tiles;
-        if (it == switch_it) { tau_mma = tau_mma_new; switch_it = 0xFFFFFFFFu; }
         TKT(1)
         mbar_wait(&t_full[ts], (it >> 1) & 1);
 #if TM_STAG
@@ -889,12 +822,10 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
 #if TM_STAG == 1
         if (h == 0 && lane == 0) mbar_arrive(&stag[(q << 1) | ts]);
 #endif
-        // dictionary norms of this tile half from the ring the TMA producer fills (broadcast reads; they overlap the TMEM reads).
-        // The folded path does not need them (only the parity of an admitted column's norm, read on the spot).
-        const uint32_t *nd_half = s_nd + (it % NRING) * BN + h * HN;
+        // dictionary norms of this tile half from the ring the TMA producer fills (broadcast reads; they overlap the TMEM reads)
         uint32_t ndA[16], ndB[16];
-        if (!fold) {
-          const uint4 *nsrc = reinterpret_cast<const uint4 *>(nd_half);
+        {
+          const uint4 *nsrc = reinterpret_cast<const uint4 *>(s_nd + (it % TK_NRING) * BN + h * HN);
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             const uint4 t4 = nsrc[v], u4 = nsrc[4 + v];
@@ -906,29 +837,14 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
 #if TM_STAG == 2
         if (h == 0 && lane == 0) mbar_arrive(&stag[(q << 1) | ts]);
 #endif
-        if (rewrite_due) {
-          // A scheduled cut has lowered tau: rewrite the query-side constants NOW.  This tile's MMAs are complete (its
-          // accumulators were just read); the next tile's are awaited here; the one after cannot be issued before every
-          // epilogue warp -- this one included -- has handed this tile's accumulator stage back below.  So the tensor pipe is
-          // idle while the constants change, and they are in force from tile it + 2 on.
-          if (h == 0) {
-            mbar_wait(&t_full[ts ^ 1], ((it + 1) >> 1) & 1);
-            tc_fence_after();
-            tk_write_a_ext(t_lane, nq, tau_mma_new);
-            tmem_st_wait();
-          }
-          rewrite_due = false;
-          switch_it = it + 2;
-        }
         tc_fence_before();          // the whole tile is in registers: hand the stage back to the tensor pipe
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[ts]);
         TKT(3)
         if (!(dbg & 8)) {
-          if (fold) {
-            tk_tile32_fold(waddr, tau_mma + 1u, col0, nd_half, n_dict - col0, ppA, xxA, loA, ppB, xxB, loB);
-          } else if (col0 + HN <= n_dict) {
-            tk_tile32(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB);
+          if (col0 + HN <= n_dict) {
+            if (nowrap) tk_tile32_nw(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB);
+            else tk_tile32(waddr, tau, nq, col0, ndA, ppA, xxA, loA, ndB, ppB, xxB, loB);
           } else {   // ragged last dictionary tile
             tk_unit(waddr, tau, nq, col0, n_dict - col0, ndA, ppA, xxA, loA);
             tk_unit(waddr, tau, nq, col0 + 16, n_dict - col0 - 16, ndB, ppB, xxB, loB);
@@ -974,12 +890,6 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
           asm volatile("bar.sync %0, 64;\n" ::"r"(2 + q) : "memory");
           waddr = (unsigned long long)(uintptr_t)(mybuf + s_cnt[warp * 32 + lane]);
           tau = min(tau, s_tau[row]);
-          if (fold && j + 2 < n_tiles) {   // the next tile exists, so its MMAs are (or will be) issued without this warp's help
-            // from the ROW's threshold only: both threads of a row must agree on the constants (their own tau may differ
-            // after an organic cut of one strip)
-            tau_mma_new = min(tau_mma, tk_tau_eff(nq, s_tau[row]));
-            rewrite_due = true;
-          }
         }
         TKT(6)
       }
@@ -1104,13 +1014,6 @@ int make_tmap_rows_u8(CUtensorMap *map, const void *base, uint64_t rows, uint32_
 size_t knn_workspace_bytes(int num_ctas) { (void)num_ctas; return 0; }   // top-k state lives in shared memory
 int knn_rows_per_cta() { return BM; }
 
-int launch_knn_ext(const uint32_t *norms, int64_t n, uint8_t *ext, cudaStream_t st) {
-  if (n <= 0) return TM_OK;
-  knn_ext_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(norms, n, reinterpret_cast<uint32_t *>(ext));
-  note_launch();
-  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
-}
-
 int launch_limb_split(const int16_t *in, int64_t n, uint8_t *limbs, uint32_t *norms, cudaStream_t st, uint32_t *norm_max) {
   if (n <= 0) return TM_OK;
   limb_split_kernel<<<(unsigned)((n + 7) / 8), 192, 0, st>>>(in, n, limbs, norms, norm_max);
@@ -1120,7 +1023,7 @@ int launch_limb_split(const int16_t *in, int64_t n, uint8_t *limbs, uint32_t *no
 
 int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const uint8_t *d_limbs, const uint32_t *d_norm,
                   int n_dict, int k, int32_t *out_idx, uint32_t *out_dist, void *ws, int num_ctas, int sort_rows,
-                  cudaStream_t st, const uint32_t *q_norm_max, const uint32_t *d_norm_max, const uint8_t *d_ext) {
+                  cudaStream_t st, const uint32_t *q_norm_max, const uint32_t *d_norm_max) {
   (void)ws;
   if (n_q <= 0) return TM_OK;
   if (k < 1 || k > KMAX || n_dict <= 0) return TM_ERR_ARG;
@@ -1129,14 +1032,12 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
   if (rc != TM_OK) return rc;
   constexpr int K1_NH = TM_K1_NH;   // column splits per tile in the k = 1 / k = 4 kernels (2: 8 epilogue warps, 4: 16)
   constexpr int SMEM_K1 = STAGES_K1 * B_TILE + BM * 8 * 4 * (K1_NH - 1) + 768 + 1024;
-  constexpr int SMEM_TK_TAIL = 256 * 4 + 256 * 4 + 128 * 4 + TK_NRING * BN * 4 + 768 + 1024;
-  constexpr int SMEM_TK = STAGES_TK * B_TILE + SMEM_TK_TAIL, SMEM_TK_FOLD = STAGES_TK_FOLD * 4 * CHUNK_B + SMEM_TK_TAIL;
+  constexpr int SMEM_TK = STAGES_TK * B_TILE + 256 * 4 + 256 * 4 + 128 * 4 + TK_NRING * BN * 4 + 768 + 1024;
   static bool attr_set[TM_MAX_DEVICES] = {};
   if (first_use_on_device(attr_set)) {
     if (cudaFuncSetAttribute(knn_i8_k1_kernel<1, K1_NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
     if (cudaFuncSetAttribute(knn_i8_k1_kernel<4, K1_NH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_K1) != cudaSuccess) return TM_ERR_CUDA;
-    if (cudaFuncSetAttribute(knn_i8_topk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK) != cudaSuccess) return TM_ERR_CUDA;
-    if (cudaFuncSetAttribute(knn_i8_topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK_FOLD) != cudaSuccess) return TM_ERR_CUDA;
+    if (cudaFuncSetAttribute(knn_i8_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TK) != cudaSuccess) return TM_ERR_CUDA;
   }
   {
     ProfScope prof(k == 1 ? "knn_k1" : (k == 4 ? "knn_k4" : "knn_topk"), st);
@@ -1168,20 +1069,8 @@ int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const
         dbg = getenv("TM_TK_DBG") ? atoi(getenv("TM_TK_DBG")) : 0;
         if (const char *e = getenv("TM_TK_CUTS")) { if (sscanf(e, "%d,%d", &cut_first, &cut_ratio) != 2) { cut_first = TK_CUT_FIRST; cut_ratio = TK_CUT_RATIO; } }
       }
-      // the folded threshold needs the dictionary-side extension rows; without them (or without norm bounds) the kernel runs its
-      // unsigned path (tx must still be a valid tensor map: it aliases the limb rows and is never read)
-      CUtensorMap tx = td;
-      const bool have_ext = d_ext && q_norm_max && d_norm_max;
-      if (have_ext) {
-        rc = make_tmap_rows_u8(&tx, d_ext, (uint64_t)n_dict, 128, BN);
-        if (rc != TM_OK) { cudaFreeAsync(raw, st); return rc; }
-      }
-      const uint32_t *qm = have_ext ? q_norm_max : nullptr, *dm = have_ext ? d_norm_max : nullptr;
-      if (have_ext)
-        knn_i8_topk_kernel<true><<<grid, TK_THREADS, SMEM_TK_FOLD, st>>>(q_limbs, td, tx, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride,
-                                                                         strip_ws, slack, dbg, cut_first, cut_ratio, qm, dm);
-      knn_i8_topk_kernel<false><<<grid, TK_THREADS, SMEM_TK, st>>>(q_limbs, td, tx, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride,
-                                                                   strip_ws, slack, dbg, cut_first, cut_ratio, qm, dm);
+      knn_i8_topk_kernel<<<grid, TK_THREADS, SMEM_TK, st>>>(q_limbs, td, q_norm, d_norm, n_q, n_dict, k, out_idx, out_dist, tile_stride, strip_ws, slack, dbg,
+                                                            cut_first, cut_ratio, q_norm_max, d_norm_max);
       cudaFreeAsync(raw, st);
     }
   }

@@ -172,21 +172,6 @@ __device__ __forceinline__ void mma_i8_tile_elect(uint32_t b_desc_lo) {
         : "memory");
   }
 }
-// the same with one more K-step per accumulator from the extension chunk of the stage (knn_i8.cu: threshold folded into the MMA)
-template <int PARITY>
-__device__ __forceinline__ void mma_i8_tile27_elect(uint32_t b_desc_lo) {
-  if (PARITY == 0) {
-    asm volatile(
-#include "knn_mma_tile27_p0.inc"
-        ::"r"(b_desc_lo)
-        : "memory");
-  } else {
-    asm volatile(
-#include "knn_mma_tile27_p1.inc"
-        ::"r"(b_desc_lo)
-        : "memory");
-  }
-}
 __device__ __forceinline__ void tc_commit_elect(uint64_t *bar) {
   asm volatile(
       "{\n\t.reg .pred pe;\n\t"

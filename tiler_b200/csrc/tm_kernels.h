@@ -36,9 +36,7 @@ int knn_rows_per_cta();
 int launch_limb_split(const int16_t *in, int64_t n, uint8_t *limbs, uint32_t *norms, cudaStream_t st, uint32_t *norm_max = nullptr);
 int launch_knn_i8(const uint8_t *q_limbs, const uint32_t *q_norm, int n_q, const uint8_t *d_limbs, const uint32_t *d_norm,
                   int n_dict, int k, int32_t *out_idx, uint32_t *out_dist, void *ws, int num_ctas, int sort_rows,
-                  cudaStream_t st, const uint32_t *q_norm_max = nullptr, const uint32_t *d_norm_max = nullptr, const uint8_t *d_ext = nullptr);
-// dictionary-side extension rows [n][128 bytes] of the top-k kernel's folded threshold (built from the 32-bit norms)
-int launch_knn_ext(const uint32_t *norms, int64_t n, uint8_t *ext, cudaStream_t st);
+                  cudaStream_t st, const uint32_t *q_norm_max = nullptr, const uint32_t *d_norm_max = nullptr);
 
 // ---- features.cu
 int launch_features_rgb(const int32_t *rgb, int64_t n, int16_t *out, cudaStream_t st);
