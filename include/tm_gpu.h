@@ -121,7 +121,7 @@ int tm_features_from_rgb_mirrored(const int32_t *rgb, const uint8_t *flags, int6
 /* palette-index tiles [n][64] + tile_pal[n] + palettes[n_pal][pal_size] -> features (PrepareReconstruct.DoPsyV, :4570-4583) */
 int tm_features_from_pal(const uint8_t *pal_idx, const int32_t *tile_pal, const int32_t *palettes, int pal_size, int n_pal,
                          int64_t n, int16_t *out);
-/* ComputeTilePsyVisFeatures: f64, mode = TPsyVisMode ordinal (0 DCT, 1 weighted, 3 special, 4 weighted special) */
+/* ComputeTilePsyVisFeatures: f64, mode = TPsyVisMode ordinal (0 DCT, 1 weighted, 2 wavelets [3-level Haar], 3 special, 4 weighted special) */
 int tm_features_f64(const int32_t *rgb, int64_t n, int mode, int use_lab, double *out);
 /* load-time canonicalisation (TFrame.AsyncLoadFromImage, :1393-1411): flips tiles in place, writes mirror flags */
 int tm_mirror_canonicalise(int32_t *rgb, int64_t n, uint8_t *flags);

@@ -283,11 +283,42 @@ void tmo_tile_features_i16(const int32_t *rgb, const uint8_t *pal_idx, const int
 }
 
 /* ComputeTilePsyVisFeatures, tilingencoder.pas:3133-3182 (wavelet mode not restated: out of scope) */
+/* WaveletGS<Double> (tilingencoder.pas:2727-2762): normalised Haar, rows then columns of the dx x dy corner of an 8-wide buffer,
+   repeated on the low-pass quadrant `depth` more times; Output may alias Data (the recursion runs in place). */
+static void wavelet_gs(const double *data, double *output, int dx, int dy, int depth) {
+  double tx[64], ty[64];
+  memset(tx, 0, sizeof tx); memset(ty, 0, sizeof ty);
+  const double factor = 1.0 / sqrt(2.0);
+  for (int y = 0; y < dy; ++y) {
+    const int off = y * 8;
+    for (int x = 0; x < dx / 2; ++x) {
+      tx[x + off] = (data[x * 2 + off] + data[(x * 2 + 1) + off]) * factor;
+      tx[(x + dx / 2) + off] = (data[x * 2 + off] - data[(x * 2 + 1) + off]) * factor;
+    }
+  }
+  for (int x = 0; x < dx; ++x)
+    for (int y = 0; y < dy / 2; ++y) {
+      ty[x + y * 8] = (tx[x + y * 2 * 8] + tx[x + (y * 2 + 1) * 8]) * factor;
+      ty[x + (y + dy / 2) * 8] = (tx[x + y * 2 * 8] - tx[x + (y * 2 + 1) * 8]) * factor;
+    }
+  for (int y = 0; y < dy; ++y) memcpy(output + y * 8, ty + y * 8, sizeof(double) * (size_t)dx);
+  if (depth > 0) wavelet_gs(output, output, dx / 2, dy / 2, depth - 1);
+}
+
 void tmo_tile_features_f64(const int32_t *rgb, const uint8_t *pal_idx, const int32_t *palette,
                            int mode, int from_pal, int use_lab, int hmirror, int vmirror, double out[TMO_DCT]) {
   init_luts();
   float cpn[3][8][8];
   tmo_convert_to_cpn(rgb, pal_idx, palette, from_pal, use_lab, hmirror, vmirror, cpn);
+  if (mode == TMO_PVS_WAVELETS) {   /* :3151-3158: three Haar levels per plane, stored through the zig-zag table like the DCT modes */
+    for (int c = 0; c < 3; ++c) {
+      double cd[64], loc[64];
+      for (int i = 0; i < 64; ++i) cd[i] = (double)(&cpn[c][0][0])[i];
+      wavelet_gs(cd, loc, 8, 8, 2);
+      for (int i = 0; i < 64; ++i) out[c * 64 + kDCTSnake[i]] = loc[i];
+    }
+    return;
+  }
   int special = (mode == TMO_PVS_SPE_DCT || mode == TMO_PVS_WEIGHTED_SPE_DCT);
   int weighted = (mode == TMO_PVS_WEIGHTED_DCT || mode == TMO_PVS_WEIGHTED_SPE_DCT);
   for (int c = 0; c < 3; ++c) {

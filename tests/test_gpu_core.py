@@ -39,7 +39,8 @@ def test_features_golden(tm):
 
 def test_features_f64_tolerance(tm, oracle):
     tiles = rand_tiles(200, 4)
-    for mode, lab in ((oracle.PVS_WEIGHTED_SPE_DCT, True), (oracle.PVS_WEIGHTED_DCT, False), (oracle.PVS_DCT, False)):
+    for mode, lab in ((oracle.PVS_WEIGHTED_SPE_DCT, True), (oracle.PVS_WEIGHTED_DCT, False), (oracle.PVS_DCT, False),
+                      (oracle.PVS_WAVELETS, False), (oracle.PVS_WAVELETS, True), (oracle.PVS_SPE_DCT, False)):
         got = tm.features_f64(tiles, mode, lab)
         want = np.stack([oracle.tile_features_f64(t, mode, lab) for t in tiles])
         if lab:   # pow() differs by ~1 ulp between libms: relative tolerance 1e-5 of the vector norm

@@ -174,3 +174,28 @@ def test_optimize_palettes_host_port_matches_pipeline_port():
     single, _ = gtm.optimize_palettes(rand_palettes(8, 16, 7), n_threads=1)
     multi, _ = gtm.optimize_palettes(rand_palettes(8, 16, 7), n_threads=8)
     assert np.array_equal(single, multi)                                       # palettes of a pass are independent: thread count is free
+
+
+def test_wavelet_features_against_numpy_haar(oracle):
+    """pvsWavelets (WaveletGS, tilingencoder.pas:2727-2762): the oracle against a numpy Haar pyramid written from the definition
+    (orthonormal 2x2 averaging / differencing on the 8x8, 4x4 and 2x2 low-pass corners); orthonormal => energy preserved."""
+    tiles = rand_tiles(50, 314)
+    snake = oracle.dct_snake()
+    for t in tiles:
+        got = oracle.tile_features_f64(t, oracle.PVS_WAVELETS, False)
+        r, g, b = (t & 255).astype(np.float64), ((t >> 8) & 255).astype(np.float64), ((t >> 16) & 255).astype(np.float64)
+        y = (r * 0.299 + g * 0.587 + b * 0.114).astype(np.float32).astype(np.float64)
+        planes = [y, ((b - y) * 0.492).astype(np.float32).astype(np.float64), ((r - y) * 0.877).astype(np.float32).astype(np.float64)]
+        for c, p in enumerate(planes):
+            a = p.reshape(8, 8).copy()
+            d = 8
+            while d >= 2:
+                blk = a[:d, :d]
+                lo, hi = (blk[:, 0::2] + blk[:, 1::2]) / np.sqrt(2), (blk[:, 0::2] - blk[:, 1::2]) / np.sqrt(2)
+                rows = np.concatenate([lo, hi], axis=1)
+                lo, hi = (rows[0::2] + rows[1::2]) / np.sqrt(2), (rows[0::2] - rows[1::2]) / np.sqrt(2)
+                a[:d, :d] = np.concatenate([lo, hi], axis=0)
+                d //= 2
+            want = np.empty(64); want[snake] = a.reshape(64)
+            assert np.allclose(got[c * 64:(c + 1) * 64], want, rtol=1e-12, atol=1e-9)
+            assert abs((got[c * 64:(c + 1) * 64] ** 2).sum() - (p ** 2).sum()) <= 1e-6 * max(1.0, (p ** 2).sum())

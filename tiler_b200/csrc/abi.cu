@@ -282,7 +282,7 @@ extern "C" int tm_features_from_pal(const uint8_t *pal_idx, const int32_t *tile_
 
 extern "C" int tm_features_f64(const int32_t *rgb, int64_t n, int mode, int use_lab, double *out) {
   RC(require_gpu());
-  if (n < 0 || mode < 0 || mode > 4 || mode == 2 || (n > 0 && (!rgb || !out))) return fail(TM_ERR_ARG, "tm_features_f64: bad argument");
+  if (n < 0 || mode < 0 || mode > 4 || (n > 0 && (!rgb || !out))) return fail(TM_ERR_ARG, "tm_features_f64: bad argument");
   std::lock_guard<std::recursive_mutex> lk(g_mu);
   Stage s(t_stream);
   const int32_t *d_rgb = s.in(rgb, (size_t)n * 64);

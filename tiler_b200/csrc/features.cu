@@ -259,6 +259,44 @@ features_f64_kernel(const int32_t *__restrict__ rgb, int64_t n, int weighted, in
   }
 }
 
+// ComputeTilePsyVisFeatures, Mode = pvsWavelets (tilingencoder.pas:3151-3158 over WaveletGS :2727-2762): three levels of the
+// normalised Haar transform per colour plane (8x8, then the 4x4 and the 2x2 low-pass corner), f64, stored through the zig-zag
+// table like the DCT modes.  Not on any default path (DitheringMode defaults to the weighted special DCT); block = one tile,
+// thread = (plane, position); same operation order as the reference, so the result is bit-exact.
+__global__ void __launch_bounds__(192, 2)
+features_wavelet_f64_kernel(const int32_t *__restrict__ rgb, int64_t n, int use_lab, double *__restrict__ out) {
+  __shared__ double s_cur[3][64], s_tmp[3][64];
+  const int t = threadIdx.x;
+  const int c = t >> 6, i = t & 63, y = i >> 3, x = i & 7;
+  const double factor = 1.0 / sqrt(2.0);
+  for (int64_t tile = blockIdx.x; tile < n; tile += gridDim.x) {
+    __syncthreads();
+    if (t < 64) {
+      const int32_t col = __ldg(rgb + tile * 64 + t);
+      float py, pu, pv;
+      if (use_lab) rgb_to_lab(col & 255, (col >> 8) & 255, (col >> 16) & 255, py, pu, pv);
+      else rgb_to_yuv(col & 255, (col >> 8) & 255, (col >> 16) & 255, py, pu, pv);
+      s_cur[0][t] = (double)py; s_cur[1][t] = (double)pu; s_cur[2][t] = (double)pv;
+    }
+    __syncthreads();
+    for (int d = 8; d >= 2; d >>= 1) {
+      if (y < d && x < d / 2) {                       // rows: low pass left, high pass right
+        const double a = s_cur[c][2 * x + 8 * y], b = s_cur[c][2 * x + 1 + 8 * y];
+        s_tmp[c][x + 8 * y] = __dmul_rn(__dadd_rn(a, b), factor);
+        s_tmp[c][x + d / 2 + 8 * y] = __dmul_rn(__dsub_rn(a, b), factor);
+      }
+      __syncthreads();
+      if (x < d && y < d / 2) {                       // columns: low pass top, high pass bottom
+        const double a = s_tmp[c][x + 8 * (2 * y)], b = s_tmp[c][x + 8 * (2 * y + 1)];
+        s_cur[c][x + 8 * y] = __dmul_rn(__dadd_rn(a, b), factor);
+        s_cur[c][x + 8 * (y + d / 2)] = __dmul_rn(__dsub_rn(a, b), factor);
+      }
+      __syncthreads();
+    }
+    out[tile * 192 + c * 64 + c_snake[i]] = s_cur[c][i];
+  }
+}
+
 // One thread per tile: quadrant luma sums, flags, in-place flip (tile stays 256 bytes in registers/L1)
 __global__ void __launch_bounds__(128) mirror_kernel(int32_t *__restrict__ rgb, int64_t n, uint8_t *__restrict__ flags) {
   const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -485,9 +523,13 @@ int launch_features_allpairs(const uint8_t *pal_idx, int64_t n_tiles, const int3
 
 int launch_features_f64(const int32_t *rgb, int64_t n, int mode, int use_lab, double *out, cudaStream_t st) {
   if (n <= 0) return TM_OK;
-  if (mode == 2) return TM_ERR_ARG;  // wavelets: not on the hot path
   int rc = features_init(st);
   if (rc) return rc;
+  if (mode == 2) {   // pvsWavelets
+    features_wavelet_f64_kernel<<<grid_for(n, 2), 192, 0, st>>>(rgb, n, use_lab, out);
+    note_launch();
+    return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+  }
   const int special = (mode == 3 || mode == 4), weighted = (mode == 1 || mode == 4);
   static bool attr[TM_MAX_DEVICES] = {};
   if (first_use_on_device(attr)) {
