@@ -68,7 +68,11 @@ tm_knn_short *ann_kdtree_short_create(int16_t **rows, int n, int dim, int bucket
 void ann_kdtree_short_destroy(tm_knn_short *h);
 /* exact NN (eps ignored: always exact); returns index, *err = sum (a-b)^2 as uint32; -1 on failure */
 int ann_kdtree_short_search(tm_knn_short *h, const int16_t *q, uint32_t eps, uint32_t *err);
-/* k nearest, ascending (distance, index); slots beyond the dataset size get idx -1 / err 0xFFFFFFFF */
+/* k nearest, ascending (distance, index); slots beyond the dataset size get idx -1 / err 0xFFFFFFFF.
+   err is the reference's Cardinal accumulator, i.e. the squared distance mod 2^32.  For k >= 2 the value 0xFFFFFFFF is also the
+   kernel's marker of a masked column, so a row whose wrapped distance is EXACTLY 0xFFFFFFFF cannot enter a top-k list; that
+   needs a true distance >= 2^32 - 1 (coefficients near the int16 limits -- real features are bounded by 13 212 per
+   coefficient, distances by 2^31) and is the one documented deviation from the brute-force order. */
 void ann_kdtree_short_search_multi(tm_knn_short *h, int *idxs, uint32_t *errs, int k, const int16_t *q, uint32_t eps);
 /* The per-query searches above (and ann_kdtree_search) are thread-safe and MICRO-BATCHED: concurrent callers on one handle
    (the host's MTProcs pool threads, tilingencoder.pas:1547, 1563, 4128) are combined into one kernel launch per batch -- a

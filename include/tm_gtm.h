@@ -18,6 +18,10 @@ extern "C" {
 /* src -> one LZMA "alone" stream (props byte, dictionary size, 8 x 0xFF, range-coded data, end marker).
    Returns the size, -1 if out_cap is too small, -2 on bad parameters. */
 int64_t tmh_lzma_encode(const uint8_t *src, int64_t n, int lc, int lp, int pb, uint32_t dict_size, uint8_t *out, int64_t out_cap);
+/* same with an explicit number of parser threads (0 = default: up to 8).  The input is parsed in fixed 256 KB blocks by the
+   threads and range-coded by the caller as blocks complete; the stream does not depend on the thread count. */
+int64_t tmh_lzma_encode_mt(const uint8_t *src, int64_t n, int lc, int lp, int pb, uint32_t dict_size, uint8_t *out, int64_t out_cap,
+                           int n_threads);
 /* decodes ONE stream starting at src; *consumed = input bytes used (streams of a GTM file follow each other back to back).
    Returns the decoded size, -1 if out_cap is too small, -2 on corrupt input. */
 int64_t tmh_lzma_decode(const uint8_t *src, int64_t n, uint8_t *out, int64_t out_cap, int64_t *consumed);

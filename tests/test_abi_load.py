@@ -34,7 +34,7 @@ def test_gtm_host_library_exports_its_header():
     src = open(os.path.join(ROOT, "include", "tm_gtm.h")).read()
     src = _re.sub(r"/\*.*?\*/", "", src, flags=_re.S)
     names = sorted(set(_re.findall(r"\b(tmh_[a-z0-9_]+)\s*\(", src)))
-    assert len(names) == 8
+    assert len(names) == 9
     for name in names:
         assert hasattr(gtm.lib(), name), name
 

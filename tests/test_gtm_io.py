@@ -44,6 +44,25 @@ def test_lzma_against_liblzma():
     assert lzma.decompress(gtm.lzma_encode(data, lc=0, lp=2, pb=0, dict_size=1 << 16), format=lzma.FORMAT_ALONE) == data
 
 
+def test_lzma_block_parallel_parse_is_thread_count_independent():
+    """Inputs of several 256 KB parse blocks: 1, 3 and 8 parser threads give the same bytes, which decode to the input (our
+    decoder; liblzma for lc = 3), with repeats and long matches across block boundaries in the data."""
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 16, 300000, dtype=np.uint8).tobytes()
+    data = base + bytes(100000) + base[:250000] + rng.integers(0, 256, 200000, dtype=np.uint8).tobytes() + base[1000:180000] * 2
+    assert len(data) > 4 * (1 << 18)
+    one = gtm.lzma_encode(data, n_threads=1)
+    assert gtm.lzma_encode(data, n_threads=3) == one and gtm.lzma_encode(data, n_threads=8) == one
+    assert gtm.lzma_decode(one)[0] == data
+    assert len(one) < 0.75 * len(data)                       # the repeated 250 KB and 179 KB spans are found across blocks
+    l3 = gtm.lzma_encode(data, lc=3, lp=0, pb=2, n_threads=4)
+    assert l3 == gtm.lzma_encode(data, lc=3, lp=0, pb=2, n_threads=1)
+    assert lzma.decompress(l3, format=lzma.FORMAT_ALONE) == data
+    out = np.empty(64, dtype=np.uint8)                        # a buffer that is too small is reported, never overrun
+    src = np.frombuffer(data, dtype=np.uint8)
+    assert gtm.lib().tmh_lzma_encode(src.ctypes.data, src.size, 8, 0, 2, 1 << 22, out.ctypes.data, out.size) == -1
+
+
 def test_lzma_back_to_back_streams():
     both = gtm.lzma_encode(b"first" * 10) + gtm.lzma_encode(b"second" * 10)
     a, ua = gtm.lzma_decode(both)

@@ -11,6 +11,11 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 
 extern "C" {
 
@@ -69,27 +74,35 @@ inline int stateAfterShortRep(int s) { return s < 7 ? 9 : 11; }
 // ------------------------------------------------------------------ encoder
 struct RangeEnc {
   uint64_t low = 0; uint32_t range = 0xFFFFFFFFu; uint8_t cache = 0; uint64_t cacheSize = 1;
-  std::vector<uint8_t> *out;
-  void shiftLow() {
+  uint8_t *out = nullptr, *out_end = nullptr;   // caller-provided buffer; `overflow` is set instead of writing past its end
+  bool overflow = false;
+  inline void put(uint8_t b) { if (out < out_end) *out++ = b; else overflow = true; }
+  inline void shiftLow() {
     if ((uint32_t)low < 0xFF000000u || (uint32_t)(low >> 32) != 0) {
       uint8_t temp = cache;
-      do { out->push_back((uint8_t)(temp + (uint8_t)(low >> 32))); temp = 0xFF; } while (--cacheSize != 0);
+      do { put((uint8_t)(temp + (uint8_t)(low >> 32))); temp = 0xFF; } while (--cacheSize != 0);
       cache = (uint8_t)((uint32_t)low >> 24);
     }
     cacheSize++;
     low = (uint64_t)((uint32_t)low << 8);
   }
-  void bit(Prob *p, uint32_t b) {
-    const uint32_t bound = (range >> kNumBitModelTotalBits) * *p;
-    if (b == 0) { range = bound; *p = (Prob)(*p + ((kBitModelTotal - *p) >> kNumMoveBits)); }
-    else { low += bound; range -= bound; *p = (Prob)(*p - (*p >> kNumMoveBits)); }
-    while (range < kTopValue) { range <<= 8; shiftLow(); }
+  // one adaptive bit, branch-free on the bit value (the bits of image data are close to unpredictable for the CPU)
+  inline void bit(Prob *p, uint32_t b) {
+    const uint32_t pv = *p;
+    const uint32_t bound = (range >> kNumBitModelTotalBits) * pv;
+    const uint32_t mask = 0u - b;                              // 0 or 0xFFFFFFFF
+    low += bound & mask;
+    range = (bound & ~mask) | ((range - bound) & mask);
+    // b == 0: p += (2048 - p) >> 5;  b == 1: p -= p >> 5
+    const uint32_t up = (kBitModelTotal - pv) >> kNumMoveBits, down = pv >> kNumMoveBits;
+    *p = (Prob)(pv + (up & ~mask) - (down & mask));
+    if (range < kTopValue) { range <<= 8; shiftLow(); }       // one step always suffices: range >= 2^24 * 31 / 2^11 before it
   }
   void direct(uint32_t v, int nbits) {
     for (int i = nbits - 1; i >= 0; --i) {
       range >>= 1;
       if ((v >> i) & 1) low += range;
-      while (range < kTopValue) { range <<= 8; shiftLow(); }
+      if (range < kTopValue) { range <<= 8; shiftLow(); }
     }
   }
   void tree(Prob *probs, int nbits, uint32_t sym) {
@@ -182,27 +195,41 @@ struct Encoder {
   }
   uint32_t matchLen(size_t pos, size_t cand, uint32_t limit) const {
     uint32_t l = 0;
+    while (l + 8 <= limit) {   // eight bytes at a time
+      uint64_t x, y;
+      memcpy(&x, src + cand + l, 8); memcpy(&y, src + pos + l, 8);
+      if (x != y) return l + (uint32_t)(__builtin_ctzll(x ^ y) >> 3);
+      l += 8;
+    }
     while (l < limit && src[cand + l] == src[pos + l]) ++l;
     return l;
   }
-  void run() {
-    constexpr int HB = 20;
-    std::vector<int64_t> head((size_t)1 << HB, -1), prev(n, -1);
-    auto h4 = [&](size_t p) { uint32_t v; memcpy(&v, src + p, 4); return (v * 2654435761u) >> (32 - HB); };
-    size_t pos = 0;
-    auto insert = [&](size_t p) { if (p + 4 <= n) { const uint32_t h = h4(p); prev[p] = head[h]; head[h] = (int64_t)p; } };
-    while (pos < n) {
-      const uint32_t limit = (uint32_t)(n - pos < (size_t)kMatchMaxLen ? n - pos : (size_t)kMatchMaxLen);
-      uint32_t bestLen = 0, bestDist = 0; int bestRep = -1;
+
+  // ---- parse: greedy LZ77 over one BLOCK of the input, independent of every other block's parse.
+  // The match finder is a hash chain over 4-byte prefixes built once for the whole input (prev[p] = the latest earlier
+  // position with p's hash), so a block sees the complete history before it.  A block starts without repeat distances
+  // (block 0: with the format's initial {0,0,0,0}) and no match crosses a block end; the decisions therefore depend on the
+  // input and the fixed block size only -- never on the thread count -- and the stream is the same however many threads parse.
+  struct Tok { uint32_t len, dist; };   // len == 1: literal; otherwise a match of distance dist + 1
+  static constexpr size_t kBlock = (size_t)1 << 18;
+  void parseBlock(size_t b0, size_t b1, const int32_t *prev, std::vector<Tok> &out) const {
+    uint32_t lr[4] = {0, 0, 0, 0};
+    int nrep = b0 == 0 ? 4 : 0;
+    out.clear();
+    out.reserve((b1 - b0) / 4 + 16);
+    size_t pos = b0;
+    while (pos < b1) {
+      const uint32_t limit = (uint32_t)(b1 - pos < (size_t)kMatchMaxLen ? b1 - pos : (size_t)kMatchMaxLen);
+      uint32_t bestLen = 0, bestDist = 0;
       if (pos > 0) {
-        for (int r = 0; r < 4; ++r) {
-          if ((size_t)reps[r] + 1 > pos) continue;
-          const uint32_t l = matchLen(pos, pos - reps[r] - 1, limit);
-          if (l >= 2 && l > bestLen) { bestLen = l; bestRep = r; }
+        for (int r = 0; r < nrep; ++r) {
+          if ((size_t)lr[r] + 1 > pos) continue;
+          const uint32_t l = matchLen(pos, pos - lr[r] - 1, limit);
+          if (l >= 2 && l > bestLen) { bestLen = l; bestDist = lr[r]; }
         }
       }
       if (pos + 4 <= n) {
-        int64_t c = head[h4(pos)];
+        int64_t c = prev[pos];
         int depth = TMH_LZMA_DEPTH;
         uint32_t mlen = bestLen >= 3 ? bestLen : 3;   // a normal match must beat the best repeat (and be >= 4)
         while (c >= 0 && depth-- > 0) {
@@ -211,17 +238,74 @@ struct Encoder {
           if (mlen >= limit) break;
           if (src[(size_t)c + mlen] == src[pos + mlen]) {
             const uint32_t l = matchLen(pos, (size_t)c, limit);
-            if (l > mlen) { mlen = l; bestLen = l; bestDist = (uint32_t)(d - 1); bestRep = -1; if (l >= 128) break; }
+            if (l > mlen) { mlen = l; bestLen = l; bestDist = (uint32_t)(d - 1); if (l >= 128) break; }
           }
           c = prev[(size_t)c];
         }
       }
-      if (bestLen < 2) { encLiteral(pos); insert(pos); ++pos; continue; }
-      if (bestRep >= 0) encRep(pos, bestRep, bestLen); else encMatch(pos, bestDist, bestLen);
-      for (uint32_t i = 0; i < bestLen; ++i) insert(pos + i);
+      if (bestLen < 2) { out.push_back({1u, 0u}); ++pos; continue; }
+      out.push_back({bestLen, bestDist});
+      int r = 0;
+      while (r < nrep && lr[r] != bestDist) ++r;
+      if (r == nrep) { if (nrep < 4) ++nrep; r = nrep - 1; }   // a new distance enters at the front, the oldest leaves
+      for (int i = r; i > 0; --i) lr[i] = lr[i - 1];
+      lr[0] = bestDist;
       pos += bestLen;
     }
-    encEndMarker(pos);
+  }
+
+  // ---- code: the token stream of a block through the range coder.  A match whose distance is one of the coder's four
+  // repeat distances is written as that repeat (the parser's own repeats always are: its list is a prefix of this one).
+  void codeBlock(size_t b0, const std::vector<Tok> &toks) {
+    size_t pos = b0;
+    for (const Tok &t : toks) {
+      if (t.len == 1) { encLiteral(pos); ++pos; continue; }
+      int r = 0;
+      while (r < 4 && !(reps[r] == t.dist && (size_t)reps[r] + 1 <= pos)) ++r;
+      if (r < 4) encRep(pos, r, t.len); else encMatch(pos, t.dist, t.len);
+      pos += t.len;
+    }
+  }
+
+  void run(int n_threads) {
+    constexpr int HB = 20;
+    std::vector<int32_t> head((size_t)1 << HB, -1), prev(n ? n : 1, -1);
+    auto h4 = [&](size_t p) { uint32_t v; memcpy(&v, src + p, 4); return (v * 2654435761u) >> (32 - HB); };
+    for (size_t p = 0; p + 4 <= n; ++p) { const uint32_t h = h4(p); prev[p] = head[h]; head[h] = (int32_t)p; }
+    const size_t nb = (n + kBlock - 1) / kBlock;
+    std::vector<std::vector<Tok>> toks(nb);
+    if (n_threads > (int)nb) n_threads = (int)nb;
+    if (n_threads <= 1) {
+      for (size_t b = 0; b < nb; ++b) {
+        parseBlock(b * kBlock, std::min(n, (b + 1) * kBlock), prev.data(), toks[b]);
+        codeBlock(b * kBlock, toks[b]);
+        std::vector<Tok>().swap(toks[b]);
+      }
+    } else {
+      // parser threads take blocks in order; this thread codes block b as soon as it is parsed
+      std::atomic<size_t> next{0};
+      std::vector<std::atomic<int>> done(nb);
+      for (auto &d : done) d.store(0, std::memory_order_relaxed);
+      std::mutex mu; std::condition_variable cv;
+      std::vector<std::thread> pool;
+      for (int t = 0; t < n_threads; ++t)
+        pool.emplace_back([&] {
+          for (;;) {
+            const size_t b = next.fetch_add(1);
+            if (b >= nb) break;
+            parseBlock(b * kBlock, std::min(n, (b + 1) * kBlock), prev.data(), toks[b]);
+            { std::lock_guard<std::mutex> lk(mu); done[b].store(1, std::memory_order_release); }
+            cv.notify_all();
+          }
+        });
+      for (size_t b = 0; b < nb; ++b) {
+        { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [&] { return done[b].load(std::memory_order_acquire) != 0; }); }
+        codeBlock(b * kBlock, toks[b]);
+        std::vector<Tok>().swap(toks[b]);
+      }
+      for (auto &th : pool) th.join();
+    }
+    encEndMarker(n);
     rc.flush();
   }
 };
@@ -270,20 +354,27 @@ uint32_t decLen(RangeDec &rc, LenProbs &lp, uint32_t posState) {
 // src -> LZMA "alone" stream (props byte, dict size, 8 x 0xFF, range-coded data with end marker).  Returns the size, or -1
 // when out_cap is too small (call again with a larger buffer; worst case is about n + n/8 + 64).
 int64_t tmh_lzma_encode(const uint8_t *src, int64_t n, int lc, int lp, int pb, uint32_t dict_size, uint8_t *out, int64_t out_cap) {
+  return tmh_lzma_encode_mt(src, n, lc, lp, pb, dict_size, out, out_cap, 0);
+}
+int64_t tmh_lzma_encode_mt(const uint8_t *src, int64_t n, int lc, int lp, int pb, uint32_t dict_size, uint8_t *out, int64_t out_cap,
+                           int n_threads) {
   if (n < 0 || lc < 0 || lc > 8 || lp < 0 || lp > 4 || pb < 0 || pb > 4) return -2;
-  std::vector<uint8_t> buf;
-  buf.reserve((size_t)n / 2 + 64);
-  buf.push_back((uint8_t)((pb * 5 + lp) * 9 + lc));
-  for (int i = 0; i < 4; ++i) buf.push_back((uint8_t)(dict_size >> (8 * i)));
-  for (int i = 0; i < 8; ++i) buf.push_back(0xFF);
+  if (n > 0x7fff0000 || out_cap < 13 + 8) return n > 0x7fff0000 ? -2 : -1;   // 32-bit chain links; header + flush always fit
+  uint8_t *o = out;
+  *o++ = (uint8_t)((pb * 5 + lp) * 9 + lc);
+  for (int i = 0; i < 4; ++i) *o++ = (uint8_t)(dict_size >> (8 * i));
+  for (int i = 0; i < 8; ++i) *o++ = 0xFF;
   Encoder e;
   e.m.init(lc, lp, pb);
-  e.rc.out = &buf;
+  e.rc.out = o; e.rc.out_end = out + out_cap;
   e.src = src; e.n = (size_t)n; e.dictSize = dict_size;
-  e.run();
-  if ((int64_t)buf.size() > out_cap) return -1;
-  memcpy(out, buf.data(), buf.size());
-  return (int64_t)buf.size();
+  // parser threads for this stream (TMH_LZMA_THREADS overrides): up to 8, never more than the cores present
+  static const int env_threads = getenv("TMH_LZMA_THREADS") ? atoi(getenv("TMH_LZMA_THREADS")) : 0;
+  int nt = n_threads > 0 ? n_threads
+                         : (env_threads > 0 ? env_threads : (int)std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())));
+  e.run(nt);
+  if (e.rc.overflow) return -1;
+  return (int64_t)(e.rc.out - out);
 }
 
 // Decodes ONE "alone" stream starting at src (stops at the end marker, or at the header's size when it is known).

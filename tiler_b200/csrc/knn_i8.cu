@@ -9,11 +9,12 @@
 // rounding anywhere.  A vector is stored as one 384-byte row [hi(192) | lo(192)] = 3 TMA/UMMA 128-byte swizzle
 // atoms, so any K-step of A can be paired with any K-step of B by descriptor arithmetic alone.
 //
-// CTA (persistent, one per SM): 256 queries (two 128-row M tiles, resident in smem) x the whole dictionary
-// streamed in 64-row N tiles through a 4-stage TMA ring.  M tile g accumulates into TMEM stage g (3 x 64 columns:
-// HH, X, LL), so the tensor pipe works on tile g^1 while the four epilogue warps of tile g fold the accumulators
-// into distances and keep, per query row (one thread = one TMEM lane = one query), either the running arg-min
-// (k = 1) or a thresholded candidate list that is cut back to the k best by a warp-cooperative radix select.
+// CTA (persistent, one per SM) = 128 query rows x the whole dictionary.  The query limb rows live in TMEM (tcgen05.st) and are
+// the A operand of TS-mode MMAs; the dictionary streams through shared memory in 64-row tiles (24 KB) on an 8-stage TMA
+// ring, 24 UTCIMMA (M128 N64 K32) per tile into one of two TMEM accumulator stages (3 x 64 columns: HH, X = HL + LH, LL).
+// Eight epilogue warps (two per TMEM lane quarter, 32 of a tile's 64 columns each) fold the accumulators into distances and
+// keep, per (query row, column half), either a running best list in registers (k = 1, k = 4) or a thresholded candidate
+// strip in an L2-resident workspace that is cut back to the k best by scheduled, row-wide loose selections (2 <= k <= 64).
 #include "tc_common.cuh"
 #include "tm_kernels.h"
 #include <cstdlib>
@@ -23,7 +24,6 @@ namespace tmg {
 
 constexpr int BM = 128;          // rows per M tile (UMMA M)
 constexpr int BN = 64;           // rows per N tile (UMMA N)
-constexpr int STAGES = 4;        // dictionary ring depth (top-k path: the candidate buffers take the rest of shared memory)
 constexpr int STAGES_K1 = 8;     // dictionary ring depth (k = 1 path)
 constexpr int ROWB = 384;        // bytes per limb row
 constexpr int CHUNK_A = BM * 128;  // one 128-byte-wide swizzle chunk of an A tile
@@ -357,6 +357,9 @@ constexpr int STAGES_TK = 8;     // dictionary ring depth of the top-k kernel
 // producer runs at most STAGES_TK tiles ahead of MMA completion, the MMAs at most 2 tiles ahead of the TMEM reads).
 constexpr int TK_NRING = STAGES_TK + 4;
 
+__device__ __forceinline__ void lds_v4(uint32_t saddr, uint32_t &a, uint32_t &b, uint32_t &c, uint32_t &d) {
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(saddr));
+}
 __device__ __forceinline__ unsigned long long ldg_key(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
@@ -494,6 +497,26 @@ __device__ __forceinline__ void tk_admit_nw(unsigned long long &waddr, uint32_t 
       : "r"(idx), "r"(e), "r"(tau1)
       : "memory");
 }
+// one column PAIR: both predicates first, the pointer bumped in place between the two predicated stores
+__device__ __forceinline__ void tk_admit2_nw(unsigned long long &waddr, uint32_t idx, uint32_t e0, uint32_t e1, uint32_t tau1) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b32 lo, hi, d0, d1, i1;\n\t"
+      "setp.lt.s32 p, %2, 0;\n\t"
+      "setp.lt.s32 q, %3, 0;\n\t"
+      "add.u32 d0, %2, %4;\n\t"
+      "add.u32 d1, %3, %4;\n\t"
+      "add.u32 i1, %1, 1;\n\t"
+      "@p st.global.v2.u32 [%0], {%1, d0};\n\t"
+      "mov.b64 {lo, hi}, %0;\n\t"
+      "@p add.u32 lo, lo, 8;\n\t"
+      "mov.b64 %0, {lo, hi};\n\t"
+      "@q st.global.v2.u32 [%0], {i1, d1};\n\t"
+      "@q add.u32 lo, lo, 8;\n\t"
+      "mov.b64 %0, {lo, hi};\n\t}\n"
+      : "+l"(waddr)
+      : "r"(idx), "r"(e0), "r"(e1), "r"(tau1)
+      : "memory");
+}
 __device__ __forceinline__ void tk_tile32_nw(unsigned long long &waddr, uint32_t tau, uint32_t nq, int col, const uint32_t (&ndA)[16],
                                              uint32_t (&ppA)[16], const uint32_t (&xxA)[16], const uint32_t (&loA)[16],
                                              const uint32_t (&ndB)[16], uint32_t (&ppB)[16], const uint32_t (&xxB)[16],
@@ -512,17 +535,11 @@ __device__ __forceinline__ void tk_tile32_nw(unsigned long long &waddr, uint32_t
   if (any != 0) {
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      if (any & (0x8000u >> e)) {
-        tk_admit_nw(waddr, (uint32_t)(col + 2 * e), ppA[2 * e], tau1);
-        tk_admit_nw(waddr, (uint32_t)(col + 2 * e + 1), ppA[2 * e + 1], tau1);
-      }
+      if (any & (0x8000u >> e)) tk_admit2_nw(waddr, (uint32_t)(col + 2 * e), ppA[2 * e], ppA[2 * e + 1], tau1);
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      if (any & (0x80u >> e)) {
-        tk_admit_nw(waddr, (uint32_t)(col + 16 + 2 * e), ppB[2 * e], tau1);
-        tk_admit_nw(waddr, (uint32_t)(col + 16 + 2 * e + 1), ppB[2 * e + 1], tau1);
-      }
+      if (any & (0x80u >> e)) tk_admit2_nw(waddr, (uint32_t)(col + 16 + 2 * e), ppB[2 * e], ppB[2 * e + 1], tau1);
     }
   }
 }
@@ -688,7 +705,7 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
   uint64_t *stag = t_empty + 2;   // [4 quarters][2 stages]: the first warp of a quarter has its TMEM reads in flight
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(stag + 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int n_tiles = (n_dict + BN - 1) / BN;
   const int n_qblocks = (n_q + BM - 1) / BM;
 
@@ -768,6 +785,8 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
     // signed comparisons are exact when no distance can reach 2^31: every squared norm below 2^29 ((|q| + |t|)^2 < 2^31)
     const bool nowrap = !(dbg & 64) && q_nmax && d_nmax && __ldg(q_nmax) < (1u << 29) && __ldg(d_nmax) < (1u << 29);
     uint32_t it = 0, w = 0;
+    int nslot = 0;                                   // it % TK_NRING, kept as a counter
+    const uint32_t s_nd_u32 = smem_u32(s_nd);
     TKT_DECL
     for (int qb = blockIdx.x; qb < n_qblocks; qb += gridDim.x, ++w) {
       const int64_t qi = (int64_t)qb * BM + row;
@@ -825,12 +844,12 @@ knn_i8_topk_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ 
         // dictionary norms of this tile half from the ring the TMA producer fills (broadcast reads; they overlap the TMEM reads)
         uint32_t ndA[16], ndB[16];
         {
-          const uint4 *nsrc = reinterpret_cast<const uint4 *>(s_nd + (it % TK_NRING) * BN + h * HN);
+          const uint32_t nsrc = s_nd_u32 + (uint32_t)(nslot * BN + h * HN) * 4u;   // explicit ld.shared: a generic load costs an address-space check
+          if (++nslot == TK_NRING) nslot = 0;
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
-            const uint4 t4 = nsrc[v], u4 = nsrc[4 + v];
-            ndA[4 * v] = t4.x; ndA[4 * v + 1] = t4.y; ndA[4 * v + 2] = t4.z; ndA[4 * v + 3] = t4.w;
-            ndB[4 * v] = u4.x; ndB[4 * v + 1] = u4.y; ndB[4 * v + 2] = u4.z; ndB[4 * v + 3] = u4.w;
+            lds_v4(nsrc + 16 * v, ndA[4 * v], ndA[4 * v + 1], ndA[4 * v + 2], ndA[4 * v + 3]);
+            lds_v4(nsrc + 64 + 16 * v, ndB[4 * v], ndB[4 * v + 1], ndB[4 * v + 2], ndB[4 * v + 3]);
           }
         }
         tmem_ld_wait();
@@ -1011,7 +1030,6 @@ int make_tmap_rows_u8(CUtensorMap *map, const void *base, uint64_t rows, uint32_
   return r == CUDA_SUCCESS ? TM_OK : TM_ERR_DRIVER;
 }
 
-size_t knn_workspace_bytes(int num_ctas) { (void)num_ctas; return 0; }   // top-k state lives in shared memory
 int knn_rows_per_cta() { return BM; }
 
 int launch_limb_split(const int16_t *in, int64_t n, uint8_t *limbs, uint32_t *norms, cudaStream_t st, uint32_t *norm_max) {

@@ -30,7 +30,6 @@ struct ProfScope {
 };
 
 // ---- knn_i8.cu
-size_t knn_workspace_bytes(int num_ctas);
 int knn_rows_per_cta();
 // norm_max (optional, device, zero-initialised by the caller): receives the largest squared norm, 0xFFFFFFFF if a row may exceed 32 bits
 int launch_limb_split(const int16_t *in, int64_t n, uint8_t *limbs, uint32_t *norms, cudaStream_t st, uint32_t *norm_max = nullptr);

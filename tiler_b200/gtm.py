@@ -28,6 +28,8 @@ def lib():
         L = C.CDLL(path)
         L.tmh_lzma_encode.restype = C.c_int64
         L.tmh_lzma_encode.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_int64]
+        L.tmh_lzma_encode_mt.restype = C.c_int64
+        L.tmh_lzma_encode_mt.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_int64, C.c_int]
         L.tmh_lzma_decode.restype = C.c_int64
         L.tmh_lzma_decode.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]
         L.tmh_gtm_write_frames.restype = C.c_int64
@@ -46,11 +48,12 @@ def lib():
 
 
 # ------------------------------------------------------------------ LZMA ("alone" container, end marker)
-def lzma_encode(data, lc=GTM_LC, lp=GTM_LP, pb=GTM_PB, dict_size=GTM_DICT):
+def lzma_encode(data, lc=GTM_LC, lp=GTM_LP, pb=GTM_PB, dict_size=GTM_DICT, n_threads=0):
+    """n_threads: parser threads inside this one stream (0 = library default); the bytes do not depend on it."""
     src = np.frombuffer(bytes(data), dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
     cap = int(src.size + src.size // 4 + 1024)
     out = np.empty(cap, dtype=np.uint8)
-    n = lib().tmh_lzma_encode(src.ctypes.data, src.size, lc, lp, pb, dict_size, out.ctypes.data, cap)
+    n = lib().tmh_lzma_encode_mt(src.ctypes.data, src.size, lc, lp, pb, dict_size, out.ctypes.data, cap, int(n_threads))
     if n < 0:
         raise RuntimeError(f"tmh_lzma_encode failed ({n})")
     return out[:n].tobytes()
@@ -89,19 +92,19 @@ def reindex(tiles_idx, tile_idx_map):
     (TileIdx >= 0, predicted items included, as the reference does), drops unused tiles, orders by (use count descending,
     palette-index bytes ascending) and remaps the tilemap.  -> (tiles [n,64] uint8, use_count [n], remapped tile_idx)."""
     tiles_idx = np.ascontiguousarray(tiles_idx, dtype=np.uint8).reshape(-1, 64)
-    tmap = np.asarray(tile_idx_map, dtype=np.int64)
+    tmap = np.ascontiguousarray(tile_idx_map, dtype=np.int32)
     as_rows = tiles_idx.view(np.dtype((np.void, 64))).reshape(-1)
     uniq, inverse = np.unique(as_rows, return_inverse=True)            # lexicographic on bytes = CompareByte order
-    valid = tmap >= 0
-    cls = np.full(tmap.shape, -1, dtype=np.int64)
-    cls[valid] = inverse[tmap[valid]]
-    use = np.bincount(cls[valid].reshape(-1), minlength=len(uniq))
+    # index -1 (no tile) reads the extra last slot of each lookup table: two gathers and one bincount over the whole tilemap
+    # instead of boolean-mask passes
+    flat = tmap.reshape(-1)
+    cls = np.append(inverse.astype(np.int32), np.int32(-1))[flat]
+    use = np.bincount(cls + 1, minlength=len(uniq) + 1)[1:]
     keep = np.nonzero(use > 0)[0]
     order = keep[np.lexsort((keep, -use[keep]))]                         # keep is already in byte order
-    new_of_cls = np.full(len(uniq), -1, dtype=np.int64)
-    new_of_cls[order] = np.arange(len(order))
-    out_map = np.full(tmap.shape, -1, dtype=np.int32)
-    out_map[valid] = new_of_cls[cls[valid]].astype(np.int32)
+    new_of_cls = np.full(len(uniq) + 1, -1, dtype=np.int32)
+    new_of_cls[order] = np.arange(len(order), dtype=np.int32)
+    out_map = new_of_cls[cls].reshape(tmap.shape)
     tiles_out = np.frombuffer(uniq[order].tobytes(), dtype=np.uint8).reshape(-1, 64).copy()
     return tiles_out, use[order].astype(np.int32), out_map
 
