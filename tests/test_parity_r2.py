@@ -249,6 +249,28 @@ def test_sliding_features_fast_mode_within_contract(tm, oracle, w, h):
     assert np.array_equal(tm.sliding_features(frame), want)
 
 
+@pytest.mark.parametrize("w,h", [(320, 184), (104, 56), (1280, 720)])
+def test_fast_mode_fused_limb_rows_equal_the_two_pass_path(tm, oracle, w, h):
+    """In the fast feature mode tm_predict_motion_frame lets the sliding-window kernel write the tensor-core search's candidate
+    operands (limb rows + norms at padded positions) itself.  The result must equal the two-pass path -- fast int16 features
+    (tm_sliding_features) split by the search (tm_motion_search) -- bit for bit: same features, only the intermediate is gone.
+    Widths whose padded pitch exceeds 8 * tiles (104 -> pitch 128) exercise the all-padding column blocks."""
+    tw, th = w // 8, h // 8
+    clip = synth.pack_rgb(synth.make_clip(w, h, 2, cut_every=0, seed=w + h, n_sprites=6))
+    prev_frame, cur = np.ascontiguousarray(clip[0]), np.ascontiguousarray(clip[1])
+    tiles = np.ascontiguousarray(cur.reshape(th, 8, tw, 8).transpose(0, 2, 1, 3).reshape(-1, 64))
+    canon, flags = tm.mirror_canonicalise(tiles)
+    mode = tm.set_feature_mode(tm.FEATURES_FAST)
+    try:
+        x1, y1, e1 = tm.predict_motion_frame(prev_frame, canon, flags, tw, th, 16)
+        dcts = tm.sliding_features(prev_frame)
+        x2, y2, e2 = tm.motion_search(tm.features_from_rgb_mirrored(canon, flags), tw, th, dcts, 16)
+    finally:
+        tm.set_feature_mode(mode)
+    assert np.array_equal(np.asarray(e1).view(np.uint32), np.asarray(e2).view(np.uint32))
+    assert np.array_equal(x1, x2) and np.array_equal(y1, y2)
+
+
 def test_fast_features_encode_psnr_within_tolerance(tm, oracle):
     """End to end with the fast sliding-window features: decoded-frame PSNR within 0.05 dB of the bit-exact encode; tile indices
     that differ are counted (they sit inside the distance tolerance of +-1 LSB features)."""

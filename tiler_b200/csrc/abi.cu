@@ -996,6 +996,25 @@ static int motion_search_dev(const int16_t *d_cur, int tw, int th, const int16_t
   return launch_motion_search_tc(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, ws, wsb, ctas, st);
 }
 
+// DoDCTs of `frame` + the window scan of every tile of the current frame.  In the fast feature mode with the tensor-core search the
+// sliding-window kernel writes the search's candidate operands (limb rows + norms) itself: no int16 intermediate, no split pass.
+// d_dcts: scratch for the int16 features of the other paths ([(w - 7) * (h - 7)][192]).
+static int sliding_motion_search_dev(const int32_t *d_frame, int w, int h, int16_t *d_dcts, const int16_t *d_cur, int tw, int th, int radius,
+                                     int32_t *d_px, int32_t *d_py, uint32_t *d_err, void *ws, size_t wsb, cudaStream_t st) {
+  static int scalar = -1;
+  if (scalar < 0) scalar = getenv("TM_MOTION_SCALAR") && atoi(getenv("TM_MOTION_SCALAR")) ? 1 : 0;
+  if (!scalar && get_feature_mode() == 1) {
+    uint8_t *c_limbs; uint32_t *c_norm; int pwp;
+    motion_tc_cand_layout(ws, tw, th, &c_limbs, &c_norm, &pwp);
+    int rc = launch_features_sliding_limbs(d_frame, w, h, c_limbs, c_norm, pwp, st);
+    if (rc != TM_OK) return rc;
+    return motion_search_dev(d_cur, tw, th, nullptr, radius, d_px, d_py, d_err, ws, wsb, st);
+  }
+  int rc = launch_features_sliding(d_frame, w, h, d_dcts, st);
+  if (rc != TM_OK) return rc;
+  return motion_search_dev(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, ws, wsb, st);
+}
+
 extern "C" int tm_sliding_features(const int32_t *frame, int w, int h, int16_t *out) {
   RC(require_gpu());
   if (!frame || !out || w < 8 || h < 8) return fail(TM_ERR_ARG, "tm_sliding_features: bad argument");
@@ -1046,8 +1065,7 @@ extern "C" int tm_predict_motion_frame(const int32_t *prev_frame, const int32_t 
   if (s.err == TM_OK) s.err = launch_features_rgb_mirrored(d_tiles, d_flags, (int64_t)nt, d_cur, s.st);
   const size_t wsb = motion_tc_ws_bytes(tw, th);
   void *ws = s.temp(wsb);
-  if (s.err == TM_OK) s.err = launch_features_sliding(d_prev, w, h, d_dcts, s.st);
-  if (s.err == TM_OK) s.err = motion_search_dev(d_cur, tw, th, d_dcts, radius, d_px, d_py, d_err, ws, wsb, s.st);
+  if (s.err == TM_OK) s.err = sliding_motion_search_dev(d_prev, w, h, d_dcts, d_cur, tw, th, radius, d_px, d_py, d_err, ws, wsb, s.st);
   RC(s.finish());
   return TM_OK;
 }
@@ -1093,8 +1111,7 @@ extern "C" int tm_reconstruct_sequence(tm_matcher *m, const int32_t *canon_tiles
     const int32_t *back = d_recon ? (f > 0 ? d_recon + fpx * (f - 1) : nullptr) : pp[f & 1];
     const bool mo = motion && f > 0;
     if (mo) {
-      s.err = launch_features_sliding(back, w, h, d_dcts, s.st);
-      if (s.err == TM_OK) s.err = motion_search_dev(d_cur + nt * 192 * f, tw, th, d_dcts, radius, mx, my, me, ws, wsb, s.st);
+      s.err = sliding_motion_search_dev(back, w, h, d_dcts, d_cur + nt * 192 * f, tw, th, radius, mx, my, me, ws, wsb, s.st);
     }
     const size_t o = nt * f;
     if (s.err == TM_OK)
@@ -1142,8 +1159,7 @@ extern "C" int tm_reconstruct_frame(tm_matcher *m, const int32_t *canon_tiles, c
     void *ws = s.temp(wsb);
     mx = (int32_t *)s.temp(nt * 4); my = (int32_t *)s.temp(nt * 4); me = (uint32_t *)s.temp(nt * 4);
     if (s.err == TM_OK) s.err = launch_features_rgb_mirrored(d_tiles, d_flags, (int64_t)nt, d_cur, s.st);
-    if (s.err == TM_OK) s.err = launch_features_sliding(d_back, w, h, d_dcts, s.st);
-    if (s.err == TM_OK) s.err = motion_search_dev(d_cur, tw, th, d_dcts, radius, mx, my, me, ws, wsb, s.st);
+    if (s.err == TM_OK) s.err = sliding_motion_search_dev(d_back, w, h, d_dcts, d_cur, tw, th, radius, mx, my, me, ws, wsb, s.st);
   }
   if (s.err == TM_OK)
     s.err = launch_reconstruct_decide(d_flags, tw, th, mx, my, me, k_tile, k_pal, k_err, m->dict_idx, m->palettes, m->pal_size, d_back, d_front,

@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(128) mirror_kernel(int32_t *__restrict__ rgb, 
 // (lut[v][u][y][x] = cos((x+1/2) u pi/8) cos((y+1/2) v pi/8) ratio[v][u], tilingencoder.pas:1709), so in exact arithmetic
 //   row pass   R[y][ox][u]      = sum_x P[y][ox+x] cos((x+1/2) u pi/8)        -- shared by the 8 windows that contain the row segment
 //   column pass F[oy][ox][v][u] = sum_j R[oy+j][ox][u] cos((j+1/2) v pi/8)
-// is 72 multiply-adds per coefficient column instead of 512.  Everything runs in f64 (B200 keeps a 1:2 FP64 rate), which is
+// is 8 + 36 f64 operations per coefficient column (the column pass split into its even and odd halves) instead of 512.  Everything runs in f64 (B200 keeps a 1:2 FP64 rate), which is
 // MORE accurate than the reference's f32 products; the result differs from the reference only where the reference's own f32
 // rounding noise (~3e-4 absolute) straddles a .5 rounding boundary: <= 1 LSB, ~5e-6 of the coefficients on the synthetic clip
 // (contract: <= 1 LSB, <= 1e-3 of the coefficients; SURVEY "Parity contract").  Selected with tm_set_feature_mode(1); the
@@ -341,32 +341,84 @@ __constant__ double c_scale[192];      // [cpn][v][u] = (double)cDCTUVRatio[v][u
 constexpr int SF_OXB = 8;              // window columns per block
 constexpr int SF_SEG = 64;             // window rows per block
 constexpr int SF_CH = 16;              // frame rows converted per chunk
+constexpr int SF_ROWP = 200;           // int16 per staged window row (192 + 8 of padding)
 
+// cos(m pi / 16), m = 1..7: every entry of the 8-point DCT basis cos((j + 1/2) v pi / 8) is +-1 or +- one of these
+// (read from constant memory once per thread and kept in uniform registers: written as literals the compiler re-materialises
+// them with two UMOVs in front of every use)
+__constant__ double c_sfc[8] = {1.0, 0.9807852804032304, 0.9238795325112867, 0.8314696123025452, 0.7071067811865476,
+                                0.5555702330196023, 0.38268343236508984, 0.19509032201612833};
+
+// Column pass of one window column: F[v] = sum_j w_j cos((j + 1/2) v pi / 8), w_j = ring[(j + PH + 1) & 7] (window row j).
+// Even / odd split (the basis is symmetric in j for even v, antisymmetric for odd v): 14 additions + 22 multiply-adds instead of
+// 64 multiply-adds, and only SEVEN distinct constants.  The direct form asked for 64 distinct f64 constants per phase; the
+// compiler kept them in uniform registers, ran out, and issued more R2UR / spill moves than DFMAs (632 + 186 against 576 in the
+// 8 unrolled phases).
 template <int PH>
-__device__ __forceinline__ double sf_col(const double (&ring)[8], int v) {
-  double f = 0.0;
-#pragma unroll
-  for (int r = 0; r < 8; ++r) f = fma(ring[r], c_cos8[v][(r - PH - 1) & 7], f);   // ring[r] holds window row (r - PH - 1) mod 8
-  return f;
+__device__ __forceinline__ void sf_cols(const double (&ring)[8], const double (&C)[8], double (&F)[8]) {
+  const double SF_C1 = C[1], SF_C2 = C[2], SF_C3 = C[3], SF_C4 = C[4], SF_C5 = C[5], SF_C6 = C[6], SF_C7 = C[7];
+#define SF_W(j) ring[((j) + PH + 1) & 7]
+  const double s0 = SF_W(0) + SF_W(7), s1 = SF_W(1) + SF_W(6), s2 = SF_W(2) + SF_W(5), s3 = SF_W(3) + SF_W(4);
+  const double d0 = SF_W(0) - SF_W(7), d1 = SF_W(1) - SF_W(6), d2 = SF_W(2) - SF_W(5), d3 = SF_W(3) - SF_W(4);
+#undef SF_W
+  const double a0 = s0 + s3, a1 = s1 + s2, b0 = s0 - s3, b1 = s1 - s2;
+  F[0] = a0 + a1;
+  F[4] = (a0 - a1) * SF_C4;
+  F[2] = fma(b0, SF_C2, b1 * SF_C6);
+  F[6] = fma(b0, SF_C6, -(b1 * SF_C2));
+  F[1] = fma(d3, SF_C7, fma(d2, SF_C5, fma(d1, SF_C3, d0 * SF_C1)));
+  F[3] = fma(d3, -SF_C5, fma(d2, -SF_C1, fma(d1, -SF_C7, d0 * SF_C3)));
+  F[5] = fma(d3, SF_C3, fma(d2, SF_C7, fma(d1, -SF_C1, d0 * SF_C5)));
+  F[7] = fma(d3, -SF_C1, fma(d2, SF_C3, fma(d1, -SF_C5, d0 * SF_C7)));
 }
 
-template <int PH>
+template <int PH, bool LIMBS>
 __device__ __forceinline__ void sf_step(const double *__restrict__ prow /* plane row, this thread's first pixel */, const double (&cu)[8],
-                                        const double (&sc)[8], const int (&dst)[8], double (&ring)[8], bool emit, int16_t *__restrict__ o) {
+                                        const double (&sc)[8], const int (&dst)[8], double (&ring)[8], const double (&C)[8], bool emit,
+                                        int16_t *__restrict__ o, uint32_t *__restrict__ s_norm /* this window's norm accumulator */) {
   double r = 0.0;
 #pragma unroll
   for (int x = 0; x < 8; ++x) r = fma(prow[x], cu[x], r);
   ring[PH] = r;
-  if (emit) {
+  if (emit) {   // block-uniform
+    double F[8];
+    sf_cols<PH>(ring, C, F);
+    if (!LIMBS) {
 #pragma unroll
-    for (int v = 0; v < 8; ++v) o[dst[v]] = (int16_t)__double2int_rn(__dmul_rn(sf_col<PH>(ring, v), sc[v]));
+      for (int v = 0; v < 8; ++v) o[dst[v]] = (int16_t)__double2int_rn(__dmul_rn(F[v], sc[v]));
+    } else {
+      // the staged row is the LIMB row [hi(192) | lo(192)] of the window, and the squares of this thread's 8 coefficients are summed
+      // over the 8 threads (u) of its (plane, window) by three shuffles: one shared-memory add per (plane, window)
+      uint8_t *ob = reinterpret_cast<uint8_t *>(o);
+      uint32_t acc = 0;
+#pragma unroll
+      for (int v = 0; v < 8; ++v) {
+        // |coefficient| <= 13 212 for 8-bit pixels (sum of the basis magnitudes x weights), so the int16 narrowing of the
+        // other path is the identity here and the bytes below are the two's-complement limbs of the same value
+        const int e = __double2int_rn(__dmul_rn(F[v], sc[v]));
+        ob[dst[v]] = (uint8_t)((uint32_t)e >> 8);
+        ob[192 + dst[v]] = (uint8_t)e;
+        acc += (uint32_t)(e * e);
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+      acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+      if ((threadIdx.x & 7) == 0) atomicAdd(s_norm, acc);
+    }
   }
 }
 
+// LIMBS = true writes what the tensor-core motion search consumes instead of the int16 features: the limb row
+// [hi(192) | lo(192)] of every window at its PADDED position (row pitch pwp, a multiple of 64) and its squared norm mod 2^32;
+// positions ox in [fw - 7, pwp) get zero rows and zero norms (grid.x covers pwp / 8 column blocks).  That is
+// cand_limb_split_kernel folded into the producer: the 349 MB int16 intermediate of a 720p frame is never written or read.
+template <bool LIMBS>
 __global__ void __launch_bounds__(192, 2)
-features_sliding_fast_kernel(const int32_t *__restrict__ frame, int fw, int fh, int16_t *__restrict__ out) {
+features_sliding_fast_kernel(const int32_t *__restrict__ frame, int fw, int fh, int16_t *__restrict__ out, uint8_t *__restrict__ limbs,
+                             uint32_t *__restrict__ norms, int pwp) {
   __shared__ double s_pl[3][SF_CH][SF_OXB + 8];          // converted planes of the current row chunk (15 of 16 columns used)
-  __shared__ __align__(16) int16_t s_out[2][SF_OXB][192];
+  __shared__ __align__(16) int16_t s_out[2][SF_OXB][SF_ROWP];   // rows padded to 400 bytes: the limb flush reads 8 rows at once
+  __shared__ uint32_t s_nrm[2][SF_OXB];
   const int t = threadIdx.x;
   const int u = t & 7, oxl = (t >> 3) & 7, cpn = t >> 6;
   const int pw = fw - 7, ph_rows = fh - 7;
@@ -374,10 +426,24 @@ features_sliding_fast_kernel(const int32_t *__restrict__ frame, int fw, int fh, 
   const int oy0 = blockIdx.y * SF_SEG;
   const int oy1 = min(oy0 + SF_SEG, ph_rows);              // window rows [oy0, oy1)
   const int y_end = oy1 + 7;                               // frame rows [oy0, y_end)
-  double cu[8], sc[8], ring[8];
+  if (LIMBS) {
+    if (t < 2 * SF_OXB) (&s_nrm[0][0])[t] = 0;
+    if (ox0 >= pw) {   // a column block of padding only: zero rows, zero norms
+      const int wdw = t / 24, seg = t % 24;
+      for (int oy = oy0; oy < oy1; ++oy) {
+        uint8_t *dst = limbs + ((int64_t)oy * pwp + ox0 + wdw) * 384 + seg * 8;
+        *reinterpret_cast<uint2 *>(dst) = make_uint2(0u, 0u);
+        *reinterpret_cast<uint2 *>(dst + 192) = make_uint2(0u, 0u);
+        if (t < SF_OXB) norms[(int64_t)oy * pwp + ox0 + t] = 0u;
+      }
+      return;
+    }
+  }
+  double cu[8], sc[8], ring[8], C[8];
   int dst[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
+    C[i] = c_sfc[i];
     cu[i] = c_cos8[u][i];
     sc[i] = c_scale[cpn * 64 + i * 8 + u];
     dst[i] = cpn * 64 + c_snake[i * 8 + u];
@@ -386,10 +452,20 @@ features_sliding_fast_kernel(const int32_t *__restrict__ frame, int fw, int fh, 
   int buf = 0;
   bool pending = false;
   int pend_oy = 0;
-  auto flush = [&](int b, int oy) {   // 8 windows x 384 bytes, contiguous in the output: thread t moves 16 bytes
-    const int wdw = t / 24;
-    if (ox0 + wdw < pw)
-      reinterpret_cast<uint4 *>(out + ((int64_t)oy * pw + ox0) * 192)[t] = reinterpret_cast<const uint4 *>(&s_out[b][0][0])[t];
+  auto flush = [&](int b, int oy) {   // 8 windows x 384 bytes: thread t moves 16 bytes of window t / 24
+    const int wdw = t / 24, seg = t % 24;
+    const bool real = ox0 + wdw < pw;
+    if (!LIMBS) {
+      if (real)
+        reinterpret_cast<uint4 *>(out + ((int64_t)oy * pw + ox0) * 192)[t] = *reinterpret_cast<const uint4 *>(&s_out[b][wdw][seg * 8]);
+    } else {
+      const uint4 v = real ? *reinterpret_cast<const uint4 *>(&s_out[b][wdw][seg * 8]) : make_uint4(0u, 0u, 0u, 0u);
+      reinterpret_cast<uint4 *>(limbs + ((int64_t)oy * pwp + ox0) * 384)[t] = v;    // padding windows: zero rows
+      if (t < SF_OXB) {   // the row's norms are complete (a barrier separates them from the adds); zero the slot for its next use
+        norms[(int64_t)oy * pwp + ox0 + t] = ox0 + t < pw ? s_nrm[b][t] : 0u;
+        s_nrm[b][t] = 0;
+      }
+    }
   };
   for (int yc = oy0; yc < y_end; yc += SF_CH) {
     __syncthreads();   // the previous chunk's planes are no longer read
@@ -413,7 +489,7 @@ features_sliding_fast_kernel(const int32_t *__restrict__ frame, int fw, int fh, 
         if (y < y_end) {                                                                                                  \
           const bool emit = y - oy0 >= 7;                                                                                 \
           if (pending) flush(buf ^ 1, pend_oy);                                                                           \
-          sf_step<PH>(&s_pl[cpn][g + PH][oxl], cu, sc, dst, ring, emit, &s_out[buf][oxl][0]);                             \
+          sf_step<PH, LIMBS>(&s_pl[cpn][g + PH][oxl], cu, sc, dst, ring, C, emit, &s_out[buf][oxl][0], &s_nrm[buf][oxl]); \
           __syncthreads();                                                                                                \
           pending = emit; pend_oy = y - 7;                                                                                \
           if (emit) buf ^= 1;                                                                                             \
@@ -488,12 +564,27 @@ int launch_features_sliding(const int32_t *frame, int w, int h, int16_t *out, cu
     rc = features_fast_init(st);
     if (rc) return rc;
     const dim3 grid((unsigned)((w - 7 + SF_OXB - 1) / SF_OXB), (unsigned)((h - 7 + SF_SEG - 1) / SF_SEG));
-    features_sliding_fast_kernel<<<grid, 192, 0, st>>>(frame, w, h, out);
+    features_sliding_fast_kernel<false><<<grid, 192, 0, st>>>(frame, w, h, out, nullptr, nullptr, 0);
     note_launch();
     return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
   }
   features_i16_kernel<4><<<grid_for((n + FEAT_NP - 1) / FEAT_NP, 3), 192, 0, st>>>(frame, nullptr, 0, nullptr, nullptr, 0, n, g_lutT_f32, out, w,
                                                                              w - 7);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+// fast mode only: the sliding-window features of `frame` straight into the motion search's candidate operands (limb rows at
+// padded positions [h - 7][pwp][384] + norms [h - 7][pwp]); see features_sliding_fast_kernel<true>
+int launch_features_sliding_limbs(const int32_t *frame, int w, int h, uint8_t *limbs, uint32_t *norms, int pwp, cudaStream_t st) {
+  if (w < 8 || h < 8 || pwp < w - 7 || (pwp % SF_OXB) != 0) return TM_ERR_ARG;
+  int rc = features_init(st);
+  if (rc) return rc;
+  rc = features_fast_init(st);
+  if (rc) return rc;
+  ProfScope prof("features_sliding", st);
+  const dim3 grid((unsigned)(pwp / SF_OXB), (unsigned)((h - 7 + SF_SEG - 1) / SF_SEG));
+  features_sliding_fast_kernel<true><<<grid, 192, 0, st>>>(frame, w, h, nullptr, limbs, norms, pwp);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }

@@ -107,7 +107,10 @@ motion_tc_kernel(const uint8_t *__restrict__ t_limbs, const uint32_t *__restrict
     const int tx1 = min(tw, bx0 + BTW) - 1, ty1 = min(th, by0 + BTH) - 1;   // last tile of the block
     const int oxmn = max(0, bx0 * 8 - R - 1), oxmx = min(w - 8, tx1 * 8 + R);
     const int oymn = max(0, by0 * 8 - R - 1), oymx = min(h - 8, ty1 * 8 + R);
-    OX0 = oxmn & ~63; OY0 = oymn;
+    // first candidate column: 16-byte alignment of the norm loads is all that is needed (the TMA box may start at any position;
+    // a last segment that runs past the row end reads the next row's positions or the zeroed slack, all masked by the
+    // epilogue) -- a 64-aligned start made interior blocks scan 4 segments of 64 columns where their 184 columns need 3
+    OX0 = oxmn & ~3; OY0 = oymn;
     n_oy = oymx - oymn + 1;
     nseg = (oxmx - OX0) / 64 + 1;
   };
@@ -205,21 +208,25 @@ motion_tc_kernel(const uint8_t *__restrict__ t_limbs, const uint32_t *__restrict
         for (int sg = 0; sg < nseg; ++sg, ++it) {
           const uint32_t ts = it & 1;
           const int ox0 = OX0 + sg * 64 + hh * HN;   // first offset of this thread's 32 columns
+          // liveness and the candidate norms do not depend on the MMA: decided / fetched BEFORE waiting for the accumulators, so the
+          // loads' latency hides behind the wait
+          const bool warp_live = warp_row_live && __any_sync(0xffffffffu, row_live && ox0 <= oxmx && ox0 + HN - 1 >= oxmn);
+          uint32_t nd[HN];
+          if (warp_live) {
+            const uint32_t *np = c_norm + (int64_t)oy * pwp + ox0;
+#pragma unroll
+            for (int v = 0; v < HN / 4; ++v) {
+              const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(np) + v);
+              nd[4 * v] = t4.x; nd[4 * v + 1] = t4.y; nd[4 * v + 2] = t4.z; nd[4 * v + 3] = t4.w;
+            }
+          }
           mbar_wait(&t_full[ts], (it >> 1) & 1);
           tc_fence_after();
-          const bool warp_live = warp_row_live && __any_sync(0xffffffffu, row_live && ox0 <= oxmx && ox0 + HN - 1 >= oxmn);
           if (!warp_live) {   // no lane of this warp has a candidate in these 32 columns: just hand the stage back
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[ts]);
             continue;
-          }
-          uint32_t nd[HN];
-          const uint32_t *np = c_norm + (int64_t)oy * pwp + ox0;
-#pragma unroll
-          for (int v = 0; v < HN / 4; ++v) {
-            const uint4 t4 = __ldg(reinterpret_cast<const uint4 *>(np) + v);
-            nd[4 * v] = t4.x; nd[4 * v + 1] = t4.y; nd[4 * v + 2] = t4.z; nd[4 * v + 3] = t4.w;
           }
           const uint32_t t_acc = t_lane + ts * ACC_COLS + hh * HN;
           uint32_t pp[HN], xx[HN], lo[HN];
@@ -287,6 +294,16 @@ size_t motion_tc_ws_bytes(int tw, int th) {
   return npad * ROWB + npad * 4 + (size_t)tw * th * (ROWB + 4) + 4096;
 }
 
+// where the candidate operands of a search live inside its workspace (for a producer that writes them directly:
+// launch_features_sliding_limbs); launch_motion_search_tc(dcts = nullptr) then skips its own split pass
+void motion_tc_cand_layout(void *ws, int tw, int th, uint8_t **c_limbs, uint32_t **c_norm, int *pwp_out) {
+  const int pw = tw * 8 - 7, ph = th * 8 - 7, pwp = (pw + 63) & ~63;
+  const size_t npad = (size_t)ph * pwp + 256;
+  *c_limbs = (uint8_t *)ws;
+  *c_norm = (uint32_t *)((uint8_t *)ws + npad * ROWB);
+  *pwp_out = pwp;
+}
+
 int launch_motion_search_tc(const int16_t *cur_feat, int tw, int th, const int16_t *dcts, int radius_setting, int32_t *pred_x,
                             int32_t *pred_y, uint32_t *err, void *ws, size_t ws_bytes, int num_ctas, cudaStream_t st) {
   if (tw < 1 || th < 1 || radius_setting < 1) return TM_ERR_ARG;
@@ -301,7 +318,7 @@ int launch_motion_search_tc(const int16_t *cur_feat, int tw, int th, const int16
   uint32_t *t_norm = (uint32_t *)p;
   ProfScope prof("motion_search", st);
   const int64_t nprow = (int64_t)ph * pwp;
-  cand_limb_split_kernel<<<(unsigned)((nprow + 7) / 8), 192, 0, st>>>(dcts, pw, ph, pwp, c_limbs, c_norm);
+  if (dcts) cand_limb_split_kernel<<<(unsigned)((nprow + 7) / 8), 192, 0, st>>>(dcts, pw, ph, pwp, c_limbs, c_norm);
   if (cudaMemsetAsync(c_limbs + (size_t)nprow * ROWB, 0, 256 * ROWB, st) != cudaSuccess) return TM_ERR_CUDA;
   if (cudaMemsetAsync(c_norm + nprow, 0, 256 * 4, st) != cudaSuccess) return TM_ERR_CUDA;
   int rc = launch_limb_split(cur_feat, (int64_t)tw * th, t_limbs, t_norm, st);

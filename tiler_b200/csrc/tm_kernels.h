@@ -47,6 +47,7 @@ int launch_features_allpairs(const uint8_t *pal_idx, int64_t n_tiles, const int3
 int launch_features_f64(const int32_t *rgb, int64_t n, int mode, int use_lab, double *out, cudaStream_t st);
 int launch_features_rgb_mirrored(const int32_t *rgb, const uint8_t *flags, int64_t n, int16_t *out, cudaStream_t st);
 int launch_features_sliding(const int32_t *frame, int w, int h, int16_t *out, cudaStream_t st);
+int launch_features_sliding_limbs(const int32_t *frame, int w, int h, uint8_t *limbs, uint32_t *norms, int pwp, cudaStream_t st);
 
 // ---- motion.cu
 // motion search of every tile of a frame against the sliding features of the previous frame buffer
@@ -54,6 +55,7 @@ int launch_motion_search(const int16_t *cur_feat, int tw, int th, const int16_t 
                          int32_t *pred_y, uint32_t *err, cudaStream_t st);
 // the same search on the tensor cores (motion_tc.cu): ws of motion_tc_ws_bytes(tw, th) bytes
 size_t motion_tc_ws_bytes(int tw, int th);
+void motion_tc_cand_layout(void *ws, int tw, int th, uint8_t **c_limbs, uint32_t **c_norm, int *pwp_out);
 int launch_motion_search_tc(const int16_t *cur_feat, int tw, int th, const int16_t *dcts, int radius_setting, int32_t *pred_x,
                             int32_t *pred_y, uint32_t *err, void *ws, size_t ws_bytes, int num_ctas, cudaStream_t st);
 // TFrame.Reconstruct's decision + frame-buffer draw for one frame; motion arrays null on the first frame of a sequence

@@ -26,10 +26,23 @@ def euclidean_to_psnr(err):
 
 def _reindex_order(tiles_rgb, use_count):
     """Order of ReindexTiles(True) (tilingencoder.pas:4626-4696, CompareTileUseCountRev :582-599): use count descending, then
-    CompareDWord on the 64 pixels (unsigned dwords, first difference decides).  One memcmp sort on big-endian bytes followed
-    by a stable sort on the use count, instead of a 65-key lexsort."""
-    be = np.ascontiguousarray(np.asarray(tiles_rgb).astype(">u4")).view(np.uint8).reshape(len(tiles_rgb), 256)
-    o1 = np.argsort(be.view(np.dtype((np.void, 256))).reshape(-1), kind="stable")
+    CompareDWord on the 64 pixels (unsigned dwords, first difference decides).  The pixel order is a sort on the first two
+    dwords packed into one uint64 key; only the rows that tie on it (flat tiles) go through the 256-byte memcmp sort.  A
+    stable sort on the use count follows."""
+    t = np.ascontiguousarray(np.asarray(tiles_rgb)).view(np.uint32).reshape(len(tiles_rgb), 64)
+    key = (t[:, 0].astype(np.uint64) << np.uint64(32)) | t[:, 1].astype(np.uint64)
+    o1 = np.argsort(key, kind="stable")
+    ks = key[o1]
+    tie = np.zeros(len(o1), dtype=bool)
+    eq = ks[1:] == ks[:-1]
+    tie[1:] |= eq
+    tie[:-1] |= eq
+    if tie.any():
+        # rows of all tie runs, re-sorted by their full big-endian bytes: the key is a prefix of those bytes, so the result is
+        # still grouped by key in ascending order and drops back into the same positions
+        idx = o1[tie]
+        be = np.ascontiguousarray(t[idx].astype(">u4")).view(np.uint8).reshape(len(idx), 256)
+        o1[tie] = idx[np.argsort(be.view(np.dtype((np.void, 256))).reshape(-1), kind="stable")]
     o2 = np.argsort(-np.asarray(use_count)[o1].astype(np.int64), kind="stable")
     return o1[o2]
 
@@ -274,13 +287,21 @@ class TilingEncoder:
         keys = ("tile_idx", "pal_idx", "pred_x", "pred_y", "is_pred", "err", "psnr")
         mine = tdist.shard_sequences([s1 - s0 + 1 for s0, s1 in sequences], world)
         local, recon_of = {}, {}
+        n_dict = int(self.tile_idx.shape[0])
         for si in mine[rank]:
             s0, s1 = sequences[si]
             r = self.matcher.reconstruct_sequence(canon[s0:s1 + 1], flags[s0:s1 + 1], tw, th, radius=radius)
             local[si] = {k: (r[k].cpu().numpy() if api._is_dev(r[k]) else r[k]) for k in keys}
+            # references per dictionary tile (Reindex's use count, predicted items included), counted where the tilemap is
+            ti = r["tile_idx"]
+            if api._is_dev(ti):
+                local[si]["use"] = torch.bincount(ti.reshape(-1).to(torch.int64) + 1, minlength=n_dict + 1)[1:].cpu().numpy()
+            else:
+                local[si]["use"] = np.bincount(np.asarray(ti).reshape(-1).astype(np.int64) + 1, minlength=n_dict + 1)[1:]
             recon_of[si] = r["recon"]        # stays on the device when the encoder is device-resident
         merged = tdist.gather_tilemaps(local, mine) if world > 1 else local
         tm = {k: np.concatenate([merged[si][k] for si in range(len(sequences))]) for k in keys}
+        tile_use = sum(merged[si]["use"] for si in range(len(sequences)))
         own = [recon_of[si] for si in sorted(recon_of)]
         recon = (torch.cat(own) if api._is_dev(own[0]) else np.concatenate(own)) if own else None   # this rank's sequences only
         tm["err"] = tm["err"].view(np.uint32)
@@ -289,7 +310,7 @@ class TilingEncoder:
         t["reconstruct"] = time.perf_counter() - t0; t0 = time.perf_counter()
         didx = self.tile_idx.cpu().numpy() if api._is_dev(self.tile_idx) else np.asarray(self.tile_idx)
         pal = self.palettes.cpu().numpy() if api._is_dev(self.palettes) else np.asarray(self.palettes)
-        final_tiles, use_count, tile_map = gtm_io.reindex(didx, tm["tile_idx"])
+        final_tiles, use_count, tile_map = gtm_io.reindex(didx, tm["tile_idx"], tile_use=tile_use)
         tm_out = dict(tm)
         tm_out["tile_idx"] = tile_map
         t["reindex"] = time.perf_counter() - t0; t0 = time.perf_counter()

@@ -86,27 +86,53 @@ def optimize_palettes(palettes, n_threads=0):
 
 
 # ------------------------------------------------------------------ dictionary bookkeeping (Reindex, tilingencoder.pas:1992-2040)
-def reindex(tiles_idx, tile_idx_map):
+def reindex(tiles_idx, tile_idx_map, tile_use=None):
     """MakeTilesUnique(False) + use counts + ReindexTiles(False) (tilingencoder.pas:2010-2037, 4720-4781, 4626-4696):
     merges dictionary tiles with identical palette indices, counts how often each is referenced by a tilemap item
     (TileIdx >= 0, predicted items included, as the reference does), drops unused tiles, orders by (use count descending,
-    palette-index bytes ascending) and remaps the tilemap.  -> (tiles [n,64] uint8, use_count [n], remapped tile_idx)."""
+    palette-index bytes ascending) and remaps the tilemap.  -> (tiles [n,64] uint8, use_count [n], remapped tile_idx).
+    tile_use (optional): references per dictionary tile, already counted (the encoder counts them on the device while the
+    tilemap is still there); without it they are counted here."""
     tiles_idx = np.ascontiguousarray(tiles_idx, dtype=np.uint8).reshape(-1, 64)
     tmap = np.ascontiguousarray(tile_idx_map, dtype=np.int32)
-    as_rows = tiles_idx.view(np.dtype((np.void, 64))).reshape(-1)
-    uniq, inverse = np.unique(as_rows, return_inverse=True)            # lexicographic on bytes = CompareByte order
-    # index -1 (no tile) reads the extra last slot of each lookup table: two gathers and one bincount over the whole tilemap
-    # instead of boolean-mask passes
+    uniq, inverse = _unique_rows64(tiles_idx)                            # lexicographic on bytes = CompareByte order
     flat = tmap.reshape(-1)
-    cls = np.append(inverse.astype(np.int32), np.int32(-1))[flat]
-    use = np.bincount(cls + 1, minlength=len(uniq) + 1)[1:]
+    if tile_use is None:
+        tile_use = np.bincount(flat + 1, minlength=len(tiles_idx) + 1)[1:]
+    use = np.bincount(inverse, weights=np.asarray(tile_use, dtype=np.float64), minlength=len(uniq)).astype(np.int64)
     keep = np.nonzero(use > 0)[0]
     order = keep[np.lexsort((keep, -use[keep]))]                         # keep is already in byte order
-    new_of_cls = np.full(len(uniq) + 1, -1, dtype=np.int32)
+    new_of_cls = np.full(len(uniq), -1, dtype=np.int32)
     new_of_cls[order] = np.arange(len(order), dtype=np.int32)
-    out_map = new_of_cls[cls].reshape(tmap.shape)
-    tiles_out = np.frombuffer(uniq[order].tobytes(), dtype=np.uint8).reshape(-1, 64).copy()
+    # one gather over the whole tilemap: index -1 (no tile) reads the extra last slot of the table
+    new_of_tile = np.append(new_of_cls[inverse], np.int32(-1)).astype(np.int32)
+    out_map = new_of_tile[flat].reshape(tmap.shape)
+    tiles_out = np.ascontiguousarray(uniq[order])
     return tiles_out, use[order].astype(np.int32), out_map
+
+
+def _unique_rows64(rows):
+    """np.unique(rows, axis=0, return_inverse=True) for uint8 [n, 64] rows in byte-lexicographic order: a sort on the first 8
+    bytes as one big-endian uint64, the 64-byte memcmp sort only for the rows that tie on it.  -> (unique rows, inverse)."""
+    n = len(rows)
+    if n == 0:
+        return rows.reshape(0, 64), np.zeros(0, dtype=np.int64)
+    key = rows[:, :8].copy().view(">u8").reshape(-1)
+    o = np.argsort(key, kind="stable")
+    ks = key[o]
+    eq = ks[1:] == ks[:-1]
+    tie = np.zeros(n, dtype=bool)
+    tie[1:] |= eq
+    tie[:-1] |= eq
+    if tie.any():
+        idx = o[tie]
+        o[tie] = idx[np.argsort(rows[idx].view(np.dtype((np.void, 64))).reshape(-1), kind="stable")]
+    srt = rows[o]
+    new = np.ones(n, dtype=bool)
+    new[1:] = (srt[1:] != srt[:-1]).any(axis=1)
+    inverse = np.empty(n, dtype=np.int64)
+    inverse[o] = np.cumsum(new) - 1
+    return srt[new], inverse
 
 
 # ------------------------------------------------------------------ writer (SaveStream)
