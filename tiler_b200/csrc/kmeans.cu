@@ -650,20 +650,26 @@ __global__ void rgb_centroid_kernel(const RgbAcc *__restrict__ acc, int64_t tota
 }
 
 // k-means++ seeding identical to the oracle's tmo_kmeanspp_init (explicit xorshift64* stream, D^2 sampling by first
-// prefix sum exceeding u).  Integer distances -> prefix sums are exact in any order.  One block per palette.
-
-__global__ void __launch_bounds__(256)
+// prefix sum exceeding u).  Integer distances -> prefix sums are exact in any order.  One 1024-thread block per palette:
+// warp w owns a contiguous range of the palette's pixels and reads it 32 consecutive pixels at a time (coalesced; the first
+// version gave every THREAD a contiguous range -- 32 cache lines per warp load, 22 ms for 16 palettes x 262 144 pixels); the
+// pick is located by the owner warp with a warp-wide inclusive scan over its range, 32 pixels per step.
+constexpr int KPP_THREADS = 1024, KPP_WARPS = KPP_THREADS / 32;
+__global__ void __launch_bounds__(KPP_THREADS)
 rgb_kmeanspp_kernel(const int32_t *__restrict__ px, const int64_t *__restrict__ off, int k, const int32_t *__restrict__ kcount,
                     unsigned long long seed, unsigned int *__restrict__ d2, double *__restrict__ cent) {
   const int p = blockIdx.x;
   const int64_t s0 = off[p], n = off[p + 1] - s0;
   const int kk = kcount[p];
   if (n <= 0 || kk <= 0) return;
-  __shared__ unsigned long long s_part[256];
+  __shared__ unsigned long long s_part[KPP_WARPS];
+  __shared__ unsigned long long s_acc;     // pixels before the owner warp's range: their summed distances
+  __shared__ double s_u;
+  __shared__ int s_owner;
   __shared__ int s_last[3];
   unsigned long long st = seed ? seed : 0x9E3779B97F4A7C15ULL;
-  const int t = threadIdx.x;
-  const int64_t per = (n + 255) / 256, a = min((int64_t)t * per, n), b = min(a + per, n);
+  const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+  const int64_t per = (n + KPP_WARPS - 1) / KPP_WARPS, a = min((int64_t)w * per, n), b = min(a + per, n);
   if (t == 0) {
     const int64_t first = (int64_t)(xorshift64s(st) % (unsigned long long)n);
     const int32_t c = px[s0 + first];
@@ -671,12 +677,12 @@ rgb_kmeanspp_kernel(const int32_t *__restrict__ px, const int64_t *__restrict__ 
     double *cv = cent + ((int64_t)p * k) * 3;
     cv[0] = s_last[0]; cv[1] = s_last[1]; cv[2] = s_last[2];
   }
-  for (int64_t i = a; i < b; ++i) d2[s0 + i] = 0xFFFFFFFFu;
+  for (int64_t i = a + lane; i < b; i += 32) d2[s0 + i] = 0xFFFFFFFFu;
   for (int c = 1; c < kk; ++c) {
     __syncthreads();
     const int lr = s_last[0], lg = s_last[1], lb = s_last[2];
     unsigned long long part = 0;
-    for (int64_t i = a; i < b; ++i) {
+    for (int64_t i = a + lane; i < b; i += 32) {
       const int32_t v = px[s0 + i];
       const int dr = (v & 255) - lr, dg = ((v >> 8) & 255) - lg, db = ((v >> 16) & 255) - lb;
       const unsigned int s = (unsigned)(dr * dr + dg * dg + db * db);
@@ -684,31 +690,52 @@ rgb_kmeanspp_kernel(const int32_t *__restrict__ px, const int64_t *__restrict__ 
       if (s < cur) { cur = s; d2[s0 + i] = s; }
       part += cur;
     }
-    s_part[t] = part;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_part[w] = part;
     __syncthreads();
     if (t == 0) {
       unsigned long long total = 0;
-      for (int i = 0; i < 256; ++i) total += s_part[i];
+      for (int i = 0; i < KPP_WARPS; ++i) total += s_part[i];
       const double u = (double)(xorshift64s(st) >> 11) * (1.0 / 9007199254740992.0) * (double)total;
-      // owner thread = first whose inclusive prefix exceeds u; stash u's remainder search bounds
+      // owner warp = first whose inclusive prefix exceeds u (none: the pick falls back to the last pixel, like the oracle's scan)
       unsigned long long acc = 0;
-      int owner = 255;
-      for (int i = 0; i < 256; ++i) {
+      int owner = -1;
+      for (int i = 0; i < KPP_WARPS; ++i) {
         if ((double)(acc + s_part[i]) > u) { owner = i; break; }
         acc += s_part[i];
       }
-      // sequential scan inside the owner's range (<= n/256 elements)
-      const int64_t oa = min((int64_t)owner * per, n), ob = min(oa + per, n);
-      int64_t pick = n - 1;
-      for (int64_t i = oa; i < ob; ++i) {
-        acc += d2[s0 + i];
-        if ((double)acc > u) { pick = i; break; }
+      s_owner = owner; s_acc = acc; s_u = u;
+      if (owner < 0) {
+        const int32_t v = px[s0 + n - 1];
+        s_last[0] = v & 255; s_last[1] = (v >> 8) & 255; s_last[2] = (v >> 16) & 255;
+        double *cv = cent + ((int64_t)p * k + c) * 3;
+        cv[0] = s_last[0]; cv[1] = s_last[1]; cv[2] = s_last[2];
       }
-      if (owner == 255 && !((double)acc > u)) pick = n - 1;
-      const int32_t v = px[s0 + pick];
-      s_last[0] = v & 255; s_last[1] = (v >> 8) & 255; s_last[2] = (v >> 16) & 255;
-      double *cv = cent + ((int64_t)p * k + c) * 3;
-      cv[0] = s_last[0]; cv[1] = s_last[1]; cv[2] = s_last[2];
+    }
+    __syncthreads();
+    if (w == s_owner) {   // first pixel of this warp's range whose inclusive prefix exceeds u
+      unsigned long long acc = s_acc;
+      const double u = s_u;
+      int64_t pick = n - 1;
+      for (int64_t j = a; j < b; j += 32) {
+        const int64_t i = j + lane;
+        unsigned long long incl = i < b ? (unsigned long long)d2[s0 + i] : 0ull;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned long long up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const unsigned hit = __ballot_sync(0xffffffffu, i < b && (double)(acc + incl) > u);
+        if (hit) { pick = j + (__ffs(hit) - 1); break; }
+        acc += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) {
+        const int32_t v = px[s0 + pick];
+        s_last[0] = v & 255; s_last[1] = (v >> 8) & 255; s_last[2] = (v >> 16) & 255;
+        double *cv = cent + ((int64_t)p * k + c) * 3;
+        cv[0] = s_last[0]; cv[1] = s_last[1]; cv[2] = s_last[2];
+      }
     }
   }
 }
@@ -831,7 +858,7 @@ int run_palette_quantise(const int32_t *rgb, const int32_t *tile_pal, int64_t n_
   if (init) CK(cudaMemcpyAsync(cent, init, (size_t)n_pal * k * 3 * 8, cudaMemcpyDefault, st));
   else {
     CK(cudaMemsetAsync(cent, 0xFF, (size_t)n_pal * k * 3 * 8, st));  // NaN fill: unused slots never win
-    rgb_kmeanspp_kernel<<<n_pal, 256, 0, st>>>(px, off, k, kcount, seed, d2, cent);
+    rgb_kmeanspp_kernel<<<n_pal, KPP_THREADS, 0, st>>>(px, off, k, kcount, seed, d2, cent);
   }
   {
     int dev = 0, sms = 148;
