@@ -138,6 +138,24 @@ def gather_rows(local_rows, n_total):
     return full
 
 
+def device_collectives():
+    """True inside an initialised NCCL group: row shards and tilemaps are then exchanged as device tensors over NVLink
+    (disjoint rows into a zero-filled full-size tensor + one all-reduce(sum) = an all-gather that needs no equal shard sizes)
+    instead of pickled host objects."""
+    return (dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+            and dist.get_backend() == "nccl")
+
+
+def allgather_rows_device(local_rows, lo, n_total, device):
+    """local_rows: this rank's rows [hi - lo, ...] (numpy or CUDA tensor) of a [n_total, ...] array -> the full array as a CUDA tensor
+    on every rank."""
+    loc = local_rows if torch.is_tensor(local_rows) else torch.from_numpy(np.ascontiguousarray(local_rows))
+    full = torch.zeros((n_total,) + tuple(loc.shape[1:]), dtype=loc.dtype, device=device)
+    full[lo:lo + loc.shape[0]] = loc.to(device, non_blocking=True)
+    dist.all_reduce(full, op=dist.ReduceOp.SUM)
+    return full
+
+
 def world_info():
     if dist is None or not dist.is_available() or not dist.is_initialized():
         return 0, 1

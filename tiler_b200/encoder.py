@@ -270,7 +270,10 @@ class TilingEncoder:
         if world > 1:
             lo, hi = tdist.shard_rows(n, rank, world)
             psnr_loc, _, _ = self.predict_motion(frames_packed, canon, flags, tw, th, radius, frame_range=(lo, hi))
-            psnr = tdist.gather_rows(psnr_loc, n)
+            if self.device is not None and tdist.device_collectives():
+                psnr = tdist.allgather_rows_device(psnr_loc, lo, n, self.device).cpu().numpy()
+            else:
+                psnr = tdist.gather_rows(psnr_loc, n)
         else:
             psnr, _, _ = self.predict_motion(frames_packed, canon, flags, tw, th, radius)
         t["predict_motion"] = time.perf_counter() - t0; t0 = time.perf_counter()
@@ -288,20 +291,47 @@ class TilingEncoder:
         mine = tdist.shard_sequences([s1 - s0 + 1 for s0, s1 in sequences], world)
         local, recon_of = {}, {}
         n_dict = int(self.tile_idx.shape[0])
+        dev_coll = world > 1 and self.device is not None and tdist.device_collectives()
+        full = None
+        tile_use_d = None
         for si in mine[rank]:
             s0, s1 = sequences[si]
             r = self.matcher.reconstruct_sequence(canon[s0:s1 + 1], flags[s0:s1 + 1], tw, th, radius=radius)
-            local[si] = {k: (r[k].cpu().numpy() if api._is_dev(r[k]) else r[k]) for k in keys}
-            # references per dictionary tile (Reindex's use count, predicted items included), counted where the tilemap is
             ti = r["tile_idx"]
+            # references per dictionary tile (Reindex's use count, predicted items included), counted where the tilemap is
             if api._is_dev(ti):
-                local[si]["use"] = torch.bincount(ti.reshape(-1).to(torch.int64) + 1, minlength=n_dict + 1)[1:].cpu().numpy()
+                use_si = torch.bincount(ti.reshape(-1).to(torch.int64) + 1, minlength=n_dict + 1)[1:]
             else:
-                local[si]["use"] = np.bincount(np.asarray(ti).reshape(-1).astype(np.int64) + 1, minlength=n_dict + 1)[1:]
+                use_si = np.bincount(np.asarray(ti).reshape(-1).astype(np.int64) + 1, minlength=n_dict + 1)[1:]
+            if dev_coll:
+                # multi-GPU, device-resident: this rank's rows go into zero-filled full-size device tensors; one all-reduce per
+                # field below is the all-gather (NCCL over NVLink instead of pickled host objects)
+                if full is None:
+                    full = {k: torch.zeros((n, nt), dtype=r[k].dtype, device=self.device) for k in keys}
+                    tile_use_d = torch.zeros(n_dict, dtype=torch.int64, device=self.device)
+                for k in keys:
+                    full[k][s0:s1 + 1] = r[k]
+                tile_use_d += use_si
+            else:
+                local[si] = {k: (r[k].cpu().numpy() if api._is_dev(r[k]) else r[k]) for k in keys}
+                local[si]["use"] = use_si.cpu().numpy() if api._is_dev(use_si) else use_si
             recon_of[si] = r["recon"]        # stays on the device when the encoder is device-resident
-        merged = tdist.gather_tilemaps(local, mine) if world > 1 else local
-        tm = {k: np.concatenate([merged[si][k] for si in range(len(sequences))]) for k in keys}
-        tile_use = sum(merged[si]["use"] for si in range(len(sequences)))
+        if dev_coll:
+            import torch.distributed as tdd
+            if full is None:   # a rank without sequences still takes part in the collectives
+                ref_dt = {"tile_idx": torch.int32, "pal_idx": torch.int32, "pred_x": torch.int32, "pred_y": torch.int32,
+                          "is_pred": torch.uint8, "err": torch.int32, "psnr": torch.float32}
+                full = {k: torch.zeros((n, nt), dtype=ref_dt[k], device=self.device) for k in keys}
+                tile_use_d = torch.zeros(n_dict, dtype=torch.int64, device=self.device)
+            for k in keys:
+                tdd.all_reduce(full[k], op=tdd.ReduceOp.SUM)
+            tdd.all_reduce(tile_use_d, op=tdd.ReduceOp.SUM)
+            tm = {k: full[k].cpu().numpy() for k in keys}
+            tile_use = tile_use_d.cpu().numpy()
+        else:
+            merged = tdist.gather_tilemaps(local, mine) if world > 1 else local
+            tm = {k: np.concatenate([merged[si][k] for si in range(len(sequences))]) for k in keys}
+            tile_use = sum(merged[si]["use"] for si in range(len(sequences)))
         own = [recon_of[si] for si in sorted(recon_of)]
         recon = (torch.cat(own) if api._is_dev(own[0]) else np.concatenate(own)) if own else None   # this rank's sequences only
         tm["err"] = tm["err"].view(np.uint32)
