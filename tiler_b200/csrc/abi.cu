@@ -199,7 +199,7 @@ struct tm_bico {
 struct tm_matcher {
   int64_t n_dict = 0; int n_pal = 0, pal_size = 0, extended = 0;
   uint8_t *dict_idx = nullptr; int32_t *dict_pal = nullptr; int32_t *palettes = nullptr;
-  int16_t *dict_feat = nullptr; int16_t *pair_feat = nullptr;
+  int16_t *dict_feat = nullptr; int16_t *pair_feat = nullptr; uint32_t *pair_norm = nullptr;   // pair_norm[t * n_pal + p] = |pair_feat row|^2 mod 2^32
   tm_knn_short *knn = nullptr;
 };
 
@@ -801,7 +801,7 @@ extern "C" int tm_matcher_destroy(tm_matcher *m) {
   if (!m) return TM_OK;
   std::lock_guard<std::recursive_mutex> lk(g_mu);
   cudaFreeAsync(m->dict_idx, t_stream); cudaFreeAsync(m->dict_pal, t_stream); cudaFreeAsync(m->palettes, t_stream);
-  cudaFreeAsync(m->dict_feat, t_stream); cudaFreeAsync(m->pair_feat, t_stream);
+  cudaFreeAsync(m->dict_feat, t_stream); cudaFreeAsync(m->pair_feat, t_stream); cudaFreeAsync(m->pair_norm, t_stream);
   tm_knn_short_destroy(m->knn);
   delete m;
   return TM_OK;
@@ -825,7 +825,8 @@ extern "C" int tm_matcher_create(const uint8_t *dict_idx, const int32_t *dict_pa
                       cudaMallocAsync((void **)&m->dict_pal, (size_t)n_dict * 4, st) != cudaSuccess ||
                       cudaMallocAsync((void **)&m->palettes, (size_t)n_pal * pal_size * 4, st) != cudaSuccess ||
                       cudaMallocAsync((void **)&m->dict_feat, (size_t)n_dict * 384, st) != cudaSuccess ||
-                      (extended && cudaMallocAsync((void **)&m->pair_feat, pair_bytes, st) != cudaSuccess)))
+                      (extended && (cudaMallocAsync((void **)&m->pair_feat, pair_bytes, st) != cudaSuccess ||
+                                    cudaMallocAsync((void **)&m->pair_norm, (size_t)n_dict * n_pal * 4, st) != cudaSuccess))))
     rc = TM_ERR_NOMEM;
   if (rc == TM_OK) {
     if (cudaMemcpyAsync(m->dict_idx, dict_idx, (size_t)n_dict * 64, cudaMemcpyDefault, st) != cudaSuccess ||
@@ -836,6 +837,7 @@ extern "C" int tm_matcher_create(const uint8_t *dict_idx, const int32_t *dict_pa
   if (rc == TM_OK) rc = launch_features_pal(m->dict_idx, m->dict_pal, m->palettes, pal_size, n_dict, m->dict_feat, st);
   if (rc == TM_OK) rc = knn_short_create_dev(m->dict_feat, n_dict, st, &m->knn);
   if (rc == TM_OK && extended) rc = launch_features_allpairs(m->dict_idx, n_dict, m->palettes, pal_size, n_pal, m->pair_feat, st);
+  if (rc == TM_OK && extended) rc = launch_row_norms(m->pair_feat, n_dict * n_pal, m->pair_norm, st);
   if (rc == TM_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = TM_ERR_CUDA;
   if (rc != TM_OK) { tm_matcher_destroy(m); return fail(rc, "tm_matcher_create"); }
   *out = m;
@@ -852,7 +854,7 @@ static int match_feat_dev(tm_matcher *m, const int16_t *d_feat, int64_t n_q, int
   if (rc) return rc;
   if (m->extended)
     return launch_match_rerank(d_feat, n_q, d_idx, kk, m->dict_pal, m->dict_idx, m->n_dict, m->palettes, m->pal_size, m->n_pal, m->pair_feat,
-                               d_tile, d_pal, d_err, s.st);
+                               m->pair_norm, d_tile, d_pal, d_err, s.st);
   return launch_match_plain(d_idx, d_dist, n_q, m->dict_pal, m->n_dict, d_tile, d_pal, d_err, s.st);
 }
 

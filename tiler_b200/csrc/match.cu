@@ -29,12 +29,34 @@ __global__ void __launch_bounds__(256) distance_pairs_kernel(const int16_t *__re
   if (lane == 0) out[i] = s;
 }
 
+// sum of squares mod 2^32 of int16 rows [n][192]: one warp per row (norms of the (tile x palette) feature table)
+__global__ void __launch_bounds__(256) row_norms_kernel(const int16_t *__restrict__ a, int64_t n, uint32_t *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= n) return;
+  const uint32_t *pa = reinterpret_cast<const uint32_t *>(a + i * 192);
+  uint32_t s = 0;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) s += sqdiff2(__ldg(pa + lane + 32 * j), 0u);
+  s = __reduce_add_sync(0xffffffffu, s);
+  if (lane == 0) out[i] = s;
+}
+
+// q . b for two packed int16 pairs through the byte dot-product unit: b = 256 bh + bl (bh signed, bl unsigned), bytes of the
+// permuted word p = [bl0, bl1, bh0, bh1]:  L += q0 bl0 + q1 bl1 (dp2a.lo, unsigned bytes), H += q0 bh0 + q1 bh1 (dp2a.hi, signed)
+__device__ __forceinline__ void dot2_limbs(uint32_t q, uint32_t b, int32_t &H, uint32_t &L) {
+  const uint32_t p = __byte_perm(b, 0u, 0x3120);
+  asm("dp2a.lo.s32.u32 %0, %1, %2, %0;" : "+r"(L) : "r"(q), "r"(p));
+  asm("dp2a.hi.s32.s32 %0, %1, %2, %0;" : "+r"(H) : "r"(q), "r"(p));
+}
+
 // Re-rank: one warp per source tile.  pair_feat = features of dictionary tile t recoloured with palette p,
 // laid out [n_dict][n_pal][192] (built once per dictionary by features_i16_kernel<2>).
 __global__ void __launch_bounds__(128)
 match_rerank_kernel(const int16_t *__restrict__ q_feat, int64_t n_q, const int32_t *__restrict__ knn_idx, int k,
                     const int32_t *__restrict__ dict_pal, int64_t n_dict, int n_pal, const int16_t *__restrict__ pair_feat,
-                    int32_t *__restrict__ out_tile, int32_t *__restrict__ out_pal, uint32_t *__restrict__ out_err) {
+                    const uint32_t *__restrict__ pair_norm, int32_t *__restrict__ out_tile, int32_t *__restrict__ out_pal,
+                    uint32_t *__restrict__ out_err) {
   __shared__ uint32_t s_q[4][96];
   __shared__ int32_t s_tile[4][64];
   __shared__ int32_t s_pal[4][64];
@@ -69,29 +91,43 @@ match_rerank_kernel(const int16_t *__restrict__ q_feat, int64_t n_q, const int32
   // 384-byte rows in whole 128-byte lines (one lane per row meant 32 different lines per load instruction and made the kernel
   // wait on L1/L2 wavefronts); the 8 partial sums are folded with three shuffles.  Every lane of a group ends up with the same
   // running best, so the final warp reduction is unchanged.
+  // The distance is |q|^2 + |b|^2 - 2 q.b (mod 2^32, the reference's Cardinal accumulator): |b|^2 comes from a table built with the
+  // pair features, q.b from the byte dot-product unit -- one permute and two dp2a per coefficient pair instead of two sign
+  // extensions, two subtractions and two multiply-adds per coefficient.
   uint32_t best_e = 0xFFFFFFFFu;
   int32_t best_t = 0x7FFFFFFF, best_p = 0x7FFFFFFF;
   const int total = n_t * n_p;
   const int grp = lane >> 3, gl = lane & 7;
   uint32_t qreg[12];                                   // this lane's 24 query coefficients: words [12 gl, 12 gl + 12)
+  uint32_t nq = 0;
 #pragma unroll
-  for (int c = 0; c < 12; ++c) qreg[c] = s_q[w][12 * gl + c];
+  for (int c = 0; c < 12; ++c) { qreg[c] = s_q[w][12 * gl + c]; nq += sqdiff2(qreg[c], 0u); }
+  nq += __shfl_xor_sync(0xffffffffu, nq, 1);
+  nq += __shfl_xor_sync(0xffffffffu, nq, 2);
+  nq += __shfl_xor_sync(0xffffffffu, nq, 4);
   for (int e0 = 0; e0 < total; e0 += 4) {
     const int e = e0 + grp;
     const bool live = e < total;
     const int32_t t = live ? s_tile[w][e / n_p] : 0, p = live ? s_pal[w][e % n_p] : 0;
-    uint32_t s = 0;
+    uint32_t dot = 0, nb = 0;
     if (live) {
-      const uint4 *pf = reinterpret_cast<const uint4 *>(pair_feat + ((size_t)t * n_pal + p) * 192) + 3 * gl;
+      const size_t prow = (size_t)t * n_pal + p;
+      const uint4 *pf = reinterpret_cast<const uint4 *>(pair_feat + prow * 192) + 3 * gl;
+      nb = __ldg(pair_norm + prow);
+      int32_t H = 0;
+      uint32_t L = 0;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const uint4 f = __ldg(pf + c);
-        s += sqdiff2(qreg[4 * c], f.x) + sqdiff2(qreg[4 * c + 1], f.y) + sqdiff2(qreg[4 * c + 2], f.z) + sqdiff2(qreg[4 * c + 3], f.w);
+        dot2_limbs(qreg[4 * c], f.x, H, L); dot2_limbs(qreg[4 * c + 1], f.y, H, L);
+        dot2_limbs(qreg[4 * c + 2], f.z, H, L); dot2_limbs(qreg[4 * c + 3], f.w, H, L);
       }
+      dot = ((uint32_t)H << 8) + L;
     }
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+    dot += __shfl_xor_sync(0xffffffffu, dot, 4);
+    const uint32_t s = nq + nb - (dot << 1);
     if (live && (s < best_e || (s == best_e && (t < best_t || (t == best_t && p < best_p))))) { best_e = s; best_t = t; best_p = p; }
   }
 #pragma unroll
@@ -210,13 +246,21 @@ int launch_distance_pairs(const int16_t *a, const int16_t *b, int64_t n, uint32_
 
 int launch_match_rerank(const int16_t *q_feat, int64_t n_q, const int32_t *knn_idx, int k, const int32_t *dict_pal,
                         const uint8_t *dict_idx, int64_t n_dict, const int32_t *palettes, int pal_size, int n_pal,
-                        const int16_t *pair_feat, int32_t *out_tile, int32_t *out_pal, uint32_t *out_err, cudaStream_t st) {
+                        const int16_t *pair_feat, const uint32_t *pair_norm, int32_t *out_tile, int32_t *out_pal, uint32_t *out_err,
+                        cudaStream_t st) {
   (void)dict_idx; (void)palettes; (void)pal_size;
   if (n_q <= 0) return TM_OK;
-  if (k < 1 || k > 64 || !pair_feat) return TM_ERR_ARG;
+  if (k < 1 || k > 64 || !pair_feat || !pair_norm) return TM_ERR_ARG;
   ProfScope prof("rerank", st);
-  match_rerank_kernel<<<(unsigned)((n_q + 3) / 4), 128, 0, st>>>(q_feat, n_q, knn_idx, k, dict_pal, n_dict, n_pal, pair_feat, out_tile,
-                                                                 out_pal, out_err);
+  match_rerank_kernel<<<(unsigned)((n_q + 3) / 4), 128, 0, st>>>(q_feat, n_q, knn_idx, k, dict_pal, n_dict, n_pal, pair_feat, pair_norm,
+                                                                 out_tile, out_pal, out_err);
+  note_launch();
+  return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
+}
+
+int launch_row_norms(const int16_t *rows, int64_t n, uint32_t *norms, cudaStream_t st) {
+  if (n <= 0) return TM_OK;
+  row_norms_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(rows, n, norms);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }

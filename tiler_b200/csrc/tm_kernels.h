@@ -96,8 +96,9 @@ int launch_dither(const int32_t *rgb, const uint8_t *mirror_flags, const int32_t
 int launch_distance_pairs(const int16_t *a, const int16_t *b, int64_t n, uint32_t *out, cudaStream_t st);
 int launch_match_rerank(const int16_t *q_feat, int64_t n_q, const int32_t *knn_idx, int k, const int32_t *dict_pal,
                         const uint8_t *dict_idx, int64_t n_dict, const int32_t *palettes, int pal_size, int n_pal,
-                        const int16_t *pair_feat /* [n_dict][n_pal][192] or null */, int32_t *out_tile, int32_t *out_pal,
-                        uint32_t *out_err, cudaStream_t st);
+                        const int16_t *pair_feat /* [n_dict][n_pal][192] */, const uint32_t *pair_norm /* [n_dict][n_pal]: |row|^2 mod 2^32 */,
+                        int32_t *out_tile, int32_t *out_pal, uint32_t *out_err, cudaStream_t st);
+int launch_row_norms(const int16_t *rows, int64_t n, uint32_t *norms, cudaStream_t st);
 int launch_knn_f64(const double *dict, int64_t n_dict, int dim, const double *q, int64_t n_q, int32_t *idx, double *dist,
                    cudaStream_t st);
 
