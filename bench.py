@@ -226,7 +226,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- setup (untimed): clip, dictionary, palettes ----
-    n_seq_local = N_SEQ if world == 1 else max(2, N_SEQ // world)   # weak scaling: every rank keeps full-size batches
+    n_seq_local = N_SEQ   # weak scaling: every rank rotates the same number of distinct full-size batches at every N (the k-NN time
+                          # depends on the data through the admission counts, so a smaller batch set would change the mix, not the work)
     host_raw, clip_frames = make_inputs(1000 * rank, n_seq_local, keep_frames=(world == 1 and not args.no_encode))
     if world > 1 and not args.no_encode:
         _, clip_frames = make_inputs(0, N_SEQ, keep_frames=True)   # the SAME 240-frame clip on every rank for the sharded encode leg
