@@ -159,6 +159,41 @@ def test_pipeline_reduce_and_reindex_semantics(oracle):
     assert (np.diff(fu) <= 0).all()
 
 
+def test_host_reindex_and_tile_order_against_pipeline_restatement():
+    """The product's host bookkeeping (packed-key sorts, one-gather remap, use counts handed in from the device) against the
+    statement-by-statement restatements in oracle/pipeline.py, on inputs with duplicate tiles, rows that tie on the packed sort
+    key, unreferenced tiles and tilemap items without a tile."""
+    from oracle import pipeline as P
+    from tiler_b200 import gtm
+    from tiler_b200.encoder import _reindex_order
+    rng = np.random.default_rng(33)
+    for n_dict, hi in ((700, 16), (300, 2), (5, 3), (1, 4)):
+        didx = rng.integers(0, hi, size=(n_dict, 64)).astype(np.uint8)
+        if n_dict >= 300:
+            didx[10:40] = didx[100:130]                                  # exact duplicates
+            didx[50:120, :8] = didx[0, :8]                               # ties on the first 8 bytes, different tails
+        tmap = rng.integers(-1, n_dict, size=(4, 500)).astype(np.int32)
+        tmap[rng.random(tmap.shape) < 0.3] = -1
+        want = P.reindex(didx, tmap)
+        got = gtm.reindex(didx, tmap)
+        use_dev = np.bincount(tmap[tmap >= 0].reshape(-1), minlength=n_dict)   # what the encoder counts on the device
+        got2 = gtm.reindex(didx, tmap, tile_use=use_dev)
+        for g in (got, got2):
+            assert np.array_equal(g[0], want[0]) and np.array_equal(g[1], want[1]) and np.array_equal(g[2], want[2])
+    none = gtm.reindex(didx, np.full((2, 3), -1, np.int32))
+    assert none[0].shape == (0, 64) and len(none[1]) == 0 and (none[2] == -1).all()
+    # ReindexTiles(True): use count descending, then the 64 pixels as unsigned dwords (first difference decides)
+    for n, hi in ((900, 1 << 24), (400, 3), (1, 9)):
+        rgb = rng.integers(0, hi, size=(n, 64), dtype=np.int64).astype(np.int32)
+        if n >= 400:
+            rgb[5:25] = rgb[200:220]
+            rgb[30:90, :2] = rgb[0, :2]
+            rgb[100:110, 0] = -7                                         # 0xFFFFFFF9: sorts last as an unsigned dword
+        use = rng.integers(1, 4, size=n)
+        keys = [(-int(use[i]), tuple(int(v) & 0xFFFFFFFF for v in rgb[i]), i) for i in range(n)]
+        assert _reindex_order(rgb, use).tolist() == [k[2] for k in sorted(keys)]
+
+
 def test_optimize_palettes_host_port_matches_pipeline_port():
     """OptimizePalettes + the Powell minimiser (tilingencoder.pas:4246-4432, powell.pas) exist twice: C++ host code of the product
     (libtm_gtm.so) and the Python restatement in oracle/pipeline.py.  The minimiser's path depends on every floating-point detail
