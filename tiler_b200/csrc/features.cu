@@ -413,9 +413,8 @@ __device__ __forceinline__ void sf_step(const double *__restrict__ prow /* plane
 // positions ox in [fw - 7, pwp) get zero rows and zero norms (grid.x covers pwp / 8 column blocks).  That is
 // cand_limb_split_kernel folded into the producer: the 349 MB int16 intermediate of a 720p frame is never written or read.
 template <bool LIMBS>
-__global__ void __launch_bounds__(192, 2)
-features_sliding_fast_kernel(const int32_t *__restrict__ frame, int fw, int fh, int16_t *__restrict__ out, uint8_t *__restrict__ limbs,
-                             uint32_t *__restrict__ norms, int pwp) {
+__device__ __forceinline__ void sf_body(const int32_t *__restrict__ frame, int fw, int fh, int16_t *__restrict__ out,
+                                        uint8_t *__restrict__ limbs, uint32_t *__restrict__ norms, int pwp) {
   __shared__ double s_pl[3][SF_CH][SF_OXB + 8];          // converted planes of the current row chunk (15 of 16 columns used)
   __shared__ __align__(16) int16_t s_out[2][SF_OXB][SF_ROWP];   // rows padded to 400 bytes: the limb flush reads 8 rows at once
   __shared__ uint32_t s_nrm[2][SF_OXB];
@@ -502,6 +501,20 @@ features_sliding_fast_kernel(const int32_t *__restrict__ frame, int fw, int fh, 
   if (pending) flush(buf ^ 1, pend_oy);
 }
 
+// Register caps, measured: the register file is four 16 K partitions, so the int16 variant at 104 registers fits only 4 warps per
+// partition and a third 6-warp block does not (ncu: launch__occupancy_limit_registers = 2); capped at 96 three blocks are
+// resident (0.194 -> 0.182 ms per 720p frame).  The limb variant got slower under the same cap (80 registers, 0.248 -> 0.276 ms)
+// and keeps its natural 109.
+__global__ void __maxnreg__(96)
+features_sliding_fast_kernel(const int32_t *__restrict__ frame, int fw, int fh, int16_t *__restrict__ out) {
+  sf_body<false>(frame, fw, fh, out, nullptr, nullptr, 0);
+}
+__global__ void __launch_bounds__(192, 2)
+features_sliding_limbs_kernel(const int32_t *__restrict__ frame, int fw, int fh, uint8_t *__restrict__ limbs, uint32_t *__restrict__ norms,
+                              int pwp) {
+  sf_body<true>(frame, fw, fh, nullptr, limbs, norms, pwp);
+}
+
 static int features_fast_init(cudaStream_t st) {
   static bool done[TM_MAX_DEVICES] = {};
   if (!first_use_on_device(done)) return TM_OK;
@@ -564,7 +577,7 @@ int launch_features_sliding(const int32_t *frame, int w, int h, int16_t *out, cu
     rc = features_fast_init(st);
     if (rc) return rc;
     const dim3 grid((unsigned)((w - 7 + SF_OXB - 1) / SF_OXB), (unsigned)((h - 7 + SF_SEG - 1) / SF_SEG));
-    features_sliding_fast_kernel<false><<<grid, 192, 0, st>>>(frame, w, h, out, nullptr, nullptr, 0);
+    features_sliding_fast_kernel<<<grid, 192, 0, st>>>(frame, w, h, out);
     note_launch();
     return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
   }
@@ -575,7 +588,7 @@ int launch_features_sliding(const int32_t *frame, int w, int h, int16_t *out, cu
 }
 
 // fast mode only: the sliding-window features of `frame` straight into the motion search's candidate operands (limb rows at
-// padded positions [h - 7][pwp][384] + norms [h - 7][pwp]); see features_sliding_fast_kernel<true>
+// padded positions [h - 7][pwp][384] + norms [h - 7][pwp]); see features_sliding_limbs_kernel
 int launch_features_sliding_limbs(const int32_t *frame, int w, int h, uint8_t *limbs, uint32_t *norms, int pwp, cudaStream_t st) {
   if (w < 8 || h < 8 || pwp < w - 7 || (pwp % SF_OXB) != 0) return TM_ERR_ARG;
   int rc = features_init(st);
@@ -584,7 +597,7 @@ int launch_features_sliding_limbs(const int32_t *frame, int w, int h, uint8_t *l
   if (rc) return rc;
   ProfScope prof("features_sliding", st);
   const dim3 grid((unsigned)(pwp / SF_OXB), (unsigned)((h - 7 + SF_SEG - 1) / SF_SEG));
-  features_sliding_fast_kernel<true><<<grid, 192, 0, st>>>(frame, w, h, nullptr, limbs, norms, pwp);
+  features_sliding_limbs_kernel<<<grid, 192, 0, st>>>(frame, w, h, limbs, norms, pwp);
   note_launch();
   return cudaGetLastError() == cudaSuccess ? TM_OK : TM_ERR_CUDA;
 }

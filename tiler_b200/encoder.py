@@ -17,11 +17,30 @@ C_PSNR_MAX = np.float64(10.0 * np.log(255.0 * 255.0 / 0.5) / np.log(10.0))   # c
 C_INV_PHI = 2.0 / (1.0 + np.sqrt(5.0))                                         # cInvPhi, utils.pas:42-43
 
 
-def euclidean_to_psnr(err):
-    """EuclideanToPSNR (utils.pas:1074-1078), vectorised: Single(d / 192) -> max 0.5 -> 10 log10(255^2 / x) -> Single."""
+def _euclidean_to_psnr_1(err):
     r = (np.asarray(err).astype(np.float64) * (1.0 / 192.0)).astype(np.float32)
     m = np.maximum(r.astype(np.float64), 0.5)
     return (10.0 * np.log10(255.0 * 255.0 / m)).astype(np.float32)
+
+
+def euclidean_to_psnr(err):
+    """EuclideanToPSNR (utils.pas:1074-1078), vectorised: Single(d / 192) -> max 0.5 -> 10 log10(255^2 / x) -> Single.
+    A whole clip's 3.4 M values are converted in slices on a few threads (numpy releases the GIL inside its loops): the same
+    element-wise operations, so the same bits, in a quarter of the time."""
+    err = np.asarray(err)
+    if err.size < (1 << 18):
+        return _euclidean_to_psnr_1(err)
+    flat = np.ascontiguousarray(err).reshape(-1)
+    out = np.empty(flat.shape, dtype=np.float32)
+    n_thr = 8
+    bounds = np.linspace(0, flat.size, n_thr + 1).astype(np.int64)
+
+    def work(i):
+        out[bounds[i]:bounds[i + 1]] = _euclidean_to_psnr_1(flat[bounds[i]:bounds[i + 1]])
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(n_thr) as pool:
+        list(pool.map(work, range(n_thr)))
+    return out.reshape(err.shape)
 
 
 def _reindex_order(tiles_rgb, use_count):

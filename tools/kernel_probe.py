@@ -29,7 +29,7 @@ api.motion_search(cur, 160, 90, d, 32)                                          
 api.set_feature_mode(api.FEATURES_FAST)                                                 # fast mode: the sliding kernel writes the search's limb rows
 t1 = torch.from_numpy(synth.frame_to_tiles(synth.pack_rgb(clip)[1])).to(dev)
 c1, f1 = api.mirror_canonicalise(t1)
-api.predict_motion_frame(frames[0], c1, f1, 160, 90, 32)                                # features_sliding_fast_kernel<true>, motion_tc_kernel
+api.predict_motion_frame(frames[0], c1, f1, 160, 90, 32)                                # features_sliding_limbs_kernel, motion_tc_kernel
 api.set_feature_mode(api.FEATURES_EXACT)
 big = canon.reshape(-1, 64).repeat(40, 1).contiguous()                                  # 3 456 000 tiles (configs[1] clip size)
 cls, n_cls = api.tile_classes(big)                                                      # tile_hash_kernel, class_boundary_kernel
