@@ -256,35 +256,50 @@ knn_i8_k1_kernel(const uint8_t *__restrict__ q_limbs, const __grid_constant__ CU
 #pragma unroll
         for (int ch = 0; ch < HN / 16; ++ch) {
           uint32_t dv[16];
-          uint32_t m = 0xFFFFFFFFu;
+          uint32_t m4[4];   // minimum of each group of four columns: the rare insertion path only walks groups that hold a candidate
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            uint32_t d = nd[ch * 16 + e];          // nq + nd
-            d -= pp[ch * 16 + e] << 9;
-            d -= lo[ch * 16 + e] << 1;
-            dv[e] = d;
-            m = min(m, d);
+          for (int g = 0; g < 4; ++g) {
+            m4[g] = 0xFFFFFFFFu;
+#pragma unroll
+            for (int e = 4 * g; e < 4 * g + 4; ++e) {
+              uint32_t d = nd[ch * 16 + e];          // nq + nd
+              d -= pp[ch * 16 + e] << 9;
+              d -= lo[ch * 16 + e] << 1;
+              dv[e] = d;
+              m4[g] = min(m4[g], d);
+            }
           }
           const int cbase = ch * 16;
           if (ncol < HN) {
-            m = 0xFFFFFFFFu;
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              if (cbase + e >= ncol) dv[e] = 0xFFFFFFFFu;
-              m = min(m, dv[e]);
+            for (int g = 0; g < 4; ++g) {
+              m4[g] = 0xFFFFFFFFu;
+#pragma unroll
+              for (int e = 4 * g; e < 4 * g + 4; ++e) {
+                if (cbase + e >= ncol) dv[e] = 0xFFFFFFFFu;
+                m4[g] = min(m4[g], dv[e]);
+              }
             }
           }
-          if (m <= best_d) {   // rare once good candidates have been seen; ties go to the lower dictionary index
+          const uint32_t m = min(min(m4[0], m4[1]), min(m4[2], m4[3]));
+          // A warp takes this branch when ANY lane has a candidate: with the KS = 4 lists of the k-means search that is a quarter of
+          // all 16-column units (32 lanes x 4 ln N insertions each), and walking all 16 columns every time made the k = 4 kernel
+          // 1.6x slower per distance than k = 1.  Ties go to the lower dictionary index.
+          if (m <= best_d) {
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              if (dv[e] == 0xFFFFFFFFu) continue;
-              unsigned long long key = ((unsigned long long)dv[e] << 32) | (uint32_t)(col0 + cbase + e);
-              if (key < bk[KS - 1]) {   // sorted insertion
+            for (int g = 0; g < 4; ++g) {
+              if (m4[g] > best_d) continue;
 #pragma unroll
-                for (int r = 0; r < KS; ++r) {
-                  if (key < bk[r]) { const unsigned long long t = bk[r]; bk[r] = key; key = t; }
+              for (int e = 4 * g; e < 4 * g + 4; ++e) {
+                if (dv[e] == 0xFFFFFFFFu) continue;
+                unsigned long long key = ((unsigned long long)dv[e] << 32) | (uint32_t)(col0 + cbase + e);
+                if (key < bk[KS - 1]) {   // sorted insertion
+#pragma unroll
+                  for (int r = 0; r < KS; ++r) {
+                    if (key < bk[r]) { const unsigned long long t = bk[r]; bk[r] = key; key = t; }
+                  }
+                  best_d = (uint32_t)(bk[KS - 1] >> 32);
                 }
-                best_d = (uint32_t)(bk[KS - 1] >> 32);
               }
             }
           }
