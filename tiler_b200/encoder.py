@@ -279,7 +279,21 @@ class TilingEncoder:
             padded[:, :H, :W] = frames_packed
             frames_packed, H, W = padded, th * 8, tw * 8
         if self.device is not None:   # frames -> tiles is a pure layout change: done on the device (torch = memory plumbing)
-            fr_dev = frames_packed if api._is_dev(frames_packed) else torch.from_numpy(np.ascontiguousarray(frames_packed)).to(self.device)
+            if api._is_dev(frames_packed):
+                fr_dev = frames_packed
+            elif world > 1 and tdist.device_collectives() and n >= world:
+                # every rank holds the clip on the host, but N ranks pushing all of it over the host links at once is the slow way
+                # round: each uploads n / N frames and the rest arrives from the peers over NVLink (one all-gather)
+                import torch.distributed as tdd
+                per = (n + world - 1) // world
+                lo_u, hi_u = min(n, rank * per), min(n, (rank + 1) * per)
+                buf = torch.zeros((world * per, H, W), dtype=torch.int32, device=self.device)
+                if hi_u > lo_u:
+                    buf[lo_u:hi_u] = torch.from_numpy(np.ascontiguousarray(frames_packed[lo_u:hi_u])).to(self.device)
+                tdd.all_gather_into_tensor(buf, buf[rank * per:(rank + 1) * per].clone())
+                fr_dev = buf[:n]
+            else:
+                fr_dev = torch.from_numpy(np.ascontiguousarray(frames_packed)).to(self.device)
             tiles = fr_dev.view(n, th, 8, tw, 8).permute(0, 1, 3, 2, 4).contiguous().view(n, nt, 64)
             frames_packed = fr_dev
         else:
