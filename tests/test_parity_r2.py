@@ -230,6 +230,24 @@ def test_two_devices_in_one_process(tm, oracle):
         assert f64.device.index == dev
 
 
+def test_sharded_encode_equals_single_process_encode():
+    """Two ranks (torchrun, NCCL): the sharded encode -- frames uploaded n / N per rank and all-gathered, PSNRs / tilemaps / use counts
+    exchanged as device tensors, LZMA chunks compressed per rank -- gives the single-process stream byte for byte, in both feature
+    modes, with uneven sequences and a frame count that is not a multiple of the world size."""
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(ROOT, "tools", "sharded_encode_check.py")],
+                       capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+    res = json.loads(line)
+    for mode in ("fast", "exact"):
+        assert res[mode]["equal"] and res[mode]["tilemap_equal"], res
+
+
 # ------------------------------------------------------------------ fast (separable f64) sliding-window features
 @pytest.mark.parametrize("w,h", [(96, 64), (100, 52), (320, 184), (15, 8)])
 def test_sliding_features_fast_mode_within_contract(tm, oracle, w, h):
