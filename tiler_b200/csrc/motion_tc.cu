@@ -26,7 +26,16 @@ namespace {
 constexpr int BM = 128, BN = 64, NST = 8, ROWB = 384;
 constexpr int CHUNK_B = BN * 128, B_TILE = 3 * CHUNK_B, ACC_COLS = 3 * BN, A_COL = 2 * ACC_COLS;
 constexpr int BTW = 16, BTH = 8;   // tiles per block: 16 wide x 8 tall = 128 MMA rows
-constexpr int MT_THREADS = 352;    // 8 epilogue warps + TMA warp + 2 MMA issuer warps
+#ifndef TM_MT_NH
+#define TM_MT_NH 4
+#endif
+// Column splits per B tile = epilogue warps per TMEM lane quarter.  A candidate row is outside the vertical window of two of the
+// eight tile rows of a block more often than not, so at any tile ~3 of 8 epilogue warps have nothing to do while the live
+// ones set the pace (ncu source page: 40 % of the epilogue warps' samples sit in the accumulator wait); four warps per quarter
+// with 16 columns each halve the live warps' work per tile.
+constexpr int MT_NH = TM_MT_NH;
+constexpr int MT_NEW = 4 * MT_NH;                    // epilogue warps; warp MT_NEW = TMA producer, MT_NEW + 1 / + 2 = MMA issuers
+constexpr int MT_THREADS = (MT_NEW + 3) * 32;
 }  // namespace
 
 // sliding features [ph * pw][192] int16 -> padded limb rows [ph][pwp][384] + norms [ph][pwp] (pad entries zero)
@@ -68,15 +77,19 @@ __global__ void __launch_bounds__(192) cand_limb_split_kernel(const int16_t *__r
   }
 }
 
+#if TM_MT_NH == 4
+__global__ void __maxnreg__(96)     // 19 warps: five per register-file partition (16 K registers) -> at most 102 each
+#else
 __global__ void __launch_bounds__(MT_THREADS, 1)
+#endif
 motion_tc_kernel(const uint8_t *__restrict__ t_limbs, const uint32_t *__restrict__ t_norm, int tw, int th,
                  const __grid_constant__ CUtensorMap tmap_c, const uint32_t *__restrict__ c_norm, int pwp, int R,
                  int32_t *__restrict__ pred_x, int32_t *__restrict__ pred_y, uint32_t *__restrict__ err_out) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t *sB = smem;
-  unsigned long long *s_merge = reinterpret_cast<unsigned long long *>(sB + NST * B_TILE);   // [128]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(s_merge + BM);
+  unsigned long long *s_merge = reinterpret_cast<unsigned long long *>(sB + NST * B_TILE);   // [MT_NH - 1][128]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(s_merge + BM * (MT_NH - 1));
   uint64_t *full = bars, *empty = bars + NST, *a_full = bars + 2 * NST, *a_empty = a_full + 1, *t_full = a_empty + 1,
            *t_empty = t_full + 2;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(t_empty + 2);
@@ -89,11 +102,11 @@ motion_tc_kernel(const uint8_t *__restrict__ t_limbs, const uint32_t *__restrict
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_full, 4);
     mbar_init(a_empty, 2);
-    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], 8); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&t_full[g], 1); mbar_init(&t_empty[g], MT_NEW); }
     fence_barrier_init();
   }
-  if (warp == 9) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  if (warp == 8 && lane == 0) tma_prefetch_desc(&tmap_c);
+  if (warp == MT_NEW + 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
+  if (warp == MT_NEW && lane == 0) tma_prefetch_desc(&tmap_c);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -115,7 +128,7 @@ motion_tc_kernel(const uint8_t *__restrict__ t_limbs, const uint32_t *__restrict
     nseg = (oxmx - OX0) / 64 + 1;
   };
 
-  if (warp == 8) {
+  if (warp == MT_NEW) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;
@@ -132,9 +145,9 @@ motion_tc_kernel(const uint8_t *__restrict__ t_limbs, const uint32_t *__restrict
           }
       }
     }
-  } else if (warp >= 9) {
+  } else if (warp > MT_NEW) {
     // ===================== two MMA issuer warps (even / odd B tiles) =====================
-    const uint32_t my_parity = (uint32_t)(warp - 9);
+    const uint32_t my_parity = (uint32_t)(warp - MT_NEW - 1);
     const uint64_t descB0 = umma_desc_sw128(smem_u32(sB));
     uint32_t it = 0, wv = 0;
     for (int b = blockIdx.x; b < n_blocks; b += gridDim.x, ++wv) {
@@ -151,7 +164,9 @@ motion_tc_kernel(const uint8_t *__restrict__ t_limbs, const uint32_t *__restrict
         mbar_wait(&t_empty[ts], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint64_t dB = descB0 + (uint64_t)((s * B_TILE) >> 4);
+#if !(defined(TM_MT_DBG) && (TM_MT_DBG & 2))   // timing experiment: no MMAs
         if (my_parity == 0) mma_i8_tile_elect<0>((uint32_t)dB); else mma_i8_tile_elect<1>((uint32_t)dB);
+#endif
         tc_commit_elect(&t_full[ts]);
         tc_commit_elect(&empty[s]);
       }
@@ -162,7 +177,7 @@ motion_tc_kernel(const uint8_t *__restrict__ t_limbs, const uint32_t *__restrict
     const int q = warp & 3, hh = warp >> 2;
     const int row = q * 32 + lane;                 // row = ty_local * 16 + tx_local
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    constexpr int HN = BN / 2;
+    constexpr int HN = BN / MT_NH;
     uint32_t it = 0, wv = 0;
     for (int b = blockIdx.x; b < n_blocks; b += gridDim.x, ++wv) {
       int bx0, by0, OX0, OY0, n_oy, nseg;
@@ -240,6 +255,9 @@ motion_tc_kernel(const uint8_t *__restrict__ t_limbs, const uint32_t *__restrict
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&t_empty[ts]);
+#if defined(TM_MT_DBG) && (TM_MT_DBG & 1)
+          continue;   // timing experiment: no epilogue arithmetic
+#endif
           if (!row_live) continue;
           const int e_lo = max(0, oxmn - ox0), e_hi = min(HN - 1, oxmx - ox0);   // this row's live columns
           if (e_lo > e_hi) continue;
@@ -266,11 +284,12 @@ motion_tc_kernel(const uint8_t *__restrict__ t_limbs, const uint32_t *__restrict
       }
       // merge the two column halves of each row on (error, scan index)
       const unsigned long long key = ((unsigned long long)best << 32) | best_p;
-      if (hh == 1) s_merge[row] = key;
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      if (hh > 0) s_merge[(hh - 1) * BM + row] = key;
+      asm volatile("bar.sync 1, %0;\n" ::"n"(MT_NEW * 32) : "memory");
       if (hh == 0 && valid) {
-        const unsigned long long o = s_merge[row];
-        const unsigned long long k2 = o < key ? o : key;
+        unsigned long long k2 = key;
+#pragma unroll
+        for (int o2 = 0; o2 < MT_NH - 1; ++o2) { const unsigned long long o = s_merge[o2 * BM + row]; k2 = o < k2 ? o : k2; }
         const uint32_t e = (uint32_t)(k2 >> 32), p = (uint32_t)k2;
         int bx = 0, byy = 0;
         if (e != 0xFFFFFFFFu || p != 0xFFFFFFFFu) {
@@ -279,13 +298,13 @@ motion_tc_kernel(const uint8_t *__restrict__ t_limbs, const uint32_t *__restrict
         }
         pred_x[tile] = bx; pred_y[tile] = byy; err_out[tile] = e;
       }
-      asm volatile("bar.sync 1, 256;\n" ::: "memory");   // s_merge is rewritten by the next tile block
+      asm volatile("bar.sync 1, %0;\n" ::"n"(MT_NEW * 32) : "memory");   // s_merge is rewritten by the next tile block
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 9) tmem_dealloc(tmem_base, 512);
+  if (warp == MT_NEW + 1) tmem_dealloc(tmem_base, 512);
 }
 
 size_t motion_tc_ws_bytes(int tw, int th) {
@@ -326,7 +345,7 @@ int launch_motion_search_tc(const int16_t *cur_feat, int tw, int th, const int16
   CUtensorMap tc;
   rc = make_tmap_rows_u8(&tc, c_limbs, (uint64_t)npad, ROWB, BN);
   if (rc != TM_OK) return rc;
-  constexpr int SMEM = NST * B_TILE + BM * 8 + 256 + 1024;
+  constexpr int SMEM = NST * B_TILE + BM * 8 * (MT_NH - 1) + 256 + 1024;
   static bool attr_set[TM_MAX_DEVICES] = {};
   if (first_use_on_device(attr_set)) {
     if (cudaFuncSetAttribute(motion_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) return TM_ERR_CUDA;
