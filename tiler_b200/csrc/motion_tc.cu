@@ -261,16 +261,18 @@ motion_tc_kernel(const uint8_t *__restrict__ t_limbs, const uint32_t *__restrict
           if (!row_live) continue;
           const int e_lo = max(0, oxmn - ox0), e_hi = min(HN - 1, oxmx - ox0);   // this row's live columns
           if (e_lo > e_hi) continue;
+          const uint32_t live_cols = ((2u << e_hi) - 1u) & ~((1u << e_lo) - 1u);   // bits e_lo..e_hi
           uint32_t m = 0xFFFFFFFFu;
           const uint32_t base = nq + pen_y;
+          const int v0 = ox0 - dx;
 #pragma unroll
           for (int e = 0; e < HN; ++e) {   // error incl. the Manhattan penalty, kept in pp[]; columns outside the window never compete
-            const uint32_t p = (pp[e] << 8) + xx[e];
-            uint32_t d = nd[e] + base;
-            d -= p << 9;
-            d -= lo[e] << 1;
-            d += (uint32_t)abs(ox0 + e - dx);
-            d = (e >= e_lo && e <= e_hi) ? d : 0xFFFFFFFFu;
+            // d = |a|^2 + |b|^2 + penalty - 2 (65536 HH + 256 X + LL)  (mod 2^32): (256 HH + X) * (-512) + s, then - LL - LL
+            const uint32_t s3 = nd[e] + base + (uint32_t)abs(v0 + e);
+            const uint32_t a = pp[e] * 256u + xx[e];
+            uint32_t d = a * 0xFFFFFE00u + s3;
+            d = d - lo[e] - lo[e];
+            d = (live_cols & (1u << e)) ? d : 0xFFFFFFFFu;   // one bit test per column instead of two range compares
             pp[e] = d;
             m = min(m, d);
           }
