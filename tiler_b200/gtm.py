@@ -184,11 +184,14 @@ def write_gtm(path_or_none, tm, tiles_idx, use_count, palettes, tw, th, sequence
                                    int(emit_skip_blocks), 1, buf.ctypes.data, cap)
         assert 0 < n <= cap
         raw = (bytes(pre) if ki == 0 else b"") + buf[:n].tobytes()
-        comp = lzma_encode(raw)
+        # chunk 0 carries the tile set and is the long pole of Save: it gets the full set of parser threads, the other chunks
+        # (compressed at the same time by the pool below) two each, so that its coder thread is not descheduled by theirs
+        comp = lzma_encode(raw, n_threads=(0 if ki == 0 or n_jobs <= 2 else 2))
         return comp, (ki, f0, len(raw), len(comp), int(round(1000.0 * f0 / fps)))
 
     from concurrent.futures import ThreadPoolExecutor
     jobs = [(ki, sq) for ki, sq in enumerate(sequences) if only is None or ki in only]
+    n_jobs = len(jobs)
     with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as pool:
         done = dict(zip([j[0] for j in jobs], pool.map(one_chunk, jobs)))
     if exchange is not None:
