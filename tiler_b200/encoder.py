@@ -346,9 +346,13 @@ class TilingEncoder:
                     full[k][s0:s1 + 1] = r[k]
                 tile_use_d += use_si
             else:
-                local[si] = {k: (r[k].cpu().numpy() if api._is_dev(r[k]) else r[k]) for k in keys}
-                local[si]["use"] = use_si.cpu().numpy() if api._is_dev(use_si) else use_si
+                # device results stay on the device until every sequence of this rank is enqueued: a .cpu() here would make the
+                # host wait for this sequence before it can launch the next one
+                local[si] = {k: r[k] for k in keys}
+                local[si]["use"] = use_si
             recon_of[si] = r["recon"]        # stays on the device when the encoder is device-resident
+        for si in local:
+            local[si] = {k: (v.cpu().numpy() if api._is_dev(v) else v) for k, v in local[si].items()}
         if dev_coll:
             import torch.distributed as tdd
             if full is None:   # a rank without sequences still takes part in the collectives
