@@ -421,18 +421,27 @@ class Matcher:
                                            C.byref(h)))
         self._h = h
 
-    def _run(self, fn, x, width, dtype, k):
+    def _run(self, fn, x, width, dtype, k, out=None):
         c = _Call(x)
         n_q = _n_rows(x, width)
-        tile, pt = c.out((n_q,), np.int32)
-        pal, pp = c.out((n_q,), np.int32)
-        err, pe = c.out((n_q,), np.uint32)
+        if out is not None and not c.dev:
+            # caller-provided HOST result arrays (tile int32, pal int32, err uint32; contiguous, n_q each) -- like the C ABI itself,
+            # where the host owns the output buffers: page-locked ones make the read-back a plain DMA instead of a staged copy
+            tile, pal, err = out
+            for a, dt in ((tile, np.int32), (pal, np.int32), (err, np.uint32)):
+                if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous and a.size == n_q):
+                    raise ValueError("out: three contiguous numpy arrays (int32, int32, uint32) of n rows")
+            pt, pp, pe = (C.c_void_p(a.ctypes.data) for a in (tile, pal, err))
+        else:
+            tile, pt = c.out((n_q,), np.int32)
+            pal, pp = c.out((n_q,), np.int32)
+            err, pe = c.out((n_q,), np.uint32)
         check(fn(self._h, c.inp(x, dtype), n_q, int(k), pt, pp, pe))
         return tile, pal, err
 
-    def match_rgb(self, rgb, k=None):
-        """Source tiles as RGB [n,64] -> (TileIdx, PalIdx, err) per tile."""
-        return self._run(_lib.lib().tm_match_tiles_rgb, rgb, 64, np.int32, k or (self.K_EPU if self.extended else 1))
+    def match_rgb(self, rgb, k=None, out=None):
+        """Source tiles as RGB [n,64] -> (TileIdx, PalIdx, err) per tile.  out: optional host result arrays to fill (see _run)."""
+        return self._run(_lib.lib().tm_match_tiles_rgb, rgb, 64, np.int32, k or (self.K_EPU if self.extended else 1), out=out)
 
     def match_rgb_mirrors(self, rgb, k=None):
         """Mirror-variant search (tm_match_tiles_rgb_mirrors). -> (tile_idx, pal_idx, err, variant); variant bit 0 / 1 = extra
