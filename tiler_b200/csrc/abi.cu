@@ -881,7 +881,7 @@ extern "C" int tm_match_tiles_rgb(tm_matcher *m, const int32_t *rgb, int64_t n_q
   int32_t *d_tile = s.out(tile_idx, (size_t)n_q), *d_pal = s.out(pal_idx, (size_t)n_q);
   uint32_t *d_err = s.out(err, (size_t)n_q);
   int16_t *d_feat = (int16_t *)s.temp((size_t)n_q * 384);
-  // A large batch of HOST tiles is uploaded in four pieces on a second stream while the pieces already on the device are
+  // A large batch of HOST tiles is uploaded in pieces on a second stream while the pieces already on the device are
   // matched: only the first piece (two k-NN waves, 10 MB of the 110 MB of a 720p sequence) stays exposed.  Pieces are
   // whole waves of k-NN query blocks (SMs x 128 rows) so the split costs the search no tail.
   const int64_t wave = (int64_t)num_sms() * knn_rows_per_cta();
@@ -899,9 +899,15 @@ extern "C" int tm_match_tiles_rgb(tm_matcher *m, const int32_t *rgb, int64_t n_q
     cudaEvent_t *ev = ev_dev[dev];
     int32_t *d_rgb = (int32_t *)s.temp((size_t)n_q * 256);
     s.any_host = true;
-    const int64_t first = 2 * wave, piece = ((n_q - first + 2) / 3 + wave - 1) / wave * wave;
-    int64_t cut[5] = {0, first, first + piece, first + 2 * piece, n_q};
-    for (int i = 2; i < 4; ++i) if (cut[i] > n_q) cut[i] = n_q;
+    // TM_MATCH_PIECES = 2..4: the first piece + 1..3 equal ones.  Default 3: every piece boundary drains the persistent k-NN kernel
+    // once (measured end to end on 432 000 tiles: 4 pieces 1.11-1.13e12, 3 pieces 1.135e12, 2 pieces 1.136e12 evals/s), and with
+    // 3 the second upload (29 MB) still hides behind the first piece on a slower host link
+    static int n_pieces = -1;
+    if (n_pieces < 0) { const char *e = getenv("TM_MATCH_PIECES"); n_pieces = e ? atoi(e) : 3; if (n_pieces < 2 || n_pieces > 4) n_pieces = 3; }
+    const int rest = n_pieces - 1;
+    const int64_t first = 2 * wave, piece = ((n_q - first + rest - 1) / rest + wave - 1) / wave * wave;
+    int64_t cut[5] = {0, first, n_q, n_q, n_q};
+    for (int i = 2; i < 4; ++i) if (i <= rest) cut[i] = first + (i - 1) * piece < n_q ? first + (i - 1) * piece : n_q;
     if (s.err == TM_OK) {
       // Copy i + 1 is queued AFTER the kernels of piece i are launched: with pageable input the host blocks inside
       // cudaMemcpyAsync while it stages the bytes, and this order lets the resident piece be matched meanwhile.  No early
